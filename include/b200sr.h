@@ -1,0 +1,112 @@
+/*
+ * b200sr.h -- C ABI of libb200sr.so: the RRDBNet generator (forward + backward) of MiNeves00/SR-GAN-FD as
+ * hand-written sm_100a CUDA kernels.
+ *
+ * What this boundary replaces in the reference (pure PyTorch, no FFI of its own -- the "binding" is the
+ * nn.Module.forward / autograd boundary):
+ *   - ESRGAN/model.py:211-232   RRDBNet._forward_impl      (= BSRGAN/model.py:366-381, Real_ESRGAN/model.py:246-263,
+ *                                                             A-ESRGAN/model.py:534-549)
+ *   - ESRGAN/model.py:49-60     _ResidualDenseBlock.forward
+ *   - ESRGAN/model.py:77-86     _ResidualResidualDenseBlock.forward
+ *   - the autograd backward of all of the above (triggered at ESRGAN/train_rrdbnet.py:261, BSRGAN/train_bsrgan.py:463)
+ * The reference-side stub that binds these entry points (ctypes, inside one torch.autograd.Function) is shown in
+ * INTEGRATION.md and shipped as sr_gan_fd_b200/function.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors); the library never frees or keeps one
+ *     past the call, except that a plan caches TMA descriptors keyed on the workspace / packed / grads addresses;
+ *   - all work is enqueued on the given stream, no hidden synchronisation (plan creation and the first call per
+ *     workspace address do host-side descriptor encoding only);
+ *   - return 0 on success, a negative b200sr_status otherwise; b200sr_last_error() gives a thread-local message;
+ *   - plain C types only (no torch / C++ types).
+ */
+#ifndef B200SR_H_
+#define B200SR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200sr_plan b200sr_plan;
+typedef void* b200sr_stream; /* cudaStream_t */
+
+enum b200sr_status {
+  B200SR_OK = 0,
+  B200SR_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  B200SR_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed       */
+  B200SR_ERR_UNSUPPORTED = -3  /* device is not sm_100                      */
+};
+
+enum b200sr_dtype { B200SR_F32 = 0, B200SR_F16 = 1, B200SR_BF16 = 2 };
+
+/* Network + problem geometry.  Mirrors the reference constructor arguments (ESRGAN/model.py:145-153):
+ * channels must be 64 and growth 32 (the only values the reference configs use; the tiles are built on them). */
+typedef struct b200sr_net_desc {
+  int32_t in_channels;  /* conv1 input channels (after Real-ESRGAN's pixel-unshuffle), 1..21 */
+  int32_t out_channels; /* conv4 output channels, 1..16 */
+  int32_t channels;     /* 64 */
+  int32_t growth;       /* 32 */
+  int32_t num_blocks;   /* RRDB count (23) */
+  int32_t n_up;         /* nearest-x2 + conv stages: 0 (x1) .. 3 (x8) */
+  int32_t batch, height, width; /* LR input geometry */
+  int32_t training;     /* 1: keep activations for backward, build the backward schedule */
+} b200sr_net_desc;
+
+/* Called from inside b200sr_backward (on the calling host thread) each time every kernel that contributes to a
+ * contiguous range [offset, offset+count) of the flat gradient buffer has been ENQUEUED on the stream: the callee
+ * may record an event and start the NCCL all-reduce of that bucket on another stream. */
+typedef void (*b200sr_bucket_cb)(void* user, int64_t offset, int64_t count);
+
+int b200sr_plan_create(const b200sr_net_desc* desc, b200sr_plan** out);
+void b200sr_plan_destroy(b200sr_plan* plan);
+
+/* sizes (bytes) of the caller-allocated buffers */
+size_t b200sr_workspace_bytes(const b200sr_plan* plan);
+size_t b200sr_packed_bytes(const b200sr_plan* plan);
+/* number of parameter tensors (2 per conv: weight, bias) and total fp32 elements, in state_dict order */
+int32_t b200sr_num_params(const b200sr_plan* plan);
+int64_t b200sr_param_numel(const b200sr_plan* plan);
+/* algorithmic FLOPs (2 x MACs of the reference graph) of one forward / one backward at the plan's geometry */
+double b200sr_flops(const b200sr_plan* plan, int backward);
+/* number of kernel launches one forward / backward enqueues */
+int32_t b200sr_num_launches(const b200sr_plan* plan, int backward);
+
+/* params: host array of b200sr_num_params() device pointers, fp32, state_dict order (conv1.weight, conv1.bias,
+ * trunk.0.rdb1.conv1.weight, ...; weights OIHW).  Re-packs them into the bf16 tiles the kernels consume. */
+int b200sr_pack_weights(b200sr_plan* plan, const float* const* params, void* packed, b200sr_stream stream);
+
+/* x: [batch, in_channels, height, width] with element strides x_strides[4] (NCHW or channels_last), dtype per
+ * b200sr_dtype.  y: [batch, out_channels, s*height, s*width] fp32 contiguous, clamped to [0,1]. */
+int b200sr_forward(b200sr_plan* plan, const void* x, int x_dtype, const int64_t* x_strides, const void* packed,
+                   void* workspace, float* y, b200sr_stream stream);
+
+/* dy: gradient w.r.t. y, fp32 contiguous.  workspace/packed must be the ones used by the matching forward.
+ * flat_grads: b200sr_param_numel() floats, OVERWRITTEN with the parameter gradients (state_dict order). */
+int b200sr_backward(b200sr_plan* plan, const float* dy, const void* packed, void* workspace, float* flat_grads,
+                    b200sr_bucket_cb cb, void* user, b200sr_stream stream);
+
+/* ---- single-layer entry points (used by the parity tests) ------------------------------------------------------
+ * x: NHWC bf16 [n*h*w][x_stride], the conv reads channels [0, cin).  w: fp32 OIHW [cout][cin][3][3], bias [cout] or
+ * NULL.  y: NHWC bf16 [n*h*w][y_stride], written at channel y_coff.  act = 1 applies LeakyReLU(0.2).
+ * scratch: >= b200sr_conv3x3_scratch_bytes(cin, cout) bytes. */
+size_t b200sr_conv3x3_scratch_bytes(int cin, int cout);
+int b200sr_conv3x3_fwd(const void* x, int n, int h, int w_, int cin, int x_stride, const float* w, const float* bias,
+                       int cout, int act, void* y, int y_stride, int y_coff, void* scratch, b200sr_stream stream);
+/* dx[n*h*w][dx_stride] (bf16, channels [dx_coff, dx_coff+cin)) = conv_transpose of dy (bf16, channels [0, cout)) */
+int b200sr_conv3x3_dgrad(const void* dy, int n, int h, int w_, int cout, int dy_stride, const float* w, int cin,
+                         void* dx, int dx_stride, int dx_coff, void* scratch, b200sr_stream stream);
+/* dw[cout][cin][3][3] fp32 += sum_pixels x (bf16, channels [0, cin)) * dy (bf16, channels [0, cout)); cin <= 128,
+ * cout <= 160.  dw must be zero-initialised by the caller for a plain gradient. */
+int b200sr_conv3x3_wgrad(const void* x, int n, int h, int w_, int cin, int x_stride, const void* dy, int cout,
+                         int dy_stride, float* dw, b200sr_stream stream);
+
+const char* b200sr_last_error(void);
+int b200sr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SR_H_ */

@@ -1,0 +1,213 @@
+// Bandwidth-bound helper kernels around the tcgen05 convs: weight re-packing (fp32 OIHW master -> bf16 K-major
+// tap-major tiles, incl. the dgrad transpose/flip, the hi/lo split and the nearest-upsample phase folding),
+// input/output layout conversion, bias gradients, and the fold of phase weight-gradients back to 3x3.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200sr {
+
+// ------------------------------------------------------------------------------------------------ weight packing
+enum PackMode : int {
+  kPackFwd = 0,      // elem(n, k, ty, tx) = W[o_off + n][i_off + k][ty][tx]
+  kPackDgrad = 1,    // elem(n, k, ty, tx) = W[o_off + k][i_off + n][2-ty][2-tx]
+  kPackUpFwd = 2,    // n = phase*64 + co: sum of the taps of W[co][k] that fold onto LR tap (ty,tx) for that phase
+  kPackUpDgrad = 3   // k = phase*64 + co, n = ci: transposed + flipped version of kPackUpFwd
+};
+
+struct PackSeg {
+  int k0, klen;   // packed K-channel range [k0, k0 + klen) served by this segment
+  int w_index;    // index into the parameter pointer table
+  int O, I;       // source tensor dims (OIHW)
+  int o_off, i_off;
+  int part;       // 0: bf16(w)   1: bf16(w - bf16(w))   (hi / lo split)
+};
+
+struct PackOp {
+  int row0;        // first packed row
+  int n_total;     // rows per (chunk, dx, dy) block
+  int n_valid;     // rows >= n_valid are zero
+  int num_chunks;  // 64-channel K chunks
+  int mode;
+  int nseg;
+  PackSeg seg[5];
+};
+
+// nearest-x2 upsample followed by a 3x3 conv == four phase convs on the LOW-RES grid.  For output phase a (0/1)
+// and low-res tap t (0,1,2 <-> offset -1,0,+1) the contributing original taps d are [lo, hi):
+//   a = 0: t=0 <- {0}, t=1 <- {1,2}, t=2 <- {}        a = 1: t=0 <- {}, t=1 <- {0,1}, t=2 <- {2}
+__host__ __device__ inline void up_phase_taps(int a, int t, int& lo, int& hi) {
+  if (a == 0) { lo = (t == 0) ? 0 : (t == 1 ? 1 : 0); hi = (t == 0) ? 1 : (t == 1 ? 3 : 0); }
+  else        { lo = (t == 0) ? 0 : (t == 1 ? 0 : 2); hi = (t == 0) ? 0 : (t == 1 ? 2 : 3); }
+}
+
+__device__ __forceinline__ float pack_fetch(const PackOp& op, const float* const* params, int n, int k, int ty, int tx) {
+  if (n >= op.n_valid) return 0.f;
+  for (int s = 0; s < op.nseg; ++s) {
+    const PackSeg& sg = op.seg[s];
+    const int kl = k - sg.k0;
+    if (kl < 0 || kl >= sg.klen) continue;
+    const float* w = params[sg.w_index];
+    float v = 0.f;
+    if (op.mode == kPackFwd) {
+      v = w[((static_cast<long long>(sg.o_off + n) * sg.I + sg.i_off + kl) * 3 + ty) * 3 + tx];
+    } else if (op.mode == kPackDgrad) {
+      v = w[((static_cast<long long>(sg.o_off + kl) * sg.I + sg.i_off + n) * 3 + (2 - ty)) * 3 + (2 - tx)];
+    } else {
+      int phase, co, ci, ry, rx;
+      if (op.mode == kPackUpFwd) { phase = n >> 6; co = n & 63; ci = kl; ry = ty; rx = tx; }
+      else                       { phase = kl >> 6; co = kl & 63; ci = n; ry = 2 - ty; rx = 2 - tx; }
+      int ylo, yhi, xlo, xhi;
+      up_phase_taps(phase >> 1, ry, ylo, yhi);
+      up_phase_taps(phase & 1, rx, xlo, xhi);
+      const float* wp = w + (static_cast<long long>(sg.o_off + co) * sg.I + sg.i_off + ci) * 9;
+      for (int dy = ylo; dy < yhi; ++dy)
+        for (int dx = xlo; dx < xhi; ++dx) v += wp[dy * 3 + dx];
+    }
+    if (sg.part == 1) v = v - __bfloat162float(__float2bfloat16_rn(v));
+    return v;
+  }
+  return 0.f;
+}
+
+// One thread per packed element.  Row layout inside an op: [chunk][dx][dy][n], 64 K-channels per row.
+__global__ void pack_weights_kernel(const PackOp* __restrict__ ops, int num_ops, const float* const* __restrict__ params,
+                                    __nv_bfloat16* __restrict__ packed, long long total_rows) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long row = idx >> 6;
+  const int kk = static_cast<int>(idx & 63);
+  if (row >= total_rows) return;
+  int lo = 0, hi = num_ops - 1;  // last op with row0 <= row
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (ops[mid].row0 <= row) lo = mid; else hi = mid - 1;
+  }
+  const PackOp& op = ops[lo];
+  const int r = static_cast<int>(row - op.row0);
+  const int n = r % op.n_total;
+  const int t = r / op.n_total;  // (chunk*3 + dx)*3 + dy
+  const int dy = t % 3, dx = (t / 3) % 3, c = t / 9;
+  float v = (c < op.num_chunks) ? pack_fetch(op, params, n, c * 64 + kk, dy, dx) : 0.f;
+  packed[idx] = __float2bfloat16_rn(v);
+}
+
+// biases: flat fp32 copy (bias_index < 0 -> zeros)
+struct BiasOp { int off; int n; int b_index; int n_valid; int rep; };  // rep: repeat period (phase convs reuse 64 biases)
+__global__ void pack_bias_kernel(const BiasOp* __restrict__ ops, int num_ops, const float* const* __restrict__ params,
+                                 float* __restrict__ out) {
+  const int o = blockIdx.x;
+  if (o >= num_ops) return;
+  const BiasOp op = ops[o];
+  for (int i = threadIdx.x; i < op.n; i += blockDim.x) {
+    const int j = op.rep > 0 ? (i % op.rep) : i;
+    out[op.off + i] = (op.b_index >= 0 && j < op.n_valid) ? params[op.b_index][j] : 0.f;
+  }
+}
+
+// -------------------------------------------------------------------------------------------- input conversion
+// x: [N, C, H, W] (any strides, fp32/fp16/bf16) -> [N*H*W, 64*chunks] bf16 with channels [hi(C) | lo(C) | hi(C) | 0..]
+// (the conv1 weights are packed as [w_hi | w_hi | w_lo], giving ~fp32-accurate products from bf16 MMAs).
+template <typename T>
+__global__ void ingest_input_kernel(const T* __restrict__ x, long long sn, long long sc, long long sh, long long sw,
+                                    int N, int C, int H, int W, __nv_bfloat16* __restrict__ out, int out_stride) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * H * W;
+  if (pix >= total) return;
+  const int xw = static_cast<int>(pix % W);
+  const int yh = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  __nv_bfloat16* o = out + pix * out_stride;
+  for (int c = 0; c < C; ++c) {
+    const float v = static_cast<float>(x[n * sn + c * sc + yh * sh + xw * sw]);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    o[c] = h;
+    o[C + c] = l;
+    o[2 * C + c] = h;
+  }
+  for (int c = 3 * C; c < out_stride; ++c) o[c] = __float2bfloat16_rn(0.f);
+}
+
+// dy: [N, C, H, W] fp32 contiguous (gradient of the clamped image) -> [N*H*W, 64] bf16, channels >= C zero,
+// multiplied by the clamp pass-through mask recorded in the forward.
+__global__ void ingest_grad_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ mask, int N, int C,
+                                   int H, int W, __nv_bfloat16* __restrict__ out, int out_stride) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long plane = static_cast<long long>(H) * W;
+  const long long total = static_cast<long long>(N) * plane;
+  if (pix >= total) return;
+  const long long n = pix / plane;
+  const long long r = pix - n * plane;
+  __nv_bfloat16* o = out + pix * out_stride;
+  for (int c = 0; c < 16; ++c) {
+    float v = 0.f;
+    if (c < C) {
+      const long long i = (n * C + c) * plane + r;
+      v = mask[i] ? dy[i] : 0.f;
+    }
+    o[c] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ bias gradients
+// db[c] += sum over pixels of g[pixel][c0 + c] for c in [0, ncols).  g is bf16 [P][stride].
+struct BiasGradSeg { int col_begin, col_end; float* out; int n_valid; };
+struct BiasGradParams { const __nv_bfloat16* g; long long P; int stride; int c0; int ncols; int nseg; BiasGradSeg seg[5]; };
+
+__global__ void bias_grad_kernel(const BiasGradParams p) {
+  // block: 256 threads = 8 pixel lanes x 32 column lanes; each column lane handles columns cl, cl+32, ...
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31;
+  const int pl = threadIdx.x >> 5;
+  for (int cb = 0; cb < p.ncols; cb += 32) {
+    const int c = cb + cl;
+    float acc = 0.f;
+    if (c < p.ncols) {
+      for (long long px = static_cast<long long>(blockIdx.x) * 8 + pl; px < p.P; px += static_cast<long long>(gridDim.x) * 8)
+        acc += __bfloat162float(p.g[px * p.stride + p.c0 + c]);
+    }
+    red[pl][cl] = acc;
+    __syncthreads();
+    if (pl == 0 && c < p.ncols) {
+      float s = 0.f;
+      for (int i = 0; i < 8; ++i) s += red[i][cl];
+      for (int sgi = 0; sgi < p.nseg; ++sgi) {
+        const BiasGradSeg& sg = p.seg[sgi];
+        if (c >= sg.col_begin && c < sg.col_end && (c - sg.col_begin) < sg.n_valid) atomicAdd(sg.out + (c - sg.col_begin), s);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------- fold phase weight grads back to 3x3
+// gp: [256 = phase*64 + co][ci_total][3][3] gradients of the four low-res phase kernels -> dW[co][ci][dy][dx] +=
+__global__ void fold_up_wgrad_kernel(const float* __restrict__ gp, float* __restrict__ dw, int CO, int CI) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= CO * CI * 9) return;
+  const int tap = idx % 9, dy = tap / 3, dx = tap % 3;
+  const int ci = (idx / 9) % CI;
+  const int co = idx / (9 * CI);
+  float s = 0.f;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      int ry = -1, rx = -1;
+      for (int t = 0; t < 3; ++t) {
+        int lo, hi;
+        up_phase_taps(a, t, lo, hi);
+        if (dy >= lo && dy < hi) ry = t;
+        up_phase_taps(b, t, lo, hi);
+        if (dx >= lo && dx < hi) rx = t;
+      }
+      s += gp[((static_cast<long long>((a * 2 + b) * CO + co)) * CI + ci) * 9 + ry * 3 + rx];
+    }
+  dw[idx] += s;
+}
+
+// out_bf16[i] = bf16(a[i] + b[i])   (gradient of conv1's output = trunk path + long skip)
+__global__ void add_to_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
+                                   long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(a[i] + b[i]);
+}
+
+}  // namespace b200sr

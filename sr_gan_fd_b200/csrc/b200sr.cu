@@ -1,0 +1,987 @@
+// libb200sr.so -- host side: network schedule ("plan"), TMA descriptor cache and the C ABI of include/b200sr.h.
+//
+// The plan turns the reference generator graph (ESRGAN/model.py:211-232 and its backward) into a flat list of
+// kernel launches over caller-owned buffers:
+//   forward : ingest -> conv1 -> 3*B dense blocks (5 convs each, writing channel slices of one dense buffer)
+//             -> conv2 (+long skip) -> n_up phase-folded upsample convs -> conv3 -> conv4 (+clamp)
+//   backward: the mirror image; every data-gradient is the SAME implicit-GEMM kernel over transposed/flipped
+//             weights reading a dense gradient buffer [dY5|dY4|dY3|dY2|dY1]; weight gradients are one tcgen05 GEMM
+//             per dense block slice (pixel axis = reduction) with fp32 reductions into the flat gradient buffer.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200sr.h"
+#include "aux_kernels.cuh"
+#include "conv_kernel.cuh"
+#include "wgrad_kernel.cuh"
+
+using namespace b200sr;
+
+// ------------------------------------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(B200SR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
+static bool g_attr_set = false;
+
+static int runtime_init() {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(B200SR_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  if (!g_num_sms) {
+    int dev = 0, major = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return fail(B200SR_ERR_UNSUPPORTED, "libb200sr needs an sm_100 device (found sm_%d*)", major);
+    CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (!g_attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    g_attr_set = true;
+  }
+  return 0;
+}
+
+// NHWC bf16 activation map: dims (C, W, H, N), box (64, 8, rows, 1), 128B swizzle, zero OOB fill.
+static int encode_act_map(CUtensorMap* m, void* base, int c_valid, int c_pix, int n, int h, int w, int box_rows) {
+  cuuint64_t dims[4] = {(cuuint64_t)c_valid, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c_pix * 2, (cuuint64_t)w * c_pix * 2, (cuuint64_t)h * w * c_pix * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B200SR_ERR_CUDA, "cuTensorMapEncodeTiled(act c=%d/%d n=%d h=%d w=%d) failed: %d", c_valid, c_pix, n, h, w, (int)r);
+  return 0;
+}
+// packed weights: [rows][64] bf16, box (64, n_cols)
+static int encode_w_map(CUtensorMap* m, void* base, long long rows, int n_cols) {
+  cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, (cuuint32_t)n_cols};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200SR_ERR_CUDA, "cuTensorMapEncodeTiled(weights rows=%lld n=%d) failed: %d", rows, n_cols, (int)r);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------ the plan
+enum RefKind { RK_NULL = 0, RK_WS, RK_PACKED, RK_Y, RK_DY, RK_GRADS };
+struct Ref {
+  int kind = RK_NULL;
+  long long off = 0;  // bytes
+};
+static Ref ws(long long off) { Ref r; r.kind = RK_WS; r.off = off; return r; }
+
+struct ActMapSpec { long long off; int c_valid, c_pix, n, h, w, box_rows; };
+
+enum StepType { ST_CONV, ST_WGRAD, ST_BIASGRAD, ST_FOLD, ST_ADD, ST_MEMSET, ST_INGEST_X, ST_INGEST_DY };
+
+struct Step {
+  int type = ST_CONV;
+  // conv
+  int amap = -1, wmap = -1;  // wmap: index into {16,32,64,128}
+  ConvParams cp;
+  Ref bias, mask, r1, r2, of, ofb, ob, cm;
+  dim3 grid;
+  int smem = 0;
+  // wgrad
+  int xmap = -1, dymap = -1;
+  WgradParams wp;
+  Ref seg_out[5];
+  // bias grad
+  BiasGradParams bp;
+  Ref bg_g;
+  // fold / add / memset / ingest
+  Ref a, b, c;
+  long long count = 0;
+  int i0 = 0, i1 = 0;
+  // gradient-bucket announcement after this step
+  long long cb_off = 0, cb_count = 0;
+};
+
+struct b200sr_plan {
+  b200sr_net_desc d;
+  int R = 0;  // dense blocks
+  int L = 0;  // upsample stages
+  int xin_stride = 64;
+  long long ws_bytes = 0;
+  long long total_rows = 0, bias_floats = 0, packed_bytes = 0;
+  std::vector<long long> param_off;  // flat fp32 offsets, 2 per conv (+ end)
+  std::vector<PackOp> pack_ops;
+  std::vector<BiasOp> bias_ops;
+  std::vector<ActMapSpec> map_specs;
+  std::vector<Step> fwd, bwd;
+  // buffers (byte offsets into the workspace)
+  long long o_xin = 0, o_t0 = 0, o_tr = 0, o_c1 = 0, o_c2 = 0, o_splt = 0, o_splc = 0, o_cmask = 0;
+  std::vector<long long> o_dense, o_spl;
+  long long o_dyp = 0, o_g3 = 0, o_gt = 0, o_gtb = 0, o_gr = 0, o_gc1 = 0, o_gc2 = 0, o_go1 = 0;
+  long long o_dyb[2] = {0, 0};
+  std::vector<long long> o_gu, o_phw;
+  // device-side tables + descriptor cache
+  PackOp* d_pack_ops = nullptr;
+  BiasOp* d_bias_ops = nullptr;
+  const float** d_params = nullptr;
+  void* cached_ws = nullptr;
+  void* cached_packed = nullptr;
+  std::vector<CUtensorMap> maps;
+  CUtensorMap wmaps[4];
+};
+
+static int wmap_index(int n_cols) { return n_cols == 16 ? 0 : n_cols == 32 ? 1 : n_cols == 64 ? 2 : 3; }
+static const int kWmapCols[4] = {16, 32, 64, 128};
+
+static long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+namespace {
+struct Builder {
+  b200sr_plan& P;
+  long long cursor = 0;
+  explicit Builder(b200sr_plan& p) : P(p) {}
+  long long alloc(long long bytes) {
+    long long o = cursor;
+    cursor = align_up(cursor + bytes, 1024);
+    return o;
+  }
+  int add_map(long long off, int c_valid, int c_pix, int n, int h, int w, int box_rows) {
+    for (size_t i = 0; i < P.map_specs.size(); ++i) {
+      const ActMapSpec& s = P.map_specs[i];
+      if (s.off == off && s.c_valid == c_valid && s.c_pix == c_pix && s.n == n && s.h == h && s.w == w && s.box_rows == box_rows)
+        return (int)i;
+    }
+    P.map_specs.push_back({off, c_valid, c_pix, n, h, w, box_rows});
+    return (int)P.map_specs.size() - 1;
+  }
+  // packed rows for an op; returns row0
+  int add_pack(PackOp op) {
+    op.row0 = (int)P.total_rows;
+    P.total_rows += (long long)op.num_chunks * 9 * op.n_total;
+    P.pack_ops.push_back(op);
+    return op.row0;
+  }
+  long long add_bias(int n, int b_index, int n_valid, int rep) {
+    BiasOp b;
+    b.off = (int)P.bias_floats;
+    b.n = n; b.b_index = b_index; b.n_valid = n_valid; b.rep = rep;
+    P.bias_floats += align_up(n, 4);
+    P.bias_ops.push_back(b);
+    return b.off;
+  }
+};
+
+ConvParams base_conv_params(int n, int h, int w, int num_chunks, int ksteps_last, int a_c0, int a_wrap, int row0,
+                            int n_cols, int n_total) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = n; p.H = h; p.W = w;
+  p.tiles_x = (w + kTileW - 1) / kTileW;
+  p.tiles_y = (h + kTileH - 1) / kTileH;
+  p.num_tiles = n * p.tiles_x * p.tiles_y;
+  p.num_chunks = num_chunks; p.ksteps_last = ksteps_last;
+  p.a_c0 = a_c0; p.a_wrap = a_wrap;
+  p.w_row0 = row0; p.n_cols = n_cols; p.n_total = n_total;
+  p.num_stages = conv_pick_stages(n_cols);
+  p.epi.alpha = 1.f; p.epi.delta = 1.f; p.epi.beta1 = 1.f; p.epi.beta2 = 1.f;
+  p.epi.res_stride = 64; p.epi.of_stride = 64;
+  p.epi.store_mode = kStorePix;
+  return p;
+}
+
+PackSeg seg(int k0, int klen, int w_index, int O, int I, int o_off, int i_off, int part) {
+  PackSeg s; s.k0 = k0; s.klen = klen; s.w_index = w_index; s.O = O; s.I = I; s.o_off = o_off; s.i_off = i_off; s.part = part;
+  return s;
+}
+}  // namespace
+
+// conv index helpers (state_dict order)
+static int conv_index_rdb(int r, int k /*1..5*/) { return 1 + r * 5 + (k - 1); }
+
+static void conv_dims(const b200sr_plan& P, int ci, int* O, int* I) {
+  const b200sr_net_desc& d = P.d;
+  const int ntrunk = P.R * 5;
+  if (ci == 0) { *O = d.channels; *I = d.in_channels; return; }
+  if (ci <= ntrunk) {
+    const int k = (ci - 1) % 5 + 1;
+    *O = (k < 5) ? d.growth : d.channels;
+    *I = d.channels + d.growth * (k - 1);
+    return;
+  }
+  const int t = ci - ntrunk - 1;  // 0: conv2, 1..L: up, L+1: conv3, L+2: conv4
+  *I = d.channels;
+  *O = (t == P.L + 2) ? d.out_channels : d.channels;
+}
+
+static int build_plan(b200sr_plan& P) {
+  const b200sr_net_desc& d = P.d;
+  if (d.channels != 64 || d.growth != 32) return fail(B200SR_ERR_INVALID, "only channels=64, growth=32 are supported (got %d, %d)", d.channels, d.growth);
+  if (d.in_channels < 1 || d.in_channels > 64) return fail(B200SR_ERR_INVALID, "in_channels must be in [1,64]");
+  if (d.out_channels < 1 || d.out_channels > 16) return fail(B200SR_ERR_INVALID, "out_channels must be in [1,16]");
+  if (d.num_blocks < 1 || d.n_up < 0 || d.n_up > 3) return fail(B200SR_ERR_INVALID, "bad num_blocks / n_up");
+  if (d.batch < 1 || d.height < 1 || d.width < 1) return fail(B200SR_ERR_INVALID, "bad geometry");
+  P.R = 3 * d.num_blocks;
+  P.L = d.n_up;
+  const int R = P.R, L = P.L;
+  const bool train = d.training != 0;
+  const int N = d.batch, H = d.height, W = d.width;
+  const long long Ppix = (long long)N * H * W;
+  const int nconv = 1 + R * 5 + 1 + L + 2;
+  const int ci_conv2 = 1 + R * 5, ci_up1 = ci_conv2 + 1, ci_conv3 = ci_conv2 + 1 + L, ci_conv4 = ci_conv3 + 1;
+
+  // flat parameter offsets
+  P.param_off.assign(2 * nconv + 1, 0);
+  {
+    long long off = 0;
+    for (int c = 0; c < nconv; ++c) {
+      int O, I;
+      conv_dims(P, c, &O, &I);
+      P.param_off[2 * c] = off; off += (long long)O * I * 9;
+      P.param_off[2 * c + 1] = off; off += O;
+    }
+    P.param_off[2 * nconv] = off;
+  }
+  auto wref = [&](int c) { Ref r; r.kind = RK_GRADS; r.off = P.param_off[2 * c] * 4; return r; };
+  auto bref = [&](int c) { Ref r; r.kind = RK_GRADS; r.off = P.param_off[2 * c + 1] * 4; return r; };
+
+  Builder B(P);
+  P.xin_stride = (int)align_up(3 * d.in_channels, 64);
+  // ---- workspace layout
+  P.o_xin = B.alloc(Ppix * P.xin_stride * 2);
+  P.o_t0 = B.alloc(Ppix * 64 * 4);
+  P.o_tr = B.alloc(Ppix * 64 * 4);
+  P.o_c1 = B.alloc(Ppix * 64 * 4);
+  P.o_c2 = B.alloc(Ppix * 64 * 4);
+  const int ndense = train ? R : 2;
+  for (int i = 0; i < ndense; ++i) P.o_dense.push_back(B.alloc(Ppix * 192 * 2));
+  P.o_splt = B.alloc(Ppix * 128 * 2);
+  for (int l = 0; l <= L; ++l) P.o_spl.push_back(B.alloc((Ppix << (2 * l)) * 128 * 2));
+  P.o_splc = B.alloc((Ppix << (2 * L)) * 128 * 2);
+  const long long HRpix = Ppix << (2 * L);
+  if (train) {
+    P.o_cmask = B.alloc(HRpix * d.out_channels);
+    P.o_dyp = B.alloc(HRpix * 64 * 2);
+    P.o_g3 = B.alloc(HRpix * 64 * 2);
+    P.o_gu.assign(L + 1, 0);
+    P.o_phw.assign(L + 1, 0);
+    for (int l = 1; l <= L; ++l) {
+      P.o_gu[l] = B.alloc((Ppix << (2 * (l - 1))) * 256 * 2);
+      P.o_phw[l] = B.alloc(256LL * 64 * 9 * 4);
+    }
+    P.o_gt = B.alloc(Ppix * 64 * 4);
+    P.o_gtb = B.alloc(Ppix * 64 * 2);
+    P.o_gr = B.alloc(Ppix * 64 * 4);
+    P.o_gc1 = B.alloc(Ppix * 64 * 4);
+    P.o_gc2 = B.alloc(Ppix * 64 * 4);
+    P.o_go1 = B.alloc(Ppix * 64 * 2);
+    P.o_dyb[0] = B.alloc(Ppix * 192 * 2);
+    P.o_dyb[1] = B.alloc(Ppix * 192 * 2);
+  }
+  P.ws_bytes = B.cursor;
+
+  auto dense_off = [&](int r) { return P.o_dense[train ? r : (r & 1)]; };
+  auto conv_step = [&](int amap, const ConvParams& cp, int grid_y) {
+    Step s;
+    s.type = ST_CONV;
+    s.amap = amap;
+    s.wmap = wmap_index(cp.n_cols);
+    s.cp = cp;
+    s.grid = dim3(1, grid_y, 1);  // x filled at launch (SM count)
+    s.smem = conv_smem_bytes(cp.n_cols, cp.num_stages);
+    return s;
+  };
+  auto packed_bias = [&](long long off_floats) { Ref r; r.kind = RK_PACKED; r.off = -1 - off_floats; return r; };  // fixed up later
+
+  // ================================================================ forward ================================================================
+  {
+    Step s; s.type = ST_INGEST_X;
+    P.fwd.push_back(s);
+  }
+  // conv1: [hi|lo|hi] input, weights [w_hi|w_hi|w_lo]
+  {
+    const int C = d.in_channels;
+    PackOp op; memset(&op, 0, sizeof(op));
+    op.n_total = 64; op.n_valid = 64; op.num_chunks = P.xin_stride / 64; op.mode = kPackFwd; op.nseg = 3;
+    op.seg[0] = seg(0, C, 0, 64, C, 0, 0, 0);
+    op.seg[1] = seg(C, C, 0, 64, C, 0, 0, 0);
+    op.seg[2] = seg(2 * C, C, 0, 64, C, 0, 0, 1);
+    const int row0 = B.add_pack(op);
+    const int last_valid = 3 * C - 64 * (op.num_chunks - 1);
+    ConvParams cp = base_conv_params(N, H, W, op.num_chunks, (last_valid + 15) / 16, 0, 1 << 20, row0, 64, 64);
+    Step s = conv_step(B.add_map(P.o_xin, P.xin_stride, P.xin_stride, N, H, W, kABoxRows), cp, 1);
+    s.bias = packed_bias(B.add_bias(64, 1, 64, 0));
+    s.of = ws(P.o_t0); s.ofb = ws(P.o_tr);
+    s.ob = ws(dense_off(0)); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 0;
+    P.fwd.push_back(s);
+  }
+  // trunk
+  for (int r = 0; r < R; ++r) {
+    const int j = r % 3;
+    const long long D = dense_off(r);
+    for (int k = 1; k <= 5; ++k) {
+      const int ci = conv_index_rdb(r, k);
+      const int cin = 64 + 32 * (k - 1), cout = (k < 5) ? 32 : 64;
+      PackOp op; memset(&op, 0, sizeof(op));
+      op.n_total = cout; op.n_valid = cout; op.num_chunks = (cin + 63) / 64; op.mode = kPackFwd; op.nseg = 1;
+      op.seg[0] = seg(0, cin, 2 * ci, cout, cin, 0, 0, 0);
+      const int row0 = B.add_pack(op);
+      ConvParams cp = base_conv_params(N, H, W, op.num_chunks, (cin - 64 * (op.num_chunks - 1)) / 16, 0, 1 << 20, row0, cout, cout);
+      Step s = conv_step(B.add_map(D, cin, 192, N, H, W, kABoxRows), cp, 1);
+      s.bias = packed_bias(B.add_bias(cout, 2 * ci + 1, cout, 0));
+      if (k < 5) {
+        s.cp.epi.act = 1;
+        s.ob = ws(D); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * (k - 1);
+      } else {
+        const long long cin_c = (j == 0) ? P.o_tr : (j == 1 ? P.o_c1 : P.o_c2);
+        const long long cout_c = (j == 0) ? P.o_c1 : (j == 1 ? P.o_c2 : P.o_tr);
+        s.cp.epi.alpha = (j == 2) ? 0.04f : 0.2f;
+        s.r1 = ws(cin_c); s.cp.epi.beta1 = (j == 2) ? 0.2f : 1.f;
+        if (j == 2) { s.r2 = ws(P.o_tr); s.cp.epi.beta2 = 1.f; }
+        s.of = ws(cout_c);
+        if (r < R - 1) {
+          s.ob = ws(dense_off(r + 1)); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 0;
+        } else {
+          s.ob = ws(P.o_splt); s.cp.epi.ob_stride = 128; s.cp.epi.ob_coff = 0; s.cp.epi.split_off = 64;
+        }
+      }
+      P.fwd.push_back(s);
+    }
+  }
+  // split-precision 64->64 conv helper (conv2, conv3): input [hi|lo] 128-wide, weights [w_hi|w_hi|w_lo]
+  auto split_pack = [&](int ci, int n_total, int n_valid, int mode) {
+    int O, I; conv_dims(P, ci, &O, &I);
+    PackOp op; memset(&op, 0, sizeof(op));
+    op.n_total = n_total; op.n_valid = n_valid; op.num_chunks = 3; op.mode = mode; op.nseg = 3;
+    op.seg[0] = seg(0, 64, 2 * ci, O, I, 0, 0, 0);
+    op.seg[1] = seg(64, 64, 2 * ci, O, I, 0, 0, 0);
+    op.seg[2] = seg(128, 64, 2 * ci, O, I, 0, 0, 1);
+    return B.add_pack(op);
+  };
+  // conv2 (+ long skip)
+  {
+    const int row0 = split_pack(ci_conv2, 64, 64, kPackFwd);
+    ConvParams cp = base_conv_params(N, H, W, 3, 4, 0, 2, row0, 64, 64);
+    Step s = conv_step(B.add_map(P.o_splt, 128, 128, N, H, W, kABoxRows), cp, 1);
+    s.bias = packed_bias(B.add_bias(64, 2 * ci_conv2 + 1, 64, 0));
+    s.r1 = ws(P.o_t0);
+    s.ob = ws(P.o_spl[0]); s.cp.epi.ob_stride = 128; s.cp.epi.split_off = 64;
+    P.fwd.push_back(s);
+  }
+  // upsample stages: nearest x2 + conv == 4 phase convs on the low-res lattice, pixel-shuffled on store
+  for (int l = 1; l <= L; ++l) {
+    const int ci = ci_up1 + (l - 1);
+    const int h = H << (l - 1), w = W << (l - 1);
+    const int row0 = split_pack(ci, 256, 256, kPackUpFwd);
+    ConvParams cp = base_conv_params(N, h, w, 3, 4, 0, 2, row0, 128, 256);
+    Step s = conv_step(B.add_map(P.o_spl[l - 1], 128, 128, N, h, w, kABoxRows), cp, 2);
+    s.bias = packed_bias(B.add_bias(256, 2 * ci + 1, 64, 64));
+    s.cp.epi.act = 1;
+    s.cp.epi.store_mode = kStoreShuffle;
+    s.ob = ws(P.o_spl[l]); s.cp.epi.ob_stride = 128; s.cp.epi.split_off = 64;
+    P.fwd.push_back(s);
+  }
+  const int hH = H << L, hW = W << L;
+  // conv3
+  {
+    const int row0 = split_pack(ci_conv3, 64, 64, kPackFwd);
+    ConvParams cp = base_conv_params(N, hH, hW, 3, 4, 0, 2, row0, 64, 64);
+    Step s = conv_step(B.add_map(P.o_spl[L], 128, 128, N, hH, hW, kABoxRows), cp, 1);
+    s.bias = packed_bias(B.add_bias(64, 2 * ci_conv3 + 1, 64, 0));
+    s.cp.epi.act = 1;
+    s.ob = ws(P.o_splc); s.cp.epi.ob_stride = 128; s.cp.epi.split_off = 64;
+    P.fwd.push_back(s);
+  }
+  // conv4 + clamp
+  {
+    const int row0 = split_pack(ci_conv4, 16, d.out_channels, kPackFwd);
+    ConvParams cp = base_conv_params(N, hH, hW, 3, 4, 0, 2, row0, 16, 16);
+    Step s = conv_step(B.add_map(P.o_splc, 128, 128, N, hH, hW, kABoxRows), cp, 1);
+    s.bias = packed_bias(B.add_bias(16, 2 * ci_conv4 + 1, d.out_channels, 0));
+    s.cp.epi.store_mode = kStoreFinal;
+    s.cp.epi.n_valid = d.out_channels;
+    s.of.kind = RK_Y;
+    if (train) s.cm = ws(P.o_cmask);
+    P.fwd.push_back(s);
+  }
+
+  // ================================================================ backward ===============================================================
+  if (train) {
+    auto wgrad_step = [&](long long x_off, int x_cvalid, int x_cpix, long long dy_off, int dy_cvalid, int dy_cpix, int n, int h, int w,
+                          int a_c0, int b_c0, int n_cols) {
+      Step s; s.type = ST_WGRAD;
+      s.xmap = B.add_map(x_off, x_cvalid, x_cpix, n, h, w, kABoxRows);
+      s.dymap = B.add_map(dy_off, dy_cvalid, dy_cpix, n, h, w, kTileH);
+      WgradParams& wp = s.wp; memset(&wp, 0, sizeof(wp));
+      wp.N = n; wp.H = h; wp.W = w;
+      wp.tiles_x = (w + kTileW - 1) / kTileW; wp.tiles_y = (h + kTileH - 1) / kTileH; wp.num_tiles = n * wp.tiles_x * wp.tiles_y;
+      wp.a_c0 = a_c0; wp.b_c0 = b_c0; wp.n_cols = n_cols; wp.n_blocks = (n_cols + 63) / 64;
+      wp.num_stages = wgrad_pick_stages(wp.n_blocks);
+      s.smem = wgrad_smem_bytes(wp.n_blocks, wp.num_stages);
+      return s;
+    };
+    auto add_seg = [&](Step& s, int cb, int ce, Ref out, int ci_total, int ci0, int co_valid) {
+      WgradSegment& g = s.wp.seg[s.wp.num_seg];
+      g.col_begin = cb; g.col_end = ce; g.out = nullptr; g.ci_total = ci_total; g.ci0 = ci0; g.co_valid = co_valid;
+      s.seg_out[s.wp.num_seg] = out;
+      s.wp.num_seg++;
+    };
+    auto biasgrad_step = [&](long long g_off, long long npix, int stride, int c0, int ncols) {
+      Step s; s.type = ST_BIASGRAD;
+      memset(&s.bp, 0, sizeof(s.bp));
+      s.bg_g = ws(g_off); s.bp.P = npix; s.bp.stride = stride; s.bp.c0 = c0; s.bp.ncols = ncols;
+      return s;
+    };
+    auto add_bseg = [&](Step& s, int cb, int ce, Ref out, int n_valid) {
+      BiasGradSeg& g = s.bp.seg[s.bp.nseg];
+      g.col_begin = cb; g.col_end = ce; g.out = nullptr; g.n_valid = n_valid;
+      s.seg_out[s.bp.nseg] = out;
+      s.bp.nseg++;
+    };
+    auto dgrad_pack1 = [&](int ci, int n_total, int klen) {  // plain single-conv dgrad: n = ci (64), k = co
+      int O, I; conv_dims(P, ci, &O, &I);
+      PackOp op; memset(&op, 0, sizeof(op));
+      op.n_total = n_total; op.n_valid = n_total; op.num_chunks = (klen + 63) / 64; op.mode = kPackDgrad; op.nseg = 1;
+      op.seg[0] = seg(0, klen, 2 * ci, O, I, 0, 0, 0);
+      return B.add_pack(op);
+    };
+    {
+      Step s; s.type = ST_MEMSET; s.a.kind = RK_GRADS; s.a.off = 0; s.count = P.param_off[2 * nconv] * 4;
+      P.bwd.push_back(s);
+      for (int l = 1; l <= L; ++l) {
+        Step m; m.type = ST_MEMSET; m.a = ws(P.o_phw[l]); m.count = 256LL * 64 * 9 * 4;
+        P.bwd.push_back(m);
+      }
+      Step g; g.type = ST_INGEST_DY;
+      P.bwd.push_back(g);
+    }
+    // conv4: wgrad, bias grad, dgrad (-> G3, masked by lrelu'(conv3 out))
+    {
+      Step w4 = wgrad_step(P.o_splc, 64, 128, P.o_dyp, 16, 64, N, hH, hW, 0, 0, 16);
+      add_seg(w4, 0, 16, wref(ci_conv4), 64, 0, d.out_channels);
+      P.bwd.push_back(w4);
+      Step b4 = biasgrad_step(P.o_dyp, HRpix, 64, 0, 16);
+      add_bseg(b4, 0, 16, bref(ci_conv4), d.out_channels);
+      P.bwd.push_back(b4);
+      const int row0 = dgrad_pack1(ci_conv4, 64, d.out_channels);
+      ConvParams cp = base_conv_params(N, hH, hW, 1, 1, 0, 1 << 20, row0, 64, 64);
+      Step s = conv_step(B.add_map(P.o_dyp, 16, 64, N, hH, hW, kABoxRows), cp, 1);
+      s.mask = ws(P.o_splc); s.cp.epi.mask_stride = 128; s.cp.epi.mask_coff = 0;
+      s.ob = ws(P.o_g3); s.cp.epi.ob_stride = 64;
+      P.bwd.push_back(s);
+    }
+    // conv3
+    {
+      Step w3 = wgrad_step(P.o_spl[L], 64, 128, P.o_g3, 64, 64, N, hH, hW, 0, 0, 64);
+      add_seg(w3, 0, 64, wref(ci_conv3), 64, 0, 64);
+      P.bwd.push_back(w3);
+      Step b3 = biasgrad_step(P.o_g3, HRpix, 64, 0, 64);
+      add_bseg(b3, 0, 64, bref(ci_conv3), 64);
+      P.bwd.push_back(b3);
+      const int row0 = dgrad_pack1(ci_conv3, 64, 64);
+      ConvParams cp = base_conv_params(N, hH, hW, 1, 4, 0, 1 << 20, row0, 64, 64);
+      Step s = conv_step(B.add_map(P.o_g3, 64, 64, N, hH, hW, kABoxRows), cp, 1);
+      if (L >= 1) {
+        s.mask = ws(P.o_spl[L]); s.cp.epi.mask_stride = 128;
+        s.ob = ws(P.o_gu[L]); s.cp.epi.ob_stride = 256; s.cp.epi.store_mode = kStoreUnshuffle;
+      } else {
+        s.of = ws(P.o_gt);
+        s.ob = ws(P.o_gtb); s.cp.epi.ob_stride = 64;
+      }
+      P.bwd.push_back(s);
+    }
+    // upsample stages, top down
+    for (int l = L; l >= 1; --l) {
+      const int ci = ci_up1 + (l - 1);
+      const int h = H << (l - 1), w = W << (l - 1);
+      const long long npix = Ppix << (2 * (l - 1));
+      for (int half = 0; half < 2; ++half) {
+        Step wu = wgrad_step(P.o_spl[l - 1], 64, 128, P.o_gu[l], 256, 256, N, h, w, 0, 128 * half, 128);
+        Ref out = ws(P.o_phw[l] + (long long)half * 128 * 64 * 9 * 4);
+        add_seg(wu, 0, 128, out, 64, 0, 128);
+        P.bwd.push_back(wu);
+      }
+      {
+        Step f; f.type = ST_FOLD; f.a = ws(P.o_phw[l]); f.b = wref(ci); f.i0 = 64; f.i1 = 64;
+        P.bwd.push_back(f);
+        Step bu = biasgrad_step(P.o_gu[l], npix, 256, 0, 256);
+        for (int ph = 0; ph < 4; ++ph) add_bseg(bu, 64 * ph, 64 * ph + 64, bref(ci), 64);
+        P.bwd.push_back(bu);
+      }
+      PackOp op; memset(&op, 0, sizeof(op));
+      op.n_total = 64; op.n_valid = 64; op.num_chunks = 4; op.mode = kPackUpDgrad; op.nseg = 1;
+      op.seg[0] = seg(0, 256, 2 * ci, 64, 64, 0, 0, 0);
+      const int row0 = B.add_pack(op);
+      ConvParams cp = base_conv_params(N, h, w, 4, 4, 0, 1 << 20, row0, 64, 64);
+      Step s = conv_step(B.add_map(P.o_gu[l], 256, 256, N, h, w, kABoxRows), cp, 1);
+      if (l >= 2) {
+        s.mask = ws(P.o_spl[l - 1]); s.cp.epi.mask_stride = 128;
+        s.ob = ws(P.o_gu[l - 1]); s.cp.epi.ob_stride = 256; s.cp.epi.store_mode = kStoreUnshuffle;
+      } else {
+        s.of = ws(P.o_gt);
+        s.ob = ws(P.o_gtb); s.cp.epi.ob_stride = 64;
+      }
+      P.bwd.push_back(s);
+    }
+    // conv2
+    {
+      Step w2 = wgrad_step(P.o_splt, 64, 128, P.o_gtb, 64, 64, N, H, W, 0, 0, 64);
+      add_seg(w2, 0, 64, wref(ci_conv2), 64, 0, 64);
+      P.bwd.push_back(w2);
+      Step b2 = biasgrad_step(P.o_gtb, Ppix, 64, 0, 64);
+      add_bseg(b2, 0, 64, bref(ci_conv2), 64);
+      P.bwd.push_back(b2);
+      const int row0 = dgrad_pack1(ci_conv2, 64, 64);
+      ConvParams cp = base_conv_params(N, H, W, 1, 4, 0, 1 << 20, row0, 64, 64);
+      Step s = conv_step(B.add_map(P.o_gtb, 64, 64, N, H, W, kABoxRows), cp, 1);
+      s.of = ws(P.o_gr);
+      s.ob = ws(P.o_dyb[0]); s.cp.epi.ob_stride = 192; s.cp.epi.delta = 0.04f;
+      // tail bucket: conv2 .. conv4 are contiguous at the end of the flat buffer
+      s.cb_off = P.param_off[2 * ci_conv2]; s.cb_count = P.param_off[2 * nconv] - P.param_off[2 * ci_conv2];
+      P.bwd.push_back(s);
+    }
+    // trunk, last dense block first
+    for (int r = R - 1; r >= 0; --r) {
+      const int j = r % 3;
+      const long long D = P.o_dense[r];
+      const long long DYc = P.o_dyb[(R - 1 - r) & 1], DYn = P.o_dyb[(R - r) & 1];
+      for (int sl = 4; sl >= 0; --sl) {
+        // gradient w.r.t. input slice sl (0: the 64-ch block input x, 1..4: growth outputs o_sl) = sum over consumer convs
+        const int c_s = (sl == 0) ? 0 : 64 + 32 * (sl - 1);
+        const int nsl = (sl == 0) ? 64 : 32;
+        const int kin = 64 + 32 * (4 - sl);  // DY prefix [dY5 | dY4 | ... | dY_{sl+1}]
+        PackOp op; memset(&op, 0, sizeof(op));
+        op.n_total = nsl; op.n_valid = nsl; op.num_chunks = (kin + 63) / 64; op.mode = kPackDgrad;
+        op.nseg = 0;
+        for (int k = 5; k > sl; --k) {
+          const int ci = conv_index_rdb(r, k);
+          const int k0 = (k == 5) ? 0 : 64 + 32 * (4 - k);
+          const int klen = (k == 5) ? 64 : 32;
+          op.seg[op.nseg++] = seg(k0, klen, 2 * ci, klen, 64 + 32 * (k - 1), 0, c_s, 0);
+        }
+        const int row0 = B.add_pack(op);
+        ConvParams cp = base_conv_params(N, H, W, op.num_chunks, (kin - 64 * (op.num_chunks - 1)) / 16, 0, 1 << 20, row0, nsl, nsl);
+        Step s = conv_step(B.add_map(DYc, kin, 192, N, H, W, kABoxRows), cp, 1);
+        if (sl > 0) {
+          s.mask = ws(D); s.cp.epi.mask_stride = 192; s.cp.epi.mask_coff = c_s;
+          s.ob = ws(DYc); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * (4 - sl);
+        } else {
+          if (j == 2) { s.r1 = ws(P.o_gr); s.cp.epi.beta1 = 0.2f; s.of = ws(P.o_gc2); s.cp.epi.delta = 0.2f; }
+          else if (j == 1) { s.r1 = ws(P.o_gc2); s.of = ws(P.o_gc1); s.cp.epi.delta = 0.2f; }
+          else { s.r1 = ws(P.o_gc1); s.r2 = ws(P.o_gr); s.of = ws(P.o_gr); s.cp.epi.delta = 0.04f; }
+          if (r > 0) { s.ob = ws(DYn); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 0; }
+        }
+        P.bwd.push_back(s);
+      }
+      // weight gradients of the five convs, re-associated by input slice
+      {
+        Step a = wgrad_step(D, 192, 192, DYc, 192, 192, N, H, W, 0, 0, 160);
+        add_seg(a, 0, 64, wref(conv_index_rdb(r, 5)), 192, 0, 64);
+        add_seg(a, 64, 96, wref(conv_index_rdb(r, 4)), 160, 0, 32);
+        add_seg(a, 96, 128, wref(conv_index_rdb(r, 3)), 128, 0, 32);
+        add_seg(a, 128, 160, wref(conv_index_rdb(r, 2)), 96, 0, 32);
+        P.bwd.push_back(a);
+        Step b = wgrad_step(D, 192, 192, DYc, 192, 192, N, H, W, 128, 0, 96);
+        add_seg(b, 0, 64, wref(conv_index_rdb(r, 5)), 192, 128, 64);
+        add_seg(b, 64, 96, wref(conv_index_rdb(r, 4)), 160, 128, 32);
+        P.bwd.push_back(b);
+        Step c = wgrad_step(D, 192, 192, DYc, 192, 192, N, H, W, 0, 160, 32);
+        add_seg(c, 0, 32, wref(conv_index_rdb(r, 1)), 64, 0, 32);
+        P.bwd.push_back(c);
+        Step bg = biasgrad_step(DYc, Ppix, 192, 0, 192);
+        add_bseg(bg, 0, 64, bref(conv_index_rdb(r, 5)), 64);
+        add_bseg(bg, 64, 96, bref(conv_index_rdb(r, 4)), 32);
+        add_bseg(bg, 96, 128, bref(conv_index_rdb(r, 3)), 32);
+        add_bseg(bg, 128, 160, bref(conv_index_rdb(r, 2)), 32);
+        add_bseg(bg, 160, 192, bref(conv_index_rdb(r, 1)), 32);
+        if (j == 0) {  // one bucket per RRDB (its 15 convs are contiguous in the flat buffer)
+          bg.cb_off = P.param_off[2 * conv_index_rdb(r, 1)];
+          bg.cb_count = P.param_off[2 * conv_index_rdb(r + 2, 5) + 2] - bg.cb_off;
+        }
+        P.bwd.push_back(bg);
+      }
+    }
+    // conv1: gradient of its output = trunk path (GR) + long skip (GT)
+    {
+      Step ad; ad.type = ST_ADD; ad.a = ws(P.o_gr); ad.b = ws(P.o_gt); ad.c = ws(P.o_go1); ad.count = Ppix * 64;
+      P.bwd.push_back(ad);
+      Step w1 = wgrad_step(P.o_xin, P.xin_stride, P.xin_stride, P.o_go1, 64, 64, N, H, W, 0, 0, 64);
+      add_seg(w1, 0, 64, wref(0), d.in_channels, 0, 64);
+      P.bwd.push_back(w1);
+      Step b1 = biasgrad_step(P.o_go1, Ppix, 64, 0, 64);
+      add_bseg(b1, 0, 64, bref(0), 64);
+      b1.cb_off = 0; b1.cb_count = P.param_off[2];
+      P.bwd.push_back(b1);
+    }
+  }
+
+  // packed buffer = bf16 tile rows followed by the fp32 biases
+  const long long bias_base = align_up(P.total_rows * 128, 1024);
+  P.packed_bytes = bias_base + P.bias_floats * 4;
+  auto fix = [&](std::vector<Step>& v) {
+    for (Step& s : v)
+      if (s.bias.kind == RK_PACKED) s.bias.off = bias_base + (-1 - s.bias.off) * 4;
+  };
+  fix(P.fwd);
+  fix(P.bwd);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------ execution
+struct Bases { void* ws; void* packed; void* y; const void* dy; void* grads; };
+static void* resolve(const Ref& r, const Bases& b) {
+  switch (r.kind) {
+    case RK_WS: return (char*)b.ws + r.off;
+    case RK_PACKED: return (char*)b.packed + r.off;
+    case RK_Y: return (char*)b.y + r.off;
+    case RK_DY: return (char*)b.dy + r.off;
+    case RK_GRADS: return (char*)b.grads + r.off;
+    default: return nullptr;
+  }
+}
+
+static int ensure_maps(b200sr_plan& P, void* wsp, void* packed) {
+  if (P.cached_ws == wsp && P.cached_packed == packed && P.maps.size() == P.map_specs.size()) return 0;
+  P.maps.resize(P.map_specs.size());
+  for (size_t i = 0; i < P.map_specs.size(); ++i) {
+    const ActMapSpec& s = P.map_specs[i];
+    int rc = encode_act_map(&P.maps[i], (char*)wsp + s.off, s.c_valid, s.c_pix, s.n, s.h, s.w, s.box_rows);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < 4; ++i) {
+    int rc = encode_w_map(&P.wmaps[i], packed, P.total_rows, kWmapCols[i]);
+    if (rc) return rc;
+  }
+  P.cached_ws = wsp;
+  P.cached_packed = packed;
+  return 0;
+}
+
+static int launch_conv(const Step& s, const CUtensorMap& tmA, const CUtensorMap& tmW, const Bases& b, cudaStream_t st) {
+  ConvParams cp = s.cp;
+  cp.epi.bias = (const float*)resolve(s.bias, b);
+  cp.epi.mask = (const __nv_bfloat16*)resolve(s.mask, b);
+  cp.epi.r1 = (const float*)resolve(s.r1, b);
+  cp.epi.r2 = (const float*)resolve(s.r2, b);
+  cp.epi.out_f32 = (float*)resolve(s.of, b);
+  cp.epi.out_f32_b = (float*)resolve(s.ofb, b);
+  cp.epi.out_bf16 = (__nv_bfloat16*)resolve(s.ob, b);
+  cp.epi.clamp_mask = (unsigned char*)resolve(s.cm, b);
+  int gx = g_num_sms / (int)s.grid.y;
+  if (gx > cp.num_tiles) gx = cp.num_tiles;
+  if (gx < 1) gx = 1;
+  conv3x3_igemm_kernel<<<dim3(gx, s.grid.y, 1), kConvThreads, s.smem, st>>>(tmA, tmW, cp);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int launch_wgrad(const Step& s, const CUtensorMap& tmX, const CUtensorMap& tmDY, const Bases& b, cudaStream_t st) {
+  WgradParams wp = s.wp;
+  for (int i = 0; i < wp.num_seg; ++i) wp.seg[i].out = (float*)resolve(s.seg_out[i], b);
+  int splits = g_num_sms / 3;
+  if (splits > wp.num_tiles) splits = wp.num_tiles;
+  if (splits < 1) splits = 1;
+  wgrad3x3_kernel<<<dim3(splits, 3, 1), kWgThreads, s.smem, st>>>(tmX, tmDY, wp);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, const void* x, int x_dtype, const int64_t* xs,
+                     b200sr_bucket_cb cb, void* user, cudaStream_t st) {
+  const b200sr_net_desc& d = P.d;
+  for (Step& s : steps) {
+    switch (s.type) {
+      case ST_CONV: {
+        int rc = launch_conv(s, P.maps[s.amap], P.wmaps[s.wmap], b, st);
+        if (rc) return rc;
+        break;
+      }
+      case ST_WGRAD: {
+        int rc = launch_wgrad(s, P.maps[s.xmap], P.maps[s.dymap], b, st);
+        if (rc) return rc;
+        break;
+      }
+      case ST_BIASGRAD: {
+        BiasGradParams bp = s.bp;
+        bp.g = (const __nv_bfloat16*)resolve(s.bg_g, b);
+        for (int i = 0; i < bp.nseg; ++i) bp.seg[i].out = (float*)resolve(s.seg_out[i], b);
+        long long blocks = (bp.P + 63) / 64;
+        if (blocks > 4 * g_num_sms) blocks = 4 * g_num_sms;
+        bias_grad_kernel<<<(int)blocks, 256, 0, st>>>(bp);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_FOLD: {
+        const int n = s.i0 * s.i1 * 9;
+        fold_up_wgrad_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)resolve(s.a, b), (float*)resolve(s.b, b), s.i0, s.i1);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_ADD: {
+        add_to_bf16_kernel<<<(int)((s.count + 255) / 256), 256, 0, st>>>((const float*)resolve(s.a, b), (const float*)resolve(s.b, b),
+                                                                        (__nv_bfloat16*)resolve(s.c, b), s.count);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_MEMSET:
+        CUDA_TRY(cudaMemsetAsync(resolve(s.a, b), 0, (size_t)s.count, st));
+        break;
+      case ST_INGEST_X: {
+        const long long npix = (long long)d.batch * d.height * d.width;
+        __nv_bfloat16* out = (__nv_bfloat16*)((char*)b.ws + P.o_xin);
+        const int blocks = (int)((npix + 127) / 128);
+        if (x_dtype == B200SR_F32)
+          ingest_input_kernel<float><<<blocks, 128, 0, st>>>((const float*)x, xs[0], xs[1], xs[2], xs[3], d.batch, d.in_channels, d.height, d.width, out, P.xin_stride);
+        else if (x_dtype == B200SR_F16)
+          ingest_input_kernel<__half><<<blocks, 128, 0, st>>>((const __half*)x, xs[0], xs[1], xs[2], xs[3], d.batch, d.in_channels, d.height, d.width, out, P.xin_stride);
+        else if (x_dtype == B200SR_BF16)
+          ingest_input_kernel<__nv_bfloat16><<<blocks, 128, 0, st>>>((const __nv_bfloat16*)x, xs[0], xs[1], xs[2], xs[3], d.batch, d.in_channels, d.height, d.width, out, P.xin_stride);
+        else
+          return fail(B200SR_ERR_INVALID, "unknown x dtype %d", x_dtype);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_INGEST_DY: {
+        const int hH = d.height << P.L, hW = d.width << P.L;
+        const long long npix = (long long)d.batch * hH * hW;
+        ingest_grad_kernel<<<(int)((npix + 127) / 128), 128, 0, st>>>((const float*)b.dy, (const unsigned char*)((char*)b.ws + P.o_cmask), d.batch,
+                                                                     d.out_channels, hH, hW, (__nv_bfloat16*)((char*)b.ws + P.o_dyp), 64);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+    }
+    if (cb && s.cb_count > 0) cb(user, s.cb_off, s.cb_count);
+  }
+  return 0;
+}
+
+// =================================================================================================== C ABI =====
+extern "C" {
+
+const char* b200sr_last_error(void) { return g_err; }
+int b200sr_version(void) { return 100; }
+
+int b200sr_plan_create(const b200sr_net_desc* desc, b200sr_plan** out) {
+  if (!desc || !out) return fail(B200SR_ERR_INVALID, "null argument");
+  b200sr_plan* p = new b200sr_plan();
+  p->d = *desc;
+  int rc = build_plan(*p);
+  if (rc) { delete p; return rc; }
+  *out = p;
+  return 0;
+}
+
+void b200sr_plan_destroy(b200sr_plan* p) {
+  if (!p) return;
+  if (p->d_pack_ops) cudaFree(p->d_pack_ops);
+  if (p->d_bias_ops) cudaFree(p->d_bias_ops);
+  if (p->d_params) cudaFree((void*)p->d_params);
+  delete p;
+}
+
+size_t b200sr_workspace_bytes(const b200sr_plan* p) { return p ? (size_t)p->ws_bytes : 0; }
+size_t b200sr_packed_bytes(const b200sr_plan* p) { return p ? (size_t)p->packed_bytes : 0; }
+int32_t b200sr_num_params(const b200sr_plan* p) { return p ? (int32_t)p->param_off.size() - 1 : 0; }
+int64_t b200sr_param_numel(const b200sr_plan* p) { return p ? p->param_off.back() : 0; }
+
+double b200sr_flops(const b200sr_plan* p, int backward) {
+  if (!p) return 0;
+  const int nconv = ((int)p->param_off.size() - 1) / 2;
+  const int ntrunk = p->R * 5;
+  double px = (double)p->d.batch * p->d.height * p->d.width, total = 0;
+  for (int c = 0; c < nconv; ++c) {
+    int O, I;
+    conv_dims(*p, c, &O, &I);
+    double res = 1;
+    if (c > ntrunk + 1) {
+      const int t = c - ntrunk - 1;
+      res = (t <= p->L) ? (double)(1 << (2 * t)) : (double)(1 << (2 * p->L));
+    }
+    const double fl = 2.0 * 9 * O * I * res * px;
+    total += backward ? fl * (c == 0 ? 1 : 2) : fl;
+  }
+  return total;
+}
+
+int32_t b200sr_num_launches(const b200sr_plan* p, int backward) {
+  if (!p) return 0;
+  const std::vector<Step>& v = backward ? p->bwd : p->fwd;
+  int n = 0;
+  for (const Step& s : v) n += (s.type != ST_MEMSET);
+  return n;
+}
+
+int b200sr_pack_weights(b200sr_plan* p, const float* const* params, void* packed, b200sr_stream stream) {
+  if (!p || !params || !packed) return fail(B200SR_ERR_INVALID, "null argument");
+  int rc = runtime_init();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int np = (int)p->param_off.size() - 1;
+  if (!p->d_pack_ops) {
+    CUDA_TRY(cudaMalloc(&p->d_pack_ops, p->pack_ops.size() * sizeof(PackOp)));
+    CUDA_TRY(cudaMalloc(&p->d_bias_ops, p->bias_ops.size() * sizeof(BiasOp)));
+    CUDA_TRY(cudaMalloc((void**)&p->d_params, np * sizeof(float*)));
+    CUDA_TRY(cudaMemcpyAsync(p->d_pack_ops, p->pack_ops.data(), p->pack_ops.size() * sizeof(PackOp), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->d_bias_ops, p->bias_ops.data(), p->bias_ops.size() * sizeof(BiasOp), cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaMemcpyAsync((void*)p->d_params, params, np * sizeof(float*), cudaMemcpyHostToDevice, st));
+  const long long total = p->total_rows * 64;
+  pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p->d_pack_ops, (int)p->pack_ops.size(), p->d_params,
+                                                                      (__nv_bfloat16*)packed, p->total_rows);
+  CUDA_TRY(cudaGetLastError());
+  const long long bias_base = align_up(p->total_rows * 128, 1024);
+  pack_bias_kernel<<<(unsigned)p->bias_ops.size(), 64, 0, st>>>(p->d_bias_ops, (int)p->bias_ops.size(), p->d_params,
+                                                               (float*)((char*)packed + bias_base));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200sr_forward(b200sr_plan* p, const void* x, int x_dtype, const int64_t* x_strides, const void* packed, void* workspace,
+                   float* y, b200sr_stream stream) {
+  if (!p || !x || !x_strides || !packed || !workspace || !y) return fail(B200SR_ERR_INVALID, "null argument");
+  int rc = runtime_init();
+  if (rc) return rc;
+  rc = ensure_maps(*p, workspace, (void*)packed);
+  if (rc) return rc;
+  Bases b{workspace, (void*)packed, y, nullptr, nullptr};
+  return run_steps(*p, p->fwd, b, x, x_dtype, x_strides, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int b200sr_backward(b200sr_plan* p, const float* dy, const void* packed, void* workspace, float* flat_grads, b200sr_bucket_cb cb,
+                    void* user, b200sr_stream stream) {
+  if (!p || !dy || !packed || !workspace || !flat_grads) return fail(B200SR_ERR_INVALID, "null argument");
+  if (!p->d.training) return fail(B200SR_ERR_INVALID, "plan was created with training=0");
+  int rc = runtime_init();
+  if (rc) return rc;
+  rc = ensure_maps(*p, workspace, (void*)packed);
+  if (rc) return rc;
+  Bases b{workspace, (void*)packed, nullptr, dy, flat_grads};
+  return run_steps(*p, p->bwd, b, nullptr, 0, nullptr, cb, user, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------ single-layer helpers
+static int pick_ncols(int cout, int* n_cols, int* grid_y) {
+  if (cout % 32 != 0 || cout < 32 || (cout > 128 && cout != 256)) return fail(B200SR_ERR_INVALID, "cout must be 32/64/96/128/256 (got %d)", cout);
+  *n_cols = cout > 128 ? 128 : cout;
+  *grid_y = cout / *n_cols;
+  if (*n_cols == 96) return fail(B200SR_ERR_INVALID, "cout 96 unsupported");
+  return 0;
+}
+
+size_t b200sr_conv3x3_scratch_bytes(int cin, int cout) {
+  const long long chunks = (cin + 63) / 64;
+  return (size_t)(align_up(chunks * 9 * cout * 128, 1024) + align_up(cout * 4, 1024) + 4096);
+}
+
+static int single_conv(int mode, const void* x, int n, int h, int w, int cin, int x_stride, const float* wt, const float* bias, int cout, int act,
+                       void* y, int y_stride, int y_coff, void* scratch, cudaStream_t st) {
+  // mode kPackFwd: y[.., cout] = conv(x[.., cin]);  kPackDgrad: "cin" = channels of the incoming gradient (= conv Cout),
+  // "cout" = channels of the produced input gradient (= conv Cin); wt is always the forward OIHW tensor.
+  int rc = runtime_init();
+  if (rc) return rc;
+  int n_cols, grid_y;
+  rc = pick_ncols(cout, &n_cols, &grid_y);
+  if (rc) return rc;
+  if (cin % 16 != 0) return fail(B200SR_ERR_INVALID, "cin must be a multiple of 16");
+  const int chunks = (cin + 63) / 64;
+  const long long rows = (long long)chunks * 9 * cout;
+  char* sc = (char*)scratch;
+  const long long bias_off = align_up(rows * 128, 1024);
+  const long long tab_off = bias_off + align_up(cout * 4, 1024);
+  PackOp op; memset(&op, 0, sizeof(op));
+  op.row0 = 0; op.n_total = cout; op.n_valid = cout; op.num_chunks = chunks; op.mode = mode; op.nseg = 1;
+  if (mode == kPackFwd) op.seg[0] = seg(0, cin, 0, cout, cin, 0, 0, 0);
+  else                  op.seg[0] = seg(0, cin, 0, cin, cout, 0, 0, 0);
+  BiasOp bo; bo.off = 0; bo.n = cout; bo.b_index = bias ? 1 : -1; bo.n_valid = cout; bo.rep = 0;
+  const float* ptrs[2] = {wt, bias};
+  CUDA_TRY(cudaMemcpyAsync(sc + tab_off, &op, sizeof(op), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(sc + tab_off + 1024, &bo, sizeof(bo), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(sc + tab_off + 2048, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
+  pack_weights_kernel<<<(unsigned)((rows * 64 + 255) / 256), 256, 0, st>>>((const PackOp*)(sc + tab_off), 1, (const float* const*)(sc + tab_off + 2048),
+                                                                          (__nv_bfloat16*)sc, rows);
+  CUDA_TRY(cudaGetLastError());
+  pack_bias_kernel<<<1, 64, 0, st>>>((const BiasOp*)(sc + tab_off + 1024), 1, (const float* const*)(sc + tab_off + 2048), (float*)(sc + bias_off));
+  CUDA_TRY(cudaGetLastError());
+  CUtensorMap tmA, tmW;
+  rc = encode_act_map(&tmA, (void*)x, cin, x_stride, n, h, w, kABoxRows);
+  if (rc) return rc;
+  rc = encode_w_map(&tmW, sc, rows, n_cols);
+  if (rc) return rc;
+  Step s;
+  s.cp = base_conv_params(n, h, w, chunks, (cin - 64 * (chunks - 1)) / 16, 0, 1 << 20, 0, n_cols, cout);
+  s.grid = dim3(1, grid_y, 1);
+  s.smem = conv_smem_bytes(n_cols, s.cp.num_stages);
+  s.cp.epi.act = act;
+  s.cp.epi.ob_stride = y_stride; s.cp.epi.ob_coff = y_coff;
+  Bases b{nullptr, nullptr, nullptr, nullptr, nullptr};
+  ConvParams& cp = s.cp;
+  cp.epi.bias = (const float*)(sc + bias_off);
+  cp.epi.out_bf16 = (__nv_bfloat16*)y;
+  int gx = g_num_sms / grid_y;
+  if (gx > cp.num_tiles) gx = cp.num_tiles;
+  conv3x3_igemm_kernel<<<dim3(gx, grid_y, 1), kConvThreads, s.smem, st>>>(tmA, tmW, cp);
+  CUDA_TRY(cudaGetLastError());
+  (void)b;
+  return 0;
+}
+
+int b200sr_conv3x3_fwd(const void* x, int n, int h, int w_, int cin, int x_stride, const float* w, const float* bias, int cout, int act,
+                       void* y, int y_stride, int y_coff, void* scratch, b200sr_stream stream) {
+  if (!x || !w || !y || !scratch) return fail(B200SR_ERR_INVALID, "null argument");
+  return single_conv(kPackFwd, x, n, h, w_, cin, x_stride, w, bias, cout, act, y, y_stride, y_coff, scratch, (cudaStream_t)stream);
+}
+
+int b200sr_conv3x3_dgrad(const void* dy, int n, int h, int w_, int cout, int dy_stride, const float* w, int cin, void* dx, int dx_stride,
+                         int dx_coff, void* scratch, b200sr_stream stream) {
+  if (!dy || !w || !dx || !scratch) return fail(B200SR_ERR_INVALID, "null argument");
+  return single_conv(kPackDgrad, dy, n, h, w_, cout, dy_stride, w, nullptr, cin, 0, dx, dx_stride, dx_coff, scratch, (cudaStream_t)stream);
+}
+
+int b200sr_conv3x3_wgrad(const void* x, int n, int h, int w_, int cin, int x_stride, const void* dy, int cout, int dy_stride, float* dw,
+                         b200sr_stream stream) {
+  if (!x || !dy || !dw) return fail(B200SR_ERR_INVALID, "null argument");
+  int rc = runtime_init();
+  if (rc) return rc;
+  if (cin > 128 || cout > 160 || cout % 16 != 0) return fail(B200SR_ERR_INVALID, "wgrad: cin <= 128, cout <= 160, cout %% 16 == 0");
+  CUtensorMap tmX, tmDY;
+  rc = encode_act_map(&tmX, (void*)x, cin, x_stride, n, h, w_, kABoxRows);
+  if (rc) return rc;
+  rc = encode_act_map(&tmDY, (void*)dy, cout, dy_stride, n, h, w_, kTileH);
+  if (rc) return rc;
+  WgradParams wp; memset(&wp, 0, sizeof(wp));
+  wp.N = n; wp.H = h; wp.W = w_;
+  wp.tiles_x = (w_ + kTileW - 1) / kTileW; wp.tiles_y = (h + kTileH - 1) / kTileH; wp.num_tiles = n * wp.tiles_x * wp.tiles_y;
+  wp.a_c0 = 0; wp.b_c0 = 0; wp.n_cols = cout; wp.n_blocks = (cout + 63) / 64;
+  wp.num_stages = wgrad_pick_stages(wp.n_blocks);
+  wp.num_seg = 1;
+  wp.seg[0].col_begin = 0; wp.seg[0].col_end = cout; wp.seg[0].out = dw; wp.seg[0].ci_total = cin; wp.seg[0].ci0 = 0; wp.seg[0].co_valid = cout;
+  int splits = g_num_sms / 3;
+  if (splits > wp.num_tiles) splits = wp.num_tiles;
+  wgrad3x3_kernel<<<dim3(splits, 3, 1), kWgThreads, wgrad_smem_bytes(wp.n_blocks, wp.num_stages), (cudaStream_t)stream>>>(tmX, tmDY, wp);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,350 @@
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on tcgen05 (sm_100a).  Used for every forward conv and
+// every data-gradient conv of the RRDBNet generator (a dgrad is the same kernel over flipped/transposed weights).
+//
+//   D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * Wt[tap][cout][cin]        (fp32 accumulate in TMEM)
+//
+// Data layout: activations are NHWC bf16, possibly a channel range of a wider "dense" buffer (the dense block writes
+// its growth channels into slices of one buffer, so no concat copy exists).  A CTA owns 128 output pixels = an
+// 8-wide x 16-tall patch of one image (UMMA M = 128, one TMEM lane per pixel).  K is walked in chunks of 64
+// channels x 3 horizontal taps: for each (chunk, dx) ONE TMA box [64 ch, 8 px, 18 rows] is loaded at x0+dx-1,y0-1
+// (out-of-image elements are zero-filled by TMA = the conv's zero padding); the three vertical taps are the same
+// smem tile at +0/+1024/+2048 bytes (8 pixels x 128 B = one 128B-swizzle atom), so they need no extra loads and
+// the UMMA descriptors stay 1024-byte aligned.  Weights are pre-packed per (chunk, dx, dy) as [cout][64] K-major
+// bf16 rows and arrive by 2-D TMA into the same 128B-swizzled layout.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> fused bias / LeakyReLU / mask / residuals -> global).  Accumulators
+// are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1 (persistent CTAs).
+#pragma once
+#include "ptx.cuh"
+
+namespace b200sr {
+
+constexpr int kTileW = 8;
+constexpr int kTileH = 16;
+constexpr int kABoxRows = kTileH + 2;                   // 18 image rows incl. the vertical halo
+constexpr int kABytes = kABoxRows * kTileW * 128;       // 18432 B per (chunk, dx) activation tile
+constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 8;
+
+enum StoreMode : int {
+  kStorePix = 0,        // same lattice position
+  kStoreShuffle = 1,    // pixel-shuffle: column group (col / 64) = phase (a, b) -> pixel (2y+a, 2x+b), channel col % 64
+  kStoreUnshuffle = 2,  // pixel-unshuffle: pixel (y, x) -> (y/2, x/2), channel ((y&1)*2 + (x&1)) * 64 + col
+  kStoreFinal = 3       // clamp to [0,1], NCHW fp32 image + clamp mask bytes (generator output head)
+};
+
+struct ConvEpilogue {
+  const float* bias;  // [n_total] or nullptr
+  float alpha;        // v = alpha * (acc + bias)
+  int act;            // 1: v = LeakyReLU_0.2(v)
+  const __nv_bfloat16* mask;  // dgrad: v *= (m > 0 ? 1 : 0.2), m = saved forward activation at the same pixel
+  int mask_stride;            // channels per pixel of the mask buffer
+  int mask_coff;
+  const float* r1;  // fp32 residuals, [pixel][res_stride], column indexed from 0
+  const float* r2;
+  float beta1, beta2;
+  int res_stride;
+  float* out_f32;    // optional fp32 copy of v ([pixel][of_stride])
+  float* out_f32_b;  // optional second fp32 copy
+  int of_stride;
+  __nv_bfloat16* out_bf16;  // optional bf16(delta * v) at channel ob_coff + col
+  int ob_stride;
+  int ob_coff;
+  float delta;
+  int split_off;  // > 0: also store lo = bf16(delta*v - hi) at channel ob_coff + split_off + col
+  int store_mode;
+  unsigned char* clamp_mask;  // kStoreFinal, may be nullptr
+  int n_valid;                // kStoreFinal: real output channels (<= 16)
+};
+
+struct ConvParams {
+  int N, H, W;  // pixel lattice the conv runs on
+  int tiles_x, tiles_y, num_tiles;
+  int num_chunks;   // K chunks of 64 channels
+  int ksteps_last;  // 16-channel k-steps issued for the last chunk (1..4); other chunks use 4
+  int a_c0;         // activation channel coordinate of chunk c: a_c0 + (c % a_wrap) * 64
+  int a_wrap;
+  int w_row0;   // first row of this conv in the packed weight matrix
+  int n_cols;   // UMMA N handled by one CTA (multiple of 16, <= 128)
+  int n_total;  // n_cols * gridDim.y
+  int num_stages;
+  ConvEpilogue epi;
+};
+
+__host__ __device__ inline int conv_stage_bytes(int n_cols) { return kABytes + 3 * n_cols * 128; }
+__host__ inline int conv_smem_bytes(int n_cols, int stages) {
+  return stages * conv_stage_bytes(n_cols) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+__host__ inline int conv_pick_stages(int n_cols) {
+  int s = (227 * 1024 - 1024 - 256) / conv_stage_bytes(n_cols);
+  return s > kMaxStages ? kMaxStages : s;
+}
+
+__device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue for one pixel and 32 (or 16) consecutive accumulator columns held in registers.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, int n, int y, int x, int col0, int ncol,
+                                                    float (&v)[32]) {
+  const ConvEpilogue& e = p.epi;
+  const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
+  // 1. bias + scale (+ activation)
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (i < ncol) {
+      float b = e.bias ? __ldg(e.bias + col0 + i) : 0.f;
+      float t = e.alpha * (v[i] + b);
+      v[i] = e.act ? lrelu02(t) : t;
+    }
+  }
+  if (e.store_mode == kStoreFinal) {
+    const long long plane = static_cast<long long>(p.H) * p.W;
+    const long long base = static_cast<long long>(n) * e.n_valid * plane + static_cast<long long>(y) * p.W + x;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < e.n_valid) {
+        float pre = v[i];
+        float cl = fminf(fmaxf(pre, 0.f), 1.f);
+        e.out_f32[base + i * plane] = cl;
+        if (e.clamp_mask) e.clamp_mask[base + i * plane] = (pre >= 0.f && pre <= 1.f) ? 1 : 0;
+      }
+    }
+    return;
+  }
+  // 2. LeakyReLU derivative mask from the saved forward activation
+  if (e.mask) {
+    const uint4* mp = reinterpret_cast<const uint4*>(e.mask + pix * e.mask_stride + e.mask_coff + col0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 m = __ldg(mp + q);
+      uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[q * 8 + 2 * j] *= (bf16_lo_to_f32(w[j]) > 0.f) ? 1.f : 0.2f;
+        v[q * 8 + 2 * j + 1] *= (bf16_hi_to_f32(w[j]) > 0.f) ? 1.f : 0.2f;
+      }
+    }
+  }
+  // 3. fp32 residuals
+  if (e.r1) {
+    const float4* rp = reinterpret_cast<const float4*>(e.r1 + pix * e.res_stride + col0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 r = __ldg(rp + q);
+      v[4 * q] += e.beta1 * r.x; v[4 * q + 1] += e.beta1 * r.y; v[4 * q + 2] += e.beta1 * r.z; v[4 * q + 3] += e.beta1 * r.w;
+    }
+  }
+  if (e.r2) {
+    const float4* rp = reinterpret_cast<const float4*>(e.r2 + pix * e.res_stride + col0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 r = __ldg(rp + q);
+      v[4 * q] += e.beta2 * r.x; v[4 * q + 1] += e.beta2 * r.y; v[4 * q + 2] += e.beta2 * r.z; v[4 * q + 3] += e.beta2 * r.w;
+    }
+  }
+  // 4. fp32 outputs (same lattice position)
+  if (e.out_f32) {
+    float4* op = reinterpret_cast<float4*>(e.out_f32 + pix * e.of_stride + col0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  if (e.out_f32_b) {
+    float4* op = reinterpret_cast<float4*>(e.out_f32_b + pix * e.of_stride + col0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  // 5. bf16 output (optionally hi/lo split), with the pixel (un)shuffle folded into the address
+  if (e.out_bf16) {
+    long long opix;
+    int ch;
+    if (e.store_mode == kStoreShuffle) {
+      const int phase = col0 >> 6;
+      opix = (static_cast<long long>(n) * (2 * p.H) + (2 * y + (phase >> 1))) * (2 * p.W) + (2 * x + (phase & 1));
+      ch = col0 & 63;
+    } else if (e.store_mode == kStoreUnshuffle) {
+      opix = (static_cast<long long>(n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+      ch = (((y & 1) << 1) | (x & 1)) * 64 + col0;
+    } else {
+      opix = pix;
+      ch = col0;
+    }
+    __nv_bfloat16* ob = e.out_bf16 + opix * e.ob_stride + e.ob_coff + ch;
+    uint32_t hi[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1]);
+    uint4* op = reinterpret_cast<uint4*>(ob);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) op[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+    if (e.split_off > 0) {
+      uint32_t lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        lo[j] = pack_bf16x2(e.delta * v[2 * j] - bf16_lo_to_f32(hi[j]), e.delta * v[2 * j + 1] - bf16_hi_to_f32(hi[j]));
+      uint4* lp = reinterpret_cast<uint4*>(ob + e.split_off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) lp[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                     const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.num_stages;
+  const int stage_bytes = conv_stage_bytes(p.n_cols);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int colbase = blockIdx.y * p.n_cols;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * p.n_cols) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmW);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ================================================= TMA producer =================================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img;
+        const int t2 = tile - n * tiles_per_img;
+        const int ty = t2 / p.tiles_x;
+        const int x0 = (t2 - ty * p.tiles_x) * kTileW;
+        const int y0 = ty * kTileH;
+        for (int c = 0; c < p.num_chunks; ++c) {
+          const int ac = p.a_c0 + (c % p.a_wrap) * 64;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const int dxi = (d == 0) ? 1 : (d == 1 ? 0 : 2);  // centre column first (see MMA loop)
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = smem + s * stage_bytes;
+            mbar_arrive_expect_tx(&full[s], stage_bytes);
+            tma_load_4d(st, &tmA, &full[s], ac, x0 + dxi - 1, y0 - 1, n);
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi)
+              tma_load_2d(st + kABytes + dyi * p.n_cols * 128, &tmW, &full[s], 0,
+                          p.w_row0 + ((c * 3 + dxi) * 3 + dyi) * p.n_total + colbase);
+            if (++s == S) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================== MMA issuer ==================================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.n_cols, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * p.n_cols;
+        uint32_t acc = 0;
+        for (int c = 0; c < p.num_chunks; ++c) {
+          const int ksteps = (c == p.num_chunks - 1) ? p.ksteps_last : 4;
+          for (int d = 0; d < 3; ++d) {
+            mbar_wait(&full[s], ph);
+            tcgen05_fence_after();
+            const uint32_t a0 = smem_u32(smem + s * stage_bytes);
+            const uint32_t b0 = a0 + kABytes;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+              const int dyi = (e == 0) ? 1 : (e == 1 ? 0 : 2);  // centre row first
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t ad = make_smem_desc(a0 + dyi * 1024 + ks * 32, 16, 1024);
+                const uint64_t bd = make_smem_desc(b0 + dyi * p.n_cols * 128 + ks * 32, 16, 1024);
+                umma_bf16_ss(d_tmem, ad, bd, idesc, acc);
+                acc = 1;
+              }
+            }
+            umma_commit(&empty[s]);  // frees the smem stage once these MMAs have drained
+            if (++s == S) { s = 0; ph ^= 1; }
+          }
+        }
+        umma_commit(&tfull[as]);  // accumulator ready for the epilogue warps
+      }
+    }
+  } else {
+    // =================================================== epilogue ===================================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int n = tile / tiles_per_img;
+      const int t2 = tile - n * tiles_per_img;
+      const int ty = t2 / p.tiles_x;
+      const int x = (t2 - ty * p.tiles_x) * kTileW + (m & 7);
+      const int y = ty * kTileH + (m >> 3);
+      const bool valid = (x < p.W) && (y < p.H);
+      const int as = it & 1;
+      mbar_wait(&tfull[as], (it >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.n_cols;
+      for (int c0 = 0; c0 < p.n_cols; c0 += 32) {
+        float v[32];
+        const int ncol = (p.n_cols - c0) >= 32 ? 32 : 16;
+        if (ncol == 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        } else {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_addr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+#pragma unroll
+          for (int i = 16; i < 32; ++i) v[i] = 0.f;
+        }
+        if (valid) conv_epilogue_store(p, n, y, x, colbase + c0, ncol, v);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace b200sr

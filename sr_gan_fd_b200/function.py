@@ -1,0 +1,183 @@
+"""The one ``torch.autograd.Function`` behind the drop-in generators: forward and backward of the whole RRDBNet
+run inside libb200sr.so (C ABI, ``include/b200sr.h``).  PyTorch is used only for device memory, streams and autograd
+bookkeeping.
+
+Replaces, in the reference, the eager module calls ``ESRGAN/model.py:211-232`` (forward) and the autograd graph that
+``scaler.scale(loss).backward()`` walks (``ESRGAN/train_rrdbnet.py:261``, ``BSRGAN/train_bsrgan.py:463``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Callable, List, Optional
+
+import torch
+
+from . import lib as _lib
+
+_DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+_MAX_PLANS = 8
+
+
+class _Plan:
+    def __init__(self, desc: dict, batch: int, height: int, width: int, training: bool) -> None:
+        lib = _lib.load()
+        nd = _lib.NetDesc(desc["in_channels"], desc["out_channels"], desc["channels"], desc["growth"],
+                          desc["num_blocks"], desc["n_up"], batch, height, width, 1 if training else 0)
+        handle = C.c_void_p()
+        _lib.check(lib.b200sr_plan_create(C.byref(nd), C.byref(handle)))
+        self.handle = handle
+        self.training = training
+        self.geometry = (batch, height, width)
+        self.scale = 1 << desc["n_up"]
+        self.out_channels = desc["out_channels"]
+        self.workspace_bytes = int(lib.b200sr_workspace_bytes(handle))
+        self.packed_bytes = int(lib.b200sr_packed_bytes(handle))
+        self.num_params = int(lib.b200sr_num_params(handle))
+        self.param_numel = int(lib.b200sr_param_numel(handle))
+        self.flops_fwd = float(lib.b200sr_flops(handle, 0))
+        self.flops_bwd = float(lib.b200sr_flops(handle, 1))
+        self.launches_fwd = int(lib.b200sr_num_launches(handle, 0))
+        self.launches_bwd = int(lib.b200sr_num_launches(handle, 1)) if training else 0
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().b200sr_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class GeneratorRuntime:
+    """Per-module native state (plans, packed weights).  Lives in ``module.__dict__['_b200_runtime']`` and is never
+    pickled, deep-copied or registered as a buffer (``AveragedModel`` zips buffers with strict=True)."""
+
+    def __init__(self) -> None:
+        self.plans: "OrderedDict[tuple, _Plan]" = OrderedDict()
+        self.packed = {}        # training flag -> uint8 tensor
+        self.packed_key = {}    # training flag -> (versions, ptrs)
+        self.pack_serial = {False: 0, True: 0}
+        # optional hook(flat_grads: Tensor, offset: int, count: int) called as gradient buckets are enqueued
+        self.grad_bucket_hook: Optional[Callable[[torch.Tensor, int, int], None]] = None
+        self.last_plan: Optional[_Plan] = None
+
+    def plan(self, desc: dict, device: torch.device, batch: int, height: int, width: int, training: bool) -> _Plan:
+        key = (device.index, batch, height, width, training)
+        p = self.plans.get(key)
+        if p is None:
+            p = _Plan(desc, batch, height, width, training)
+            self.plans[key] = p
+            while len(self.plans) > _MAX_PLANS:
+                self.plans.popitem(last=False)
+        else:
+            self.plans.move_to_end(key)
+        self.last_plan = p
+        return p
+
+    def packed_weights(self, plan: _Plan, params: List[torch.Tensor], stream: int) -> torch.Tensor:
+        t = plan.training
+        key = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        buf = self.packed.get(t)
+        if buf is not None and buf.device == params[0].device and self.packed_key.get(t) == key:
+            return buf
+        if buf is None or buf.device != params[0].device or buf.numel() != plan.packed_bytes:
+            buf = torch.empty(plan.packed_bytes, dtype=torch.uint8, device=params[0].device)
+            self.packed[t] = buf
+        ptrs = (C.c_void_p * len(params))(*key[1])
+        _lib.check(_lib.load().b200sr_pack_weights(plan.handle, ptrs, C.c_void_p(buf.data_ptr()), C.c_void_p(stream)))
+        self.packed_key[t] = key
+        self.pack_serial[t] += 1
+        return buf
+
+
+class _RRDBNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, training, *params):
+        lib = _lib.load()
+        rt: GeneratorRuntime = module._runtime()
+        desc = module.net_desc()
+        n, c, h, w = x.shape
+        if c != desc["in_channels"]:
+            raise RuntimeError(f"expected {desc['in_channels']} input channels, got {c}")
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            plan = rt.plan(desc, x.device, n, h, w, training)
+            packed = rt.packed_weights(plan, [p.detach() for p in params], stream)
+            workspace = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=x.device)
+            y = torch.empty((n, plan.out_channels, h * plan.scale, w * plan.scale), dtype=torch.float32, device=x.device)
+            strides = (C.c_int64 * 4)(*x.stride())
+            _lib.check(lib.b200sr_forward(plan.handle, C.c_void_p(x.data_ptr()), _DTYPES[x.dtype], strides,
+                                          C.c_void_p(packed.data_ptr()), C.c_void_p(workspace.data_ptr()),
+                                          C.c_void_p(y.data_ptr()), C.c_void_p(stream)))
+        if training:
+            ctx.plan = plan
+            ctx.rt = rt
+            ctx.workspace = workspace
+            ctx.packed = packed
+            ctx.pack_serial = rt.pack_serial[True]
+            ctx.param_shapes = [tuple(p.shape) for p in params]
+            ctx.x_keepalive = x
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        plan: _Plan = ctx.plan
+        rt: GeneratorRuntime = ctx.rt
+        if ctx.workspace is None:
+            raise RuntimeError("the B200 generator supports one backward per forward (activations already released)")
+        if rt.pack_serial[True] != ctx.pack_serial:
+            raise RuntimeError("generator weights were re-packed between this forward and its backward")
+        dy = dy.contiguous().float()
+        with torch.cuda.device(dy.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            flat = torch.empty(plan.param_numel, dtype=torch.float32, device=dy.device)  # fresh per backward
+            hook = rt.grad_bucket_hook
+            if hook is not None:
+                cb = _lib.BUCKET_CB(lambda user, off, cnt: hook(flat, int(off), int(cnt)))
+            else:
+                cb = _lib.BUCKET_CB()
+            _lib.check(lib.b200sr_backward(plan.handle, C.c_void_p(dy.data_ptr()), C.c_void_p(ctx.packed.data_ptr()),
+                                           C.c_void_p(ctx.workspace.data_ptr()), C.c_void_p(flat.data_ptr()), cb, None,
+                                           C.c_void_p(stream)))
+        ctx.workspace = None
+        ctx.x_keepalive = None
+        grads = []
+        off = 0
+        for i, shp in enumerate(ctx.param_shapes):
+            numel = 1
+            for s in shp:
+                numel *= s
+            grads.append(flat[off:off + numel].view(shp) if ctx.needs_input_grad[3 + i] else None)
+            off += numel
+        return (None, None, None, *grads)
+
+
+def generator_forward(module, x: torch.Tensor) -> torch.Tensor:
+    """Entry used by the drop-in modules' ``forward``."""
+    if not x.is_cuda:
+        raise RuntimeError(
+            "sr_gan_fd_b200 generators run only on CUDA (sm_100a) tensors; there is no CPU / eager fallback. "
+            "Move the model and input to a B200 device.")
+    if x.dim() != 4:
+        raise RuntimeError(f"expected NCHW input, got shape {tuple(x.shape)}")
+    if x.dtype not in _DTYPES:
+        x = x.float()
+    params = []
+    for conv in module._conv_list():
+        params.append(conv.weight)
+        params.append(conv.bias)
+    for p in params:
+        if p.dtype != torch.float32 or not p.is_contiguous() or p.device != x.device:
+            raise RuntimeError("generator parameters must be contiguous fp32 tensors on the input's device")
+    training = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    if x.requires_grad and training:
+        raise NotImplementedError("gradient w.r.t. the LR input is not produced by the B200 generator path")
+    return _RRDBNetFn.apply(module, x, training, *params)
+
+
+def attach_grad_bucket_hook(module, hook: Optional[Callable[[torch.Tensor, int, int], None]]) -> None:
+    """Data-parallel training: ``hook(flat_grads, offset, count)`` is called from inside backward each time a
+    contiguous bucket of the flat gradient buffer has been fully enqueued (see ``sr_gan_fd_b200.dist``)."""
+    module._runtime().grad_bucket_hook = hook

@@ -1,0 +1,145 @@
+"""GPU parity of the single-layer C-ABI entry points (tcgen05 implicit-GEMM conv / dgrad / wgrad) against torch fp32
+convolutions evaluated on the same bf16-rounded operands.  Tolerances: the kernels multiply bf16 x bf16 exactly and
+accumulate in fp32, so only summation order and the final bf16 store rounding (2^-9 relative) differ."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from sr_gan_fd_b200 import lib
+    return lib, lib.load()
+
+
+def _nhwc(t, stride, coff=0):
+    """NCHW fp32 -> NHWC bf16 buffer [N,H,W,stride] with the tensor at channel offset coff (rest = NaN canary... zeros)."""
+    n, c, h, w = t.shape
+    buf = torch.zeros(n, h, w, stride, dtype=torch.bfloat16, device=t.device)
+    buf[..., coff:coff + c] = t.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return buf
+
+
+def _run_fwd(x, w, b, act, x_stride, y_stride, y_coff):
+    lib, L = _lib()
+    n, cin, h, ww = x.shape
+    cout = w.shape[0]
+    xb = _nhwc(x, x_stride)
+    if x_stride > cin:  # junk in the channels the conv must not read
+        xb[..., cin:] = 7.0
+    y = torch.full((n, h, ww, y_stride), -3.0, dtype=torch.bfloat16, device=x.device)
+    scratch = torch.empty(L.b200sr_conv3x3_scratch_bytes(cin, cout), dtype=torch.uint8, device=x.device)
+    st = torch.cuda.current_stream().cuda_stream
+    lib.check(L.b200sr_conv3x3_fwd(C.c_void_p(xb.data_ptr()), n, h, ww, cin, x_stride, C.c_void_p(w.data_ptr()),
+                                   C.c_void_p(b.data_ptr()) if b is not None else None, cout, act,
+                                   C.c_void_p(y.data_ptr()), y_stride, y_coff, C.c_void_p(scratch.data_ptr()), C.c_void_p(st)))
+    torch.cuda.synchronize()
+    return y
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+CASES_FWD = [
+    # n, h, w, cin, cout, act, x_stride, y_stride, y_coff
+    (1, 16, 8, 64, 32, 1, 64, 32, 0),        # exactly one tile
+    (2, 19, 13, 64, 32, 1, 192, 192, 64),    # ragged edges, dense-buffer strides
+    (1, 33, 20, 96, 32, 1, 192, 192, 96),    # partial last K chunk (2 k-steps)
+    (2, 16, 24, 128, 32, 1, 192, 192, 128),
+    (1, 40, 17, 160, 32, 1, 192, 192, 160),
+    (2, 32, 32, 192, 64, 0, 192, 64, 0),     # conv5 shape, no activation
+    (1, 7, 5, 64, 64, 0, 64, 64, 0),         # image smaller than a tile
+    (1, 24, 16, 128, 128, 1, 128, 128, 0),   # N = 128
+    (1, 16, 16, 64, 256, 0, 64, 256, 0),     # two column groups (grid.y = 2)
+    (3, 64, 64, 64, 32, 1, 192, 192, 64),    # multi-tile persistent loop (> 148 tiles? no: 96)
+    (16, 64, 64, 192, 64, 0, 192, 64, 0),    # 512 tiles: persistent CTAs loop, accumulator double buffering
+]
+
+
+@pytest.mark.parametrize("case", CASES_FWD)
+def test_conv_fwd(case):
+    n, h, w, cin, cout, act, xs, ys, yc = case
+    torch.manual_seed(1)
+    dev = torch.device("cuda", 0)
+    x = torch.randn(n, cin, h, w, device=dev)
+    wt = torch.randn(cout, cin, 3, 3, device=dev) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, device=dev) * 0.1
+    y = _run_fwd(x, wt, b, act, xs, ys, yc)
+    ref = F.conv2d(_bf(x), _bf(wt), b, padding=1)
+    if act:
+        ref = F.leaky_relu(ref, 0.2)
+    got = y[..., yc:yc + cout].float().permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item()
+    tol = 2.0 ** -7 * ref.abs().max().item() + 1e-4
+    assert err <= tol, f"conv fwd mismatch: max err {err} tol {tol}"
+    # channels outside the written slice must be untouched
+    if ys > cout:
+        other = torch.cat([y[..., :yc], y[..., yc + cout:]], -1)
+        assert torch.all(other.float() == -3.0)
+    rel = (got - ref).norm() / ref.norm()
+    assert rel < 3e-3
+
+
+CASES_DGRAD = [
+    (2, 19, 13, 64, 32),    # conv Cin=64 <- dY 32 ch
+    (1, 32, 24, 64, 64),
+    (2, 16, 16, 32, 96),    # dY 96 channels (partial chunk) -> 32-channel slice
+    (1, 20, 12, 64, 192),
+]
+
+
+@pytest.mark.parametrize("case", CASES_DGRAD)
+def test_conv_dgrad(case):
+    n, h, w, cin, cout = case
+    lib, L = _lib()
+    torch.manual_seed(2)
+    dev = torch.device("cuda", 0)
+    dy = torch.randn(n, cout, h, w, device=dev)
+    wt = torch.randn(cout, cin, 3, 3, device=dev) * 0.1
+    dyb = _nhwc(dy, cout)
+    dx = torch.zeros(n, h, w, cin, dtype=torch.bfloat16, device=dev)
+    scratch = torch.empty(L.b200sr_conv3x3_scratch_bytes(cout, cin), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    lib.check(L.b200sr_conv3x3_dgrad(C.c_void_p(dyb.data_ptr()), n, h, w, cout, cout, C.c_void_p(wt.data_ptr()), cin,
+                                     C.c_void_p(dx.data_ptr()), cin, 0, C.c_void_p(scratch.data_ptr()), C.c_void_p(st)))
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input((n, cin, h, w), _bf(wt), _bf(dy), padding=1)
+    got = dx.float().permute(0, 3, 1, 2)
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 3e-3, f"dgrad rel err {rel}"
+
+
+CASES_WGRAD = [
+    (1, 16, 8, 64, 32),
+    (2, 19, 13, 64, 64),
+    (2, 32, 32, 128, 160),
+    (1, 24, 40, 96, 96),
+    (4, 64, 64, 128, 160),
+    (2, 16, 16, 64, 16),
+]
+
+
+@pytest.mark.parametrize("case", CASES_WGRAD)
+def test_conv_wgrad(case):
+    n, h, w, cin, cout = case
+    lib, L = _lib()
+    torch.manual_seed(3)
+    dev = torch.device("cuda", 0)
+    x = torch.randn(n, cin, h, w, device=dev)
+    dy = torch.randn(n, cout, h, w, device=dev)
+    xs = 192 if cin <= 192 else cin
+    xb = _nhwc(x, xs)
+    xb[..., cin:] = 5.0
+    dyb = _nhwc(dy, cout)
+    dw = torch.zeros(cout, cin, 3, 3, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    lib.check(L.b200sr_conv3x3_wgrad(C.c_void_p(xb.data_ptr()), n, h, w, cin, xs, C.c_void_p(dyb.data_ptr()), cout, cout,
+                                     C.c_void_p(dw.data_ptr()), C.c_void_p(st)))
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(_bf(x), (cout, cin, 3, 3), _bf(dy), padding=1)
+    rel = ((dw - ref).norm() / ref.norm()).item()
+    assert rel < 1e-3, f"wgrad rel err {rel}"

@@ -1,0 +1,146 @@
+"""GPU parity of the drop-in generators (whole network through the C ABI) against the fp32 CPU oracle.
+
+Tolerances are the ones BASELINE.json's north_star states: SR relative L2 <= 5e-3, PSNR/SSIM (Y channel, crop 4)
+within 0.01 dB / 1e-4, gradients relative L2 <= 1e-2 -- all versus the fp32 reference arithmetic on the same
+synthetic inputs and random-init weights."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import rrdbnet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+DEV = torch.device("cuda", 0)
+TOL_SR, TOL_GRAD, TOL_PSNR, TOL_SSIM = 5e-3, 1e-2, 0.01, 1e-4
+
+
+def _build(factory="rrdbnet_x4", in_range=False, seed=0, **kw):
+    import sr_gan_fd_b200 as b200
+    torch.manual_seed(seed)
+    net = getattr(b200, factory)(**kw)
+    params = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    if in_range:
+        params = orc.in_range_fixture(params)
+        net.load_state_dict(params)
+    return net.to(DEV), params
+
+
+def _fwd_check(net, params, lr, pixel_unshuffle=1):
+    net.eval()
+    with torch.no_grad():
+        sr = net(lr.to(DEV)).cpu()
+    ref = orc.rrdbnet_forward(params, lr.float(), pixel_unshuffle)
+    assert sr.shape == ref.shape and sr.dtype == torch.float32
+    assert float(sr.min()) >= 0.0 and float(sr.max()) <= 1.0
+    return sr, ref, orc.rel_l2(sr, ref)
+
+
+@pytest.mark.parametrize("factory,kw,shape", [
+    ("rrdbnet_x4", dict(num_blocks=1), (1, 3, 16, 8)),
+    ("rrdbnet_x4", dict(num_blocks=2), (2, 3, 24, 20)),
+    ("rrdbnet_x4", dict(num_blocks=23), (2, 3, 32, 32)),
+    ("rrdbnet_x2", dict(num_blocks=2), (1, 3, 19, 13)),
+    ("rrdbnet_x8", dict(num_blocks=1), (1, 3, 12, 10)),
+    ("rrdbnet_x1", dict(num_blocks=1), (1, 3, 20, 20)),
+    ("bsrgan_x2", dict(num_rrdb=2), (2, 3, 18, 30)),
+    ("bsrgan_x4", dict(num_rrdb=1), (1, 3, 30, 31)),
+    ("real_rrdbnet_x4", dict(in_channels=3, out_channels=3, channels=64, growth_channels=32, num_rrdb=1), (1, 3, 17, 9)),
+])
+def test_forward_random_init(factory, kw, shape):
+    net, params = _build(factory, **kw)
+    lr = torch.rand(*shape)
+    sr, ref, err = _fwd_check(net, params, lr)
+    assert err <= TOL_SR, f"{factory}{shape}: SR rel-L2 {err:.3e}"
+
+
+def test_forward_in_range_psnr_ssim():
+    net, params = _build("rrdbnet_x4", in_range=True, num_blocks=23)
+    lr = torch.rand(2, 3, 32, 32)
+    gt = torch.rand(2, 3, 128, 128)
+    sr, ref, err = _fwd_check(net, params, lr)
+    assert float(ref.std()) > 0.05  # the fixture really spans [0, 1]
+    assert err <= TOL_SR, f"SR rel-L2 {err:.3e}"
+    d_psnr = (orc.psnr_y(sr, gt) - orc.psnr_y(ref, gt)).abs().max().item()
+    d_ssim = (orc.ssim_y(sr, gt) - orc.ssim_y(ref, gt)).abs().max().item()
+    assert d_psnr <= TOL_PSNR and d_ssim <= TOL_SSIM, (d_psnr, d_ssim)
+
+
+def test_forward_input_layouts_and_dtypes():
+    net, params = _build("rrdbnet_x4", in_range=True, num_blocks=1)
+    lr = torch.rand(2, 3, 20, 12)
+    net.eval()
+    with torch.no_grad():
+        base = net(lr.to(DEV))
+        cl = net(lr.to(DEV).contiguous(memory_format=torch.channels_last))
+        assert torch.equal(base, cl)
+        h = net(lr.to(DEV).half())
+        assert orc.rel_l2(h, base) < 2e-3
+        with torch.autocast("cuda", dtype=torch.float16):
+            ac = net(lr.to(DEV))
+        assert torch.equal(base, ac)
+
+
+def _grad_check(factory, kw, shape, in_range, loss_scale=1.0):
+    net, params = _build(factory, in_range=in_range, **kw)
+    net.train()
+    lr = torch.rand(*shape)
+    s = net.upscale_factor
+    gt = torch.rand(shape[0], 3, shape[2] * s, shape[3] * s)
+    sr = net(lr.to(DEV))
+    loss = F.l1_loss(sr, gt.to(DEV))
+    (loss * loss_scale).backward()
+    sr_ref, loss_ref, grads_ref = orc.rrdbnet_l1_step(params, lr, gt, loss_scale)
+    assert orc.rel_l2(sr, sr_ref) <= TOL_SR
+    names = list(grads_ref.keys())
+    got = {n: p.grad.detach().cpu() for n, p in net.named_parameters()}
+    assert list(got.keys()) == names
+    flat = torch.cat([got[n].flatten() for n in names])
+    flat_ref = torch.cat([grads_ref[n].flatten() for n in names])
+    err = orc.rel_l2(flat, flat_ref)
+    worst = max((orc.rel_l2(got[n], grads_ref[n]), n) for n in names if float(grads_ref[n].norm()) > 0)
+    return err, worst
+
+
+@pytest.mark.parametrize("factory,kw,shape,in_range", [
+    ("rrdbnet_x4", dict(num_blocks=1), (1, 3, 16, 8), True),
+    ("rrdbnet_x4", dict(num_blocks=2), (2, 3, 24, 20), True),
+    ("rrdbnet_x4", dict(num_blocks=2), (2, 3, 24, 20), False),
+    ("rrdbnet_x2", dict(num_blocks=1), (1, 3, 19, 13), True),
+    ("rrdbnet_x1", dict(num_blocks=1), (2, 3, 16, 16), True),
+    ("rrdbnet_x4", dict(num_blocks=23), (2, 3, 32, 32), True),
+])
+def test_gradients(factory, kw, shape, in_range):
+    err, worst = _grad_check(factory, kw, shape, in_range)
+    assert err <= TOL_GRAD, f"flat grad rel-L2 {err:.3e}, worst tensor {worst}"
+    assert worst[0] <= 5e-2, f"worst per-tensor grad rel-L2 {worst}"
+
+
+def test_gradients_with_gradscaler_scale():
+    err, worst = _grad_check("rrdbnet_x4", dict(num_blocks=2), (1, 3, 16, 16), True, loss_scale=65536.0)
+    assert err <= TOL_GRAD, (err, worst)
+
+
+def test_module_protocol_on_gpu():
+    """deepcopy (AveragedModel), zero_grad(set_to_none), second backward on a new forward, no_grad saves nothing."""
+    net, params = _build("rrdbnet_x4", in_range=True, num_blocks=1)
+    lr = torch.rand(1, 3, 16, 16, device=DEV)
+    ema = copy.deepcopy(net)
+    with torch.no_grad():
+        a = net(lr)
+        b = ema(lr)
+    assert torch.equal(a, b)
+    for _ in range(2):
+        net.zero_grad(set_to_none=True)
+        net(lr).mean().backward()
+    g1 = net.conv1.weight.grad.clone()
+    net.zero_grad(set_to_none=True)
+    net(lr).mean().backward()
+    assert torch.allclose(g1, net.conv1.weight.grad, rtol=1e-3, atol=1e-7)
+    # weights change -> re-pack -> output changes
+    with torch.no_grad():
+        net.conv4.bias.add_(0.05)
+        c = net(lr)
+    assert not torch.equal(a, c)
