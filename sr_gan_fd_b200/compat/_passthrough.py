@@ -1,0 +1,39 @@
+"""Re-export everything the reference's own model.py defines (discriminators, ContentLoss, ...) so that only the
+generator classes / factories are overridden.  The reference file is executed where it lies, never copied."""
+import importlib.util
+import os
+import sys
+
+
+def load_reference_model(folder: str):
+    root = os.environ.get("SRGANFD_REFERENCE", "/root/reference")
+    path = os.path.join(root, folder, "model.py")
+    if not os.path.isfile(path):
+        return None
+    name = f"_srganfd_reference_{folder.replace('-', '_').lower()}_model"
+    if name in sys.modules:
+        return sys.modules[name]
+    sys.dont_write_bytecode = True
+    here = os.path.join(root, folder)
+    added = here not in sys.path
+    if added:
+        sys.path.append(here)
+    try:
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    except Exception:
+        sys.modules.pop(name, None)
+        return None
+    return mod
+
+
+def export(namespace: dict, folder: str, overrides: dict) -> None:
+    ref = load_reference_model(folder)
+    if ref is not None:
+        for k, v in ref.__dict__.items():
+            if not k.startswith("__"):
+                namespace.setdefault(k, v)
+    namespace.update(overrides)
+    namespace["__all__"] = sorted(k for k in namespace if not k.startswith("_"))

@@ -60,6 +60,8 @@ class GeneratorRuntime:
         self.pack_serial = {False: 0, True: 0}
         # optional hook(flat_grads: Tensor, offset: int, count: int) called as gradient buckets are enqueued
         self.grad_bucket_hook: Optional[Callable[[torch.Tensor, int, int], None]] = None
+        # optional hook(flat_grads) called once backward has enqueued all of its kernels
+        self.grad_done_hook: Optional[Callable[[torch.Tensor], None]] = None
         self.last_plan: Optional[_Plan] = None
 
     def plan(self, desc: dict, device: torch.device, batch: int, height: int, width: int, training: bool) -> _Plan:
@@ -141,6 +143,8 @@ class _RRDBNetFn(torch.autograd.Function):
             _lib.check(lib.b200sr_backward(plan.handle, C.c_void_p(dy.data_ptr()), C.c_void_p(ctx.packed.data_ptr()),
                                            C.c_void_p(ctx.workspace.data_ptr()), C.c_void_p(flat.data_ptr()), cb, None,
                                            C.c_void_p(stream)))
+            if rt.grad_done_hook is not None:
+                rt.grad_done_hook(flat)
         ctx.workspace = None
         ctx.x_keepalive = None
         grads = []

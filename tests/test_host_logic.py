@@ -1,0 +1,131 @@
+"""CPU: host-side logic of the drop-in (module protocol, C-ABI symbols, plan bookkeeping).  No GPU compute calls."""
+import copy
+import ctypes as C
+import io
+import os
+import pickle
+import re
+
+import pytest
+import torch
+
+import sr_gan_fd_b200 as b200
+from oracle import rrdbnet_oracle as orc
+from sr_gan_fd_b200 import lib as b200lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from sr_gan_fd_b200.build import build_native
+    build_native()
+    return b200lib.load()
+
+
+def test_header_symbols_are_exported(L):
+    hdr = open(os.path.join(ROOT, "include", "b200sr.h")).read()
+    declared = set(re.findall(r"\b(b200sr_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"b200sr_bucket_cb"}
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/b200sr.h but not exported by libb200sr.so"
+    assert set(b200lib.SIGNATURES) == declared
+    assert L.b200sr_version() >= 100
+
+
+def _plan(L, training, batch=16, h=64, w=64, blocks=23, n_up=2, **kw):
+    nd = b200lib.NetDesc(kw.get("cin", 3), kw.get("cout", 3), kw.get("channels", 64), kw.get("growth", 32), blocks, n_up, batch, h, w,
+                         1 if training else 0)
+    handle = C.c_void_p()
+    rc = L.b200sr_plan_create(C.byref(nd), C.byref(handle))
+    return rc, handle
+
+
+def test_plan_bookkeeping_matches_work_model(L):
+    rc, h = _plan(L, True)
+    assert rc == 0
+    try:
+        assert L.b200sr_num_params(h) == 702
+        assert L.b200sr_param_numel(h) == 16_697_987
+        px = 16 * 64 * 64
+        assert L.b200sr_flops(h, 0) == orc.flops_per_lr_pixel() * px
+        assert L.b200sr_flops(h, 1) == orc.flops_per_lr_pixel(backward=True) * px
+        assert L.b200sr_num_launches(h, 0) == 1 + 351  # ingest + one launch per conv (upsample convs: 1 launch, 2 column groups)
+        assert L.b200sr_workspace_bytes(h) > 69 * px * 192 * 2
+        assert L.b200sr_packed_bytes(h) > 2 * 16_697_987
+    finally:
+        L.b200sr_plan_destroy(h)
+    rc, h = _plan(L, False)
+    assert rc == 0
+    assert L.b200sr_workspace_bytes(h) < 2 * 2 ** 30
+    L.b200sr_plan_destroy(h)
+
+
+def test_plan_rejects_unsupported_configs(L):
+    for kw in (dict(channels=32), dict(growth=16), dict(cout=17), dict(cin=0)):
+        rc, h = _plan(L, False, **kw)
+        assert rc < 0 and L.b200sr_last_error()
+    rc, h = _plan(L, False, blocks=0)
+    assert rc < 0
+
+
+def test_state_dict_layout():
+    net = b200.rrdbnet_x4()
+    sd = net.state_dict()
+    assert len(sd) == 702 and sum(v.numel() for v in sd.values()) == 16_697_987
+    names = orc.conv_names(23, 2)
+    assert list(sd.keys()) == [n + s for n in names for s in (".weight", ".bias")]
+    shapes = orc.conv_shapes(3, 3, 64, 32, 23, 2)
+    for n, (co, ci) in shapes.items():
+        assert tuple(sd[n + ".weight"].shape) == (co, ci, 3, 3) and sd[n + ".weight"].dtype == torch.float32
+    assert sum(v.numel() for v in b200.bsrgan_x2().state_dict().values()) == 16_661_059
+
+
+def test_module_protocol_cpu():
+    torch.manual_seed(0)
+    net = b200.rrdbnet_x4(num_blocks=1)
+    net._runtime()  # native runtime state must not leak into copies / pickles / state_dict
+    ema = torch.optim.swa_utils.AveragedModel(net, avg_fn=lambda a, m, n: 0.999 * a + 0.001 * m)
+    ema.update_parameters(net)
+    assert "_b200_runtime" not in ema.module.__dict__
+    blob = pickle.dumps(net)
+    net2 = pickle.loads(blob)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+    buf = io.BytesIO()
+    torch.save({"state_dict": net.state_dict()}, buf)
+    buf.seek(0)
+    net3 = b200.rrdbnet_x4(num_blocks=1)
+    net3.load_state_dict(torch.load(buf)["state_dict"])
+    net.zero_grad(set_to_none=True)
+    net.train(); net.eval()
+    assert len(list(net.buffers())) == 0
+    assert copy.deepcopy(net).conv1.weight.data_ptr() != net.conv1.weight.data_ptr()
+
+
+def test_cpu_input_fails_loudly():
+    net = b200.rrdbnet_x4(num_blocks=1)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        net(torch.rand(1, 3, 8, 8))
+
+
+def test_factories_and_kwargs():
+    assert b200.rrdbnet_x2(num_blocks=1).upscale_factor == 2
+    assert hasattr(b200.rrdbnet_x8(num_blocks=1), "upsampling3")
+    assert not hasattr(b200.rrdbnet_x1(num_blocks=1), "upsampling1")
+    m = b200.bsrgan_x2(num_rrdb=1)
+    assert hasattr(m, "upsampling1") and not hasattr(m, "upsampling2")
+    r = b200.RealRRDBNet(3, 3, 64, 32, 1, 2)
+    assert r.conv1.in_channels == 12 and hasattr(r, "upsampling2")
+
+
+def test_compat_shims_export_reference_names():
+    import importlib
+    e = importlib.import_module("sr_gan_fd_b200.compat.esrgan_model")
+    for n in ("RRDBNet", "rrdbnet_x1", "rrdbnet_x2", "rrdbnet_x4", "rrdbnet_x8"):
+        assert n in e.__dict__
+    bs = importlib.import_module("sr_gan_fd_b200.compat.bsrgan_model")
+    for n in ("BSRGAN", "bsrgan_x2", "bsrgan_x4"):
+        assert n in bs.__dict__
+    re_ = importlib.import_module("sr_gan_fd_b200.compat.real_esrgan_model")
+    assert "RRDBNet" in re_.__dict__ and "rrdbnet_x4" in re_.__dict__

@@ -144,3 +144,72 @@ def test_module_protocol_on_gpu():
         net.conv4.bias.add_(0.05)
         c = net(lr)
     assert not torch.equal(a, c)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# committed golden vectors (generated by oracle/make_golden.py from the reference's own model.py)
+# ---------------------------------------------------------------------------------------------------------------
+import glob
+import os
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_against_reference_golden_vectors(path):
+    import sr_gan_fd_b200 as b200
+    fix = torch.load(path)
+    torch.manual_seed(fix["seed"])
+    cls = {"esrgan": b200.RRDBNet, "bsrgan": b200.BSRGAN, "real": b200.RealRRDBNet}[fix["flavour"]]
+    net = cls(3, 3, 64, 32, fix["num_blocks"], fix["scale"])
+    if fix["in_range"]:
+        net.load_state_dict(orc.in_range_fixture({k: v.detach().clone() for k, v in net.state_dict().items()}))
+    net = net.to(DEV).train()
+    sr = net(fix["lr"].to(DEV))
+    loss = F.l1_loss(sr, fix["gt"].to(DEV))
+    loss.backward()
+    assert orc.rel_l2(sr, fix["sr"]) <= TOL_SR
+    assert abs(float(loss) - float(fix["loss"])) <= 1e-4
+    grads = {n: p.grad.detach().cpu() for n, p in net.named_parameters()}
+    for k, g in fix["grads"].items():
+        assert orc.rel_l2(grads[k], g) <= 3e-2, (k, orc.rel_l2(grads[k], g))
+    # flat-gradient norm check over ALL tensors via the stored per-tensor norms
+    num = sum((float(grads[k].double().norm()) - n) ** 2 for k, n in fix["grad_norms"].items())
+    den = sum(n ** 2 for n in fix["grad_norms"].values())
+    assert (num / den) ** 0.5 <= TOL_GRAD
+
+
+def test_tiled_inference_matches_whole_frame():
+    from sr_gan_fd_b200 import tile
+    net, params = _build("rrdbnet_x4", in_range=True, num_blocks=2)
+    net.eval()
+    lr = torch.rand(1, 3, 96, 40, device=DEV)
+    with torch.no_grad():
+        whole = net(lr)
+    outs = []
+    for rank in range(2):
+        out, (r0, r1) = tile.tiled_forward(net, lr, 4, num_bands=4, halo=16, rank=rank, world_size=2)
+        outs.append(out[:, :, r0:r1])
+    stitched = torch.cat(outs, 2)
+    assert stitched.shape == whole.shape
+    assert orc.rel_l2(stitched, whole) < 2e-3
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 at full size (16 x 64x64, 23 RRDB): size-independent properties instead of a CPU oracle run --
+    batch independence (image i of the batch == the same image run alone) and gradient linearity in the loss scale."""
+    net, params = _build("rrdbnet_x4", in_range=True, num_blocks=23)
+    net.train()
+    lr = torch.rand(16, 3, 64, 64, device=DEV)
+    gt = torch.rand(16, 3, 256, 256, device=DEV)
+    sr = net(lr)
+    F.l1_loss(sr, gt).backward()
+    g1 = torch.cat([p.grad.flatten() for p in net.parameters()]).clone()
+    assert torch.isfinite(g1).all() and float(g1.norm()) > 0
+    with torch.no_grad():
+        alone = net(lr[5:6])
+    assert orc.rel_l2(alone, sr[5:6]) < 1e-5
+    net.zero_grad(set_to_none=True)
+    (F.l1_loss(net(lr), gt) * 1024.0).backward()
+    g2 = torch.cat([p.grad.flatten() for p in net.parameters()])
+    assert orc.rel_l2(g2 / 1024.0, g1) < 2e-3
