@@ -45,7 +45,7 @@ enum b200sr_dtype { B200SR_F32 = 0, B200SR_F16 = 1, B200SR_BF16 = 2 };
 /* Network + problem geometry.  Mirrors the reference constructor arguments (ESRGAN/model.py:145-153):
  * channels must be 64 and growth 32 (the only values the reference configs use; the tiles are built on them). */
 typedef struct b200sr_net_desc {
-  int32_t in_channels;  /* conv1 input channels (after Real-ESRGAN's pixel-unshuffle), 1..21 */
+  int32_t in_channels;  /* conv1 input channels (after Real-ESRGAN's pixel-unshuffle), 1..64 */
   int32_t out_channels; /* conv4 output channels, 1..16 */
   int32_t channels;     /* 64 */
   int32_t growth;       /* 32 */
@@ -98,10 +98,11 @@ int b200sr_conv3x3_fwd(const void* x, int n, int h, int w_, int cin, int x_strid
 /* dx[n*h*w][dx_stride] (bf16, channels [dx_coff, dx_coff+cin)) = conv_transpose of dy (bf16, channels [0, cout)) */
 int b200sr_conv3x3_dgrad(const void* dy, int n, int h, int w_, int cout, int dy_stride, const float* w, int cin,
                          void* dx, int dx_stride, int dx_coff, void* scratch, b200sr_stream stream);
-/* dw[cout][cin][3][3] fp32 += sum_pixels x (bf16, channels [0, cin)) * dy (bf16, channels [0, cout)); cin <= 128,
- * cout <= 160.  dw must be zero-initialised by the caller for a plain gradient. */
+/* dw[cout][cin][3][3] fp32 = sum_pixels x (bf16, channels [0, cin)) * dy (bf16, channels [0, cout)); cin <= 128,
+ * cout <= 160, cout % 16 == 0.  dw is overwritten.  scratch: >= b200sr_conv3x3_wgrad_scratch_bytes(cin, cout). */
+size_t b200sr_conv3x3_wgrad_scratch_bytes(int cin, int cout);
 int b200sr_conv3x3_wgrad(const void* x, int n, int h, int w_, int cin, int x_stride, const void* dy, int cout,
-                         int dy_stride, float* dw, b200sr_stream stream);
+                         int dy_stride, float* dw, void* scratch, b200sr_stream stream);
 
 const char* b200sr_last_error(void);
 int b200sr_version(void);

@@ -149,58 +149,102 @@ __global__ void ingest_grad_kernel(const float* __restrict__ dy, const unsigned 
 }
 
 // ------------------------------------------------------------------------------------------------ bias gradients
-// db[c] += sum over pixels of g[pixel][c0 + c] for c in [0, ncols).  g is bf16 [P][stride].
+// db[c] += sum over pixels of g[pixel][c0 + c] for c in [0, ncols).  g is bf16 [P][stride]; ncols is even.
+// Thread layout: (ncols/2) channel-pair lanes x PL pixel lanes, so a warp reads consecutive channels of one pixel row
+// (coalesced); pixel lanes are reduced through shared memory, one atomicAdd per channel and block.
 struct BiasGradSeg { int col_begin, col_end; float* out; int n_valid; };
 struct BiasGradParams { const __nv_bfloat16* g; long long P; int stride; int c0; int ncols; int nseg; BiasGradSeg seg[5]; };
+constexpr int kBiasGradThreads = 256;
 
-__global__ void bias_grad_kernel(const BiasGradParams p) {
-  // block: 256 threads = 8 pixel lanes x 32 column lanes; each column lane handles columns cl, cl+32, ...
-  __shared__ float red[8][33];
-  const int cl = threadIdx.x & 31;
-  const int pl = threadIdx.x >> 5;
-  for (int cb = 0; cb < p.ncols; cb += 32) {
-    const int c = cb + cl;
-    float acc = 0.f;
-    if (c < p.ncols) {
-      for (long long px = static_cast<long long>(blockIdx.x) * 8 + pl; px < p.P; px += static_cast<long long>(gridDim.x) * 8)
-        acc += __bfloat162float(p.g[px * p.stride + p.c0 + c]);
+__global__ void __launch_bounds__(kBiasGradThreads) bias_grad_kernel(const BiasGradParams p) {
+  __shared__ float2 red[kBiasGradThreads];
+  const int half = p.ncols >> 1;              // channel pairs
+  const int PL = kBiasGradThreads / half;     // pixel lanes per block
+  const int cp = threadIdx.x % half;
+  const int pl = threadIdx.x / half;
+  float2 acc = make_float2(0.f, 0.f);
+  if (pl < PL) {
+    const __nv_bfloat162* base = reinterpret_cast<const __nv_bfloat162*>(p.g + p.c0) + cp;
+    const long long step = static_cast<long long>(gridDim.x) * PL;
+    for (long long px = static_cast<long long>(blockIdx.x) * PL + pl; px < p.P; px += step) {
+      const float2 v = __bfloat1622float2(base[px * (p.stride >> 1)]);
+      acc.x += v.x; acc.y += v.y;
     }
-    red[pl][cl] = acc;
-    __syncthreads();
-    if (pl == 0 && c < p.ncols) {
-      float s = 0.f;
-      for (int i = 0; i < 8; ++i) s += red[i][cl];
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (pl == 0) {
+    for (int i = 1; i < PL; ++i) { acc.x += red[i * half + cp].x; acc.y += red[i * half + cp].y; }
+    for (int k = 0; k < 2; ++k) {
+      const int c = 2 * cp + k;
+      const float s = k ? acc.y : acc.x;
       for (int sgi = 0; sgi < p.nseg; ++sgi) {
         const BiasGradSeg& sg = p.seg[sgi];
         if (c >= sg.col_begin && c < sg.col_end && (c - sg.col_begin) < sg.n_valid) atomicAdd(sg.out + (c - sg.col_begin), s);
       }
     }
-    __syncthreads();
   }
 }
 
-// ---------------------------------------------------------------------------- fold phase weight grads back to 3x3
-// gp: [256 = phase*64 + co][ci_total][3][3] gradients of the four low-res phase kernels -> dW[co][ci][dy][dx] +=
-__global__ void fold_up_wgrad_kernel(const float* __restrict__ gp, float* __restrict__ dw, int CO, int CI) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= CO * CI * 9) return;
-  const int tap = idx % 9, dy = tap / 3, dx = tap % 3;
-  const int ci = (idx / 9) % CI;
-  const int co = idx / (9 * CI);
-  float s = 0.f;
-  for (int a = 0; a < 2; ++a)
-    for (int b = 0; b < 2; ++b) {
-      int ry = -1, rx = -1;
-      for (int t = 0; t < 3; ++t) {
-        int lo, hi;
-        up_phase_taps(a, t, lo, hi);
-        if (dy >= lo && dy < hi) ry = t;
-        up_phase_taps(b, t, lo, hi);
-        if (dx >= lo && dx < hi) rx = t;
+// ------------------------------------------------------------ unpack staged weight gradients to the OIHW flat buffer
+// src: [tap][ci][co_pad] fp32 staging tensor written by wgrad3x3_kernel;  dst: [co][ci][3][3] (state_dict layout).
+// fold = 1: src holds the four low-res phase kernels of an upsample conv ([tap][ci][4*64]) and they are folded back
+// onto the 3x3 taps of the original weight (see up_phase_taps).
+struct UnpackOp { long long src_off; long long dst_off; int co, ci, co_pad, fold; int block0; int nblocks; };
+
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const UnpackOp* __restrict__ ops, int op_begin, int op_end,
+                                                           const float* __restrict__ staging, float* __restrict__ grads) {
+  // find the op this block works on (ops of one launch have consecutive block ranges starting at ops[op_begin].block0)
+  const int b = blockIdx.x + ops[op_begin].block0;
+  int lo = op_begin, hi = op_end - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (ops[mid].block0 <= b) lo = mid; else hi = mid - 1;
+  }
+  const UnpackOp op = ops[lo];
+  // one block = 32 co x 32 ci tile, all 9 taps, staged through smem so both sides are coalesced
+  __shared__ float tile[9][32][33];
+  const int tiles_co = (op.co + 31) / 32;
+  const int tb = b - op.block0;
+  const int co0 = (tb % tiles_co) * 32, ci0 = (tb / tiles_co) * 32;
+  const float* src = staging + op.src_off;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int tap = 0; tap < 9; ++tap) {
+    for (int r = ty; r < 32; r += 8) {
+      const int ci = ci0 + r, co = co0 + tx;
+      float v = 0.f;
+      if (ci < op.ci && co < op.co) {
+        if (!op.fold) {
+          v = src[(static_cast<long long>(tap) * op.ci + ci) * op.co_pad + co];
+        } else {
+          const int dy = tap / 3, dx = tap % 3;
+          for (int ph = 0; ph < 4; ++ph) {
+            int ry = -1, rx = -1;
+            for (int t = 0; t < 3; ++t) {
+              int l, h;
+              up_phase_taps(ph >> 1, t, l, h);
+              if (dy >= l && dy < h) ry = t;
+              up_phase_taps(ph & 1, t, l, h);
+              if (dx >= l && dx < h) rx = t;
+            }
+            v += src[(static_cast<long long>(ry * 3 + rx) * op.ci + ci) * op.co_pad + ph * 64 + co];
+          }
+        }
       }
-      s += gp[((static_cast<long long>((a * 2 + b) * CO + co)) * CI + ci) * 9 + ry * 3 + rx];
+      tile[tap][r][tx] = v;  // [ci][co]
     }
-  dw[idx] += s;
+  }
+  __syncthreads();
+  float* dst = grads + op.dst_off;
+  // write: for each co row of the tile, 32 ci x 9 taps contiguous floats
+  for (int cr = ty; cr < 32; cr += 8) {
+    const int co = co0 + cr;
+    if (co >= op.co) continue;
+    for (int e = tx; e < 32 * 9; e += 32) {
+      const int ci = ci0 + e / 9, tap = e % 9;
+      if (ci < op.ci) dst[(static_cast<long long>(co) * op.ci + ci) * 9 + tap] = tile[tap][e / 9][cr];
+    }
+  }
 }
 
 // out_bf16[i] = bf16(a[i] + b[i])   (gradient of conv1's output = trunk path + long skip)

@@ -100,7 +100,7 @@ static Ref ws(long long off) { Ref r; r.kind = RK_WS; r.off = off; return r; }
 
 struct ActMapSpec { long long off; int c_valid, c_pix, n, h, w, box_rows; };
 
-enum StepType { ST_CONV, ST_WGRAD, ST_BIASGRAD, ST_FOLD, ST_ADD, ST_MEMSET, ST_INGEST_X, ST_INGEST_DY };
+enum StepType { ST_CONV, ST_WGRAD, ST_BIASGRAD, ST_UNPACK, ST_ADD, ST_MEMSET, ST_INGEST_X, ST_INGEST_DY };
 
 struct Step {
   int type = ST_CONV;
@@ -142,7 +142,12 @@ struct b200sr_plan {
   std::vector<long long> o_dense, o_spl;
   long long o_dyp = 0, o_g3 = 0, o_gt = 0, o_gtb = 0, o_gr = 0, o_gc1 = 0, o_gc2 = 0, o_go1 = 0;
   long long o_dyb[2] = {0, 0};
-  std::vector<long long> o_gu, o_phw;
+  std::vector<long long> o_gu;
+  long long gw_bytes = 0;
+  long long o_gw = 0;                 // staged weight gradients, per conv [tap][ci][co_pad] fp32
+  std::vector<long long> gw_off;      // float offsets per conv into the staging buffer
+  std::vector<UnpackOp> unpack_ops;   // one per conv, conv order
+  UnpackOp* d_unpack_ops = nullptr;
   // device-side tables + descriptor cache
   PackOp* d_pack_ops = nullptr;
   BiasOp* d_bias_ops = nullptr;
@@ -264,7 +269,7 @@ static int build_plan(b200sr_plan& P) {
     }
     P.param_off[2 * nconv] = off;
   }
-  auto wref = [&](int c) { Ref r; r.kind = RK_GRADS; r.off = P.param_off[2 * c] * 4; return r; };
+  auto wref = [&](int c) { return ws(P.o_gw + P.gw_off[c] * 4); };  // weight gradients are staged, then unpacked
   auto bref = [&](int c) { Ref r; r.kind = RK_GRADS; r.off = P.param_off[2 * c + 1] * 4; return r; };
 
   Builder B(P);
@@ -286,10 +291,27 @@ static int build_plan(b200sr_plan& P) {
     P.o_dyp = B.alloc(HRpix * 64 * 2);
     P.o_g3 = B.alloc(HRpix * 64 * 2);
     P.o_gu.assign(L + 1, 0);
-    P.o_phw.assign(L + 1, 0);
-    for (int l = 1; l <= L; ++l) {
-      P.o_gu[l] = B.alloc((Ppix << (2 * (l - 1))) * 256 * 2);
-      P.o_phw[l] = B.alloc(256LL * 64 * 9 * 4);
+    for (int l = 1; l <= L; ++l) P.o_gu[l] = B.alloc((Ppix << (2 * (l - 1))) * 256 * 2);
+    {
+      // weight-gradient staging: per conv [9][ci][co_pad] fp32 (upsample convs: the four phase kernels, co = 256)
+      long long off = 0;
+      int blocks = 0;
+      P.gw_off.assign(nconv, 0);
+      for (int c = 0; c < nconv; ++c) {
+        int O, I;
+        conv_dims(P, c, &O, &I);
+        const bool is_up = (c >= ci_up1 && c < ci_conv3);
+        const int co_stage = is_up ? 256 : (int)align_up(O, 4);
+        P.gw_off[c] = off;
+        UnpackOp u;
+        u.src_off = off; u.dst_off = P.param_off[2 * c]; u.co = O; u.ci = I; u.co_pad = co_stage; u.fold = is_up ? 1 : 0;
+        u.block0 = blocks; u.nblocks = ((O + 31) / 32) * ((I + 31) / 32);
+        blocks += u.nblocks;
+        P.unpack_ops.push_back(u);
+        off += align_up(9LL * I * co_stage, 4);
+      }
+      P.o_gw = B.alloc(off * 4);
+      P.gw_bytes = off * 4;
     }
     P.o_gt = B.alloc(Ppix * 64 * 4);
     P.o_gtb = B.alloc(Ppix * 64 * 2);
@@ -442,9 +464,9 @@ static int build_plan(b200sr_plan& P) {
       s.smem = wgrad_smem_bytes(wp.n_blocks, wp.num_stages);
       return s;
     };
-    auto add_seg = [&](Step& s, int cb, int ce, Ref out, int ci_total, int ci0, int co_valid) {
+    auto add_seg = [&](Step& s, int cb, int ce, Ref out, int ci_total, int ci0, int co_pad) {
       WgradSegment& g = s.wp.seg[s.wp.num_seg];
-      g.col_begin = cb; g.col_end = ce; g.out = nullptr; g.ci_total = ci_total; g.ci0 = ci0; g.co_valid = co_valid;
+      g.col_begin = cb; g.col_end = ce; g.out = nullptr; g.ci_total = ci_total; g.ci0 = ci0; g.co_pad = co_pad;
       s.seg_out[s.wp.num_seg] = out;
       s.wp.num_seg++;
     };
@@ -460,6 +482,11 @@ static int build_plan(b200sr_plan& P) {
       s.seg_out[s.bp.nseg] = out;
       s.bp.nseg++;
     };
+    auto unpack_step = [&](int c_begin, int c_end) {  // staged weight grads of convs [c_begin, c_end) -> flat buffer, then announce
+      Step s; s.type = ST_UNPACK; s.i0 = c_begin; s.i1 = c_end;
+      s.cb_off = P.param_off[2 * c_begin]; s.cb_count = P.param_off[2 * c_end] - s.cb_off;
+      return s;
+    };
     auto dgrad_pack1 = [&](int ci, int n_total, int klen) {  // plain single-conv dgrad: n = ci (64), k = co
       int O, I; conv_dims(P, ci, &O, &I);
       PackOp op; memset(&op, 0, sizeof(op));
@@ -470,17 +497,15 @@ static int build_plan(b200sr_plan& P) {
     {
       Step s; s.type = ST_MEMSET; s.a.kind = RK_GRADS; s.a.off = 0; s.count = P.param_off[2 * nconv] * 4;
       P.bwd.push_back(s);
-      for (int l = 1; l <= L; ++l) {
-        Step m; m.type = ST_MEMSET; m.a = ws(P.o_phw[l]); m.count = 256LL * 64 * 9 * 4;
-        P.bwd.push_back(m);
-      }
+      Step m; m.type = ST_MEMSET; m.a = ws(P.o_gw); m.count = P.gw_bytes;
+      P.bwd.push_back(m);
       Step g; g.type = ST_INGEST_DY;
       P.bwd.push_back(g);
     }
     // conv4: wgrad, bias grad, dgrad (-> G3, masked by lrelu'(conv3 out))
     {
       Step w4 = wgrad_step(P.o_splc, 64, 128, P.o_dyp, 16, 64, N, hH, hW, 0, 0, 16);
-      add_seg(w4, 0, 16, wref(ci_conv4), 64, 0, d.out_channels);
+      add_seg(w4, 0, 16, wref(ci_conv4), 64, 0, (int)align_up(d.out_channels, 4));
       P.bwd.push_back(w4);
       Step b4 = biasgrad_step(P.o_dyp, HRpix, 64, 0, 16);
       add_bseg(b4, 0, 16, bref(ci_conv4), d.out_channels);
@@ -519,13 +544,12 @@ static int build_plan(b200sr_plan& P) {
       const long long npix = Ppix << (2 * (l - 1));
       for (int half = 0; half < 2; ++half) {
         Step wu = wgrad_step(P.o_spl[l - 1], 64, 128, P.o_gu[l], 256, 256, N, h, w, 0, 128 * half, 128);
-        Ref out = ws(P.o_phw[l] + (long long)half * 128 * 64 * 9 * 4);
-        add_seg(wu, 0, 128, out, 64, 0, 128);
+        Ref out = wref(ci);
+        out.off += (long long)half * 128 * 4;  // columns [128*half, +128) of the [tap][64][256] staging tensor
+        add_seg(wu, 0, 128, out, 64, 0, 256);
         P.bwd.push_back(wu);
       }
       {
-        Step f; f.type = ST_FOLD; f.a = ws(P.o_phw[l]); f.b = wref(ci); f.i0 = 64; f.i1 = 64;
-        P.bwd.push_back(f);
         Step bu = biasgrad_step(P.o_gu[l], npix, 256, 0, 256);
         for (int ph = 0; ph < 4; ++ph) add_bseg(bu, 64 * ph, 64 * ph + 64, bref(ci), 64);
         P.bwd.push_back(bu);
@@ -558,9 +582,9 @@ static int build_plan(b200sr_plan& P) {
       Step s = conv_step(B.add_map(P.o_gtb, 64, 64, N, H, W, kABoxRows), cp, 1);
       s.of = ws(P.o_gr);
       s.ob = ws(P.o_dyb[0]); s.cp.epi.ob_stride = 192; s.cp.epi.delta = 0.04f;
-      // tail bucket: conv2 .. conv4 are contiguous at the end of the flat buffer
-      s.cb_off = P.param_off[2 * ci_conv2]; s.cb_count = P.param_off[2 * nconv] - P.param_off[2 * ci_conv2];
       P.bwd.push_back(s);
+      // tail bucket: conv2 .. conv4 are contiguous at the end of the flat buffer
+      P.bwd.push_back(unpack_step(ci_conv2, nconv));
     }
     // trunk, last dense block first
     for (int r = R - 1; r >= 0; --r) {
@@ -616,11 +640,9 @@ static int build_plan(b200sr_plan& P) {
         add_bseg(bg, 96, 128, bref(conv_index_rdb(r, 3)), 32);
         add_bseg(bg, 128, 160, bref(conv_index_rdb(r, 2)), 32);
         add_bseg(bg, 160, 192, bref(conv_index_rdb(r, 1)), 32);
-        if (j == 0) {  // one bucket per RRDB (its 15 convs are contiguous in the flat buffer)
-          bg.cb_off = P.param_off[2 * conv_index_rdb(r, 1)];
-          bg.cb_count = P.param_off[2 * conv_index_rdb(r + 2, 5) + 2] - bg.cb_off;
-        }
         P.bwd.push_back(bg);
+        if (j == 0)  // one bucket per RRDB (its 15 convs are contiguous in the flat buffer)
+          P.bwd.push_back(unpack_step(conv_index_rdb(r, 1), conv_index_rdb(r + 2, 5) + 1));
       }
     }
     // conv1: gradient of its output = trunk path (GR) + long skip (GT)
@@ -632,8 +654,8 @@ static int build_plan(b200sr_plan& P) {
       P.bwd.push_back(w1);
       Step b1 = biasgrad_step(P.o_go1, Ppix, 64, 0, 64);
       add_bseg(b1, 0, 64, bref(0), 64);
-      b1.cb_off = 0; b1.cb_count = P.param_off[2];
       P.bwd.push_back(b1);
+      P.bwd.push_back(unpack_step(0, 1));
     }
   }
 
@@ -727,15 +749,17 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         BiasGradParams bp = s.bp;
         bp.g = (const __nv_bfloat16*)resolve(s.bg_g, b);
         for (int i = 0; i < bp.nseg; ++i) bp.seg[i].out = (float*)resolve(s.seg_out[i], b);
-        long long blocks = (bp.P + 63) / 64;
-        if (blocks > 4 * g_num_sms) blocks = 4 * g_num_sms;
-        bias_grad_kernel<<<(int)blocks, 256, 0, st>>>(bp);
+        const int pl = kBiasGradThreads / (bp.ncols / 2);
+        long long blocks = (bp.P + pl * 16 - 1) / (pl * 16);
+        if (blocks > 2 * g_num_sms) blocks = 2 * g_num_sms;
+        bias_grad_kernel<<<(int)blocks, kBiasGradThreads, 0, st>>>(bp);
         CUDA_TRY(cudaGetLastError());
         break;
       }
-      case ST_FOLD: {
-        const int n = s.i0 * s.i1 * 9;
-        fold_up_wgrad_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)resolve(s.a, b), (float*)resolve(s.b, b), s.i0, s.i1);
+      case ST_UNPACK: {
+        int blocks = 0;
+        for (int c = s.i0; c < s.i1; ++c) blocks += P.unpack_ops[c].nblocks;
+        unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(P.d_unpack_ops, s.i0, s.i1, (const float*)((char*)b.ws + P.o_gw), (float*)b.grads);
         CUDA_TRY(cudaGetLastError());
         break;
       }
@@ -798,6 +822,7 @@ void b200sr_plan_destroy(b200sr_plan* p) {
   if (p->d_pack_ops) cudaFree(p->d_pack_ops);
   if (p->d_bias_ops) cudaFree(p->d_bias_ops);
   if (p->d_params) cudaFree((void*)p->d_params);
+  if (p->d_unpack_ops) cudaFree(p->d_unpack_ops);
   delete p;
 }
 
@@ -877,6 +902,11 @@ int b200sr_backward(b200sr_plan* p, const float* dy, const void* packed, void* w
   if (rc) return rc;
   rc = ensure_maps(*p, workspace, (void*)packed);
   if (rc) return rc;
+  if (!p->d_unpack_ops) {
+    CUDA_TRY(cudaMalloc(&p->d_unpack_ops, p->unpack_ops.size() * sizeof(UnpackOp)));
+    CUDA_TRY(cudaMemcpyAsync(p->d_unpack_ops, p->unpack_ops.data(), p->unpack_ops.size() * sizeof(UnpackOp), cudaMemcpyHostToDevice,
+                             (cudaStream_t)stream));
+  }
   Bases b{workspace, (void*)packed, nullptr, dy, flat_grads};
   return run_steps(*p, p->bwd, b, nullptr, 0, nullptr, cb, user, (cudaStream_t)stream);
 }
@@ -959,27 +989,42 @@ int b200sr_conv3x3_dgrad(const void* dy, int n, int h, int w_, int cout, int dy_
   return single_conv(kPackDgrad, dy, n, h, w_, cout, dy_stride, w, nullptr, cin, 0, dx, dx_stride, dx_coff, scratch, (cudaStream_t)stream);
 }
 
+size_t b200sr_conv3x3_wgrad_scratch_bytes(int cin, int cout) {
+  return (size_t)(align_up(9LL * cin * align_up(cout, 4) * 4, 1024) + 1024);
+}
+
 int b200sr_conv3x3_wgrad(const void* x, int n, int h, int w_, int cin, int x_stride, const void* dy, int cout, int dy_stride, float* dw,
-                         b200sr_stream stream) {
-  if (!x || !dy || !dw) return fail(B200SR_ERR_INVALID, "null argument");
+                         void* scratch, b200sr_stream stream) {
+  if (!x || !dy || !dw || !scratch) return fail(B200SR_ERR_INVALID, "null argument");
   int rc = runtime_init();
   if (rc) return rc;
   if (cin > 128 || cout > 160 || cout % 16 != 0) return fail(B200SR_ERR_INVALID, "wgrad: cin <= 128, cout <= 160, cout %% 16 == 0");
+  cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmX, tmDY;
   rc = encode_act_map(&tmX, (void*)x, cin, x_stride, n, h, w_, kABoxRows);
   if (rc) return rc;
   rc = encode_act_map(&tmDY, (void*)dy, cout, dy_stride, n, h, w_, kTileH);
   if (rc) return rc;
+  const long long stage_bytes = align_up(9LL * cin * cout * 4, 1024);
+  float* staging = (float*)scratch;
+  CUDA_TRY(cudaMemsetAsync(staging, 0, (size_t)stage_bytes, st));
   WgradParams wp; memset(&wp, 0, sizeof(wp));
   wp.N = n; wp.H = h; wp.W = w_;
   wp.tiles_x = (w_ + kTileW - 1) / kTileW; wp.tiles_y = (h + kTileH - 1) / kTileH; wp.num_tiles = n * wp.tiles_x * wp.tiles_y;
   wp.a_c0 = 0; wp.b_c0 = 0; wp.n_cols = cout; wp.n_blocks = (cout + 63) / 64;
   wp.num_stages = wgrad_pick_stages(wp.n_blocks);
   wp.num_seg = 1;
-  wp.seg[0].col_begin = 0; wp.seg[0].col_end = cout; wp.seg[0].out = dw; wp.seg[0].ci_total = cin; wp.seg[0].ci0 = 0; wp.seg[0].co_valid = cout;
+  wp.seg[0].col_begin = 0; wp.seg[0].col_end = cout; wp.seg[0].out = staging; wp.seg[0].ci_total = cin; wp.seg[0].ci0 = 0; wp.seg[0].co_pad = cout;
   int splits = g_num_sms / 3;
   if (splits > wp.num_tiles) splits = wp.num_tiles;
-  wgrad3x3_kernel<<<dim3(splits, 3, 1), kWgThreads, wgrad_smem_bytes(wp.n_blocks, wp.num_stages), (cudaStream_t)stream>>>(tmX, tmDY, wp);
+  wgrad3x3_kernel<<<dim3(splits, 3, 1), kWgThreads, wgrad_smem_bytes(wp.n_blocks, wp.num_stages), st>>>(tmX, tmDY, wp);
+  CUDA_TRY(cudaGetLastError());
+  UnpackOp u;
+  u.src_off = 0; u.dst_off = 0; u.co = cout; u.ci = cin; u.co_pad = cout; u.fold = 0; u.block0 = 0;
+  u.nblocks = ((cout + 31) / 32) * ((cin + 31) / 32);
+  UnpackOp* d_u = (UnpackOp*)((char*)scratch + stage_bytes);
+  CUDA_TRY(cudaMemcpyAsync(d_u, &u, sizeof(u), cudaMemcpyHostToDevice, st));
+  unpack_wgrad_kernel<<<u.nblocks, 256, 0, st>>>(d_u, 0, 1, staging, dw);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -233,21 +233,22 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   if (warp == 0) {
     // ================================================= TMA producer =================================================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n = tile / tiles_per_img;
-        const int t2 = tile - n * tiles_per_img;
-        const int ty = t2 / p.tiles_x;
-        const int x0 = (t2 - ty * p.tiles_x) * kTileW;
-        const int y0 = ty * kTileH;
-        for (int c = 0; c < p.num_chunks; ++c) {
-          const int ac = p.a_c0 + (c % p.a_wrap) * 64;
+    // (whole warp walks the loop so the index math stays warp-uniform; one elected lane issues)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_img;
+      const int t2 = tile - n * tiles_per_img;
+      const int ty = t2 / p.tiles_x;
+      const int x0 = (t2 - ty * p.tiles_x) * kTileW;
+      const int y0 = ty * kTileH;
+      for (int c = 0; c < p.num_chunks; ++c) {
+        const int ac = p.a_c0 + (c % p.a_wrap) * 64;
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const int dxi = (d == 0) ? 1 : (d == 1 ? 0 : 2);  // centre column first (see MMA loop)
-            mbar_wait(&empty[s], ph ^ 1);
+        for (int d = 0; d < 3; ++d) {
+          const int dxi = (d == 0) ? 1 : (d == 1 ? 0 : 2);  // centre column first (see MMA loop)
+          mbar_wait(&empty[s], ph ^ 1);
+          if (elect_one_sync()) {
             uint8_t* st = smem + s * stage_bytes;
             mbar_arrive_expect_tx(&full[s], stage_bytes);
             tma_load_4d(st, &tmA, &full[s], ac, x0 + dxi - 1, y0 - 1, n);
@@ -255,47 +256,55 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int dyi = 0; dyi < 3; ++dyi)
               tma_load_2d(st + kABytes + dyi * p.n_cols * 128, &tmW, &full[s], 0,
                           p.w_row0 + ((c * 3 + dxi) * 3 + dyi) * p.n_total + colbase);
-            if (++s == S) { s = 0; ph ^= 1; }
           }
+          __syncwarp();
+          if (++s == S) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================================== MMA issuer ==================================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.n_cols, 0, 0);
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + as * p.n_cols;
-        uint32_t acc = 0;
-        for (int c = 0; c < p.num_chunks; ++c) {
-          const int ksteps = (c == p.num_chunks - 1) ? p.ksteps_last : 4;
-          for (int d = 0; d < 3; ++d) {
-            mbar_wait(&full[s], ph);
-            tcgen05_fence_after();
+    // Whole warp runs the loop (uniform address math), one elected lane issues.  Descriptor hi words are loop
+    // invariant; a K-step / vertical-tap advance is one 32-bit add on the lo word.
+    const uint32_t idesc = make_idesc_bf16(128, p.n_cols, 0, 0);
+    constexpr uint32_t kHi = smem_desc_hi(1024);
+    const uint32_t b_dy = static_cast<uint32_t>(p.n_cols) * 8;  // (n_cols * 128 B) >> 4
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + as * p.n_cols;
+      for (int c = 0; c < p.num_chunks; ++c) {
+        const int ksteps = (c == p.num_chunks - 1) ? p.ksteps_last : 4;
+        for (int d = 0; d < 3; ++d) {
+          mbar_wait(&full[s], ph);
+          tcgen05_fence_after();
+          if (elect_one_sync()) {
             const uint32_t a0 = smem_u32(smem + s * stage_bytes);
-            const uint32_t b0 = a0 + kABytes;
+            const uint32_t a_lo = smem_desc_lo(a0, 16);
+            const uint32_t b_lo = smem_desc_lo(a0 + kABytes, 16);
+            const uint32_t first = (c | d) ? 1u : 0u;  // very first MMA of the tile overwrites the accumulator
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
               const int dyi = (e == 0) ? 1 : (e == 1 ? 0 : 2);  // centre row first
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t ad = make_smem_desc(a0 + dyi * 1024 + ks * 32, 16, 1024);
-                const uint64_t bd = make_smem_desc(b0 + dyi * p.n_cols * 128 + ks * 32, 16, 1024);
-                umma_bf16_ss(d_tmem, ad, bd, idesc, acc);
-                acc = 1;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks < ksteps)
+                  umma_bf16_ss_lohi(d_tmem, a_lo + dyi * 64 + ks * 2, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
+                                    (e == 0 && ks == 0) ? first : 1u);
               }
             }
             umma_commit(&empty[s]);  // frees the smem stage once these MMAs have drained
-            if (++s == S) { s = 0; ph ^= 1; }
           }
+          __syncwarp();
+          if (++s == S) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[as]);  // accumulator ready for the epilogue warps
       }
+      if (elect_one_sync()) umma_commit(&tfull[as]);  // accumulator ready for the epilogue warps
+      __syncwarp();
     }
   } else {
     // =================================================== epilogue ===================================================

@@ -9,7 +9,8 @@
 // TMA boxes), N = up to 160 output-gradient channels -- for a dense block that is the concatenation
 // [dY5|dY4|dY3|dY2|dY1] of all consumers of the input slice, so the X tile is read once for all five convs
 // ("re-associated by input slice").  The accumulators (3 x N <= 480 TMEM columns) live in TMEM for the whole
-// pixel loop and are flushed once with fp32 reductions (red.global.add) into the OIHW gradient tensors.
+// pixel loop and are flushed once with 16-byte vector reductions (red.global.add.v4.f32) into a [tap][ci][co] fp32
+// staging tensor; a small unpack kernel transposes that to the OIHW gradient layout per gradient bucket.
 #pragma once
 #include "conv_kernel.cuh"
 
@@ -20,11 +21,11 @@ constexpr int kWgThreads = 192;
 constexpr int kWgMaxSeg = 5;
 
 struct WgradSegment {
-  int col_begin, col_end;  // accumulator columns of this conv's output channels
-  float* out;              // gradient tensor, [co][ci_total][3][3] fp32 (OIHW)
+  int col_begin, col_end;  // accumulator columns of this conv's output channels (multiples of 16)
+  float* out;              // gradient staging tensor, [tap][ci_total][co_pad] fp32 (co fastest -> 16 B vector reductions)
   int ci_total;            // input channels of that conv
   int ci0;                 // conv input channel of accumulator row 0
-  int co_valid;            // columns (col - col_begin) >= co_valid are padding
+  int co_pad;              // output channels rounded up to a multiple of 4
 };
 
 struct WgradParams {
@@ -86,53 +87,56 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const bool has_work = static_cast<int>(blockIdx.x) < p.num_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n = tile / tiles_per_img;
-        const int t2 = tile - n * tiles_per_img;
-        const int ty = t2 / p.tiles_x;
-        const int x0 = (t2 - ty * p.tiles_x) * kTileW;
-        const int y0 = ty * kTileH;
-        mbar_wait(&empty[s], ph ^ 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_img;
+      const int t2 = tile - n * tiles_per_img;
+      const int ty = t2 / p.tiles_x;
+      const int x0 = (t2 - ty * p.tiles_x) * kTileW;
+      const int y0 = ty * kTileH;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one_sync()) {
         uint8_t* st = smem + s * stage_bytes;
         mbar_arrive_expect_tx(&full[s], stage_bytes);
         tma_load_4d(st, &tmX, &full[s], p.a_c0, x0 + dxi - 1, y0 - 1, n);
         tma_load_4d(st + kABytes, &tmX, &full[s], p.a_c0 + 64, x0 + dxi - 1, y0 - 1, n);
         for (int j = 0; j < p.n_blocks; ++j)
           tma_load_4d(st + 2 * kABytes + j * kWgBBytes, &tmDY, &full[s], p.b_c0 + 64 * j, x0, y0, n);
-        if (++s == S) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.n_cols, 1, 1);  // both operands MN-major
-      int s = 0;
-      uint32_t ph = 0;
-      uint32_t acc = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&full[s], ph);
-        tcgen05_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, p.n_cols, 1, 1);  // both operands MN-major
+    constexpr uint32_t kHi = smem_desc_hi(1024);
+    int s = 0;
+    uint32_t ph = 0;
+    uint32_t acc = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&full[s], ph);
+      tcgen05_fence_after();
+      if (elect_one_sync()) {
         const uint32_t a0 = smem_u32(smem + s * stage_bytes);
-        const uint32_t b0 = a0 + 2 * kABytes;
+        const uint32_t a_lo = smem_desc_lo(a0, kABytes);                  // LBO = stride between the two 64-ch M blocks
+        const uint32_t b_lo = smem_desc_lo(a0 + 2 * kABytes, kWgBBytes);  // LBO = stride between 64-ch N blocks
 #pragma unroll
         for (int dyi = 0; dyi < 3; ++dyi) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {  // 16 pixels (two 8-pixel patch rows) per UMMA
-            const uint64_t ad = make_smem_desc(a0 + dyi * 1024 + ks * 2048, kABytes, 1024);
-            const uint64_t bd = make_smem_desc(b0 + ks * 2048, kWgBBytes, 1024);
-            umma_bf16_ss(tmem_base + dyi * p.n_cols, ad, bd, idesc, (ks == 0) ? acc : 1u);
-          }
+          for (int ks = 0; ks < 8; ++ks)  // 16 pixels (two 8-pixel patch rows) per UMMA
+            umma_bf16_ss_lohi(tmem_base + dyi * p.n_cols, a_lo + dyi * 64 + ks * 128, b_lo + ks * 128, kHi, idesc,
+                              (ks == 0) ? acc : 1u);
         }
-        acc = 1;
         umma_commit(&empty[s]);
-        if (++s == S) { s = 0; ph ^= 1; }
       }
-      umma_commit(done);
+      __syncwarp();
+      acc = 1;
+      if (++s == S) { s = 0; ph ^= 1; }
     }
+    if (elect_one_sync()) umma_commit(done);
+    __syncwarp();
   } else if (has_work) {
-    // epilogue: flush the three accumulators with fp32 reductions into the OIHW gradient tensors
+    // epilogue: flush the three accumulators with 16-byte fp32 vector reductions into [tap][ci][co] staging tensors
     const int q = warp & 3;
     const int m = q * 32 + lane;  // accumulator row = input channel a_c0 + m
     mbar_wait(done, 0);
@@ -143,18 +147,18 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + dyi * p.n_cols + c0, r);
         tmem_ld_wait();
+        int sgi = 0;
+        while (sgi < p.num_seg - 1 && c0 >= p.seg[sgi].col_end) ++sgi;
+        const WgradSegment& sg = p.seg[sgi];
+        const int co = c0 - sg.col_begin;
+        const int ci = sg.ci0 + m;
+        if (c0 >= sg.col_begin && c0 < sg.col_end && ci < sg.ci_total) {
+          float* dst = sg.out + (static_cast<long long>(tap) * sg.ci_total + ci) * sg.co_pad + co;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = c0 + i;
-          for (int sgi = 0; sgi < p.num_seg; ++sgi) {
-            const WgradSegment& sg = p.seg[sgi];
-            if (col >= sg.col_begin && col < sg.col_end) {
-              const int co = col - sg.col_begin;
-              const int ci = sg.ci0 + m;
-              if (co < sg.co_valid && ci < sg.ci_total)
-                atomicAdd(sg.out + (static_cast<long long>(co) * sg.ci_total + ci) * 9 + tap, __uint_as_float(r[i]));
-            }
-          }
+          for (int j = 0; j < 4; ++j)
+            if (co + 4 * j < sg.co_pad)
+              red_add_v4_f32(dst + 4 * j, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                             __uint_as_float(r[4 * j + 3]));
         }
       }
     }

@@ -135,10 +135,11 @@ def test_conv_wgrad(case):
     xb = _nhwc(x, xs)
     xb[..., cin:] = 5.0
     dyb = _nhwc(dy, cout)
-    dw = torch.zeros(cout, cin, 3, 3, device=dev)
+    dw = torch.full((cout, cin, 3, 3), 9.0, device=dev)  # overwritten
+    scratch = torch.empty(L.b200sr_conv3x3_wgrad_scratch_bytes(cin, cout), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     lib.check(L.b200sr_conv3x3_wgrad(C.c_void_p(xb.data_ptr()), n, h, w, cin, xs, C.c_void_p(dyb.data_ptr()), cout, cout,
-                                     C.c_void_p(dw.data_ptr()), C.c_void_p(st)))
+                                     C.c_void_p(dw.data_ptr()), C.c_void_p(scratch.data_ptr()), C.c_void_p(st)))
     torch.cuda.synchronize()
     ref = torch.nn.grad.conv2d_weight(_bf(x), (cout, cin, 3, 3), _bf(dy), padding=1)
     rel = ((dw - ref).norm() / ref.norm()).item()

@@ -53,10 +53,11 @@ def run_wgrad(x, dy):
     cout = dy.shape[1]
     xb = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
     dyb = dy.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-    dw = torch.zeros(cout, cin, 3, 3, device=dev)
+    dw = torch.full((cout, cin, 3, 3), 9.0, device=dev)
+    scratch = torch.empty(L.b200sr_conv3x3_wgrad_scratch_bytes(cin, cout), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     lib.check(L.b200sr_conv3x3_wgrad(C.c_void_p(xb.data_ptr()), n, h, ww, cin, cin, C.c_void_p(dyb.data_ptr()), cout, cout,
-                                     C.c_void_p(dw.data_ptr()), C.c_void_p(st)))
+                                     C.c_void_p(dw.data_ptr()), C.c_void_p(scratch.data_ptr()), C.c_void_p(st)))
     torch.cuda.synchronize()
     return dw
 
