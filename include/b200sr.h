@@ -106,6 +106,9 @@ int b200sr_conv3x3_wgrad(const void* x, int n, int h, int w_, int cin, int x_str
 
 const char* b200sr_last_error(void);
 int b200sr_version(void);
+/* timing probes for profiling only (results become wrong): bit0 no epilogue traffic, bit1 no MMAs, bit2 no activation
+ * loads, bit3 no weight loads in the conv kernel.  0 = normal operation (default). */
+void b200sr_debug_set(int flags);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
 static bool g_attr_set = false;
+static int g_debug = 0;  // timing probes only (b200sr_debug_set)
 
 static int runtime_init() {
   if (!g_encode) {
@@ -711,6 +712,7 @@ static int launch_conv(const Step& s, const CUtensorMap& tmA, const CUtensorMap&
   cp.epi.out_f32_b = (float*)resolve(s.ofb, b);
   cp.epi.out_bf16 = (__nv_bfloat16*)resolve(s.ob, b);
   cp.epi.clamp_mask = (unsigned char*)resolve(s.cm, b);
+  cp.debug = g_debug;
   int gx = g_num_sms / (int)s.grid.y;
   if (gx > cp.num_tiles) gx = cp.num_tiles;
   if (gx < 1) gx = 1;
@@ -806,6 +808,7 @@ extern "C" {
 
 const char* b200sr_last_error(void) { return g_err; }
 int b200sr_version(void) { return 100; }
+void b200sr_debug_set(int flags) { g_debug = flags; }
 
 int b200sr_plan_create(const b200sr_net_desc* desc, b200sr_plan** out) {
   if (!desc || !out) return fail(B200SR_ERR_INVALID, "null argument");

@@ -69,6 +69,7 @@ struct ConvParams {
   int n_cols;   // UMMA N handled by one CTA (multiple of 16, <= 128)
   int n_total;  // n_cols * gridDim.y
   int num_stages;
+  int debug;  // bit0: epilogue skips global traffic, bit1: no MMAs, bit2: no activation loads, bit3: no weight loads (timing probes)
   ConvEpilogue epi;
 };
 
@@ -250,12 +251,15 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_wait(&empty[s], ph ^ 1);
           if (elect_one_sync()) {
             uint8_t* st = smem + s * stage_bytes;
-            mbar_arrive_expect_tx(&full[s], stage_bytes);
-            tma_load_4d(st, &tmA, &full[s], ac, x0 + dxi - 1, y0 - 1, n);
+            const int dbg_bytes = ((p.debug & 4) ? 0 : kABytes) + ((p.debug & 8) ? 0 : 3 * p.n_cols * 128);
+            if (dbg_bytes) mbar_arrive_expect_tx(&full[s], dbg_bytes); else mbar_arrive(&full[s]);
+            if (!(p.debug & 4)) tma_load_4d(st, &tmA, &full[s], ac, x0 + dxi - 1, y0 - 1, n);
+            if (!(p.debug & 8)) {
 #pragma unroll
-            for (int dyi = 0; dyi < 3; ++dyi)
-              tma_load_2d(st + kABytes + dyi * p.n_cols * 128, &tmW, &full[s], 0,
-                          p.w_row0 + ((c * 3 + dxi) * 3 + dyi) * p.n_total + colbase);
+              for (int dyi = 0; dyi < 3; ++dyi)
+                tma_load_2d(st + kABytes + dyi * p.n_cols * 128, &tmW, &full[s], 0,
+                            p.w_row0 + ((c * 3 + dxi) * 3 + dyi) * p.n_total + colbase);
+            }
           }
           __syncwarp();
           if (++s == S) { s = 0; ph ^= 1; }
@@ -292,7 +296,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               const int dyi = (e == 0) ? 1 : (e == 1 ? 0 : 2);  // centre row first
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                if (ks < ksteps)
+                if (ks < ksteps && !(p.debug & 2))
                   umma_bf16_ss_lohi(d_tmem, a_lo + dyi * 64 + ks * 2, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
                                     (e == 0 && ks == 0) ? first : 1u);
               }
@@ -340,7 +344,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
           for (int i = 16; i < 32; ++i) v[i] = 0.f;
         }
-        if (valid) conv_epilogue_store(p, n, y, x, colbase + c0, ncol, v);
+        if (valid && !(p.debug & 1)) conv_epilogue_store(p, n, y, x, colbase + c0, ncol, v);
       }
       tcgen05_fence_before();
       __syncwarp();

@@ -47,6 +47,7 @@ SIGNATURES = {
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200sr_last_error": (C.c_char_p, []),
     "b200sr_version": (C.c_int, []),
+    "b200sr_debug_set": (None, [C.c_int]),
 }
 
 
