@@ -60,7 +60,7 @@ static int runtime_init() {
     CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   if (!g_attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(conv3x3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr_set = true;
   }
@@ -100,8 +100,9 @@ struct Ref {
 static Ref ws(long long off) { Ref r; r.kind = RK_WS; r.off = off; return r; }
 
 struct ActMapSpec { long long off; int c_valid, c_pix, n, h, w, box_rows; };
+struct Bases { void* ws; void* packed; void* y; const void* dy; void* grads; };
 
-enum StepType { ST_CONV, ST_WGRAD, ST_BIASGRAD, ST_UNPACK, ST_ADD, ST_MEMSET, ST_INGEST_X, ST_INGEST_DY };
+enum StepType { ST_CONV, ST_CHAIN, ST_WGRAD, ST_BIASGRAD, ST_UNPACK, ST_ADD, ST_MEMSET, ST_INGEST_X, ST_INGEST_DY };
 
 struct Step {
   int type = ST_CONV;
@@ -111,6 +112,7 @@ struct Step {
   Ref bias, mask, r1, r2, of, ofb, ob, cm;
   dim3 grid;
   int smem = 0;
+  int layer0 = 0, nlayers = 0, chain_grid = 0;  // ST_CHAIN: range of the plan's layer list
   // wgrad
   int xmap = -1, dymap = -1;
   WgradParams wp;
@@ -142,7 +144,7 @@ struct b200sr_plan {
   long long o_xin = 0, o_t0 = 0, o_tr = 0, o_c1 = 0, o_c2 = 0, o_splt = 0, o_splc = 0, o_cmask = 0;
   std::vector<long long> o_dense, o_spl;
   long long o_dyp = 0, o_g3 = 0, o_gt = 0, o_gtb = 0, o_gr = 0, o_gc1 = 0, o_gc2 = 0, o_go1 = 0;
-  long long o_dyb[2] = {0, 0};
+  long long o_dyb[6] = {0, 0, 0, 0, 0, 0};
   std::vector<long long> o_gu;
   long long gw_bytes = 0;
   long long o_gw = 0;                 // staged weight gradients, per conv [tap][ci][co_pad] fp32
@@ -156,7 +158,11 @@ struct b200sr_plan {
   void* cached_ws = nullptr;
   void* cached_packed = nullptr;
   std::vector<CUtensorMap> maps;
-  CUtensorMap wmaps[4];
+  WeightMaps wmaps;
+  std::vector<Step> layer_steps;      // every conv launch of fwd then bwd, in execution order (= layer list)
+  std::vector<LayerDesc> h_layers;
+  LayerDesc* d_layers = nullptr;
+  unsigned int* d_barrier = nullptr;
 };
 
 static int wmap_index(int n_cols) { return n_cols == 16 ? 0 : n_cols == 32 ? 1 : n_cols == 64 ? 2 : 3; }
@@ -211,6 +217,8 @@ ConvParams base_conv_params(int n, int h, int w, int num_chunks, int ksteps_last
   p.num_chunks = num_chunks; p.ksteps_last = ksteps_last;
   p.a_c0 = a_c0; p.a_wrap = a_wrap;
   p.w_row0 = row0; p.n_cols = n_cols; p.n_total = n_total;
+  p.col_groups = n_total / n_cols;
+  p.wmap = wmap_index(n_cols);
   p.num_stages = conv_pick_stages(n_cols);
   p.epi.alpha = 1.f; p.epi.delta = 1.f; p.epi.beta1 = 1.f; p.epi.beta2 = 1.f;
   p.epi.res_stride = 64; p.epi.of_stride = 64;
@@ -320,8 +328,7 @@ static int build_plan(b200sr_plan& P) {
     P.o_gc1 = B.alloc(Ppix * 64 * 4);
     P.o_gc2 = B.alloc(Ppix * 64 * 4);
     P.o_go1 = B.alloc(Ppix * 64 * 2);
-    P.o_dyb[0] = B.alloc(Ppix * 192 * 2);
-    P.o_dyb[1] = B.alloc(Ppix * 192 * 2);
+    for (int i = 0; i < 6; ++i) P.o_dyb[i] = B.alloc(Ppix * 192 * 2);
   }
   P.ws_bytes = B.cursor;
 
@@ -332,8 +339,8 @@ static int build_plan(b200sr_plan& P) {
     s.amap = amap;
     s.wmap = wmap_index(cp.n_cols);
     s.cp = cp;
-    s.grid = dim3(1, grid_y, 1);  // x filled at launch (SM count)
-    s.smem = conv_smem_bytes(cp.n_cols, cp.num_stages);
+    s.grid = dim3(1, grid_y, 1);
+    s.smem = kConvSmemBytes;
     return s;
   };
   auto packed_bias = [&](long long off_floats) { Ref r; r.kind = RK_PACKED; r.off = -1 - off_floats; return r; };  // fixed up later
@@ -503,29 +510,40 @@ static int build_plan(b200sr_plan& P) {
       Step g; g.type = ST_INGEST_DY;
       P.bwd.push_back(g);
     }
+    // Launch order inside one gradient bucket: all data-gradient convs first (they form ONE chain launch), then the
+    // weight/bias-gradient kernels that consume what the chain produced, then the unpack + bucket announcement.
+    std::vector<Step> seg_convs, seg_others;
+    auto emit = [&](const Step& st) {
+      if (st.type == ST_CONV) seg_convs.push_back(st); else seg_others.push_back(st);
+      if (st.type == ST_UNPACK) {
+        for (const Step& c : seg_convs) P.bwd.push_back(c);
+        for (const Step& o : seg_others) P.bwd.push_back(o);
+        seg_convs.clear(); seg_others.clear();
+      }
+    };
     // conv4: wgrad, bias grad, dgrad (-> G3, masked by lrelu'(conv3 out))
     {
       Step w4 = wgrad_step(P.o_splc, 64, 128, P.o_dyp, 16, 64, N, hH, hW, 0, 0, 16);
       add_seg(w4, 0, 16, wref(ci_conv4), 64, 0, (int)align_up(d.out_channels, 4));
-      P.bwd.push_back(w4);
+      emit(w4);
       Step b4 = biasgrad_step(P.o_dyp, HRpix, 64, 0, 16);
       add_bseg(b4, 0, 16, bref(ci_conv4), d.out_channels);
-      P.bwd.push_back(b4);
+      emit(b4);
       const int row0 = dgrad_pack1(ci_conv4, 64, d.out_channels);
       ConvParams cp = base_conv_params(N, hH, hW, 1, 1, 0, 1 << 20, row0, 64, 64);
       Step s = conv_step(B.add_map(P.o_dyp, 16, 64, N, hH, hW, kABoxRows), cp, 1);
       s.mask = ws(P.o_splc); s.cp.epi.mask_stride = 128; s.cp.epi.mask_coff = 0;
       s.ob = ws(P.o_g3); s.cp.epi.ob_stride = 64;
-      P.bwd.push_back(s);
+      emit(s);
     }
     // conv3
     {
       Step w3 = wgrad_step(P.o_spl[L], 64, 128, P.o_g3, 64, 64, N, hH, hW, 0, 0, 64);
       add_seg(w3, 0, 64, wref(ci_conv3), 64, 0, 64);
-      P.bwd.push_back(w3);
+      emit(w3);
       Step b3 = biasgrad_step(P.o_g3, HRpix, 64, 0, 64);
       add_bseg(b3, 0, 64, bref(ci_conv3), 64);
-      P.bwd.push_back(b3);
+      emit(b3);
       const int row0 = dgrad_pack1(ci_conv3, 64, 64);
       ConvParams cp = base_conv_params(N, hH, hW, 1, 4, 0, 1 << 20, row0, 64, 64);
       Step s = conv_step(B.add_map(P.o_g3, 64, 64, N, hH, hW, kABoxRows), cp, 1);
@@ -536,7 +554,7 @@ static int build_plan(b200sr_plan& P) {
         s.of = ws(P.o_gt);
         s.ob = ws(P.o_gtb); s.cp.epi.ob_stride = 64;
       }
-      P.bwd.push_back(s);
+      emit(s);
     }
     // upsample stages, top down
     for (int l = L; l >= 1; --l) {
@@ -548,12 +566,12 @@ static int build_plan(b200sr_plan& P) {
         Ref out = wref(ci);
         out.off += (long long)half * 128 * 4;  // columns [128*half, +128) of the [tap][64][256] staging tensor
         add_seg(wu, 0, 128, out, 64, 0, 256);
-        P.bwd.push_back(wu);
+        emit(wu);
       }
       {
         Step bu = biasgrad_step(P.o_gu[l], npix, 256, 0, 256);
         for (int ph = 0; ph < 4; ++ph) add_bseg(bu, 64 * ph, 64 * ph + 64, bref(ci), 64);
-        P.bwd.push_back(bu);
+        emit(bu);
       }
       PackOp op; memset(&op, 0, sizeof(op));
       op.n_total = 64; op.n_valid = 64; op.num_chunks = 4; op.mode = kPackUpDgrad; op.nseg = 1;
@@ -568,30 +586,32 @@ static int build_plan(b200sr_plan& P) {
         s.of = ws(P.o_gt);
         s.ob = ws(P.o_gtb); s.cp.epi.ob_stride = 64;
       }
-      P.bwd.push_back(s);
+      emit(s);
     }
     // conv2
     {
       Step w2 = wgrad_step(P.o_splt, 64, 128, P.o_gtb, 64, 64, N, H, W, 0, 0, 64);
       add_seg(w2, 0, 64, wref(ci_conv2), 64, 0, 64);
-      P.bwd.push_back(w2);
+      emit(w2);
       Step b2 = biasgrad_step(P.o_gtb, Ppix, 64, 0, 64);
       add_bseg(b2, 0, 64, bref(ci_conv2), 64);
-      P.bwd.push_back(b2);
+      emit(b2);
       const int row0 = dgrad_pack1(ci_conv2, 64, 64);
       ConvParams cp = base_conv_params(N, H, W, 1, 4, 0, 1 << 20, row0, 64, 64);
       Step s = conv_step(B.add_map(P.o_gtb, 64, 64, N, H, W, kABoxRows), cp, 1);
       s.of = ws(P.o_gr);
-      s.ob = ws(P.o_dyb[0]); s.cp.epi.ob_stride = 192; s.cp.epi.delta = 0.04f;
-      P.bwd.push_back(s);
+      s.ob = ws(P.o_dyb[3 * ((d.num_blocks - 1) & 1)]); s.cp.epi.ob_stride = 192; s.cp.epi.delta = 0.04f;
+      emit(s);
       // tail bucket: conv2 .. conv4 are contiguous at the end of the flat buffer
-      P.bwd.push_back(unpack_step(ci_conv2, nconv));
+      emit(unpack_step(ci_conv2, nconv));
     }
     // trunk, last dense block first
     for (int r = R - 1; r >= 0; --r) {
       const int j = r % 3;
       const long long D = P.o_dense[r];
-      const long long DYc = P.o_dyb[(R - 1 - r) & 1], DYn = P.o_dyb[(R - r) & 1];
+      const int blk = r / 3;
+      const long long DYc = P.o_dyb[3 * (blk & 1) + (2 - j)];
+      const long long DYn = (j > 0) ? P.o_dyb[3 * (blk & 1) + (2 - (j - 1))] : P.o_dyb[3 * ((blk + 1) & 1)];
       for (int sl = 4; sl >= 0; --sl) {
         // gradient w.r.t. input slice sl (0: the 64-ch block input x, 1..4: growth outputs o_sl) = sum over consumer convs
         const int c_s = (sl == 0) ? 0 : 64 + 32 * (sl - 1);
@@ -618,7 +638,7 @@ static int build_plan(b200sr_plan& P) {
           else { s.r1 = ws(P.o_gc1); s.r2 = ws(P.o_gr); s.of = ws(P.o_gr); s.cp.epi.delta = 0.04f; }
           if (r > 0) { s.ob = ws(DYn); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 0; }
         }
-        P.bwd.push_back(s);
+        emit(s);
       }
       // weight gradients of the five convs, re-associated by input slice
       {
@@ -627,36 +647,36 @@ static int build_plan(b200sr_plan& P) {
         add_seg(a, 64, 96, wref(conv_index_rdb(r, 4)), 160, 0, 32);
         add_seg(a, 96, 128, wref(conv_index_rdb(r, 3)), 128, 0, 32);
         add_seg(a, 128, 160, wref(conv_index_rdb(r, 2)), 96, 0, 32);
-        P.bwd.push_back(a);
+        emit(a);
         Step b = wgrad_step(D, 192, 192, DYc, 192, 192, N, H, W, 128, 0, 96);
         add_seg(b, 0, 64, wref(conv_index_rdb(r, 5)), 192, 128, 64);
         add_seg(b, 64, 96, wref(conv_index_rdb(r, 4)), 160, 128, 32);
-        P.bwd.push_back(b);
+        emit(b);
         Step c = wgrad_step(D, 192, 192, DYc, 192, 192, N, H, W, 0, 160, 32);
         add_seg(c, 0, 32, wref(conv_index_rdb(r, 1)), 64, 0, 32);
-        P.bwd.push_back(c);
+        emit(c);
         Step bg = biasgrad_step(DYc, Ppix, 192, 0, 192);
         add_bseg(bg, 0, 64, bref(conv_index_rdb(r, 5)), 64);
         add_bseg(bg, 64, 96, bref(conv_index_rdb(r, 4)), 32);
         add_bseg(bg, 96, 128, bref(conv_index_rdb(r, 3)), 32);
         add_bseg(bg, 128, 160, bref(conv_index_rdb(r, 2)), 32);
         add_bseg(bg, 160, 192, bref(conv_index_rdb(r, 1)), 32);
-        P.bwd.push_back(bg);
+        emit(bg);
         if (j == 0)  // one bucket per RRDB (its 15 convs are contiguous in the flat buffer)
-          P.bwd.push_back(unpack_step(conv_index_rdb(r, 1), conv_index_rdb(r + 2, 5) + 1));
+          emit(unpack_step(conv_index_rdb(r, 1), conv_index_rdb(r + 2, 5) + 1));
       }
     }
     // conv1: gradient of its output = trunk path (GR) + long skip (GT)
     {
       Step ad; ad.type = ST_ADD; ad.a = ws(P.o_gr); ad.b = ws(P.o_gt); ad.c = ws(P.o_go1); ad.count = Ppix * 64;
-      P.bwd.push_back(ad);
+      emit(ad);
       Step w1 = wgrad_step(P.o_xin, P.xin_stride, P.xin_stride, P.o_go1, 64, 64, N, H, W, 0, 0, 64);
       add_seg(w1, 0, 64, wref(0), d.in_channels, 0, 64);
-      P.bwd.push_back(w1);
+      emit(w1);
       Step b1 = biasgrad_step(P.o_go1, Ppix, 64, 0, 64);
       add_bseg(b1, 0, 64, bref(0), 64);
-      P.bwd.push_back(b1);
-      P.bwd.push_back(unpack_step(0, 1));
+      emit(b1);
+      emit(unpack_step(0, 1));
     }
   }
 
@@ -669,11 +689,28 @@ static int build_plan(b200sr_plan& P) {
   };
   fix(P.fwd);
   fix(P.bwd);
+  // merge consecutive conv launches into chains over one global layer list
+  auto chainify = [&](std::vector<Step>& v) {
+    std::vector<Step> out;
+    for (Step& s : v) {
+      if (s.type != ST_CONV) { out.push_back(s); continue; }
+      const int work = s.cp.num_tiles * s.cp.col_groups;
+      if (out.empty() || out.back().type != ST_CHAIN) {
+        Step c; c.type = ST_CHAIN; c.layer0 = (int)P.layer_steps.size(); c.nlayers = 0; c.chain_grid = 0;
+        out.push_back(c);
+      }
+      out.back().nlayers++;
+      if (work > out.back().chain_grid) out.back().chain_grid = work;
+      P.layer_steps.push_back(s);
+    }
+    v.swap(out);
+  };
+  chainify(P.fwd);
+  chainify(P.bwd);
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------ execution
-struct Bases { void* ws; void* packed; void* y; const void* dy; void* grads; };
 static void* resolve(const Ref& r, const Bases& b) {
   switch (r.kind) {
     case RK_WS: return (char*)b.ws + r.off;
@@ -685,7 +722,8 @@ static void* resolve(const Ref& r, const Bases& b) {
   }
 }
 
-static int ensure_maps(b200sr_plan& P, void* wsp, void* packed) {
+static void* resolve(const Ref& r, const Bases& b);
+static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st) {
   if (P.cached_ws == wsp && P.cached_packed == packed && P.maps.size() == P.map_specs.size()) return 0;
   P.maps.resize(P.map_specs.size());
   for (size_t i = 0; i < P.map_specs.size(); ++i) {
@@ -694,30 +732,51 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed) {
     if (rc) return rc;
   }
   for (int i = 0; i < 4; ++i) {
-    int rc = encode_w_map(&P.wmaps[i], packed, P.total_rows, kWmapCols[i]);
+    int rc = encode_w_map(&P.wmaps.m[i], packed, P.total_rows, kWmapCols[i]);
     if (rc) return rc;
   }
+  // device-resident layer list (pointers resolved against this workspace / packed buffer)
+  Bases b{wsp, packed, nullptr, nullptr, nullptr};
+  P.h_layers.resize(P.layer_steps.size());
+  for (size_t i = 0; i < P.layer_steps.size(); ++i) {
+    const Step& s = P.layer_steps[i];
+    LayerDesc& L = P.h_layers[i];
+    L.tmA = P.maps[s.amap];
+    L.p = s.cp;
+    L.p.epi.bias = (const float*)resolve(s.bias, b);
+    L.p.epi.mask = (const __nv_bfloat16*)resolve(s.mask, b);
+    L.p.epi.r1 = (const float*)resolve(s.r1, b);
+    L.p.epi.r2 = (const float*)resolve(s.r2, b);
+    L.p.epi.out_f32 = (float*)resolve(s.of, b);   // RK_Y resolves to nullptr here: the final layer uses the y_dyn kernel argument
+    L.p.epi.out_f32_b = (float*)resolve(s.ofb, b);
+    L.p.epi.out_bf16 = (__nv_bfloat16*)resolve(s.ob, b);
+    L.p.epi.clamp_mask = (unsigned char*)resolve(s.cm, b);
+  }
+  if (!P.d_layers) {
+    CUDA_TRY(cudaMalloc(&P.d_layers, P.h_layers.size() * sizeof(LayerDesc)));
+    CUDA_TRY(cudaMalloc(&P.d_barrier, 256));
+  }
+  CUDA_TRY(cudaMemcpyAsync(P.d_layers, P.h_layers.data(), P.h_layers.size() * sizeof(LayerDesc), cudaMemcpyHostToDevice, st));
   P.cached_ws = wsp;
   P.cached_packed = packed;
   return 0;
 }
 
-static int launch_conv(const Step& s, const CUtensorMap& tmA, const CUtensorMap& tmW, const Bases& b, cudaStream_t st) {
-  ConvParams cp = s.cp;
-  cp.epi.bias = (const float*)resolve(s.bias, b);
-  cp.epi.mask = (const __nv_bfloat16*)resolve(s.mask, b);
-  cp.epi.r1 = (const float*)resolve(s.r1, b);
-  cp.epi.r2 = (const float*)resolve(s.r2, b);
-  cp.epi.out_f32 = (float*)resolve(s.of, b);
-  cp.epi.out_f32_b = (float*)resolve(s.ofb, b);
-  cp.epi.out_bf16 = (__nv_bfloat16*)resolve(s.ob, b);
-  cp.epi.clamp_mask = (unsigned char*)resolve(s.cm, b);
-  cp.debug = g_debug;
-  int gx = g_num_sms / (int)s.grid.y;
-  if (gx > cp.num_tiles) gx = cp.num_tiles;
-  if (gx < 1) gx = 1;
-  conv3x3_igemm_kernel<<<dim3(gx, s.grid.y, 1), kConvThreads, s.smem, st>>>(tmA, tmW, cp);
-  CUDA_TRY(cudaGetLastError());
+static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStream_t st) {
+  int grid = s.chain_grid < g_num_sms ? s.chain_grid : g_num_sms;
+  if (grid < 1) grid = 1;
+  const LayerDesc* layers = P.d_layers + s.layer0;
+  int nl = s.nlayers;
+  float* y = (float*)b.y;
+  int dbg = g_debug;
+  unsigned int* ctr = P.d_barrier;
+  if (nl > 1) CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
+  void* args[] = {(void*)&layers, (void*)&nl, (void*)&P.wmaps, (void*)&ctr, (void*)&y, (void*)&dbg};
+  if (nl > 1) {
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)conv3x3_chain_kernel, dim3(grid), dim3(kConvThreads), args, (size_t)kConvSmemBytes, st));
+  } else {
+    CUDA_TRY(cudaLaunchKernel((const void*)conv3x3_chain_kernel, dim3(grid), dim3(kConvThreads), args, (size_t)kConvSmemBytes, st));
+  }
   return 0;
 }
 
@@ -737,8 +796,10 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
   const b200sr_net_desc& d = P.d;
   for (Step& s : steps) {
     switch (s.type) {
-      case ST_CONV: {
-        int rc = launch_conv(s, P.maps[s.amap], P.wmaps[s.wmap], b, st);
+      case ST_CONV:
+        return fail(B200SR_ERR_INVALID, "internal: unchained conv step");
+      case ST_CHAIN: {
+        int rc = launch_chain(P, s, b, st);
         if (rc) return rc;
         break;
       }
@@ -826,6 +887,8 @@ void b200sr_plan_destroy(b200sr_plan* p) {
   if (p->d_bias_ops) cudaFree(p->d_bias_ops);
   if (p->d_params) cudaFree((void*)p->d_params);
   if (p->d_unpack_ops) cudaFree(p->d_unpack_ops);
+  if (p->d_layers) cudaFree(p->d_layers);
+  if (p->d_barrier) cudaFree(p->d_barrier);
   delete p;
 }
 
@@ -891,7 +954,7 @@ int b200sr_forward(b200sr_plan* p, const void* x, int x_dtype, const int64_t* x_
   if (!p || !x || !x_strides || !packed || !workspace || !y) return fail(B200SR_ERR_INVALID, "null argument");
   int rc = runtime_init();
   if (rc) return rc;
-  rc = ensure_maps(*p, workspace, (void*)packed);
+  rc = ensure_maps(*p, workspace, (void*)packed, (cudaStream_t)stream);
   if (rc) return rc;
   Bases b{workspace, (void*)packed, y, nullptr, nullptr};
   return run_steps(*p, p->fwd, b, x, x_dtype, x_strides, nullptr, nullptr, (cudaStream_t)stream);
@@ -903,7 +966,7 @@ int b200sr_backward(b200sr_plan* p, const float* dy, const void* packed, void* w
   if (!p->d.training) return fail(B200SR_ERR_INVALID, "plan was created with training=0");
   int rc = runtime_init();
   if (rc) return rc;
-  rc = ensure_maps(*p, workspace, (void*)packed);
+  rc = ensure_maps(*p, workspace, (void*)packed, (cudaStream_t)stream);
   if (rc) return rc;
   if (!p->d_unpack_ops) {
     CUDA_TRY(cudaMalloc(&p->d_unpack_ops, p->unpack_ops.size() * sizeof(UnpackOp)));
@@ -925,7 +988,7 @@ static int pick_ncols(int cout, int* n_cols, int* grid_y) {
 
 size_t b200sr_conv3x3_scratch_bytes(int cin, int cout) {
   const long long chunks = (cin + 63) / 64;
-  return (size_t)(align_up(chunks * 9 * cout * 128, 1024) + align_up(cout * 4, 1024) + 4096);
+  return (size_t)(align_up(chunks * 9 * cout * 128, 1024) + align_up(cout * 4, 1024) + 4096 + 1024);
 }
 
 static int single_conv(int mode, const void* x, int n, int h, int w, int cin, int x_stride, const float* wt, const float* bias, int cout, int act,
@@ -962,21 +1025,26 @@ static int single_conv(int mode, const void* x, int n, int h, int w, int cin, in
   if (rc) return rc;
   rc = encode_w_map(&tmW, sc, rows, n_cols);
   if (rc) return rc;
-  Step s;
-  s.cp = base_conv_params(n, h, w, chunks, (cin - 64 * (chunks - 1)) / 16, 0, 1 << 20, 0, n_cols, cout);
-  s.grid = dim3(1, grid_y, 1);
-  s.smem = conv_smem_bytes(n_cols, s.cp.num_stages);
-  s.cp.epi.act = act;
-  s.cp.epi.ob_stride = y_stride; s.cp.epi.ob_coff = y_coff;
-  Bases b{nullptr, nullptr, nullptr, nullptr, nullptr};
-  ConvParams& cp = s.cp;
-  cp.epi.bias = (const float*)(sc + bias_off);
-  cp.epi.out_bf16 = (__nv_bfloat16*)y;
-  int gx = g_num_sms / grid_y;
-  if (gx > cp.num_tiles) gx = cp.num_tiles;
-  conv3x3_igemm_kernel<<<dim3(gx, grid_y, 1), kConvThreads, s.smem, st>>>(tmA, tmW, cp);
-  CUDA_TRY(cudaGetLastError());
-  (void)b;
+  LayerDesc L;
+  L.tmA = tmA;
+  L.p = base_conv_params(n, h, w, chunks, (cin - 64 * (chunks - 1)) / 16, 0, 1 << 20, 0, n_cols, cout);
+  L.p.epi.act = act;
+  L.p.epi.ob_stride = y_stride; L.p.epi.ob_coff = y_coff;
+  L.p.epi.bias = (const float*)(sc + bias_off);
+  L.p.epi.out_bf16 = (__nv_bfloat16*)y;
+  WeightMaps wm;
+  memset(&wm, 0, sizeof(wm));
+  wm.m[L.p.wmap] = tmW;
+  CUDA_TRY(cudaMemcpyAsync(sc + tab_off + 3072, &L, sizeof(L), cudaMemcpyHostToDevice, st));
+  const int work = L.p.num_tiles * L.p.col_groups;
+  int grid = work < g_num_sms ? work : g_num_sms;
+  const LayerDesc* layers = (const LayerDesc*)(sc + tab_off + 3072);
+  int nl = 1, dbg = g_debug;
+  unsigned int* ctr = nullptr;
+  float* ydyn = nullptr;
+  void* args[] = {(void*)&layers, (void*)&nl, (void*)&wm, (void*)&ctr, (void*)&ydyn, (void*)&dbg};
+  CUDA_TRY(cudaLaunchKernel((const void*)conv3x3_chain_kernel, dim3(grid), dim3(kConvThreads), args, (size_t)kConvSmemBytes, st));
+  (void)grid_y;
   return 0;
 }
 

@@ -66,19 +66,18 @@ struct ConvParams {
   int a_c0;         // activation channel coordinate of chunk c: a_c0 + (c % a_wrap) * 64
   int a_wrap;
   int w_row0;   // first row of this conv in the packed weight matrix
-  int n_cols;   // UMMA N handled by one CTA (multiple of 16, <= 128)
-  int n_total;  // n_cols * gridDim.y
+  int n_cols;   // UMMA N handled by one work item (multiple of 16, <= 128)
+  int n_total;  // n_cols * col_groups
+  int col_groups;  // work item w -> tile w / col_groups, column group w % col_groups
+  int wmap;        // which weight tensor map (box rows = n_cols): 0:16 1:32 2:64 3:128
   int num_stages;
-  int debug;  // bit0: epilogue skips global traffic, bit1: no MMAs, bit2: no activation loads, bit3: no weight loads (timing probes)
   ConvEpilogue epi;
 };
 
 __host__ __device__ inline int conv_stage_bytes(int n_cols) { return kABytes + 3 * n_cols * 128; }
-__host__ inline int conv_smem_bytes(int n_cols, int stages) {
-  return stages * conv_stage_bytes(n_cols) + 1024 /*align slack*/ + 256 /*barriers*/;
-}
+constexpr int kConvSmemBytes = 227 * 1024;  // always requested in full: ring + 1 KB (barriers, layer params) + align slack
 __host__ inline int conv_pick_stages(int n_cols) {
-  int s = (227 * 1024 - 1024 - 256) / conv_stage_bytes(n_cols);
+  int s = (227 * 1024 - 1024 - 2048) / conv_stage_bytes(n_cols);
   return s > kMaxStages ? kMaxStages : s;
 }
 
@@ -86,19 +85,31 @@ __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Epilogue for one pixel and 32 (or 16) consecutive accumulator columns held in registers.
+//   sbias : this layer's bias vector staged in shared memory (indexed by global column)
+//   res   : beta1*r1 + beta2*r2 for these 32 columns, prefetched before the accumulator was ready (or nullptr)
+//   maskw : 16 words = 32 bf16 saved activations for the LeakyReLU-derivative mask, prefetched (or nullptr)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, int n, int y, int x, int col0, int ncol,
+__device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, float* y_dyn, const float* sbias, const float* res,
+                                                    const uint32_t* maskw, int n, int y, int x, int col0, int ncol,
                                                     float (&v)[32]) {
   const ConvEpilogue& e = p.epi;
   const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
   // 1. bias + scale (+ activation)
+  if (ncol == 32) {
+    const float4* b4 = reinterpret_cast<const float4*>(sbias + col0);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    if (i < ncol) {
-      float b = e.bias ? __ldg(e.bias + col0 + i) : 0.f;
-      float t = e.alpha * (v[i] + b);
-      v[i] = e.act ? lrelu02(t) : t;
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = b4[q];
+      v[4 * q] = e.alpha * (v[4 * q] + b.x); v[4 * q + 1] = e.alpha * (v[4 * q + 1] + b.y);
+      v[4 * q + 2] = e.alpha * (v[4 * q + 2] + b.z); v[4 * q + 3] = e.alpha * (v[4 * q + 3] + b.w);
     }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = e.alpha * (v[i] + sbias[col0 + i]);
+  }
+  if (e.act) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);  // LeakyReLU(0.2)
   }
   if (e.store_mode == kStoreFinal) {
     const long long plane = static_cast<long long>(p.H) * p.W;
@@ -108,42 +119,24 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, int n, 
       if (i < e.n_valid) {
         float pre = v[i];
         float cl = fminf(fmaxf(pre, 0.f), 1.f);
-        e.out_f32[base + i * plane] = cl;
+        y_dyn[base + i * plane] = cl;  // the generator output tensor is passed per launch, not baked into the layer list
         if (e.clamp_mask) e.clamp_mask[base + i * plane] = (pre >= 0.f && pre <= 1.f) ? 1 : 0;
       }
     }
     return;
   }
   // 2. LeakyReLU derivative mask from the saved forward activation
-  if (e.mask) {
-    const uint4* mp = reinterpret_cast<const uint4*>(e.mask + pix * e.mask_stride + e.mask_coff + col0);
+  if (maskw) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 m = __ldg(mp + q);
-      uint32_t w[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[q * 8 + 2 * j] *= (bf16_lo_to_f32(w[j]) > 0.f) ? 1.f : 0.2f;
-        v[q * 8 + 2 * j + 1] *= (bf16_hi_to_f32(w[j]) > 0.f) ? 1.f : 0.2f;
-      }
+    for (int j = 0; j < 16; ++j) {
+      v[2 * j] *= (bf16_lo_to_f32(maskw[j]) > 0.f) ? 1.f : 0.2f;
+      v[2 * j + 1] *= (bf16_hi_to_f32(maskw[j]) > 0.f) ? 1.f : 0.2f;
     }
   }
-  // 3. fp32 residuals
-  if (e.r1) {
-    const float4* rp = reinterpret_cast<const float4*>(e.r1 + pix * e.res_stride + col0);
+  // 3. fp32 residuals (already combined)
+  if (res) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 r = __ldg(rp + q);
-      v[4 * q] += e.beta1 * r.x; v[4 * q + 1] += e.beta1 * r.y; v[4 * q + 2] += e.beta1 * r.z; v[4 * q + 3] += e.beta1 * r.w;
-    }
-  }
-  if (e.r2) {
-    const float4* rp = reinterpret_cast<const float4*>(e.r2 + pix * e.res_stride + col0);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 r = __ldg(rp + q);
-      v[4 * q] += e.beta2 * r.x; v[4 * q + 1] += e.beta2 * r.y; v[4 * q + 2] += e.beta2 * r.z; v[4 * q + 3] += e.beta2 * r.w;
-    }
+    for (int i = 0; i < 32; ++i) v[i] += res[i];
   }
   // 4. fp32 outputs (same lattice position)
   if (e.out_f32) {
@@ -191,30 +184,60 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, int n, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// One layer = one 3x3 conv over one pixel lattice.  A launch executes a CHAIN of layers: persistent CTAs (one per SM,
+// cooperative launch) walk the layer list, each taking work items blockIdx.x, +gridDim.x, ... of every layer, with a
+// grid-wide barrier between layers (layer l+1 reads the halo pixels other CTAs produced in layer l).  The whole
+// forward pass (351 convs) is ONE launch; pipeline state (smem ring, TMEM, mbarriers) is set up once.
+// ---------------------------------------------------------------------------------------------------------------
+struct alignas(128) LayerDesc {
+  CUtensorMap tmA;  // activation tensor map of this layer (lives in global memory, read by TMA through a generic address)
+  ConvParams p;
+};
+struct WeightMaps { CUtensorMap m[4]; };
+
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // cumulativity: every store of this CTA observed through bar.sync is released at gpu scope
+    atomicAdd(ctr, 1u);
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v < target && clock64() - t0 > 4000000000LL) {
+        printf("b200sr: grid barrier timeout (block %d: %u < %u)\n", blockIdx.x, v, target);
+        __trap();
+      }
+    } while (v < target);
+    asm volatile("fence.proxy.async.global;" ::: "memory");  // later TMA (async proxy) reads see those generic-proxy stores
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                     const ConvParams p) {
+conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const __grid_constant__ WeightMaps wmaps,
+                     unsigned int* barrier_ctr, float* y_dyn, int debug) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int S = p.num_stages;
-  const int stage_bytes = conv_stage_bytes(p.n_cols);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
+  // fixed region at the END of the dynamic smem: barriers, TMEM slot, current layer parameters
+  constexpr int kRingBytes = 227 * 1024 - 1024 - 2048;  // usable by the stage ring (host picks num_stages against this)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  ConvParams* sp = reinterpret_cast<ConvParams*>(smem + kRingBytes + 256);
+  float* sbias = reinterpret_cast<float*>(smem + kRingBytes + 1024);  // up to 256 floats
+  static_assert(sizeof(ConvParams) <= 512, "ConvParams must fit the reserved smem slot");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int colbase = blockIdx.y * p.n_cols;
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * p.n_cols) tmem_cols <<= 1;
+  constexpr uint32_t kTmemCols = 512;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tmA);
-    prefetch_tensormap(&tmW);
-    for (int s = 0; s < S; ++s) {
+    for (int i = 0; i < 4; ++i) prefetch_tensormap(&wmaps.m[i]);
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -224,131 +247,205 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  uint32_t ring_bits = 0;  // per-stage phase parity (producer: empty barriers, MMA warp: full barriers)
+  int it = 0;              // work items done by this CTA so far (accumulator stage = it & 1), identical in all roles
 
-  if (warp == 0) {
-    // ================================================= TMA producer =================================================
-    // (whole warp walks the loop so the index math stays warp-uniform; one elected lane issues)
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int n = tile / tiles_per_img;
-      const int t2 = tile - n * tiles_per_img;
-      const int ty = t2 / p.tiles_x;
-      const int x0 = (t2 - ty * p.tiles_x) * kTileW;
-      const int y0 = ty * kTileH;
-      for (int c = 0; c < p.num_chunks; ++c) {
-        const int ac = p.a_c0 + (c % p.a_wrap) * 64;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const int dxi = (d == 0) ? 1 : (d == 1 ? 0 : 2);  // centre column first (see MMA loop)
-          mbar_wait(&empty[s], ph ^ 1);
-          if (elect_one_sync()) {
-            uint8_t* st = smem + s * stage_bytes;
-            const int dbg_bytes = ((p.debug & 4) ? 0 : kABytes) + ((p.debug & 8) ? 0 : 3 * p.n_cols * 128);
-            if (dbg_bytes) mbar_arrive_expect_tx(&full[s], dbg_bytes); else mbar_arrive(&full[s]);
-            if (!(p.debug & 4)) tma_load_4d(st, &tmA, &full[s], ac, x0 + dxi - 1, y0 - 1, n);
-            if (!(p.debug & 8)) {
-#pragma unroll
-              for (int dyi = 0; dyi < 3; ++dyi)
-                tma_load_2d(st + kABytes + dyi * p.n_cols * 128, &tmW, &full[s], 0,
-                            p.w_row0 + ((c * 3 + dxi) * 3 + dyi) * p.n_total + colbase);
-            }
-          }
-          __syncwarp();
-          if (++s == S) { s = 0; ph ^= 1; }
-        }
-      }
+  for (int l = 0; l < num_layers; ++l) {
+    // ---- stage this layer's parameters in smem
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&layers[l].p);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(sp);
+      for (int i = threadIdx.x; i < static_cast<int>(sizeof(ConvParams) / 4); i += kConvThreads) dst[i] = __ldg(src + i);
     }
-  } else if (warp == 1) {
-    // ================================================== MMA issuer ==================================================
-    // Whole warp runs the loop (uniform address math), one elected lane issues.  Descriptor hi words are loop
-    // invariant; a K-step / vertical-tap advance is one 32-bit add on the lo word.
-    const uint32_t idesc = make_idesc_bf16(128, p.n_cols, 0, 0);
-    constexpr uint32_t kHi = smem_desc_hi(1024);
-    const uint32_t b_dy = static_cast<uint32_t>(p.n_cols) * 8;  // (n_cols * 128 B) >> 4
-    int s = 0;
-    uint32_t ph = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
-      tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + as * p.n_cols;
-      for (int c = 0; c < p.num_chunks; ++c) {
-        const int ksteps = (c == p.num_chunks - 1) ? p.ksteps_last : 4;
-        for (int d = 0; d < 3; ++d) {
-          mbar_wait(&full[s], ph);
-          tcgen05_fence_after();
-          if (elect_one_sync()) {
-            const uint32_t a0 = smem_u32(smem + s * stage_bytes);
-            const uint32_t a_lo = smem_desc_lo(a0, 16);
-            const uint32_t b_lo = smem_desc_lo(a0 + kABytes, 16);
-            const uint32_t first = (c | d) ? 1u : 0u;  // very first MMA of the tile overwrites the accumulator
+    __syncthreads();
+    const ConvParams& p = *sp;
+    for (int i = threadIdx.x; i < p.n_total; i += kConvThreads) sbias[i] = p.epi.bias ? __ldg(p.epi.bias + i) : 0.f;
+    __syncthreads();
+    const int S = p.num_stages;
+    const int stage_bytes = conv_stage_bytes(p.n_cols);
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int num_work = p.num_tiles * p.col_groups;
+    const CUtensorMap* tmA = &layers[l].tmA;
+    const CUtensorMap* tmW = &wmaps.m[p.wmap];
+
+    if (warp == 0) {
+      // ================================================= TMA producer ===============================================
+      // (whole warp walks the loop so the index math stays warp-uniform; one elected lane issues)
+      int s = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int tile = w / p.col_groups;
+        const int colbase = (w - tile * p.col_groups) * p.n_cols;
+        const int n = tile / tiles_per_img;
+        const int t2 = tile - n * tiles_per_img;
+        const int ty = t2 / p.tiles_x;
+        const int x0 = (t2 - ty * p.tiles_x) * kTileW;
+        const int y0 = ty * kTileH;
+        for (int c = 0; c < ((debug & 32) ? 0 : p.num_chunks); ++c) {
+          const int ac = p.a_c0 + (c % p.a_wrap) * 64;
 #pragma unroll
-            for (int e = 0; e < 3; ++e) {
-              const int dyi = (e == 0) ? 1 : (e == 1 ? 0 : 2);  // centre row first
+          for (int d = 0; d < 3; ++d) {
+            const int dxi = (d == 0) ? 1 : (d == 1 ? 0 : 2);  // centre column first (see MMA loop)
+            mbar_wait(&empty[s], ((ring_bits >> s) & 1u) ^ 1u);
+            if (elect_one_sync()) {
+              uint8_t* st = smem + s * stage_bytes;
+              const int dbg_bytes = ((debug & 4) ? 0 : kABytes) + ((debug & 8) ? 0 : 3 * p.n_cols * 128);
+              if (dbg_bytes) mbar_arrive_expect_tx(&full[s], dbg_bytes); else mbar_arrive(&full[s]);
+              if (!(debug & 4)) tma_load_4d(st, tmA, &full[s], ac, x0 + dxi - 1, y0 - 1, n);
+              if (!(debug & 8)) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (ks < ksteps && !(p.debug & 2))
-                  umma_bf16_ss_lohi(d_tmem, a_lo + dyi * 64 + ks * 2, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
-                                    (e == 0 && ks == 0) ? first : 1u);
+                for (int dyi = 0; dyi < 3; ++dyi)
+                  tma_load_2d(st + kABytes + dyi * p.n_cols * 128, tmW, &full[s], 0,
+                              p.w_row0 + ((c * 3 + dxi) * 3 + dyi) * p.n_total + colbase);
               }
             }
-            umma_commit(&empty[s]);  // frees the smem stage once these MMAs have drained
+            __syncwarp();
+            ring_bits ^= (1u << s);
+            if (++s == S) s = 0;
           }
-          __syncwarp();
-          if (++s == S) { s = 0; ph ^= 1; }
         }
       }
-      if (elect_one_sync()) umma_commit(&tfull[as]);  // accumulator ready for the epilogue warps
-      __syncwarp();
+    } else if (warp == 1) {
+      // ================================================== MMA issuer ================================================
+      // Whole warp runs the loop (uniform address math), one elected lane issues.  Descriptor hi words are loop
+      // invariant; a K-step / vertical-tap advance is one 32-bit add on the lo word.
+      const uint32_t idesc = make_idesc_bf16(128, p.n_cols, 0, 0);
+      constexpr uint32_t kHi = smem_desc_hi(1024);
+      const uint32_t b_dy = static_cast<uint32_t>(p.n_cols) * 8;  // (n_cols * 128 B) >> 4
+      int s = 0;
+      int my_it = it;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++my_it) {
+        const int as = my_it & 1;
+        mbar_wait(&tempty[as], ((my_it >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int c = 0; c < ((debug & 32) ? 0 : p.num_chunks); ++c) {
+          const int ksteps = (c == p.num_chunks - 1) ? p.ksteps_last : 4;
+          for (int d = 0; d < 3; ++d) {
+            mbar_wait(&full[s], (ring_bits >> s) & 1u);
+            tcgen05_fence_after();
+            if (elect_one_sync()) {
+              const uint32_t a0 = smem_u32(smem + s * stage_bytes);
+              const uint32_t a_lo = smem_desc_lo(a0, 16);
+              const uint32_t b_lo = smem_desc_lo(a0 + kABytes, 16);
+              const uint32_t first = (c | d) ? 1u : 0u;  // very first MMA of the tile overwrites the accumulator
+#pragma unroll
+              for (int e = 0; e < 3; ++e) {
+                const int dyi = (e == 0) ? 1 : (e == 1 ? 0 : 2);  // centre row first
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks < ksteps && !(debug & 2))
+                    umma_bf16_ss_lohi(d_tmem, a_lo + dyi * 64 + ks * 2, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
+                                      (e == 0 && ks == 0) ? first : 1u);
+                }
+              }
+              umma_commit(&empty[s]);  // frees the smem stage once these MMAs have drained
+            }
+            __syncwarp();
+            ring_bits ^= (1u << s);
+            if (++s == S) s = 0;
+          }
+        }
+        if (elect_one_sync()) umma_commit(&tfull[as]);  // accumulator ready for the epilogue warps
+        __syncwarp();
+      }
+    } else {
+      // =================================================== epilogue =================================================
+      const int q = warp & 3;  // TMEM lane quarter this warp may read
+      const int m = q * 32 + lane;
+      int my_it = it;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++my_it) {
+        const int tile = w / p.col_groups;
+        const int colbase = (w - tile * p.col_groups) * p.n_cols;
+        const int n = tile / tiles_per_img;
+        const int t2 = tile - n * tiles_per_img;
+        const int ty = t2 / p.tiles_x;
+        const int x = (t2 - ty * p.tiles_x) * kTileW + (m & 7);
+        const int y = ty * kTileH + (m >> 3);
+        const bool valid = (x < p.W) && (y < p.H);
+        const int as = my_it & 1;
+        // Operands that do not depend on the accumulator are fetched BEFORE waiting for the MMAs, so their L2 latency
+        // hides behind the tensor work: combined fp32 residual (<= 64 columns) and the LeakyReLU-derivative mask words.
+        const ConvEpilogue& e = p.epi;
+        const bool pre = valid && p.n_cols <= 64 && !(debug & 1);
+        const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
+        float res[64];
+        uint32_t maskw[32];
+        const bool has_res = (e.r1 != nullptr);
+        const bool has_mask = (e.mask != nullptr);
+        if (pre && has_res) {
+          const float4* r1p = reinterpret_cast<const float4*>(e.r1 + pix * e.res_stride + colbase);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            if (4 * q < p.n_cols) {
+              const float4 r = __ldg(r1p + q);
+              res[4 * q] = e.beta1 * r.x; res[4 * q + 1] = e.beta1 * r.y; res[4 * q + 2] = e.beta1 * r.z; res[4 * q + 3] = e.beta1 * r.w;
+            }
+          }
+          if (e.r2) {
+            const float4* r2p = reinterpret_cast<const float4*>(e.r2 + pix * e.res_stride + colbase);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              if (4 * q < p.n_cols) {
+                const float4 r = __ldg(r2p + q);
+                res[4 * q] += e.beta2 * r.x; res[4 * q + 1] += e.beta2 * r.y; res[4 * q + 2] += e.beta2 * r.z; res[4 * q + 3] += e.beta2 * r.w;
+              }
+            }
+          }
+        }
+        if (pre && has_mask) {
+          const uint4* mp = reinterpret_cast<const uint4*>(e.mask + pix * e.mask_stride + e.mask_coff + colbase);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (8 * q < p.n_cols) {
+              const uint4 m4 = __ldg(mp + q);
+              maskw[4 * q] = m4.x; maskw[4 * q + 1] = m4.y; maskw[4 * q + 2] = m4.z; maskw[4 * q + 3] = m4.w;
+            }
+          }
+        }
+        mbar_wait(&tfull[as], (my_it >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int c0 = g * 32;
+          if (c0 < p.n_cols) {
+            float v[32];
+            const int ncol = (p.n_cols - c0) >= 32 ? 32 : 16;
+            if (ncol == 32) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(t_addr + c0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            } else {
+              uint32_t r[16];
+              tmem_ld_32x32b_x16(t_addr + c0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+#pragma unroll
+              for (int i = 16; i < 32; ++i) v[i] = 0.f;
+            }
+            if (valid && !(debug & 1))
+              conv_epilogue_store(p, y_dyn, sbias, (has_res && g < 2) ? &res[(g & 1) * 32] : nullptr,
+                                  (has_mask && g < 2) ? &maskw[(g & 1) * 16] : nullptr, n, y, x, colbase + c0, ncol, v);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+      }
     }
-  } else {
-    // =================================================== epilogue ===================================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int m = q * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int n = tile / tiles_per_img;
-      const int t2 = tile - n * tiles_per_img;
-      const int ty = t2 / p.tiles_x;
-      const int x = (t2 - ty * p.tiles_x) * kTileW + (m & 7);
-      const int y = ty * kTileH + (m >> 3);
-      const bool valid = (x < p.W) && (y < p.H);
-      const int as = it & 1;
-      mbar_wait(&tfull[as], (it >> 1) & 1);
-      tcgen05_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.n_cols;
-      for (int c0 = 0; c0 < p.n_cols; c0 += 32) {
-        float v[32];
-        const int ncol = (p.n_cols - c0) >= 32 ? 32 : 16;
-        if (ncol == 32) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_addr + c0, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        } else {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(t_addr + c0, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-#pragma unroll
-          for (int i = 16; i < 32; ++i) v[i] = 0.f;
-        }
-        if (valid && !(p.debug & 1)) conv_epilogue_store(p, n, y, x, colbase + c0, ncol, v);
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+    // every role advanced by the same number of work items
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) ++it;
+    if (l + 1 < num_layers) {
+      if (debug & 16) __syncthreads(); else grid_barrier(barrier_ctr, static_cast<unsigned int>(l + 1) * gridDim.x);
     }
   }
 
@@ -356,7 +453,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 

@@ -51,7 +51,7 @@ def test_plan_bookkeeping_matches_work_model(L):
         px = 16 * 64 * 64
         assert L.b200sr_flops(h, 0) == orc.flops_per_lr_pixel() * px
         assert L.b200sr_flops(h, 1) == orc.flops_per_lr_pixel(backward=True) * px
-        assert L.b200sr_num_launches(h, 0) == 1 + 351  # ingest + one launch per conv (upsample convs: 1 launch, 2 column groups)
+        assert L.b200sr_num_launches(h, 0) == 2  # ingest + ONE chain launch for all 351 convs
         assert L.b200sr_workspace_bytes(h) > 69 * px * 192 * 2
         assert L.b200sr_packed_bytes(h) > 2 * 16_697_987
     finally:
