@@ -9,6 +9,7 @@
 //             per dense block slice (pixel axis = reduction) with fp32 reductions into the flat gradient buffer.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,6 +43,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
 static bool g_attr_set = false;
+static int g_ctas_per_sm = 1;
 static int g_debug = 0;  // timing probes only (b200sr_debug_set)
 
 static int runtime_init() {
@@ -60,8 +62,26 @@ static int runtime_init() {
     CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   if (!g_attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(2)));
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (const char* e = getenv("B200SR_CTAS_PER_SM")) g_ctas_per_sm = (atoi(e) == 1) ? 1 : 2;
+    if (g_ctas_per_sm == 2) {
+      int occ = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv3x3_chain_kernel<2>, kConvThreads, conv_smem_bytes(2)));
+      if (occ < 2) {
+        fprintf(stderr, "b200sr: 2 CTAs/SM not resident (occupancy %d), using 1\n", occ);
+        for (int kb = 32; kb <= 112; kb += 8) {
+          int o2 = 0;
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, conv3x3_chain_kernel<2>, kConvThreads, kb * 1024);
+          fprintf(stderr, "  smem %d KB -> occupancy %d\n", kb, o2);
+        }
+        cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, conv3x3_chain_kernel<2>);
+        fprintf(stderr, "  regs %d static smem %zu local %zu maxThreads %d\n", fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxThreadsPerBlock);
+        g_ctas_per_sm = 1;
+      }
+    }
+    CUDA_TRY(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     g_attr_set = true;
   }
   return 0;
@@ -115,8 +135,9 @@ struct Step {
   int layer0 = 0, nlayers = 0, chain_grid = 0;  // ST_CHAIN: range of the plan's layer list
   // wgrad
   int xmap = -1, dymap = -1;
-  WgradParams wp;
-  Ref seg_out[5];
+  WgradBatch wb;
+  Ref seg_out[5];                 // bias-grad kernel outputs
+  Ref wseg_out[kWgMaxProblems][5];  // wgrad batch outputs
   // bias grad
   BiasGradParams bp;
   Ref bg_g;
@@ -340,7 +361,7 @@ static int build_plan(b200sr_plan& P) {
     s.wmap = wmap_index(cp.n_cols);
     s.cp = cp;
     s.grid = dim3(1, grid_y, 1);
-    s.smem = kConvSmemBytes;
+    s.smem = 0;
     return s;
   };
   auto packed_bias = [&](long long off_floats) { Ref r; r.kind = RK_PACKED; r.off = -1 - off_floats; return r; };  // fixed up later
@@ -459,24 +480,34 @@ static int build_plan(b200sr_plan& P) {
 
   // ================================================================ backward ===============================================================
   if (train) {
-    auto wgrad_step = [&](long long x_off, int x_cvalid, int x_cpix, long long dy_off, int dy_cvalid, int dy_cpix, int n, int h, int w,
-                          int a_c0, int b_c0, int n_cols) {
+    // a wgrad launch = batch of problems over one (X, dY) tensor-map pair
+    auto wgrad_batch = [&](long long x_off, int x_cvalid, int x_cpix, long long dy_off, int dy_cvalid, int dy_cpix, int n, int h, int w) {
       Step s; s.type = ST_WGRAD;
       s.xmap = B.add_map(x_off, x_cvalid, x_cpix, n, h, w, kABoxRows);
       s.dymap = B.add_map(dy_off, dy_cvalid, dy_cpix, n, h, w, kTileH);
-      WgradParams& wp = s.wp; memset(&wp, 0, sizeof(wp));
-      wp.N = n; wp.H = h; wp.W = w;
-      wp.tiles_x = (w + kTileW - 1) / kTileW; wp.tiles_y = (h + kTileH - 1) / kTileH; wp.num_tiles = n * wp.tiles_x * wp.tiles_y;
-      wp.a_c0 = a_c0; wp.b_c0 = b_c0; wp.n_cols = n_cols; wp.n_blocks = (n_cols + 63) / 64;
-      wp.num_stages = wgrad_pick_stages(wp.n_blocks);
-      s.smem = wgrad_smem_bytes(wp.n_blocks, wp.num_stages);
+      WgradBatch& wb = s.wb; memset(&wb, 0, sizeof(wb));
+      wb.N = n; wb.H = h; wb.W = w;
+      wb.tiles_x = (w + kTileW - 1) / kTileW; wb.tiles_y = (h + kTileH - 1) / kTileH; wb.num_tiles = n * wb.tiles_x * wb.tiles_y;
       return s;
     };
-    auto add_seg = [&](Step& s, int cb, int ce, Ref out, int ci_total, int ci0, int co_pad) {
-      WgradSegment& g = s.wp.seg[s.wp.num_seg];
+    auto add_problem = [&](Step& s, int a_c0, int b_c0, int n_cols, int bias_mode) {
+      WgradParams& wp = s.wb.prob[s.wb.num_problems++];
+      wp.a_c0 = a_c0; wp.b_c0 = b_c0; wp.n_cols = n_cols; wp.n_blocks = (n_cols + 63) / 64; wp.bias_mode = bias_mode;
+      return s.wb.num_problems - 1;
+    };
+    auto add_seg = [&](Step& s, int cb, int ce, Ref out, int ci_total, int ci0, int co_pad) {  // to the LAST problem added
+      const int pj = s.wb.num_problems - 1;
+      WgradParams& wp = s.wb.prob[pj];
+      WgradSegment& g = wp.seg[wp.num_seg];
       g.col_begin = cb; g.col_end = ce; g.out = nullptr; g.ci_total = ci_total; g.ci0 = ci0; g.co_pad = co_pad;
-      s.seg_out[s.wp.num_seg] = out;
-      s.wp.num_seg++;
+      s.wseg_out[pj][wp.num_seg] = out;
+      wp.num_seg++;
+    };
+    auto wgrad_step = [&](long long x_off, int x_cvalid, int x_cpix, long long dy_off, int dy_cvalid, int dy_cpix, int n, int h, int w,
+                          int a_c0, int b_c0, int n_cols) {  // single-problem launch
+      Step s = wgrad_batch(x_off, x_cvalid, x_cpix, dy_off, dy_cvalid, dy_cpix, n, h, w);
+      add_problem(s, a_c0, b_c0, n_cols, 0);
+      return s;
     };
     auto biasgrad_step = [&](long long g_off, long long npix, int stride, int c0, int ncols) {
       Step s; s.type = ST_BIASGRAD;
@@ -642,26 +673,25 @@ static int build_plan(b200sr_plan& P) {
       }
       // weight gradients of the five convs, re-associated by input slice
       {
-        Step a = wgrad_step(D, 192, 192, DYc, 192, 192, N, H, W, 0, 0, 160);
-        add_seg(a, 0, 64, wref(conv_index_rdb(r, 5)), 192, 0, 64);
-        add_seg(a, 64, 96, wref(conv_index_rdb(r, 4)), 160, 0, 32);
-        add_seg(a, 96, 128, wref(conv_index_rdb(r, 3)), 128, 0, 32);
-        add_seg(a, 128, 160, wref(conv_index_rdb(r, 2)), 96, 0, 32);
-        emit(a);
-        Step b = wgrad_step(D, 192, 192, DYc, 192, 192, N, H, W, 128, 0, 96);
-        add_seg(b, 0, 64, wref(conv_index_rdb(r, 5)), 192, 128, 64);
-        add_seg(b, 64, 96, wref(conv_index_rdb(r, 4)), 160, 128, 32);
-        emit(b);
-        Step c = wgrad_step(D, 192, 192, DYc, 192, 192, N, H, W, 0, 160, 32);
-        add_seg(c, 0, 32, wref(conv_index_rdb(r, 1)), 64, 0, 32);
-        emit(c);
-        Step bg = biasgrad_step(DYc, Ppix, 192, 0, 192);
-        add_bseg(bg, 0, 64, bref(conv_index_rdb(r, 5)), 64);
-        add_bseg(bg, 64, 96, bref(conv_index_rdb(r, 4)), 32);
-        add_bseg(bg, 96, 128, bref(conv_index_rdb(r, 3)), 32);
-        add_bseg(bg, 128, 160, bref(conv_index_rdb(r, 2)), 32);
-        add_bseg(bg, 160, 192, bref(conv_index_rdb(r, 1)), 32);
-        emit(bg);
+        // ONE launch per dense block: three channel-block problems + the bias gradients (all-ones A operand)
+        Step wg = wgrad_batch(D, 192, 192, DYc, 192, 192, N, H, W);
+        add_problem(wg, 0, 0, 160, 0);   // x, o1, o2 rows x [dY5|dY4|dY3|dY2]
+        add_seg(wg, 0, 64, wref(conv_index_rdb(r, 5)), 192, 0, 64);
+        add_seg(wg, 64, 96, wref(conv_index_rdb(r, 4)), 160, 0, 32);
+        add_seg(wg, 96, 128, wref(conv_index_rdb(r, 3)), 128, 0, 32);
+        add_seg(wg, 128, 160, wref(conv_index_rdb(r, 2)), 96, 0, 32);
+        add_problem(wg, 128, 0, 96, 0);  // o3, o4 rows x [dY5|dY4]
+        add_seg(wg, 0, 64, wref(conv_index_rdb(r, 5)), 192, 128, 64);
+        add_seg(wg, 64, 96, wref(conv_index_rdb(r, 4)), 160, 128, 32);
+        add_problem(wg, 0, 160, 32, 0);  // x rows x dY1 (conv1)
+        add_seg(wg, 0, 32, wref(conv_index_rdb(r, 1)), 64, 0, 32);
+        add_problem(wg, 0, 0, 192, 1);   // bias gradients: column sums of [dY5|dY4|dY3|dY2|dY1]
+        add_seg(wg, 0, 64, bref(conv_index_rdb(r, 5)), 1, 0, 64);
+        add_seg(wg, 64, 96, bref(conv_index_rdb(r, 4)), 1, 0, 32);
+        add_seg(wg, 96, 128, bref(conv_index_rdb(r, 3)), 1, 0, 32);
+        add_seg(wg, 128, 160, bref(conv_index_rdb(r, 2)), 1, 0, 32);
+        add_seg(wg, 160, 192, bref(conv_index_rdb(r, 1)), 1, 0, 32);
+        emit(wg);
         if (j == 0)  // one bucket per RRDB (its 15 convs are contiguous in the flat buffer)
           emit(unpack_step(conv_index_rdb(r, 1), conv_index_rdb(r + 2, 5) + 1));
       }
@@ -763,8 +793,10 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
 }
 
 static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStream_t st) {
-  int grid = s.chain_grid < g_num_sms ? s.chain_grid : g_num_sms;
+  const int cps = g_ctas_per_sm;
+  int grid = s.chain_grid < cps * g_num_sms ? s.chain_grid : cps * g_num_sms;
   if (grid < 1) grid = 1;
+  const void* fn = cps == 1 ? (const void*)conv3x3_chain_kernel<1> : (const void*)conv3x3_chain_kernel<2>;
   const LayerDesc* layers = P.d_layers + s.layer0;
   int nl = s.nlayers;
   float* y = (float*)b.y;
@@ -773,20 +805,39 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   if (nl > 1) CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
   void* args[] = {(void*)&layers, (void*)&nl, (void*)&P.wmaps, (void*)&ctr, (void*)&y, (void*)&dbg};
   if (nl > 1) {
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)conv3x3_chain_kernel, dim3(grid), dim3(kConvThreads), args, (size_t)kConvSmemBytes, st));
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(cps), st));
   } else {
-    CUDA_TRY(cudaLaunchKernel((const void*)conv3x3_chain_kernel, dim3(grid), dim3(kConvThreads), args, (size_t)kConvSmemBytes, st));
+    CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(cps), st));
   }
   return 0;
 }
 
 static int launch_wgrad(const Step& s, const CUtensorMap& tmX, const CUtensorMap& tmDY, const Bases& b, cudaStream_t st) {
-  WgradParams wp = s.wp;
-  for (int i = 0; i < wp.num_seg; ++i) wp.seg[i].out = (float*)resolve(s.seg_out[i], b);
-  int splits = g_num_sms / 3;
-  if (splits > wp.num_tiles) splits = wp.num_tiles;
-  if (splits < 1) splits = 1;
-  wgrad3x3_kernel<<<dim3(splits, 3, 1), kWgThreads, s.smem, st>>>(tmX, tmDY, wp);
+  WgradBatch wb = s.wb;
+  // deal the CTAs of one wave out in proportion to each problem's cost (max of tensor cycles and L2->SM bytes / 42 B per clock)
+  double work[kWgMaxProblems], total = 0;
+  for (int j = 0; j < wb.num_problems; ++j) {
+    WgradParams& wp = wb.prob[j];
+    for (int i = 0; i < wp.num_seg; ++i) wp.seg[i].out = (float*)resolve(s.wseg_out[j][i], b);
+    const int nacc = wp.bias_mode ? 1 : 3;
+    const double mma = nacc * 8.0 * (wp.n_cols / 2.0);
+    const double ld = wgrad_stage_bytes(wp) / 42.0;
+    work[j] = (mma > ld ? mma : ld) * nacc;
+    total += work[j];
+  }
+  int ctas = 0;
+  for (int j = 0; j < wb.num_problems; ++j) {
+    WgradParams& wp = wb.prob[j];
+    const int ntap = wp.bias_mode ? 1 : 3;
+    int splits = (int)(g_num_sms * work[j] / total / ntap + 0.5);
+    if (splits < 1) splits = 1;
+    if (splits > wb.num_tiles) splits = wb.num_tiles;
+    wp.splits = splits;
+    wb.cta_begin[j] = ctas;
+    ctas += splits * ntap;
+  }
+  wb.cta_begin[wb.num_problems] = ctas;
+  wgrad3x3_kernel<<<dim3(ctas), kWgThreads, kWgSmemBytes, st>>>(tmX, tmDY, wb);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -1043,7 +1094,7 @@ static int single_conv(int mode, const void* x, int n, int h, int w, int cin, in
   unsigned int* ctr = nullptr;
   float* ydyn = nullptr;
   void* args[] = {(void*)&layers, (void*)&nl, (void*)&wm, (void*)&ctr, (void*)&ydyn, (void*)&dbg};
-  CUDA_TRY(cudaLaunchKernel((const void*)conv3x3_chain_kernel, dim3(grid), dim3(kConvThreads), args, (size_t)kConvSmemBytes, st));
+  CUDA_TRY(cudaLaunchKernel((const void*)conv3x3_chain_kernel<1>, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   (void)grid_y;
   return 0;
 }
@@ -1079,16 +1130,19 @@ int b200sr_conv3x3_wgrad(const void* x, int n, int h, int w_, int cin, int x_str
   const long long stage_bytes = align_up(9LL * cin * cout * 4, 1024);
   float* staging = (float*)scratch;
   CUDA_TRY(cudaMemsetAsync(staging, 0, (size_t)stage_bytes, st));
-  WgradParams wp; memset(&wp, 0, sizeof(wp));
-  wp.N = n; wp.H = h; wp.W = w_;
-  wp.tiles_x = (w_ + kTileW - 1) / kTileW; wp.tiles_y = (h + kTileH - 1) / kTileH; wp.num_tiles = n * wp.tiles_x * wp.tiles_y;
+  WgradBatch wb; memset(&wb, 0, sizeof(wb));
+  wb.N = n; wb.H = h; wb.W = w_;
+  wb.tiles_x = (w_ + kTileW - 1) / kTileW; wb.tiles_y = (h + kTileH - 1) / kTileH; wb.num_tiles = n * wb.tiles_x * wb.tiles_y;
+  wb.num_problems = 1;
+  WgradParams& wp = wb.prob[0];
   wp.a_c0 = 0; wp.b_c0 = 0; wp.n_cols = cout; wp.n_blocks = (cout + 63) / 64;
-  wp.num_stages = wgrad_pick_stages(wp.n_blocks);
   wp.num_seg = 1;
   wp.seg[0].col_begin = 0; wp.seg[0].col_end = cout; wp.seg[0].out = staging; wp.seg[0].ci_total = cin; wp.seg[0].ci0 = 0; wp.seg[0].co_pad = cout;
   int splits = g_num_sms / 3;
-  if (splits > wp.num_tiles) splits = wp.num_tiles;
-  wgrad3x3_kernel<<<dim3(splits, 3, 1), kWgThreads, wgrad_smem_bytes(wp.n_blocks, wp.num_stages), st>>>(tmX, tmDY, wp);
+  if (splits > wb.num_tiles) splits = wb.num_tiles;
+  wp.splits = splits;
+  wb.cta_begin[0] = 0; wb.cta_begin[1] = splits * 3;
+  wgrad3x3_kernel<<<dim3(splits * 3), kWgThreads, kWgSmemBytes, st>>>(tmX, tmDY, wb);
   CUDA_TRY(cudaGetLastError());
   UnpackOp u;
   u.src_off = 0; u.dst_off = 0; u.co = cout; u.ci = cin; u.co_pad = cout; u.fold = 0; u.block0 = 0;

@@ -75,9 +75,9 @@ struct ConvParams {
 };
 
 __host__ __device__ inline int conv_stage_bytes(int n_cols) { return kABytes + 3 * n_cols * 128; }
-constexpr int kConvSmemBytes = 227 * 1024;  // always requested in full: ring + 1 KB (barriers, layer params) + align slack
-__host__ inline int conv_pick_stages(int n_cols) {
-  int s = (227 * 1024 - 1024 - 2048) / conv_stage_bytes(n_cols);
+__host__ __device__ constexpr int conv_smem_bytes(int ctas_per_sm) { return ctas_per_sm == 1 ? 227 * 1024 : 112 * 1024; }
+__host__ inline int conv_pick_stages(int n_cols) {  // informational (the kernel sizes its ring itself)
+  int s = (227 * 1024 - 1024 - 3072) / conv_stage_bytes(n_cols);
   return s > kMaxStages ? kMaxStages : s;
 }
 
@@ -214,26 +214,31 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+// kCtasPerSm = 1: one CTA owns the SM (227 KB ring, 512 TMEM columns); 2: two co-resident CTAs (113 KB, 256 columns each)
+// interleave their pipelines, hiding each other's barrier / epilogue / first-load latencies.
+template <int kCtasPerSm>
+__global__ void __launch_bounds__(kCtasPerSm == 1 ? kConvThreads : 208, kCtasPerSm)  // 208: caps registers at 152 so two CTAs fit
 conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const __grid_constant__ WeightMaps wmaps,
                      unsigned int* barrier_ctr, float* y_dyn, int debug) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // fixed region at the END of the dynamic smem: barriers, TMEM slot, current layer parameters
-  constexpr int kRingBytes = 227 * 1024 - 1024 - 2048;  // usable by the stage ring (host picks num_stages against this)
+  constexpr int kRingBytes = conv_smem_bytes(kCtasPerSm) - 1024 - 3072;  // usable by the stage ring
+  constexpr int kAccStride = (kCtasPerSm == 1) ? 256 : 128;                // TMEM columns between the two accumulators
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  ConvParams* sp = reinterpret_cast<ConvParams*>(smem + kRingBytes + 256);
-  float* sbias = reinterpret_cast<float*>(smem + kRingBytes + 1024);  // up to 256 floats
-  static_assert(sizeof(ConvParams) <= 512, "ConvParams must fit the reserved smem slot");
+  // two slots (current / next layer): parameters 2 x 384 B at +256, bias vectors 2 x 1 KB at +1024
+  uint8_t* sp_base = smem + kRingBytes + 256;
+  float* sbias_base = reinterpret_cast<float*>(smem + kRingBytes + 1024);
+  static_assert(sizeof(ConvParams) <= 384, "ConvParams must fit the reserved smem slot");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kTmemCols = (kCtasPerSm == 1) ? 512 : 256;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tensormap(&wmaps.m[i]);
@@ -247,7 +252,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) tmem_alloc_imm<kTmemCols>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -257,18 +262,21 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
   int it = 0;              // work items done by this CTA so far (accumulator stage = it & 1), identical in all roles
 
   for (int l = 0; l < num_layers; ++l) {
-    // ---- stage this layer's parameters in smem
-    {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(&layers[l].p);
+    // ---- layer parameters + bias live in smem slot (l & 1); layer 0 is staged here, later layers were prefetched by the
+    //      epilogue warps while the previous layer ran (keeps two dependent global-load latencies off the critical path)
+    ConvParams* sp = reinterpret_cast<ConvParams*>(sp_base + (l & 1) * 384);
+    float* sbias = sbias_base + (l & 1) * 256;
+    if (l == 0) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&layers[0].p);
       uint32_t* dst = reinterpret_cast<uint32_t*>(sp);
       for (int i = threadIdx.x; i < static_cast<int>(sizeof(ConvParams) / 4); i += kConvThreads) dst[i] = __ldg(src + i);
+      __syncthreads();
+      for (int i = threadIdx.x; i < sp->n_total; i += kConvThreads) sbias[i] = sp->epi.bias ? __ldg(sp->epi.bias + i) : 0.f;
+      __syncthreads();
     }
-    __syncthreads();
     const ConvParams& p = *sp;
-    for (int i = threadIdx.x; i < p.n_total; i += kConvThreads) sbias[i] = p.epi.bias ? __ldg(p.epi.bias + i) : 0.f;
-    __syncthreads();
-    const int S = p.num_stages;
     const int stage_bytes = conv_stage_bytes(p.n_cols);
+    const int S = (kRingBytes / stage_bytes) > kMaxStages ? kMaxStages : (kRingBytes / stage_bytes);
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int num_work = p.num_tiles * p.col_groups;
     const CUtensorMap* tmA = &layers[l].tmA;
@@ -323,7 +331,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
         const int as = my_it & 1;
         mbar_wait(&tempty[as], ((my_it >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + as * 256;
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
         for (int c = 0; c < ((debug & 32) ? 0 : p.num_chunks); ++c) {
           const int ksteps = (c == p.num_chunks - 1) ? p.ksteps_last : 4;
           for (int d = 0; d < 3; ++d) {
@@ -358,6 +366,16 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
       // =================================================== epilogue =================================================
       const int q = warp & 3;  // TMEM lane quarter this warp may read
       const int m = q * 32 + lane;
+      if (l + 1 < num_layers) {  // prefetch the next layer's parameters and bias into the other smem slot
+        const int t = threadIdx.x - 64;  // 0..127
+        const ConvParams* np = &layers[l + 1].p;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sp_base + ((l + 1) & 1) * 384);
+        if (t < static_cast<int>(sizeof(ConvParams) / 4)) dst[t] = __ldg(reinterpret_cast<const uint32_t*>(np) + t);
+        const float* nb = np->epi.bias;
+        const int nt = np->n_total;
+        float* bdst = sbias_base + ((l + 1) & 1) * 256;
+        for (int i = t; i < nt; i += 128) bdst[i] = nb ? __ldg(nb + i) : 0.f;
+      }
       int my_it = it;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++my_it) {
         const int tile = w / p.col_groups;
@@ -410,7 +428,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
         }
         mbar_wait(&tfull[as], (my_it >> 1) & 1);
         tcgen05_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int c0 = g * 32;
@@ -453,7 +471,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_imm<kTmemCols>(tmem_base);
   }
 }
 

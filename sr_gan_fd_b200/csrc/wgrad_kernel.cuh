@@ -11,6 +11,11 @@
 // ("re-associated by input slice").  The accumulators (3 x N <= 480 TMEM columns) live in TMEM for the whole
 // pixel loop and are flushed once with 16-byte vector reductions (red.global.add.v4.f32) into a [tap][ci][co] fp32
 // staging tensor; a small unpack kernel transposes that to the OIHW gradient layout per gradient bucket.
+//
+// One launch carries a BATCH of up to four such problems over the same two tensor maps (the three channel-block
+// problems of a dense block + its bias gradients), with the CTAs dealt out in proportion to each problem's cost so
+// the whole dense block is one balanced wave.  The bias gradient is the same GEMM with an all-ones A operand
+// (column sums of dY), so it rides the same pipeline and flush.
 #pragma once
 #include "conv_kernel.cuh"
 
@@ -19,6 +24,8 @@ namespace b200sr {
 constexpr int kWgBBytes = kTileH * kTileW * 128;  // 16384 B per 64-channel dY tile
 constexpr int kWgThreads = 192;
 constexpr int kWgMaxSeg = 5;
+constexpr int kWgMaxProblems = 4;
+constexpr int kWgOnesBytes = 4096;  // two 64-channel M blocks x 16 pixels x 128 B of bf16 1.0 (A operand of the bias-gradient problem)
 
 struct WgradSegment {
   int col_begin, col_end;  // accumulator columns of this conv's output channels (multiples of 16)
@@ -29,34 +36,37 @@ struct WgradSegment {
 };
 
 struct WgradParams {
-  int N, H, W;
-  int tiles_x, tiles_y, num_tiles;
   int a_c0;      // first X channel (accumulator row 0); two 64-channel boxes are loaded
   int b_c0;      // first dY channel (accumulator column 0)
-  int n_cols;    // UMMA N (multiple of 16, <= 160)
+  int n_cols;    // UMMA N (multiple of 16, <= 160; bias problem: <= 256)
   int n_blocks;  // ceil(n_cols / 64) dY boxes per tile
-  int num_stages;
+  int bias_mode; // 1: A = all ones, one accumulator, no X loads, no taps: column sums of dY
+  int splits;    // pixel-tile splits of this problem (CTAs = splits * (bias_mode ? 1 : 3))
   int num_seg;
   WgradSegment seg[kWgMaxSeg];
 };
 
-__host__ __device__ inline int wgrad_stage_bytes(int n_blocks) { return 2 * kABytes + n_blocks * kWgBBytes; }
-__host__ inline int wgrad_smem_bytes(int n_blocks, int stages) {
-  return stages * wgrad_stage_bytes(n_blocks) + 1024 + 256;
+struct WgradBatch {
+  int N, H, W;
+  int tiles_x, tiles_y, num_tiles;
+  int num_problems;
+  int cta_begin[kWgMaxProblems + 1];
+  WgradParams prob[kWgMaxProblems];
+};
+
+__host__ __device__ inline int wgrad_stage_bytes(const WgradParams& p) {
+  return (p.bias_mode ? 0 : 2 * kABytes) + p.n_blocks * kWgBBytes;
 }
-__host__ inline int wgrad_pick_stages(int n_blocks) {
-  int s = (227 * 1024 - 1024 - 256) / wgrad_stage_bytes(n_blocks);
-  return s > 4 ? 4 : s;
-}
+constexpr int kWgSmemBytes = 227 * 1024;
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
-                const WgradParams p) {
+                const __grid_constant__ WgradBatch batch) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int S = p.num_stages;
-  const int stage_bytes = wgrad_stage_bytes(p.n_blocks);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
+  constexpr int kRing = kWgSmemBytes - 1024 - kWgOnesBytes - 1024;
+  uint8_t* ones = smem + kRing;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRing + kWgOnesBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + 4;
   uint64_t* done = bars + 8;
@@ -64,45 +74,61 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int dxi = blockIdx.y;  // horizontal tap owned by this CTA
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < 3u * p.n_cols) tmem_cols <<= 1;
+  // which problem / tap / split does this CTA own
+  int pj = 0;
+  while (pj + 1 < batch.num_problems && static_cast<int>(blockIdx.x) >= batch.cta_begin[pj + 1]) ++pj;
+  const WgradParams& p = batch.prob[pj];
+  const int local = blockIdx.x - batch.cta_begin[pj];
+  const int ntap = p.bias_mode ? 1 : 3;
+  const int dxi = p.bias_mode ? 1 : (local % 3);  // horizontal tap owned by this CTA
+  const int split = local / ntap;
+  const int nacc = p.bias_mode ? 1 : 3;
+  const int stage_bytes = wgrad_stage_bytes(p);
+  int S = kRing / stage_bytes;
+  if (S > 4) S = 4;
+  const int b_off = p.bias_mode ? 0 : 2 * kABytes;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmX);
     prefetch_tensormap(&tmDY);
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     mbar_init(done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 1) tmem_alloc_imm<512>(tmem_slot);
+  if (p.bias_mode) {
+    for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += kWgThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;  // bf16 1.0 x2
+    fence_proxy_async_smem();
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const bool has_work = static_cast<int>(blockIdx.x) < p.num_tiles;
+  const int tiles_per_img = batch.tiles_x * batch.tiles_y;
+  const bool has_work = split < batch.num_tiles;
 
   if (warp == 0) {
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = split; tile < batch.num_tiles; tile += p.splits) {
       const int n = tile / tiles_per_img;
       const int t2 = tile - n * tiles_per_img;
-      const int ty = t2 / p.tiles_x;
-      const int x0 = (t2 - ty * p.tiles_x) * kTileW;
+      const int ty = t2 / batch.tiles_x;
+      const int x0 = (t2 - ty * batch.tiles_x) * kTileW;
       const int y0 = ty * kTileH;
       mbar_wait(&empty[s], ph ^ 1);
       if (elect_one_sync()) {
         uint8_t* st = smem + s * stage_bytes;
         mbar_arrive_expect_tx(&full[s], stage_bytes);
-        tma_load_4d(st, &tmX, &full[s], p.a_c0, x0 + dxi - 1, y0 - 1, n);
-        tma_load_4d(st + kABytes, &tmX, &full[s], p.a_c0 + 64, x0 + dxi - 1, y0 - 1, n);
+        if (!p.bias_mode) {
+          tma_load_4d(st, &tmX, &full[s], p.a_c0, x0 + dxi - 1, y0 - 1, n);
+          tma_load_4d(st + kABytes, &tmX, &full[s], p.a_c0 + 64, x0 + dxi - 1, y0 - 1, n);
+        }
         for (int j = 0; j < p.n_blocks; ++j)
-          tma_load_4d(st + 2 * kABytes + j * kWgBBytes, &tmDY, &full[s], p.b_c0 + 64 * j, x0, y0, n);
+          tma_load_4d(st + b_off + j * kWgBBytes, &tmDY, &full[s], p.b_c0 + 64 * j, x0, y0, n);
       }
       __syncwarp();
       if (++s == S) { s = 0; ph ^= 1; }
@@ -113,19 +139,25 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     int s = 0;
     uint32_t ph = 0;
     uint32_t acc = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = split; tile < batch.num_tiles; tile += p.splits) {
       mbar_wait(&full[s], ph);
       tcgen05_fence_after();
       if (elect_one_sync()) {
         const uint32_t a0 = smem_u32(smem + s * stage_bytes);
-        const uint32_t a_lo = smem_desc_lo(a0, kABytes);                  // LBO = stride between the two 64-ch M blocks
-        const uint32_t b_lo = smem_desc_lo(a0 + 2 * kABytes, kWgBBytes);  // LBO = stride between 64-ch N blocks
+        const uint32_t b_lo = smem_desc_lo(a0 + b_off, kWgBBytes);  // LBO = stride between 64-ch N blocks
+        if (p.bias_mode) {
+          const uint32_t o_lo = smem_desc_lo(smem_u32(ones), 2048);  // every K step reads the same all-ones tile
 #pragma unroll
-        for (int dyi = 0; dyi < 3; ++dyi) {
+          for (int ks = 0; ks < 8; ++ks) umma_bf16_ss_lohi(tmem_base, o_lo, b_lo + ks * 128, kHi, idesc, (ks == 0) ? acc : 1u);
+        } else {
+          const uint32_t a_lo = smem_desc_lo(a0, kABytes);  // LBO = stride between the two 64-ch M blocks
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // 16 pixels (two 8-pixel patch rows) per UMMA
-            umma_bf16_ss_lohi(tmem_base + dyi * p.n_cols, a_lo + dyi * 64 + ks * 128, b_lo + ks * 128, kHi, idesc,
-                              (ks == 0) ? acc : 1u);
+          for (int dyi = 0; dyi < 3; ++dyi) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)  // 16 pixels (two 8-pixel patch rows) per UMMA
+              umma_bf16_ss_lohi(tmem_base + dyi * p.n_cols, a_lo + dyi * 64 + ks * 128, b_lo + ks * 128, kHi, idesc,
+                                (ks == 0) ? acc : 1u);
+          }
         }
         umma_commit(&empty[s]);
       }
@@ -136,13 +168,13 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (elect_one_sync()) umma_commit(done);
     __syncwarp();
   } else if (has_work) {
-    // epilogue: flush the three accumulators with 16-byte fp32 vector reductions into [tap][ci][co] staging tensors
+    // epilogue: flush the accumulators with 16-byte fp32 vector reductions into [tap][ci][co] staging tensors
     const int q = warp & 3;
     const int m = q * 32 + lane;  // accumulator row = input channel a_c0 + m
     mbar_wait(done, 0);
     tcgen05_fence_after();
-    for (int dyi = 0; dyi < 3; ++dyi) {
-      const int tap = dyi * 3 + dxi;
+    for (int dyi = 0; dyi < nacc; ++dyi) {
+      const int tap = p.bias_mode ? 0 : dyi * 3 + dxi;
       for (int c0 = 0; c0 < p.n_cols; c0 += 16) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + dyi * p.n_cols + c0, r);
@@ -168,7 +200,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    tmem_dealloc_imm<512>(tmem_base);
   }
 }
 
