@@ -483,11 +483,11 @@ static int build_plan(b200sr_plan& P) {
     // a wgrad launch = batch of problems over one (X, dY) tensor-map pair
     auto wgrad_batch = [&](long long x_off, int x_cvalid, int x_cpix, long long dy_off, int dy_cvalid, int dy_cpix, int n, int h, int w) {
       Step s; s.type = ST_WGRAD;
-      s.xmap = B.add_map(x_off, x_cvalid, x_cpix, n, h, w, kABoxRows);
-      s.dymap = B.add_map(dy_off, dy_cvalid, dy_cpix, n, h, w, kTileH);
+      s.xmap = B.add_map(x_off, x_cvalid, x_cpix, n, h, w, kWgXRows);
+      s.dymap = B.add_map(dy_off, dy_cvalid, dy_cpix, n, h, w, kWgTileH);
       WgradBatch& wb = s.wb; memset(&wb, 0, sizeof(wb));
       wb.N = n; wb.H = h; wb.W = w;
-      wb.tiles_x = (w + kTileW - 1) / kTileW; wb.tiles_y = (h + kTileH - 1) / kTileH; wb.num_tiles = n * wb.tiles_x * wb.tiles_y;
+      wb.tiles_x = (w + kTileW - 1) / kTileW; wb.tiles_y = (h + kWgTileH - 1) / kWgTileH; wb.num_tiles = n * wb.tiles_x * wb.tiles_y;
       return s;
     };
     auto add_problem = [&](Step& s, int a_c0, int b_c0, int n_cols, int bias_mode) {
@@ -1123,16 +1123,16 @@ int b200sr_conv3x3_wgrad(const void* x, int n, int h, int w_, int cin, int x_str
   if (cin > 128 || cout > 160 || cout % 16 != 0) return fail(B200SR_ERR_INVALID, "wgrad: cin <= 128, cout <= 160, cout %% 16 == 0");
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmX, tmDY;
-  rc = encode_act_map(&tmX, (void*)x, cin, x_stride, n, h, w_, kABoxRows);
+  rc = encode_act_map(&tmX, (void*)x, cin, x_stride, n, h, w_, kWgXRows);
   if (rc) return rc;
-  rc = encode_act_map(&tmDY, (void*)dy, cout, dy_stride, n, h, w_, kTileH);
+  rc = encode_act_map(&tmDY, (void*)dy, cout, dy_stride, n, h, w_, kWgTileH);
   if (rc) return rc;
   const long long stage_bytes = align_up(9LL * cin * cout * 4, 1024);
   float* staging = (float*)scratch;
   CUDA_TRY(cudaMemsetAsync(staging, 0, (size_t)stage_bytes, st));
   WgradBatch wb; memset(&wb, 0, sizeof(wb));
   wb.N = n; wb.H = h; wb.W = w_;
-  wb.tiles_x = (w_ + kTileW - 1) / kTileW; wb.tiles_y = (h + kTileH - 1) / kTileH; wb.num_tiles = n * wb.tiles_x * wb.tiles_y;
+  wb.tiles_x = (w_ + kTileW - 1) / kTileW; wb.tiles_y = (h + kWgTileH - 1) / kWgTileH; wb.num_tiles = n * wb.tiles_x * wb.tiles_y;
   wb.num_problems = 1;
   WgradParams& wp = wb.prob[0];
   wp.a_c0 = 0; wp.b_c0 = 0; wp.n_cols = cout; wp.n_blocks = (cout + 63) / 64;

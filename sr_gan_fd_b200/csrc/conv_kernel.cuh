@@ -21,9 +21,9 @@
 namespace b200sr {
 
 constexpr int kTileW = 8;
-constexpr int kTileH = 16;
-constexpr int kABoxRows = kTileH + 2;                   // 18 image rows incl. the vertical halo
-constexpr int kABytes = kABoxRows * kTileW * 128;       // 18432 B per (chunk, dx) activation tile
+constexpr int kTileH = 32;                              // a work item = 8 x 32 pixels = two M=128 halves sharing every weight tile
+constexpr int kABoxRows = kTileH + 2;                   // 34 image rows incl. the vertical halo
+constexpr int kABytes = kABoxRows * kTileW * 128;       // 34816 B per (chunk, dx) activation tile
 constexpr int kConvThreads = 192;
 constexpr int kMaxStages = 8;
 
@@ -347,9 +347,13 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
                 const int dyi = (e == 0) ? 1 : (e == 1 ? 0 : 2);  // centre row first
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                  if (ks < ksteps && !(debug & 2))
+                  if (ks < ksteps && !(debug & 2)) {
+                    // the two 128-pixel halves (image rows 0-15 / 16-31 of the tile) reuse the same weight tile
                     umma_bf16_ss_lohi(d_tmem, a_lo + dyi * 64 + ks * 2, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
                                       (e == 0 && ks == 0) ? first : 1u);
+                    umma_bf16_ss_lohi(d_tmem + 128, a_lo + (dyi + 16) * 64 + ks * 2, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
+                                      (e == 0 && ks == 0) ? first : 1u);
+                  }
                 }
               }
               umma_commit(&empty[s]);  // frees the smem stage once these MMAs have drained
@@ -384,9 +388,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
         const int t2 = tile - n * tiles_per_img;
         const int ty = t2 / p.tiles_x;
         const int x = (t2 - ty * p.tiles_x) * kTileW + (m & 7);
-        const int y = ty * kTileH + (m >> 3);
-        const bool valid = (x < p.W) && (y < p.H);
         const int as = my_it & 1;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+        const int y = ty * kTileH + half * 16 + (m >> 3);
+        const bool valid = (x < p.W) && (y < p.H);
         // Operands that do not depend on the accumulator are fetched BEFORE waiting for the MMAs, so their L2 latency
         // hides behind the tensor work: combined fp32 residual (<= 64 columns) and the LeakyReLU-derivative mask words.
         const ConvEpilogue& e = p.epi;
@@ -426,9 +432,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
             }
           }
         }
-        mbar_wait(&tfull[as], (my_it >> 1) & 1);
-        tcgen05_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+        if (half == 0) {
+          mbar_wait(&tfull[as], (my_it >> 1) & 1);
+          tcgen05_fence_after();
+        }
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int c0 = g * 32;
@@ -455,6 +463,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
                                   (has_mask && g < 2) ? &maskw[(g & 1) * 16] : nullptr, n, y, x, colbase + c0, ncol, v);
           }
         }
+        }  // half
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[as]);

@@ -21,7 +21,10 @@
 
 namespace b200sr {
 
-constexpr int kWgBBytes = kTileH * kTileW * 128;  // 16384 B per 64-channel dY tile
+constexpr int kWgTileH = 16;                          // wgrad K-tile: 8 x 16 pixels
+constexpr int kWgXRows = kWgTileH + 2;
+constexpr int kWgXBytes = kWgXRows * kTileW * 128;   // 18432 B per 64-channel haloed X tile
+constexpr int kWgBBytes = kWgTileH * kTileW * 128;   // 16384 B per 64-channel dY tile
 constexpr int kWgThreads = 192;
 constexpr int kWgMaxSeg = 5;
 constexpr int kWgMaxProblems = 4;
@@ -55,7 +58,7 @@ struct WgradBatch {
 };
 
 __host__ __device__ inline int wgrad_stage_bytes(const WgradParams& p) {
-  return (p.bias_mode ? 0 : 2 * kABytes) + p.n_blocks * kWgBBytes;
+  return (p.bias_mode ? 0 : 2 * kWgXBytes) + p.n_blocks * kWgBBytes;
 }
 constexpr int kWgSmemBytes = 227 * 1024;
 
@@ -86,7 +89,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int stage_bytes = wgrad_stage_bytes(p);
   int S = kRing / stage_bytes;
   if (S > 4) S = 4;
-  const int b_off = p.bias_mode ? 0 : 2 * kABytes;
+  const int b_off = p.bias_mode ? 0 : 2 * kWgXBytes;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmX);
@@ -118,14 +121,14 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int t2 = tile - n * tiles_per_img;
       const int ty = t2 / batch.tiles_x;
       const int x0 = (t2 - ty * batch.tiles_x) * kTileW;
-      const int y0 = ty * kTileH;
+      const int y0 = ty * kWgTileH;
       mbar_wait(&empty[s], ph ^ 1);
       if (elect_one_sync()) {
         uint8_t* st = smem + s * stage_bytes;
         mbar_arrive_expect_tx(&full[s], stage_bytes);
         if (!p.bias_mode) {
           tma_load_4d(st, &tmX, &full[s], p.a_c0, x0 + dxi - 1, y0 - 1, n);
-          tma_load_4d(st + kABytes, &tmX, &full[s], p.a_c0 + 64, x0 + dxi - 1, y0 - 1, n);
+          tma_load_4d(st + kWgXBytes, &tmX, &full[s], p.a_c0 + 64, x0 + dxi - 1, y0 - 1, n);
         }
         for (int j = 0; j < p.n_blocks; ++j)
           tma_load_4d(st + b_off + j * kWgBBytes, &tmDY, &full[s], p.b_c0 + 64 * j, x0, y0, n);
@@ -150,7 +153,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) umma_bf16_ss_lohi(tmem_base, o_lo, b_lo + ks * 128, kHi, idesc, (ks == 0) ? acc : 1u);
         } else {
-          const uint32_t a_lo = smem_desc_lo(a0, kABytes);  // LBO = stride between the two 64-ch M blocks
+          const uint32_t a_lo = smem_desc_lo(a0, kWgXBytes);  // LBO = stride between the two 64-ch M blocks
 #pragma unroll
           for (int dyi = 0; dyi < 3; ++dyi) {
 #pragma unroll
