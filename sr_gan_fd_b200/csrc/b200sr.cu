@@ -63,24 +63,6 @@ static int runtime_init() {
   }
   if (!g_attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
-    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(2)));
-    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (const char* e = getenv("B200SR_CTAS_PER_SM")) g_ctas_per_sm = (atoi(e) == 1) ? 1 : 2;
-    if (g_ctas_per_sm == 2) {
-      int occ = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv3x3_chain_kernel<2>, kConvThreads, conv_smem_bytes(2)));
-      if (occ < 2) {
-        fprintf(stderr, "b200sr: 2 CTAs/SM not resident (occupancy %d), using 1\n", occ);
-        for (int kb = 32; kb <= 112; kb += 8) {
-          int o2 = 0;
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, conv3x3_chain_kernel<2>, kConvThreads, kb * 1024);
-          fprintf(stderr, "  smem %d KB -> occupancy %d\n", kb, o2);
-        }
-        cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, conv3x3_chain_kernel<2>);
-        fprintf(stderr, "  regs %d static smem %zu local %zu maxThreads %d\n", fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxThreadsPerBlock);
-        g_ctas_per_sm = 1;
-      }
-    }
     CUDA_TRY(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     g_attr_set = true;
   }
@@ -796,7 +778,7 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   const int cps = g_ctas_per_sm;
   int grid = s.chain_grid < cps * g_num_sms ? s.chain_grid : cps * g_num_sms;
   if (grid < 1) grid = 1;
-  const void* fn = cps == 1 ? (const void*)conv3x3_chain_kernel<1> : (const void*)conv3x3_chain_kernel<2>;
+  const void* fn = (const void*)conv3x3_chain_kernel<1>;
   const LayerDesc* layers = P.d_layers + s.layer0;
   int nl = s.nlayers;
   float* y = (float*)b.y;
@@ -871,9 +853,15 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         break;
       }
       case ST_UNPACK: {
+        // without a bucket callback nobody consumes gradients early: unpack everything once, at the last bucket (conv1)
+        int c0 = s.i0, c1 = s.i1;
+        if (!cb) {
+          if (s.i0 != 0) break;
+          c1 = (int)P.unpack_ops.size();
+        }
         int blocks = 0;
-        for (int c = s.i0; c < s.i1; ++c) blocks += P.unpack_ops[c].nblocks;
-        unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(P.d_unpack_ops, s.i0, s.i1, (const float*)((char*)b.ws + P.o_gw), (float*)b.grads);
+        for (int c = c0; c < c1; ++c) blocks += P.unpack_ops[c].nblocks;
+        unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(P.d_unpack_ops, c0, c1, (const float*)((char*)b.ws + P.o_gw), (float*)b.grads);
         CUDA_TRY(cudaGetLastError());
         break;
       }

@@ -24,7 +24,7 @@ constexpr int kTileW = 8;
 constexpr int kTileH = 32;                              // a work item = 8 x 32 pixels = two M=128 halves sharing every weight tile
 constexpr int kABoxRows = kTileH + 2;                   // 34 image rows incl. the vertical halo
 constexpr int kABytes = kABoxRows * kTileW * 128;       // 34816 B per (chunk, dx) activation tile
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of the upper 128-pixel half, warps 6-9 of the lower half
 constexpr int kMaxStages = 8;
 
 enum StoreMode : int {
@@ -217,7 +217,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
 // kCtasPerSm = 1: one CTA owns the SM (227 KB ring, 512 TMEM columns); 2: two co-resident CTAs (113 KB, 256 columns each)
 // interleave their pipelines, hiding each other's barrier / epilogue / first-load latencies.
 template <int kCtasPerSm>
-__global__ void __launch_bounds__(kCtasPerSm == 1 ? kConvThreads : 208, kCtasPerSm)  // 208: caps registers at 152 so two CTAs fit
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const __grid_constant__ WeightMaps wmaps,
                      unsigned int* barrier_ctr, float* y_dyn, int debug) {
   extern __shared__ uint8_t smem_raw[];
@@ -248,7 +248,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], 8);
     }
     fence_barrier_init();
   }
@@ -371,14 +371,14 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
       const int q = warp & 3;  // TMEM lane quarter this warp may read
       const int m = q * 32 + lane;
       if (l + 1 < num_layers) {  // prefetch the next layer's parameters and bias into the other smem slot
-        const int t = threadIdx.x - 64;  // 0..127
+        const int t = threadIdx.x - 64;  // 0..255
         const ConvParams* np = &layers[l + 1].p;
         uint32_t* dst = reinterpret_cast<uint32_t*>(sp_base + ((l + 1) & 1) * 384);
         if (t < static_cast<int>(sizeof(ConvParams) / 4)) dst[t] = __ldg(reinterpret_cast<const uint32_t*>(np) + t);
         const float* nb = np->epi.bias;
         const int nt = np->n_total;
         float* bdst = sbias_base + ((l + 1) & 1) * 256;
-        for (int i = t; i < nt; i += 128) bdst[i] = nb ? __ldg(nb + i) : 0.f;
+        for (int i = t; i < nt; i += 256) bdst[i] = nb ? __ldg(nb + i) : 0.f;
       }
       int my_it = it;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++my_it) {
@@ -389,8 +389,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
         const int ty = t2 / p.tiles_x;
         const int x = (t2 - ty * p.tiles_x) * kTileW + (m & 7);
         const int as = my_it & 1;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
+        {
+        const int half = (warp >= 6) ? 1 : 0;  // each half of the work item has its own four epilogue warps
         const int y = ty * kTileH + half * 16 + (m >> 3);
         const bool valid = (x < p.W) && (y < p.H);
         // Operands that do not depend on the accumulator are fetched BEFORE waiting for the MMAs, so their L2 latency
@@ -432,10 +432,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
             }
           }
         }
-        if (half == 0) {
-          mbar_wait(&tfull[as], (my_it >> 1) & 1);
-          tcgen05_fence_after();
-        }
+        mbar_wait(&tfull[as], (my_it >> 1) & 1);
+        tcgen05_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
