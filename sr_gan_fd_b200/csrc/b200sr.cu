@@ -69,11 +69,12 @@ static int runtime_init() {
   return 0;
 }
 
-// NHWC bf16 activation map: dims (C, W, H, N), box (64, 8, rows, 1), 128B swizzle, zero OOB fill.
+// NHWC bf16 activation map: dims (C, W, H, N), box (64, 10 | 8, rows, 1), 128B swizzle, zero OOB fill.
 static int encode_act_map(CUtensorMap* m, void* base, int c_valid, int c_pix, int n, int h, int w, int box_rows) {
+  const int box_w = (box_rows == kABoxRows) ? kABoxW : kTileW;  // conv tiles carry the horizontal halo, wgrad tiles do not
   cuuint64_t dims[4] = {(cuuint64_t)c_valid, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c_pix * 2, (cuuint64_t)w * c_pix * 2, (cuuint64_t)h * w * c_pix * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -4,17 +4,20 @@
 //   D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * Wt[tap][cout][cin]        (fp32 accumulate in TMEM)
 //
 // Data layout: activations are NHWC bf16, possibly a channel range of a wider "dense" buffer (the dense block writes
-// its growth channels into slices of one buffer, so no concat copy exists).  A CTA owns 128 output pixels = an
-// 8-wide x 16-tall patch of one image (UMMA M = 128, one TMEM lane per pixel).  K is walked in chunks of 64
-// channels x 3 horizontal taps: for each (chunk, dx) ONE TMA box [64 ch, 8 px, 18 rows] is loaded at x0+dx-1,y0-1
-// (out-of-image elements are zero-filled by TMA = the conv's zero padding); the three vertical taps are the same
-// smem tile at +0/+1024/+2048 bytes (8 pixels x 128 B = one 128B-swizzle atom), so they need no extra loads and
-// the UMMA descriptors stay 1024-byte aligned.  Weights are pre-packed per (chunk, dx, dy) as [cout][64] K-major
-// bf16 rows and arrive by 2-D TMA into the same 128B-swizzled layout.
+// its growth channels into slices of one buffer, so no concat copy exists).  A work item = an 8-wide x 32-tall patch
+// of one image = two M = 128 halves (one TMEM lane per pixel) that share every weight tile.  K is walked in chunks of
+// 64 channels: per chunk ONE 4-D TMA box [64 ch, 10 px, 34 rows] (the patch plus a 1-pixel halo; out-of-image
+// elements are zero-filled by TMA = the conv's zero padding) serves all nine taps -- the UMMA descriptor of tap
+// (dy,dx) simply starts (dy*10+dx) rows = (dy*10+dx)*128 B into the tile with a 1280 B stride between 8-row groups.
+// (Measured on B200, tools/probe_desc.cu: the 128B swizzle is applied on absolute shared-memory address bits, so
+// start addresses that are not 1024-byte aligned and strides that are not multiples of 1024 read exactly the rows
+// TMA wrote; the descriptor's base_offset field must stay 0.)  Weights are pre-packed per (chunk, dx, dy) as
+// [cout][64] K-major bf16 rows and stream through their own smem ring, three taps (one dx column) per slot.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> fused bias / LeakyReLU / mask / residuals -> global).  Accumulators
-// are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1 (persistent CTAs).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 / 6..9 = epilogue of the upper / lower 128-pixel half (TMEM -> registers -> fused bias / LeakyReLU /
+// mask / residuals -> global).  Accumulators are double buffered in TMEM so the epilogue of item i overlaps the MMAs
+// of item i+1 (persistent CTAs).
 #pragma once
 #include "ptx.cuh"
 
@@ -23,7 +26,11 @@ namespace b200sr {
 constexpr int kTileW = 8;
 constexpr int kTileH = 32;                              // a work item = 8 x 32 pixels = two M=128 halves sharing every weight tile
 constexpr int kABoxRows = kTileH + 2;                   // 34 image rows incl. the vertical halo
-constexpr int kABytes = kABoxRows * kTileW * 128;       // 34816 B per (chunk, dx) activation tile
+constexpr int kABoxW = kTileW + 2;                      // 10 pixels incl. the horizontal halo
+constexpr int kABytes = kABoxRows * kABoxW * 128;       // 43520 B: one haloed activation tile per 64-channel chunk
+constexpr int kASlot = 44032;                           // A-ring slot (1024-byte multiple)
+constexpr int kMaxAStages = 4;
+constexpr int kMaxWStages = 6;
 constexpr int kConvThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of the upper 128-pixel half, warps 6-9 of the lower half
 constexpr int kMaxStages = 8;
 
@@ -74,12 +81,9 @@ struct ConvParams {
   ConvEpilogue epi;
 };
 
-__host__ __device__ inline int conv_stage_bytes(int n_cols) { return kABytes + 3 * n_cols * 128; }
+__host__ __device__ inline int conv_wslot_bytes(int n_cols) { return 3 * n_cols * 128; }  // the three dy taps of one dx column
 __host__ __device__ constexpr int conv_smem_bytes(int ctas_per_sm) { return ctas_per_sm == 1 ? 227 * 1024 : 112 * 1024; }
-__host__ inline int conv_pick_stages(int n_cols) {  // informational (the kernel sizes its ring itself)
-  int s = (227 * 1024 - 1024 - 3072) / conv_stage_bytes(n_cols);
-  return s > kMaxStages ? kMaxStages : s;
-}
+__host__ inline int conv_pick_stages(int n_cols) { return n_cols >= 128 ? 2 : 3; }  // A-ring depth (informational)
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 
@@ -226,9 +230,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
   constexpr int kRingBytes = conv_smem_bytes(kCtasPerSm) - 1024 - 3072;  // usable by the stage ring
   constexpr int kAccStride = (kCtasPerSm == 1) ? 256 : 128;                // TMEM columns between the two accumulators
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kMaxStages;
-  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + kMaxAStages;
+  uint64_t* fullW = bars + 2 * kMaxAStages;
+  uint64_t* emptyW = fullW + kMaxWStages;
+  uint64_t* tfull = emptyW + kMaxWStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   // two slots (current / next layer): parameters 2 x 384 B at +256, bias vectors 2 x 1 KB at +1024
@@ -242,9 +248,13 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tensormap(&wmaps.m[i]);
-    for (int s = 0; s < kMaxStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+    for (int s = 0; s < kMaxAStages; ++s) {
+      mbar_init(&fullA[s], 1);
+      mbar_init(&emptyA[s], 1);
+    }
+    for (int s = 0; s < kMaxWStages; ++s) {
+      mbar_init(&fullW[s], 1);
+      mbar_init(&emptyW[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -258,7 +268,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  uint32_t ring_bits = 0;  // per-stage phase parity (producer: empty barriers, MMA warp: full barriers)
+  uint32_t ringA_bits = 0, ringW_bits = 0;  // per-slot phase parity (producer: empty barriers, MMA warp: full barriers)
   int it = 0;              // work items done by this CTA so far (accumulator stage = it & 1), identical in all roles
 
   for (int l = 0; l < num_layers; ++l) {
@@ -275,8 +285,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
       __syncthreads();
     }
     const ConvParams& p = *sp;
-    const int stage_bytes = conv_stage_bytes(p.n_cols);
-    const int S = (kRingBytes / stage_bytes) > kMaxStages ? kMaxStages : (kRingBytes / stage_bytes);
+    // smem rings of this layer: SA activation slots, then SW weight slots
+    const int wslot = conv_wslot_bytes(p.n_cols);
+    const int SA = (p.n_cols >= 128) ? 2 : 3;
+    const int SW = ((kRingBytes - SA * kASlot) / wslot) > kMaxWStages ? kMaxWStages : ((kRingBytes - SA * kASlot) / wslot);
+    uint8_t* smemW = smem + SA * kASlot;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int num_work = p.num_tiles * p.col_groups;
     const CUtensorMap* tmA = &layers[l].tmA;
@@ -285,7 +298,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
     if (warp == 0) {
       // ================================================= TMA producer ===============================================
       // (whole warp walks the loop so the index math stays warp-uniform; one elected lane issues)
-      int s = 0;
+      int sa = 0, sw = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int tile = w / p.col_groups;
         const int colbase = (w - tile * p.col_groups) * p.n_cols;
@@ -296,25 +309,34 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
         const int y0 = ty * kTileH;
         for (int c = 0; c < ((debug & 32) ? 0 : p.num_chunks); ++c) {
           const int ac = p.a_c0 + (c % p.a_wrap) * 64;
+          mbar_wait(&emptyA[sa], ((ringA_bits >> sa) & 1u) ^ 1u);
+          if (elect_one_sync()) {
+            if (debug & 4) mbar_arrive(&fullA[sa]);
+            else {
+              mbar_arrive_expect_tx(&fullA[sa], kABytes);
+              tma_load_4d(smem + sa * kASlot, tmA, &fullA[sa], ac, x0 - 1, y0 - 1, n);
+            }
+          }
+          __syncwarp();
+          ringA_bits ^= (1u << sa);
+          if (++sa == SA) sa = 0;
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             const int dxi = (d == 0) ? 1 : (d == 1 ? 0 : 2);  // centre column first (see MMA loop)
-            mbar_wait(&empty[s], ((ring_bits >> s) & 1u) ^ 1u);
+            mbar_wait(&emptyW[sw], ((ringW_bits >> sw) & 1u) ^ 1u);
             if (elect_one_sync()) {
-              uint8_t* st = smem + s * stage_bytes;
-              const int dbg_bytes = ((debug & 4) ? 0 : kABytes) + ((debug & 8) ? 0 : 3 * p.n_cols * 128);
-              if (dbg_bytes) mbar_arrive_expect_tx(&full[s], dbg_bytes); else mbar_arrive(&full[s]);
-              if (!(debug & 4)) tma_load_4d(st, tmA, &full[s], ac, x0 + dxi - 1, y0 - 1, n);
-              if (!(debug & 8)) {
+              if (debug & 8) mbar_arrive(&fullW[sw]);
+              else {
+                mbar_arrive_expect_tx(&fullW[sw], wslot);
 #pragma unroll
                 for (int dyi = 0; dyi < 3; ++dyi)
-                  tma_load_2d(st + kABytes + dyi * p.n_cols * 128, tmW, &full[s], 0,
+                  tma_load_2d(smemW + sw * wslot + dyi * p.n_cols * 128, tmW, &fullW[sw], 0,
                               p.w_row0 + ((c * 3 + dxi) * 3 + dyi) * p.n_total + colbase);
               }
             }
             __syncwarp();
-            ring_bits ^= (1u << s);
-            if (++s == S) s = 0;
+            ringW_bits ^= (1u << sw);
+            if (++sw == SW) sw = 0;
           }
         }
       }
@@ -323,9 +345,10 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
       // Whole warp runs the loop (uniform address math), one elected lane issues.  Descriptor hi words are loop
       // invariant; a K-step / vertical-tap advance is one 32-bit add on the lo word.
       const uint32_t idesc = make_idesc_bf16(128, p.n_cols, 0, 0);
-      constexpr uint32_t kHi = smem_desc_hi(1024);
+      constexpr uint32_t kHi = smem_desc_hi(1024);            // weights: 8-row groups 1024 B apart
+      constexpr uint32_t kHiA = smem_desc_hi(kABoxW * 128);   // activations: 8 pixels of a patch row, rows 1280 B apart
       const uint32_t b_dy = static_cast<uint32_t>(p.n_cols) * 8;  // (n_cols * 128 B) >> 4
-      int s = 0;
+      int sa = 0, sw = 0;
       int my_it = it;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++my_it) {
         const int as = my_it & 1;
@@ -334,36 +357,41 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
         const uint32_t d_tmem = tmem_base + as * kAccStride;
         for (int c = 0; c < ((debug & 32) ? 0 : p.num_chunks); ++c) {
           const int ksteps = (c == p.num_chunks - 1) ? p.ksteps_last : 4;
+          mbar_wait(&fullA[sa], (ringA_bits >> sa) & 1u);
+          const uint32_t a_lo = smem_desc_lo(smem_u32(smem + sa * kASlot), 16);
           for (int d = 0; d < 3; ++d) {
-            mbar_wait(&full[s], (ring_bits >> s) & 1u);
+            const int dxi = (d == 0) ? 1 : (d == 1 ? 0 : 2);
+            mbar_wait(&fullW[sw], (ringW_bits >> sw) & 1u);
             tcgen05_fence_after();
             if (elect_one_sync()) {
-              const uint32_t a0 = smem_u32(smem + s * stage_bytes);
-              const uint32_t a_lo = smem_desc_lo(a0, 16);
-              const uint32_t b_lo = smem_desc_lo(a0 + kABytes, 16);
-              const uint32_t first = (c | d) ? 1u : 0u;  // very first MMA of the tile overwrites the accumulator
+              const uint32_t b_lo = smem_desc_lo(smem_u32(smemW + sw * wslot), 16);
+              const uint32_t first = (c | d) ? 1u : 0u;  // very first MMA of the item overwrites the accumulators
 #pragma unroll
               for (int e = 0; e < 3; ++e) {
                 const int dyi = (e == 0) ? 1 : (e == 1 ? 0 : 2);  // centre row first
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                   if (ks < ksteps && !(debug & 2)) {
-                    // the two 128-pixel halves (image rows 0-15 / 16-31 of the tile) reuse the same weight tile
-                    umma_bf16_ss_lohi(d_tmem, a_lo + dyi * 64 + ks * 2, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
-                                      (e == 0 && ks == 0) ? first : 1u);
-                    umma_bf16_ss_lohi(d_tmem + 128, a_lo + (dyi + 16) * 64 + ks * 2, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
-                                      (e == 0 && ks == 0) ? first : 1u);
+                    // tap (dy,dx) = the haloed tile shifted by (dy*10+dx) rows of 128 B; the two 128-pixel halves
+                    // (patch rows 0-15 / 16-31) reuse the same weight tile
+                    const uint32_t a_tap = a_lo + (dyi * kABoxW + dxi) * 8 + ks * 2;
+                    umma_bf16_ss_lohi2(d_tmem, a_tap, kHiA, b_lo + dyi * b_dy + ks * 2, kHi, idesc, (e == 0 && ks == 0) ? first : 1u);
+                    umma_bf16_ss_lohi2(d_tmem + 128, a_tap + 16 * kABoxW * 8, kHiA, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
+                                       (e == 0 && ks == 0) ? first : 1u);
                   }
                 }
               }
-              umma_commit(&empty[s]);  // frees the smem stage once these MMAs have drained
+              umma_commit(&emptyW[sw]);                 // frees the weight slot once these MMAs have drained
+              if (d == 2) umma_commit(&emptyA[sa]);     // ... and the activation tile after its last column
             }
             __syncwarp();
-            ring_bits ^= (1u << s);
-            if (++s == S) s = 0;
+            ringW_bits ^= (1u << sw);
+            if (++sw == SW) sw = 0;
           }
+          ringA_bits ^= (1u << sa);
+          if (++sa == SA) sa = 0;
         }
-        if (elect_one_sync()) umma_commit(&tfull[as]);  // accumulator ready for the epilogue warps
+        if (elect_one_sync()) umma_commit(&tfull[as]);  // accumulators ready for the epilogue warps
         __syncwarp();
       }
     } else {
