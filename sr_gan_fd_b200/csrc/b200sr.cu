@@ -116,6 +116,7 @@ struct Step {
   dim3 grid;
   int smem = 0;
   int layer0 = 0, nlayers = 0, chain_grid = 0;  // ST_CHAIN: range of the plan's layer list
+  int entry0 = 0, nentries = 0;                 // ... and of its entry list (filled when the device tables are built)
   // wgrad
   int xmap = -1, dymap = -1;
   WgradBatch wb;
@@ -166,7 +167,9 @@ struct b200sr_plan {
   std::vector<Step> layer_steps;      // every conv launch of fwd then bwd, in execution order (= layer list)
   std::vector<LayerDesc> h_layers;
   LayerDesc* d_layers = nullptr;
-  unsigned int* d_barrier = nullptr;
+  std::vector<EntryDesc> h_entries;   // (layer, image group) entries of every chain, chain after chain
+  EntryDesc* d_entries = nullptr;
+  unsigned int* d_counters = nullptr; // per-entry completion counters of the chain being launched
 };
 
 static int wmap_index(int n_cols) { return n_cols == 16 ? 0 : n_cols == 32 ? 1 : n_cols == 64 ? 2 : 3; }
@@ -429,7 +432,7 @@ static int build_plan(b200sr_plan& P) {
     const int ci = ci_up1 + (l - 1);
     const int h = H << (l - 1), w = W << (l - 1);
     const int row0 = split_pack(ci, 256, 256, kPackUpFwd);
-    ConvParams cp = base_conv_params(N, h, w, 3, 4, 0, 2, row0, 128, 256);
+    ConvParams cp = base_conv_params(N, h, w, 3, 4, 0, 2, row0, 64, 256);  // 4 column groups (phases) of 64
     Step s = conv_step(B.add_map(P.o_spl[l - 1], 128, 128, N, h, w, kABoxRows), cp, 2);
     s.bias = packed_bias(B.add_bias(256, 2 * ci + 1, 64, 64));
     s.cp.epi.act = 1;
@@ -765,9 +768,41 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
     L.p.epi.out_bf16 = (__nv_bfloat16*)resolve(s.ob, b);
     L.p.epi.clamp_mask = (unsigned char*)resolve(s.cm, b);
   }
+  // entry lists: every layer of a chain is split into (up to) two image groups that flow through the chain independently
+  if (P.h_entries.empty()) {
+    auto build_entries = [&](std::vector<Step>& steps) {
+      for (Step& s : steps) {
+        if (s.type != ST_CHAIN) continue;
+        const int grid = s.chain_grid < g_num_sms ? s.chain_grid : g_num_sms;
+        const int groups = P.d.batch >= 2 ? 2 : 1;
+        s.entry0 = (int)P.h_entries.size();
+        for (int l = 0; l < s.nlayers; ++l) {
+          const ConvParams& cp = P.layer_steps[s.layer0 + l].cp;
+          const int tpi = cp.tiles_x * cp.tiles_y;
+          int work0 = 0;
+          for (int g = 0; g < groups; ++g) {
+            const int img_lo = (int)((long long)P.d.batch * g / groups), img_hi = (int)((long long)P.d.batch * (g + 1) / groups);
+            EntryDesc e; memset(&e, 0, sizeof(e));
+            e.layer = s.layer0 + l;
+            e.tile_lo = img_lo * tpi; e.tile_hi = img_hi * tpi;
+            e.dep = (l > 0) ? ((l - 1) * groups + g) : -1;
+            const int work = (e.tile_hi - e.tile_lo) * cp.col_groups;
+            e.rot = (g == 0) ? 0 : (work0 % grid);  // the second group starts where the first one's last round ended
+            if (g == 0) work0 = work;
+            P.h_entries.push_back(e);
+          }
+        }
+        s.nentries = (int)P.h_entries.size() - s.entry0;
+      }
+    };
+    build_entries(P.fwd);
+    build_entries(P.bwd);
+  }
   if (!P.d_layers) {
     CUDA_TRY(cudaMalloc(&P.d_layers, P.h_layers.size() * sizeof(LayerDesc)));
-    CUDA_TRY(cudaMalloc(&P.d_barrier, 256));
+    CUDA_TRY(cudaMalloc(&P.d_entries, P.h_entries.size() * sizeof(EntryDesc)));
+    CUDA_TRY(cudaMalloc(&P.d_counters, 16384));
+    CUDA_TRY(cudaMemcpyAsync(P.d_entries, P.h_entries.data(), P.h_entries.size() * sizeof(EntryDesc), cudaMemcpyHostToDevice, st));
   }
   CUDA_TRY(cudaMemcpyAsync(P.d_layers, P.h_layers.data(), P.h_layers.size() * sizeof(LayerDesc), cudaMemcpyHostToDevice, st));
   P.cached_ws = wsp;
@@ -776,21 +811,22 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
 }
 
 static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStream_t st) {
-  const int cps = g_ctas_per_sm;
-  int grid = s.chain_grid < cps * g_num_sms ? s.chain_grid : cps * g_num_sms;
+  int grid = s.chain_grid < g_num_sms ? s.chain_grid : g_num_sms;
   if (grid < 1) grid = 1;
-  const void* fn = (const void*)conv3x3_chain_kernel<1>;
-  const LayerDesc* layers = P.d_layers + s.layer0;
-  int nl = s.nlayers;
+  if (s.nentries * (int)sizeof(unsigned int) > 16384) return fail(B200SR_ERR_INVALID, "chain too long (%d entries)", s.nentries);
+  const LayerDesc* layers = P.d_layers;
+  const EntryDesc* entries = P.d_entries + s.entry0;
+  int ne = s.nentries;
   float* y = (float*)b.y;
   int dbg = g_debug;
-  unsigned int* ctr = P.d_barrier;
-  if (nl > 1) CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
-  void* args[] = {(void*)&layers, (void*)&nl, (void*)&P.wmaps, (void*)&ctr, (void*)&y, (void*)&dbg};
-  if (nl > 1) {
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(cps), st));
+  unsigned int* ctr = P.d_counters;
+  CUDA_TRY(cudaMemsetAsync(ctr, 0, (size_t)ne * sizeof(unsigned int), st));
+  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&P.wmaps, (void*)&ctr, (void*)&y, (void*)&dbg};
+  const void* fn = (const void*)conv3x3_chain_kernel<1>;
+  if (ne > 1) {
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   } else {
-    CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(cps), st));
+    CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   }
   return 0;
 }
@@ -928,7 +964,8 @@ void b200sr_plan_destroy(b200sr_plan* p) {
   if (p->d_params) cudaFree((void*)p->d_params);
   if (p->d_unpack_ops) cudaFree(p->d_unpack_ops);
   if (p->d_layers) cudaFree(p->d_layers);
-  if (p->d_barrier) cudaFree(p->d_barrier);
+  if (p->d_entries) cudaFree(p->d_entries);
+  if (p->d_counters) cudaFree(p->d_counters);
   delete p;
 }
 
@@ -1019,10 +1056,9 @@ int b200sr_backward(b200sr_plan* p, const float* dy, const void* packed, void* w
 
 // ------------------------------------------------------------------------------------------ single-layer helpers
 static int pick_ncols(int cout, int* n_cols, int* grid_y) {
-  if (cout % 32 != 0 || cout < 32 || (cout > 128 && cout != 256)) return fail(B200SR_ERR_INVALID, "cout must be 32/64/96/128/256 (got %d)", cout);
-  *n_cols = cout > 128 ? 128 : cout;
+  if (cout % 32 != 0 || cout < 32 || cout > 256) return fail(B200SR_ERR_INVALID, "cout must be a multiple of 32 in [32, 256] (got %d)", cout);
+  *n_cols = (cout % 64 == 0) ? 64 : 32;
   *grid_y = cout / *n_cols;
-  if (*n_cols == 96) return fail(B200SR_ERR_INVALID, "cout 96 unsupported");
   return 0;
 }
 
@@ -1076,13 +1112,18 @@ static int single_conv(int mode, const void* x, int n, int h, int w, int cin, in
   memset(&wm, 0, sizeof(wm));
   wm.m[L.p.wmap] = tmW;
   CUDA_TRY(cudaMemcpyAsync(sc + tab_off + 3072, &L, sizeof(L), cudaMemcpyHostToDevice, st));
+  EntryDesc ent; memset(&ent, 0, sizeof(ent));
+  ent.layer = 0; ent.tile_lo = 0; ent.tile_hi = L.p.num_tiles; ent.dep = -1; ent.rot = 0;
+  CUDA_TRY(cudaMemcpyAsync(sc + tab_off + 3072 + 512, &ent, sizeof(ent), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(sc + tab_off + 3072 + 640, 0, 64, st));
   const int work = L.p.num_tiles * L.p.col_groups;
   int grid = work < g_num_sms ? work : g_num_sms;
   const LayerDesc* layers = (const LayerDesc*)(sc + tab_off + 3072);
-  int nl = 1, dbg = g_debug;
-  unsigned int* ctr = nullptr;
+  const EntryDesc* entries = (const EntryDesc*)(sc + tab_off + 3072 + 512);
+  int ne = 1, dbg = g_debug;
+  unsigned int* ctr = (unsigned int*)(sc + tab_off + 3072 + 640);
   float* ydyn = nullptr;
-  void* args[] = {(void*)&layers, (void*)&nl, (void*)&wm, (void*)&ctr, (void*)&ydyn, (void*)&dbg};
+  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&wm, (void*)&ctr, (void*)&ydyn, (void*)&dbg};
   CUDA_TRY(cudaLaunchKernel((const void*)conv3x3_chain_kernel<1>, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   (void)grid_y;
   return 0;

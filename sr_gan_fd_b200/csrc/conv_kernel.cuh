@@ -73,7 +73,7 @@ struct ConvParams {
   int a_c0;         // activation channel coordinate of chunk c: a_c0 + (c % a_wrap) * 64
   int a_wrap;
   int w_row0;   // first row of this conv in the packed weight matrix
-  int n_cols;   // UMMA N handled by one work item (multiple of 16, <= 128)
+  int n_cols;   // UMMA N handled by one work item (16, 32 or 64)
   int n_total;  // n_cols * col_groups
   int col_groups;  // work item w -> tile w / col_groups, column group w % col_groups
   int wmap;        // which weight tensor map (box rows = n_cols): 0:16 1:32 2:64 3:128
@@ -188,78 +188,81 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, float* 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One layer = one 3x3 conv over one pixel lattice.  A launch executes a CHAIN of layers: persistent CTAs (one per SM,
-// cooperative launch) walk the layer list, each taking work items blockIdx.x, +gridDim.x, ... of every layer, with a
-// grid-wide barrier between layers (layer l+1 reads the halo pixels other CTAs produced in layer l).  The whole
-// forward pass (351 convs) is ONE launch; pipeline state (smem ring, TMEM, mbarriers) is set up once.
+// One layer = one 3x3 conv over one pixel lattice.  A launch executes a CHAIN of ENTRIES: entry = (layer, image group).
+// Persistent CTAs (one per SM, cooperative launch) walk the entry list; the three warp roles of a CTA run through
+// it asynchronously from each other.  There is no grid-wide barrier: every entry has a completion counter that each
+// CTA's epilogue bumps when its stores for that entry are done, and an entry's inputs are only read once the counter
+// of the entry it depends on (the previous layer OF THE SAME IMAGE GROUP) shows all CTAs.  With two image groups the
+// dependency / TMA / epilogue latency of one group hides behind the other group's tensor work.  The whole forward
+// pass (351 convs) is ONE launch; pipeline state (smem rings, TMEM, mbarriers) is set up once.
 // ---------------------------------------------------------------------------------------------------------------
 struct alignas(128) LayerDesc {
   CUtensorMap tmA;  // activation tensor map of this layer (lives in global memory, read by TMA through a generic address)
   ConvParams p;
 };
 struct WeightMaps { CUtensorMap m[4]; };
+struct alignas(32) EntryDesc {
+  int layer;             // index into the layer list handed to the kernel
+  int tile_lo, tile_hi;  // pixel tiles of this entry (an image group of the layer)
+  int dep;               // entry whose completion gates this entry's input reads (-1: inputs exist before the launch)
+  int rot;               // CTA rotation: virtual CTA v = (blockIdx.x - rot) mod gridDim.x takes items v, v + gridDim.x, ...
+  int pad[3];
+};
 
-__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();  // cumulativity: every store of this CTA observed through bar.sync is released at gpu scope
-    atomicAdd(ctr, 1u);
-    const long long t0 = clock64();
-    unsigned int v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-      if (v < target && clock64() - t0 > 4000000000LL) {
-        printf("b200sr: grid barrier timeout (block %d: %u < %u)\n", blockIdx.x, v, target);
-        __trap();
-      }
-    } while (v < target);
-    asm volatile("fence.proxy.async.global;" ::: "memory");  // later TMA (async proxy) reads see those generic-proxy stores
-  }
-  __syncthreads();
+constexpr int kWGranule = 12288;   // weight ring granule = one (chunk, dx) stage of a 32-column layer (3 taps x 32 x 128 B)
+constexpr int kWGranules = 7;
+constexpr int kNumASlots = 3;
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
+// Wait until every CTA has finished entry `dep` (one lane polls; bounded so a broken chain traps instead of hanging).
+__device__ __forceinline__ void wait_entry_done(const unsigned int* counters, int dep, unsigned int need) {
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(counters + dep) < need) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("b200sr: dependency wait timeout (block %d entry %d)\n", blockIdx.x, dep);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
 
-// kCtasPerSm = 1: one CTA owns the SM (227 KB ring, 512 TMEM columns); 2: two co-resident CTAs (113 KB, 256 columns each)
-// interleave their pipelines, hiding each other's barrier / epilogue / first-load latencies.
-template <int kCtasPerSm>
+template <int kUnused>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const __grid_constant__ WeightMaps wmaps,
-                     unsigned int* barrier_ctr, float* y_dyn, int debug) {
+conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __restrict__ entries, int num_entries,
+                     const __grid_constant__ WeightMaps wmaps, unsigned int* counters, float* y_dyn, int debug) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // fixed region at the END of the dynamic smem: barriers, TMEM slot, current layer parameters
-  constexpr int kRingBytes = conv_smem_bytes(kCtasPerSm) - 1024 - 3072;  // usable by the stage ring
-  constexpr int kAccStride = (kCtasPerSm == 1) ? 256 : 128;                // TMEM columns between the two accumulators
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
+  // [ A ring: 3 x 44032 | W ring: 7 x 12288 | barriers 256 B | epilogue params 2 x 384 B | epilogue bias 2 x 1 KB ]
+  uint8_t* smemW = smem + kNumASlots * kASlot;
+  uint8_t* fixed = smemW + kWGranules * kWGranule;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fixed);
   uint64_t* fullA = bars;
-  uint64_t* emptyA = bars + kMaxAStages;
-  uint64_t* fullW = bars + 2 * kMaxAStages;
-  uint64_t* emptyW = fullW + kMaxWStages;
-  uint64_t* tfull = emptyW + kMaxWStages;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  // two slots (current / next layer): parameters 2 x 384 B at +256, bias vectors 2 x 1 KB at +1024
-  uint8_t* sp_base = smem + kRingBytes + 256;
-  float* sbias_base = reinterpret_cast<float*>(smem + kRingBytes + 1024);
-  static_assert(sizeof(ConvParams) <= 384, "ConvParams must fit the reserved smem slot");
+  uint64_t* emptyA = bars + 4;
+  uint64_t* fullW = bars + 8;
+  uint64_t* emptyW = bars + 16;
+  uint64_t* tfull = bars + 24;
+  uint64_t* tempty = bars + 26;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint8_t* sp_base = fixed + 256;
+  float* sbias_base = reinterpret_cast<float*>(fixed + 1024);
+  static_assert(sizeof(ConvParams) <= 320, "ConvParams + EntryDesc must fit the 384-byte smem slot");
+  static_assert(kNumASlots * kASlot + kWGranules * kWGranule + 3072 + 1024 <= conv_smem_bytes(1), "smem budget");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t kTmemCols = (kCtasPerSm == 1) ? 512 : 256;
+  const unsigned int grid = gridDim.x;
+  constexpr uint32_t kTmemCols = 512;
+  constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages (each: two halves x <= 128 columns)
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tensormap(&wmaps.m[i]);
-    for (int s = 0; s < kMaxAStages; ++s) {
-      mbar_init(&fullA[s], 1);
-      mbar_init(&emptyA[s], 1);
-    }
-    for (int s = 0; s < kMaxWStages; ++s) {
-      mbar_init(&fullW[s], 1);
-      mbar_init(&emptyW[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 8);
-    }
+    for (int s = 0; s < 4; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&fullW[s], 1); mbar_init(&emptyW[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_imm<kTmemCols>(tmem_slot);
@@ -268,237 +271,263 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, int num_layers, const
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  uint32_t ringA_bits = 0, ringW_bits = 0;  // per-slot phase parity (producer: empty barriers, MMA warp: full barriers)
-  int it = 0;              // work items done by this CTA so far (accumulator stage = it & 1), identical in all roles
-
-  for (int l = 0; l < num_layers; ++l) {
-    // ---- layer parameters + bias live in smem slot (l & 1); layer 0 is staged here, later layers were prefetched by the
-    //      epilogue warps while the previous layer ran (keeps two dependent global-load latencies off the critical path)
-    ConvParams* sp = reinterpret_cast<ConvParams*>(sp_base + (l & 1) * 384);
-    float* sbias = sbias_base + (l & 1) * 256;
-    if (l == 0) {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(&layers[0].p);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(sp);
-      for (int i = threadIdx.x; i < static_cast<int>(sizeof(ConvParams) / 4); i += kConvThreads) dst[i] = __ldg(src + i);
-      __syncthreads();
-      for (int i = threadIdx.x; i < sp->n_total; i += kConvThreads) sbias[i] = sp->epi.bias ? __ldg(sp->epi.bias + i) : 0.f;
-      __syncthreads();
-    }
-    const ConvParams& p = *sp;
-    // smem rings of this layer: SA activation slots, then SW weight slots
-    const int wslot = conv_wslot_bytes(p.n_cols);
-    const int SA = (p.n_cols >= 128) ? 2 : 3;
-    const int SW = ((kRingBytes - SA * kASlot) / wslot) > kMaxWStages ? kMaxWStages : ((kRingBytes - SA * kASlot) / wslot);
-    uint8_t* smemW = smem + SA * kASlot;
-    const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const int num_work = p.num_tiles * p.col_groups;
-    const CUtensorMap* tmA = &layers[l].tmA;
-    const CUtensorMap* tmW = &wmaps.m[p.wmap];
-
-    if (warp == 0) {
-      // ================================================= TMA producer ===============================================
-      // (whole warp walks the loop so the index math stays warp-uniform; one elected lane issues)
-      int sa = 0, sw = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int tile = w / p.col_groups;
-        const int colbase = (w - tile * p.col_groups) * p.n_cols;
+  if (warp == 0) {
+    // ================================================= TMA producer =================================================
+    // (whole warp walks the loops so the index math stays warp-uniform; one elected lane issues)
+    uint32_t eA_bits = 0, eW_bits = 0;  // phase parity per A slot / W granule (empty barriers)
+    int sa = 0, gw = 0;
+    for (int e = 0; e < num_entries; ++e) {
+      const EntryDesc* ed = entries + e;
+      const int tile_lo = __ldcg(&ed->tile_lo), tile_hi = __ldcg(&ed->tile_hi), dep = __ldcg(&ed->dep), rot = __ldcg(&ed->rot);
+      const LayerDesc* L = layers + __ldcg(&ed->layer);
+      const ConvParams* gp = &L->p;
+      const int tiles_x = __ldcg(&gp->tiles_x), tiles_y = __ldcg(&gp->tiles_y), num_chunks = __ldcg(&gp->num_chunks);
+      const int a_c0 = __ldcg(&gp->a_c0), a_wrap = __ldcg(&gp->a_wrap), w_row0 = __ldcg(&gp->w_row0);
+      const int n_cols = __ldcg(&gp->n_cols), n_total = __ldcg(&gp->n_total), col_groups = __ldcg(&gp->col_groups);
+      const CUtensorMap* tmA = &L->tmA;
+      const CUtensorMap* tmW = &wmaps.m[__ldcg(&gp->wmap)];
+      const int tiles_per_img = tiles_x * tiles_y;
+      const int num_work = (tile_hi - tile_lo) * col_groups;
+      const int g = (n_cols + 31) >> 5;  // W granules per stage (1 or 2)
+      const int wbytes = 3 * n_cols * 128;
+      const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
+      if (v < num_work && dep >= 0) {
+        if (lane == 0 && !(debug & 16)) {
+          wait_entry_done(counters, dep, grid);
+          asm volatile("fence.proxy.async.global;" ::: "memory");  // TMA (async proxy) reads after generic-proxy stores
+        }
+        __syncwarp();
+      }
+      for (int w = v; w < num_work; w += static_cast<int>(grid)) {
+        const int tile = tile_lo + w / col_groups;
+        const int colbase = (w % col_groups) * n_cols;
         const int n = tile / tiles_per_img;
         const int t2 = tile - n * tiles_per_img;
-        const int ty = t2 / p.tiles_x;
-        const int x0 = (t2 - ty * p.tiles_x) * kTileW;
+        const int ty = t2 / tiles_x;
+        const int x0 = (t2 - ty * tiles_x) * kTileW;
         const int y0 = ty * kTileH;
-        for (int c = 0; c < ((debug & 32) ? 0 : p.num_chunks); ++c) {
-          const int ac = p.a_c0 + (c % p.a_wrap) * 64;
-          mbar_wait(&emptyA[sa], ((ringA_bits >> sa) & 1u) ^ 1u);
+        for (int c = 0; c < num_chunks; ++c) {
+          const int ac = a_c0 + (c % a_wrap) * 64;
+          mbar_wait(&emptyA[sa], ((eA_bits >> sa) & 1u) ^ 1u);
           if (elect_one_sync()) {
-            if (debug & 4) mbar_arrive(&fullA[sa]);
-            else {
-              mbar_arrive_expect_tx(&fullA[sa], kABytes);
-              tma_load_4d(smem + sa * kASlot, tmA, &fullA[sa], ac, x0 - 1, y0 - 1, n);
-            }
+            mbar_arrive_expect_tx(&fullA[sa], kABytes);
+            tma_load_4d(smem + sa * kASlot, tmA, &fullA[sa], ac, x0 - 1, y0 - 1, n);
           }
           __syncwarp();
-          ringA_bits ^= (1u << sa);
-          if (++sa == SA) sa = 0;
+          eA_bits ^= (1u << sa);
+          if (++sa == kNumASlots) sa = 0;
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             const int dxi = (d == 0) ? 1 : (d == 1 ? 0 : 2);  // centre column first (see MMA loop)
-            mbar_wait(&emptyW[sw], ((ringW_bits >> sw) & 1u) ^ 1u);
+            if (gw + g > kWGranules) gw = 0;
+            for (int j = 0; j < g; ++j) mbar_wait(&emptyW[gw + j], ((eW_bits >> (gw + j)) & 1u) ^ 1u);
             if (elect_one_sync()) {
-              if (debug & 8) mbar_arrive(&fullW[sw]);
-              else {
-                mbar_arrive_expect_tx(&fullW[sw], wslot);
+              mbar_arrive_expect_tx(&fullW[gw], wbytes);
 #pragma unroll
-                for (int dyi = 0; dyi < 3; ++dyi)
-                  tma_load_2d(smemW + sw * wslot + dyi * p.n_cols * 128, tmW, &fullW[sw], 0,
-                              p.w_row0 + ((c * 3 + dxi) * 3 + dyi) * p.n_total + colbase);
-              }
+              for (int dyi = 0; dyi < 3; ++dyi)
+                tma_load_2d(smemW + gw * kWGranule + dyi * n_cols * 128, tmW, &fullW[gw], 0,
+                            w_row0 + ((c * 3 + dxi) * 3 + dyi) * n_total + colbase);
             }
             __syncwarp();
-            ringW_bits ^= (1u << sw);
-            if (++sw == SW) sw = 0;
+            for (int j = 0; j < g; ++j) eW_bits ^= (1u << (gw + j));
+            gw += g;
           }
         }
       }
-    } else if (warp == 1) {
-      // ================================================== MMA issuer ================================================
-      // Whole warp runs the loop (uniform address math), one elected lane issues.  Descriptor hi words are loop
-      // invariant; a K-step / vertical-tap advance is one 32-bit add on the lo word.
-      const uint32_t idesc = make_idesc_bf16(128, p.n_cols, 0, 0);
-      constexpr uint32_t kHi = smem_desc_hi(1024);            // weights: 8-row groups 1024 B apart
-      constexpr uint32_t kHiA = smem_desc_hi(kABoxW * 128);   // activations: 8 pixels of a patch row, rows 1280 B apart
-      const uint32_t b_dy = static_cast<uint32_t>(p.n_cols) * 8;  // (n_cols * 128 B) >> 4
-      int sa = 0, sw = 0;
-      int my_it = it;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++my_it) {
-        const int as = my_it & 1;
-        mbar_wait(&tempty[as], ((my_it >> 1) & 1) ^ 1);
+    }
+  } else if (warp == 1) {
+    // ================================================== MMA issuer ==================================================
+    // Whole warp runs the loops (uniform address math), one elected lane issues.  Descriptor hi words are loop
+    // invariant; a K-step / tap advance is one 32-bit add on the lo word.
+    constexpr uint32_t kHi = smem_desc_hi(1024);            // weights: 8-row groups 1024 B apart
+    constexpr uint32_t kHiA = smem_desc_hi(kABoxW * 128);   // activations: 8 pixels of a patch row, rows 1280 B apart
+    uint32_t fA_bits = 0, fW_bits = 0;  // phase parity per A slot / W granule (full barriers)
+    int sa = 0, gw = 0;
+    int it = 0;
+    for (int e = 0; e < num_entries; ++e) {
+      const EntryDesc* ed = entries + e;
+      const int tile_lo = __ldcg(&ed->tile_lo), tile_hi = __ldcg(&ed->tile_hi), rot = __ldcg(&ed->rot);
+      const ConvParams* gp = &(layers + __ldcg(&ed->layer))->p;
+      const int num_chunks = __ldcg(&gp->num_chunks), ksteps_last = __ldcg(&gp->ksteps_last);
+      const int n_cols = __ldcg(&gp->n_cols), col_groups = __ldcg(&gp->col_groups);
+      const int num_work = (tile_hi - tile_lo) * col_groups;
+      const int g = (n_cols + 31) >> 5;
+      const uint32_t idesc = make_idesc_bf16(128, n_cols, 0, 0);
+      const uint32_t b_dy = static_cast<uint32_t>(n_cols) * 8;  // (n_cols * 128 B) >> 4
+      const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
+      for (int w = v; w < num_work; w += static_cast<int>(grid), ++it) {
+        const int as = it & 1;
+        mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * kAccStride;
-        for (int c = 0; c < ((debug & 32) ? 0 : p.num_chunks); ++c) {
-          const int ksteps = (c == p.num_chunks - 1) ? p.ksteps_last : 4;
-          mbar_wait(&fullA[sa], (ringA_bits >> sa) & 1u);
+        for (int c = 0; c < num_chunks; ++c) {
+          const int ksteps = (c == num_chunks - 1) ? ksteps_last : 4;
+          mbar_wait(&fullA[sa], (fA_bits >> sa) & 1u);
           const uint32_t a_lo = smem_desc_lo(smem_u32(smem + sa * kASlot), 16);
           for (int d = 0; d < 3; ++d) {
             const int dxi = (d == 0) ? 1 : (d == 1 ? 0 : 2);
-            mbar_wait(&fullW[sw], (ringW_bits >> sw) & 1u);
+            if (gw + g > kWGranules) gw = 0;
+            mbar_wait(&fullW[gw], (fW_bits >> gw) & 1u);
             tcgen05_fence_after();
             if (elect_one_sync()) {
-              const uint32_t b_lo = smem_desc_lo(smem_u32(smemW + sw * wslot), 16);
+              const uint32_t b_lo = smem_desc_lo(smem_u32(smemW + gw * kWGranule), 16);
               const uint32_t first = (c | d) ? 1u : 0u;  // very first MMA of the item overwrites the accumulators
 #pragma unroll
-              for (int e = 0; e < 3; ++e) {
-                const int dyi = (e == 0) ? 1 : (e == 1 ? 0 : 2);  // centre row first
+              for (int t = 0; t < 3; ++t) {
+                const int dyi = (t == 0) ? 1 : (t == 1 ? 0 : 2);  // centre row first
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                   if (ks < ksteps && !(debug & 2)) {
                     // tap (dy,dx) = the haloed tile shifted by (dy*10+dx) rows of 128 B; the two 128-pixel halves
                     // (patch rows 0-15 / 16-31) reuse the same weight tile
                     const uint32_t a_tap = a_lo + (dyi * kABoxW + dxi) * 8 + ks * 2;
-                    umma_bf16_ss_lohi2(d_tmem, a_tap, kHiA, b_lo + dyi * b_dy + ks * 2, kHi, idesc, (e == 0 && ks == 0) ? first : 1u);
+                    umma_bf16_ss_lohi2(d_tmem, a_tap, kHiA, b_lo + dyi * b_dy + ks * 2, kHi, idesc, (t == 0 && ks == 0) ? first : 1u);
                     umma_bf16_ss_lohi2(d_tmem + 128, a_tap + 16 * kABoxW * 8, kHiA, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
-                                       (e == 0 && ks == 0) ? first : 1u);
+                                       (t == 0 && ks == 0) ? first : 1u);
                   }
                 }
               }
-              umma_commit(&emptyW[sw]);                 // frees the weight slot once these MMAs have drained
-              if (d == 2) umma_commit(&emptyA[sa]);     // ... and the activation tile after its last column
+              for (int j = 0; j < g; ++j) umma_commit(&emptyW[gw + j]);  // frees the weight granules once these MMAs drained
+              if (d == 2) umma_commit(&emptyA[sa]);                      // ... and the activation tile after its last column
             }
             __syncwarp();
-            ringW_bits ^= (1u << sw);
-            if (++sw == SW) sw = 0;
+            fW_bits ^= (1u << gw);
+            gw += g;
           }
-          ringA_bits ^= (1u << sa);
-          if (++sa == SA) sa = 0;
+          fA_bits ^= (1u << sa);
+          if (++sa == kNumASlots) sa = 0;
         }
         if (elect_one_sync()) umma_commit(&tfull[as]);  // accumulators ready for the epilogue warps
         __syncwarp();
       }
-    } else {
-      // =================================================== epilogue =================================================
-      const int q = warp & 3;  // TMEM lane quarter this warp may read
-      const int m = q * 32 + lane;
-      if (l + 1 < num_layers) {  // prefetch the next layer's parameters and bias into the other smem slot
-        const int t = threadIdx.x - 64;  // 0..255
-        const ConvParams* np = &layers[l + 1].p;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(sp_base + ((l + 1) & 1) * 384);
-        if (t < static_cast<int>(sizeof(ConvParams) / 4)) dst[t] = __ldg(reinterpret_cast<const uint32_t*>(np) + t);
-        const float* nb = np->epi.bias;
-        const int nt = np->n_total;
-        float* bdst = sbias_base + ((l + 1) & 1) * 256;
-        for (int i = t; i < nt; i += 256) bdst[i] = nb ? __ldg(nb + i) : 0.f;
+    }
+  } else {
+    // =================================================== epilogue ===================================================
+    // Eight warps; warps 2-5 own the upper 128-pixel half of every work item, warps 6-9 the lower half.  Layer
+    // parameters + bias are staged in two smem slots private to these warps (the next entry is prefetched while the
+    // current one runs); they synchronise among themselves with named barrier 1.
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    const int half = (warp >= 6) ? 1 : 0;
+    const int et = threadIdx.x - 64;  // 0..255
+    auto stage_entry = [&](int e) {
+      const EntryDesc* ed = entries + e;
+      const ConvParams* gp = &(layers + __ldcg(&ed->layer))->p;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(sp_base + (e & 1) * 384);
+      if (et < static_cast<int>(sizeof(ConvParams) / 4)) dst[et] = __ldcg(reinterpret_cast<const uint32_t*>(gp) + et);
+      if (et >= 80 && et < 88) dst[et] = __ldcg(reinterpret_cast<const uint32_t*>(ed) + (et - 80));  // EntryDesc at +320 B
+      const float* nb = reinterpret_cast<const float*>(__ldcg(reinterpret_cast<const unsigned long long*>(&gp->epi.bias)));
+      const int nt = __ldcg(&gp->n_total);
+      float* bdst = sbias_base + (e & 1) * 256;
+      for (int i = et; i < nt; i += 256) bdst[i] = nb ? __ldcg(nb + i) : 0.f;
+    };
+    stage_entry(0);
+    int it = 0;
+    for (int e = 0; e < num_entries; ++e) {
+      epi_bar_sync();  // slot (e & 1) is complete and visible; every epilogue thread has left entry e-1
+      if (e + 1 < num_entries) stage_entry(e + 1);
+      const ConvParams& p = *reinterpret_cast<const ConvParams*>(sp_base + (e & 1) * 384);
+      const EntryDesc& ent = *reinterpret_cast<const EntryDesc*>(sp_base + (e & 1) * 384 + 320);
+      const float* sbias = sbias_base + (e & 1) * 256;
+      const int tiles_per_img = p.tiles_x * p.tiles_y;
+      const int num_work = (ent.tile_hi - ent.tile_lo) * p.col_groups;
+      const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(ent.rot)) % grid);
+      if (v < num_work && ent.dep >= 0) {
+        // residuals / masks written by the entry we depend on are read before the accumulator is ready: check it too
+        if (et == 0 && !(debug & 16)) {
+          wait_entry_done(counters, ent.dep, grid);
+          __threadfence();
+        }
+        epi_bar_sync();
       }
-      int my_it = it;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++my_it) {
-        const int tile = w / p.col_groups;
-        const int colbase = (w - tile * p.col_groups) * p.n_cols;
+      for (int w = v; w < num_work; w += static_cast<int>(grid), ++it) {
+        const int tile = ent.tile_lo + w / p.col_groups;
+        const int colbase = (w % p.col_groups) * p.n_cols;
         const int n = tile / tiles_per_img;
         const int t2 = tile - n * tiles_per_img;
         const int ty = t2 / p.tiles_x;
         const int x = (t2 - ty * p.tiles_x) * kTileW + (m & 7);
-        const int as = my_it & 1;
-        {
-        const int half = (warp >= 6) ? 1 : 0;  // each half of the work item has its own four epilogue warps
         const int y = ty * kTileH + half * 16 + (m >> 3);
         const bool valid = (x < p.W) && (y < p.H);
+        const int as = it & 1;
         // Operands that do not depend on the accumulator are fetched BEFORE waiting for the MMAs, so their L2 latency
         // hides behind the tensor work: combined fp32 residual (<= 64 columns) and the LeakyReLU-derivative mask words.
-        const ConvEpilogue& e = p.epi;
-        const bool pre = valid && p.n_cols <= 64 && !(debug & 1);
+        const ConvEpilogue& ep = p.epi;
+        const bool pre = valid && !(debug & 1);
         const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
         float res[64];
         uint32_t maskw[32];
-        const bool has_res = (e.r1 != nullptr);
-        const bool has_mask = (e.mask != nullptr);
+        const bool has_res = (ep.r1 != nullptr);
+        const bool has_mask = (ep.mask != nullptr);
         if (pre && has_res) {
-          const float4* r1p = reinterpret_cast<const float4*>(e.r1 + pix * e.res_stride + colbase);
+          const float4* r1p = reinterpret_cast<const float4*>(ep.r1 + pix * ep.res_stride + colbase);
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            if (4 * q < p.n_cols) {
-              const float4 r = __ldg(r1p + q);
-              res[4 * q] = e.beta1 * r.x; res[4 * q + 1] = e.beta1 * r.y; res[4 * q + 2] = e.beta1 * r.z; res[4 * q + 3] = e.beta1 * r.w;
+          for (int k = 0; k < 16; ++k) {
+            if (4 * k < p.n_cols) {
+              const float4 r = __ldcg(r1p + k);
+              res[4 * k] = ep.beta1 * r.x; res[4 * k + 1] = ep.beta1 * r.y; res[4 * k + 2] = ep.beta1 * r.z; res[4 * k + 3] = ep.beta1 * r.w;
             }
           }
-          if (e.r2) {
-            const float4* r2p = reinterpret_cast<const float4*>(e.r2 + pix * e.res_stride + colbase);
+          if (ep.r2) {
+            const float4* r2p = reinterpret_cast<const float4*>(ep.r2 + pix * ep.res_stride + colbase);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              if (4 * q < p.n_cols) {
-                const float4 r = __ldg(r2p + q);
-                res[4 * q] += e.beta2 * r.x; res[4 * q + 1] += e.beta2 * r.y; res[4 * q + 2] += e.beta2 * r.z; res[4 * q + 3] += e.beta2 * r.w;
+            for (int k = 0; k < 16; ++k) {
+              if (4 * k < p.n_cols) {
+                const float4 r = __ldcg(r2p + k);
+                res[4 * k] += ep.beta2 * r.x; res[4 * k + 1] += ep.beta2 * r.y; res[4 * k + 2] += ep.beta2 * r.z; res[4 * k + 3] += ep.beta2 * r.w;
               }
             }
           }
         }
         if (pre && has_mask) {
-          const uint4* mp = reinterpret_cast<const uint4*>(e.mask + pix * e.mask_stride + e.mask_coff + colbase);
+          const uint4* mp = reinterpret_cast<const uint4*>(ep.mask + pix * ep.mask_stride + ep.mask_coff + colbase);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (8 * q < p.n_cols) {
-              const uint4 m4 = __ldg(mp + q);
-              maskw[4 * q] = m4.x; maskw[4 * q + 1] = m4.y; maskw[4 * q + 2] = m4.z; maskw[4 * q + 3] = m4.w;
+          for (int k = 0; k < 8; ++k) {
+            if (8 * k < p.n_cols) {
+              const uint4 m4 = __ldcg(mp + k);
+              maskw[4 * k] = m4.x; maskw[4 * k + 1] = m4.y; maskw[4 * k + 2] = m4.z; maskw[4 * k + 3] = m4.w;
             }
           }
         }
-        mbar_wait(&tfull[as], (my_it >> 1) & 1);
+        mbar_wait(&tfull[as], (it >> 1) & 1);
         tcgen05_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * 128;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int c0 = g * 32;
+        for (int gq = 0; gq < 2; ++gq) {
+          const int c0 = gq * 32;
           if (c0 < p.n_cols) {
-            float v[32];
+            float vv[32];
             const int ncol = (p.n_cols - c0) >= 32 ? 32 : 16;
             if (ncol == 32) {
               uint32_t r[32];
               tmem_ld_32x32b_x32(t_addr + c0, r);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 32; ++i) vv[i] = __uint_as_float(r[i]);
             } else {
               uint32_t r[16];
               tmem_ld_32x32b_x16(t_addr + c0, r);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 16; ++i) vv[i] = __uint_as_float(r[i]);
 #pragma unroll
-              for (int i = 16; i < 32; ++i) v[i] = 0.f;
+              for (int i = 16; i < 32; ++i) vv[i] = 0.f;
             }
-            if (valid && !(debug & 1))
-              conv_epilogue_store(p, y_dyn, sbias, (has_res && g < 2) ? &res[(g & 1) * 32] : nullptr,
-                                  (has_mask && g < 2) ? &maskw[(g & 1) * 16] : nullptr, n, y, x, colbase + c0, ncol, v);
+            if (pre)
+              conv_epilogue_store(p, y_dyn, sbias, has_res ? &res[gq * 32] : nullptr, has_mask ? &maskw[gq * 16] : nullptr, n, y, x,
+                                  colbase + c0, ncol, vv);
           }
         }
-        }  // half
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[as]);
       }
-    }
-    // every role advanced by the same number of work items
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) ++it;
-    if (l + 1 < num_layers) {
-      if (debug & 16) __syncthreads(); else grid_barrier(barrier_ctr, static_cast<unsigned int>(l + 1) * gridDim.x);
+      // announce: this CTA's part of entry e is stored (cumulativity: bar.sync + gpu-scope fence by the signalling thread)
+      epi_bar_sync();
+      if (et == 0) {
+        __threadfence();
+        atomicAdd(counters + e, 1u);
+      }
     }
   }
 

@@ -18,9 +18,9 @@ def t_fwd():
         for _ in range(5): net(lr)
         e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / 5
-names = {0: "normal", 1: "no epilogue traffic", 2: "no MMA", 3: "no MMA, no epilogue", 4: "no A loads", 8: "no W loads", 12: "no loads", 13: "no loads, no epi", 15: "nothing (pipeline skeleton)", 14: "no loads no mma"}
-names.update({31: 'skeleton, no grid barrier', 47: 'skeleton, no stage ring', 63: 'skeleton, no ring, no barrier', 16: 'normal minus grid barrier (wrong results)'})
-for f in [0, 1, 15, 31, 47, 63, 16]:
+names = {0: "normal", 1: "no epilogue traffic", 2: "no MMA", 3: "no MMA, no epilogue traffic", 16: "no dependency waits (wrong results)",
+         19: "no MMA, no epilogue traffic, no dependency waits"}
+for f in [0, 1, 2, 3, 16, 19]:
     L.b200sr_debug_set(f)
-    print(f"flags {f:2d} {names[f]:32s} fwd {t_fwd():7.3f} ms", flush=True)
+    print(f"flags {f:2d} {names[f]:50s} fwd {t_fwd():7.3f} ms", flush=True)
 L.b200sr_debug_set(0)
