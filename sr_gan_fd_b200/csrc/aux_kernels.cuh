@@ -247,11 +247,31 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const UnpackOp* __res
   }
 }
 
-// out_bf16[i] = bf16(a[i] + b[i])   (gradient of conv1's output = trunk path + long skip)
-__global__ void add_to_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
-                                   long long n) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __float2bfloat16_rn(a[i] + b[i]);
+// out_bf16[pixel][64] = bf16(a + b) where a, b are fp32 carriers in the tile-blocked layout of the conv epilogues
+// ([tile][half][16-byte chunk][pixel-in-half][4]); tiles are 8 x 32 pixels, halves 8 x 16.
+__global__ void add_carriers_to_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
+                                            int N, int H, int W, int tiles_x, int tiles_y) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // ((tile*2+half)*16 + chunk)*128 + m
+  const long long total = static_cast<long long>(N) * tiles_x * tiles_y * 2 * 16 * 128;
+  if (idx >= total) return;
+  const int m = static_cast<int>(idx & 127);
+  const int chunk = static_cast<int>((idx >> 7) & 15);
+  const int half = static_cast<int>((idx >> 11) & 1);
+  const long long tile = idx >> 12;
+  const int tpi = tiles_x * tiles_y;
+  const int n = static_cast<int>(tile / tpi);
+  const int t2 = static_cast<int>(tile - static_cast<long long>(n) * tpi);
+  const int ty = t2 / tiles_x;
+  const int x = (t2 - ty * tiles_x) * 8 + (m & 7);
+  const int y = ty * 32 + half * 16 + (m >> 3);
+  if (x >= W || y >= H) return;
+  const float4 va = *reinterpret_cast<const float4*>(a + idx * 4);
+  const float4 vb = *reinterpret_cast<const float4*>(b + idx * 4);
+  __nv_bfloat16* o = out + ((static_cast<long long>(n) * H + y) * W + x) * 64 + chunk * 4;
+  uint2 pk;
+  pk.x = pack_bf16x2(va.x + vb.x, va.y + vb.y);
+  pk.y = pack_bf16x2(va.z + vb.z, va.w + vb.w);
+  *reinterpret_cast<uint2*>(o) = pk;
 }
 
 }  // namespace b200sr

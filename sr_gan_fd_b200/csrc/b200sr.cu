@@ -292,10 +292,12 @@ static int build_plan(b200sr_plan& P) {
   P.xin_stride = (int)align_up(3 * d.in_channels, 64);
   // ---- workspace layout
   P.o_xin = B.alloc(Ppix * P.xin_stride * 2);
-  P.o_t0 = B.alloc(Ppix * 64 * 4);
-  P.o_tr = B.alloc(Ppix * 64 * 4);
-  P.o_c1 = B.alloc(Ppix * 64 * 4);
-  P.o_c2 = B.alloc(Ppix * 64 * 4);
+  // fp32 carriers: tile-blocked layout over the LR lattice's 8 x 32 tiles (padded to whole tiles)
+  const long long carrier_bytes = (long long)N * ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH) * kCarrierBytesPerTile;
+  P.o_t0 = B.alloc(carrier_bytes);
+  P.o_tr = B.alloc(carrier_bytes);
+  P.o_c1 = B.alloc(carrier_bytes);
+  P.o_c2 = B.alloc(carrier_bytes);
   const int ndense = train ? R : 2;
   for (int i = 0; i < ndense; ++i) P.o_dense.push_back(B.alloc(Ppix * 192 * 2));
   P.o_splt = B.alloc(Ppix * 128 * 2);
@@ -329,11 +331,11 @@ static int build_plan(b200sr_plan& P) {
       P.o_gw = B.alloc(off * 4);
       P.gw_bytes = off * 4;
     }
-    P.o_gt = B.alloc(Ppix * 64 * 4);
+    P.o_gt = B.alloc(carrier_bytes);
     P.o_gtb = B.alloc(Ppix * 64 * 2);
-    P.o_gr = B.alloc(Ppix * 64 * 4);
-    P.o_gc1 = B.alloc(Ppix * 64 * 4);
-    P.o_gc2 = B.alloc(Ppix * 64 * 4);
+    P.o_gr = B.alloc(carrier_bytes);
+    P.o_gc1 = B.alloc(carrier_bytes);
+    P.o_gc2 = B.alloc(carrier_bytes);
     P.o_go1 = B.alloc(Ppix * 64 * 2);
     for (int i = 0; i < 6; ++i) P.o_dyb[i] = B.alloc(Ppix * 192 * 2);
   }
@@ -903,8 +905,10 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         break;
       }
       case ST_ADD: {
-        add_to_bf16_kernel<<<(int)((s.count + 255) / 256), 256, 0, st>>>((const float*)resolve(s.a, b), (const float*)resolve(s.b, b),
-                                                                        (__nv_bfloat16*)resolve(s.c, b), s.count);
+        const int tx = (d.width + kTileW - 1) / kTileW, ty = (d.height + kTileH - 1) / kTileH;
+        const long long total = (long long)d.batch * tx * ty * 2 * 16 * 128;
+        add_carriers_to_bf16_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>((const float*)resolve(s.a, b), (const float*)resolve(s.b, b),
+                                                                               (__nv_bfloat16*)resolve(s.c, b), d.batch, d.height, d.width, tx, ty);
         CUDA_TRY(cudaGetLastError());
         break;
       }

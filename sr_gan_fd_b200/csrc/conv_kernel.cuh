@@ -48,7 +48,9 @@ struct ConvEpilogue {
   const __nv_bfloat16* mask;  // dgrad: v *= (m > 0 ? 1 : 0.2), m = saved forward activation at the same pixel
   int mask_stride;            // channels per pixel of the mask buffer
   int mask_coff;
-  const float* r1;  // fp32 residuals, [pixel][res_stride], column indexed from 0
+  // fp32 residual carriers use a TILE-BLOCKED layout private to the epilogues: [tile][half][16-byte chunk][pixel-in-half]
+  // [4 floats], so the 32 lanes (= 32 pixels) of a warp access 512 contiguous bytes per instruction (4 wavefronts, not 32)
+  const float* r1;
   const float* r2;
   float beta1, beta2;
   int res_stride;
@@ -85,6 +87,13 @@ __host__ __device__ inline int conv_wslot_bytes(int n_cols) { return 3 * n_cols 
 __host__ __device__ constexpr int conv_smem_bytes(int ctas_per_sm) { return ctas_per_sm == 1 ? 227 * 1024 : 112 * 1024; }
 __host__ inline int conv_pick_stages(int n_cols) { return n_cols >= 128 ? 2 : 3; }  // A-ring depth (informational)
 
+// tile-blocked carrier layout: float offset of (tile, half, pixel m, chunk 0); consecutive 16-byte chunks are 512 floats apart
+constexpr int kCarrierChunkStride = 128 * 4;
+__host__ __device__ inline long long carrier_base(int tile, int half, int m) {
+  return ((static_cast<long long>(tile) * 2 + half) * 16 * 128 + m) * 4;
+}
+constexpr long long kCarrierBytesPerTile = 2LL * 16 * 128 * 16;  // 65536
+
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -94,8 +103,8 @@ __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * 
 //   maskw : 16 words = 32 bf16 saved activations for the LeakyReLU-derivative mask, prefetched (or nullptr)
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, float* y_dyn, const float* sbias, const float* res,
-                                                    const uint32_t* maskw, int n, int y, int x, int col0, int ncol,
-                                                    float (&v)[32]) {
+                                                    const uint32_t* maskw, long long cbase, int n, int y, int x, int col0,
+                                                    int ncol, float (&v)[32]) {
   const ConvEpilogue& e = p.epi;
   const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
   // 1. bias + scale (+ activation)
@@ -144,14 +153,16 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, float* 
   }
   // 4. fp32 outputs (same lattice position)
   if (e.out_f32) {
-    float4* op = reinterpret_cast<float4*>(e.out_f32 + pix * e.of_stride + col0);
+    float* op = e.out_f32 + cbase + (col0 >> 2) * kCarrierChunkStride;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(op + q * kCarrierChunkStride) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
   if (e.out_f32_b) {
-    float4* op = reinterpret_cast<float4*>(e.out_f32_b + pix * e.of_stride + col0);
+    float* op = e.out_f32_b + cbase + (col0 >> 2) * kCarrierChunkStride;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(op + q * kCarrierChunkStride) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
   // 5. bf16 output (optionally hi/lo split), with the pixel (un)shuffle folded into the address
   if (e.out_bf16) {
@@ -455,25 +466,26 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const ConvEpilogue& ep = p.epi;
         const bool pre = valid && !(debug & 1);
         const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
+        const long long cbase = carrier_base(tile, half, m);
         float res[64];
         uint32_t maskw[32];
         const bool has_res = (ep.r1 != nullptr);
         const bool has_mask = (ep.mask != nullptr);
         if (pre && has_res) {
-          const float4* r1p = reinterpret_cast<const float4*>(ep.r1 + pix * ep.res_stride + colbase);
+          const float* r1p = ep.r1 + cbase + (colbase >> 2) * kCarrierChunkStride;
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             if (4 * k < p.n_cols) {
-              const float4 r = __ldcg(r1p + k);
+              const float4 r = __ldcg(reinterpret_cast<const float4*>(r1p + k * kCarrierChunkStride));
               res[4 * k] = ep.beta1 * r.x; res[4 * k + 1] = ep.beta1 * r.y; res[4 * k + 2] = ep.beta1 * r.z; res[4 * k + 3] = ep.beta1 * r.w;
             }
           }
           if (ep.r2) {
-            const float4* r2p = reinterpret_cast<const float4*>(ep.r2 + pix * ep.res_stride + colbase);
+            const float* r2p = ep.r2 + cbase + (colbase >> 2) * kCarrierChunkStride;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               if (4 * k < p.n_cols) {
-                const float4 r = __ldcg(r2p + k);
+                const float4 r = __ldcg(reinterpret_cast<const float4*>(r2p + k * kCarrierChunkStride));
                 res[4 * k] += ep.beta2 * r.x; res[4 * k + 1] += ep.beta2 * r.y; res[4 * k + 2] += ep.beta2 * r.z; res[4 * k + 3] += ep.beta2 * r.w;
               }
             }
@@ -514,8 +526,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
               for (int i = 16; i < 32; ++i) vv[i] = 0.f;
             }
             if (pre)
-              conv_epilogue_store(p, y_dyn, sbias, has_res ? &res[gq * 32] : nullptr, has_mask ? &maskw[gq * 16] : nullptr, n, y, x,
-                                  colbase + c0, ncol, vv);
+              conv_epilogue_store(p, y_dyn, sbias, has_res ? &res[gq * 32] : nullptr, has_mask ? &maskw[gq * 16] : nullptr, cbase, n, y,
+                                  x, colbase + c0, ncol, vv);
           }
         }
         tcgen05_fence_before();
