@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kBiasGradThreads) bias_grad_kernel(const BiasG
 }
 
 // ------------------------------------------------------------ unpack staged weight gradients to the OIHW flat buffer
-// src: [tap][ci][co_pad] fp32 staging tensor written by wgrad3x3_kernel;  dst: [co][ci][3][3] (state_dict layout).
+// src: [tap][co_pad/4][ci][4] fp32 staging tensor written by wgrad3x3_kernel;  dst: [co][ci][3][3] (state_dict layout).
 // fold = 1: src holds the four low-res phase kernels of an upsample conv ([tap][ci][4*64]) and they are folded back
 // onto the 3x3 taps of the original weight (see up_phase_taps).
 struct UnpackOp { long long src_off; long long dst_off; int co, ci, co_pad, fold; int block0; int nblocks; };
@@ -211,11 +211,11 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const UnpackOp* __res
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int tap = 0; tap < 9; ++tap) {
     for (int r = ty; r < 32; r += 8) {
-      const int ci = ci0 + r, co = co0 + tx;
+      const int ci = ci0 + tx, co = co0 + r;  // consecutive threads -> consecutive ci (16-byte stride in the staging layout)
       float v = 0.f;
       if (ci < op.ci && co < op.co) {
         if (!op.fold) {
-          v = src[(static_cast<long long>(tap) * op.ci + ci) * op.co_pad + co];
+          v = src[((static_cast<long long>(tap) * (op.co_pad >> 2) + (co >> 2)) * op.ci + ci) * 4 + (co & 3)];
         } else {
           const int dy = tap / 3, dx = tap % 3;
           for (int ph = 0; ph < 4; ++ph) {
@@ -227,11 +227,12 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const UnpackOp* __res
               up_phase_taps(ph & 1, t, l, h);
               if (dx >= l && dx < h) rx = t;
             }
-            v += src[(static_cast<long long>(ry * 3 + rx) * op.ci + ci) * op.co_pad + ph * 64 + co];
+            const int cc = ph * 64 + co;
+            v += src[((static_cast<long long>(ry * 3 + rx) * (op.co_pad >> 2) + (cc >> 2)) * op.ci + ci) * 4 + (cc & 3)];
           }
         }
       }
-      tile[tap][r][tx] = v;  // [ci][co]
+      tile[tap][tx][r] = v;  // [ci][co]
     }
   }
   __syncthreads();

@@ -583,7 +583,7 @@ static int build_plan(b200sr_plan& P) {
       for (int half = 0; half < 2; ++half) {
         Step wu = wgrad_step(P.o_spl[l - 1], 64, 128, P.o_gu[l], 256, 256, N, h, w, 0, 128 * half, 128);
         Ref out = wref(ci);
-        out.off += (long long)half * 128 * 4;  // columns [128*half, +128) of the [tap][64][256] staging tensor
+        out.off += (long long)half * 32 * 64 * 4 * 4;  // 16-byte column chunks [32*half, +32) of the [tap][64 chunks][64 ci][4] staging tensor
         add_seg(wu, 0, 128, out, 64, 0, 256);
         emit(wu);
       }

@@ -9,8 +9,8 @@
 // TMA boxes), N = up to 160 output-gradient channels -- for a dense block that is the concatenation
 // [dY5|dY4|dY3|dY2|dY1] of all consumers of the input slice, so the X tile is read once for all five convs
 // ("re-associated by input slice").  The accumulators (3 x N <= 480 TMEM columns) live in TMEM for the whole
-// pixel loop and are flushed once with 16-byte vector reductions (red.global.add.v4.f32) into a [tap][ci][co] fp32
-// staging tensor; a small unpack kernel transposes that to the OIHW gradient layout per gradient bucket.
+// pixel loop and are flushed once with 16-byte vector reductions (red.global.add.v4.f32) into a [tap][co/4][ci][4]
+// fp32 staging tensor; a small unpack kernel transposes that to the OIHW gradient layout per gradient bucket.
 //
 // One launch carries a BATCH of up to four such problems over the same two tensor maps (the three channel-block
 // problems of a dense block + its bias gradients), with the CTAs dealt out in proportion to each problem's cost so
@@ -32,7 +32,8 @@ constexpr int kWgOnesBytes = 4096;  // two 64-channel M blocks x 16 pixels x 128
 
 struct WgradSegment {
   int col_begin, col_end;  // accumulator columns of this conv's output channels (multiples of 16)
-  float* out;              // gradient staging tensor, [tap][ci_total][co_pad] fp32 (co fastest -> 16 B vector reductions)
+  float* out;              // gradient staging tensor, [tap][co_pad/4][ci_total][4] fp32: the 32 lanes (= input channels) of a
+                           // warp reduce into 512 contiguous bytes per instruction (4 L1 wavefronts instead of 32)
   int ci_total;            // input channels of that conv
   int ci0;                 // conv input channel of accumulator row 0
   int co_pad;              // output channels rounded up to a multiple of 4
@@ -188,12 +189,12 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int co = c0 - sg.col_begin;
         const int ci = sg.ci0 + m;
         if (c0 >= sg.col_begin && c0 < sg.col_end && ci < sg.ci_total) {
-          float* dst = sg.out + (static_cast<long long>(tap) * sg.ci_total + ci) * sg.co_pad + co;
+          float* dst = sg.out + ((static_cast<long long>(tap) * (sg.co_pad >> 2) + (co >> 2)) * sg.ci_total + ci) * 4;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (co + 4 * j < sg.co_pad)
-              red_add_v4_f32(dst + 4 * j, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                             __uint_as_float(r[4 * j + 3]));
+              red_add_v4_f32(dst + static_cast<long long>(j) * sg.ci_total * 4, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         }
       }
     }
