@@ -221,8 +221,8 @@ struct alignas(32) EntryDesc {
 };
 
 constexpr int kWGranule = 12288;   // weight ring granule = one (chunk, dx) stage of a 32-column layer (3 taps x 32 x 128 B)
-constexpr int kWGranules = 7;
-constexpr int kNumASlots = 3;
+constexpr int kWGranules = 10;
+constexpr int kNumASlots = 2;
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
@@ -247,21 +247,21 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
                      const __grid_constant__ WeightMaps wmaps, unsigned int* counters, float* y_dyn, int debug) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // [ A ring: 3 x 44032 | W ring: 7 x 12288 | barriers 256 B | epilogue params 2 x 384 B | epilogue bias 2 x 1 KB ]
+  // [ A ring: kNumASlots x 44032 | W ring: kWGranules x 12288 | barriers 256 B | epilogue params 2 x 384 B | epilogue bias 2 x 1 KB ]
   uint8_t* smemW = smem + kNumASlots * kASlot;
   uint8_t* fixed = smemW + kWGranules * kWGranule;
   uint64_t* bars = reinterpret_cast<uint64_t*>(fixed);
-  uint64_t* fullA = bars;
-  uint64_t* emptyA = bars + 4;
-  uint64_t* fullW = bars + 8;
-  uint64_t* emptyW = bars + 16;
-  uint64_t* tfull = bars + 24;
-  uint64_t* tempty = bars + 26;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* fullA = bars;        // [4]
+  uint64_t* emptyA = bars + 4;   // [4]
+  uint64_t* fullW = bars + 8;    // [10]
+  uint64_t* emptyW = bars + 18;  // [10]
+  uint64_t* tfull = bars + 28;
+  uint64_t* tempty = bars + 30;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 3072);
   uint8_t* sp_base = fixed + 256;
   float* sbias_base = reinterpret_cast<float*>(fixed + 1024);
   static_assert(sizeof(ConvParams) <= 320, "ConvParams + EntryDesc must fit the 384-byte smem slot");
-  static_assert(kNumASlots * kASlot + kWGranules * kWGranule + 3072 + 1024 <= conv_smem_bytes(1), "smem budget");
+  static_assert(kNumASlots * kASlot + kWGranules * kWGranule + 3072 + 64 + 1024 <= conv_smem_bytes(1), "smem budget");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -272,7 +272,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tensormap(&wmaps.m[i]);
     for (int s = 0; s < 4; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
-    for (int s = 0; s < 8; ++s) { mbar_init(&fullW[s], 1); mbar_init(&emptyW[s], 1); }
+    for (int s = 0; s < kWGranules; ++s) { mbar_init(&fullW[s], 1); mbar_init(&emptyW[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
     fence_barrier_init();
   }
