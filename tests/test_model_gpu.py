@@ -213,3 +213,41 @@ def test_full_size_config2_properties():
     (F.l1_loss(net(lr), gt) * 1024.0).backward()
     g2 = torch.cat([p.grad.flatten() for p in net.parameters()])
     assert orc.rel_l2(g2 / 1024.0, g1) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# edge cases the reference scripts exercise: batch 1, odd sizes, images smaller than a tile
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1, 3, 120, 123), (1, 3, 5, 7), (3, 3, 33, 9), (1, 3, 64, 64), (5, 3, 16, 40)])
+def test_forward_edge_shapes(shape):
+    net, params = _build("rrdbnet_x4", in_range=True, num_blocks=2)
+    sr, ref, err = _fwd_check(net, params, torch.rand(*shape))
+    assert err <= TOL_SR, f"{shape}: SR rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 40, 24), (3, 3, 17, 31)])
+def test_gradients_edge_shapes(shape):
+    """batch 1 (single image group in the chain) and an odd batch (uneven image groups)."""
+    err, worst = _grad_check("rrdbnet_x4", dict(num_blocks=2), shape, True)
+    assert err <= TOL_GRAD, (err, worst)
+
+
+def test_bias_gradients_match():
+    """the bias gradients ride the wgrad kernel (all-ones A operand): check them tensor by tensor."""
+    net, params = _build("rrdbnet_x4", in_range=True, num_blocks=1)
+    net.train()
+    lr, gt = torch.rand(2, 3, 24, 16), torch.rand(2, 3, 96, 64)
+    F.l1_loss(net(lr.to(DEV)), gt.to(DEV)).backward()
+    _, _, ref = orc.rrdbnet_l1_step(params, lr, gt)
+    for n, p in net.named_parameters():
+        if n.endswith(".bias"):
+            assert orc.rel_l2(p.grad, ref[n]) <= 3e-2, (n, orc.rel_l2(p.grad, ref[n]))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_two_gpus():
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", os.path.join(root, "tools", "dp_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
