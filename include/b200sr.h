@@ -104,6 +104,19 @@ size_t b200sr_conv3x3_wgrad_scratch_bytes(int cin, int cout);
 int b200sr_conv3x3_wgrad(const void* x, int n, int h, int w_, int cin, int x_stride, const void* dy, int cout,
                          int dy_stride, float* dw, void* scratch, b200sr_stream stream);
 
+/* ---- next to the path: fused GradScaler-unscale + Adam + EMA over a list of fp32 tensors --------------
+ * Replaces optimizer.step() + AveragedModel.update_parameters() of ESRGAN/train_rrdbnet.py:263-267 (torch.optim.Adam
+ * semantics with L2 weight decay; EMA rule ema <- (1-d)*ema + d*p of train_rrdbnet.py:182, first update copies).
+ * tensor_table: DEVICE array of n_tensors records {float* p; const float* g; float* m; float* v; float* ema (or NULL);
+ * int64 numel; int64 block0} where block0 = running sum of ceil(numel/1024); total_blocks = that sum over all tensors;
+ * block_tensor: DEVICE int32[total_blocks], block -> tensor index.  step: DEVICE float scalar, Adam steps taken so far
+ * (advanced by the call unless skipped).  grad_scale / found_inf: device scalars or NULL (GradScaler protocol: gradients
+ * are divided by *grad_scale; when *found_inf > 0 the Adam update is skipped -- the EMA still updates, as the reference
+ * calls update_parameters unconditionally). */
+int b200sr_fused_adam_ema(const void* tensor_table, const int32_t* block_tensor, int n_tensors, int64_t total_blocks, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, float* step, float ema_decay, int ema_copy,
+                          const float* grad_scale, const float* found_inf, b200sr_stream stream);
+
 const char* b200sr_last_error(void);
 int b200sr_version(void);
 /* timing probes for profiling only (results become wrong): bit0 no epilogue traffic, bit1 no MMAs, bit2 no activation

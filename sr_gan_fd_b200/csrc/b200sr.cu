@@ -9,6 +9,7 @@
 //             per dense block slice (pixel axis = reduction) with fp32 reductions into the flat gradient buffer.
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -17,6 +18,7 @@
 #include "../../include/b200sr.h"
 #include "aux_kernels.cuh"
 #include "conv_kernel.cuh"
+#include "optim_kernels.cuh"
 #include "wgrad_kernel.cuh"
 
 using namespace b200sr;
@@ -1184,6 +1186,22 @@ int b200sr_conv3x3_wgrad(const void* x, int n, int h, int w_, int cin, int x_str
   UnpackOp* d_u = (UnpackOp*)((char*)scratch + stage_bytes);
   CUDA_TRY(cudaMemcpyAsync(d_u, &u, sizeof(u), cudaMemcpyHostToDevice, st));
   unpack_wgrad_kernel<<<u.nblocks, 256, 0, st>>>(d_u, 0, 1, staging, dw);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ fused optimizer
+int b200sr_fused_adam_ema(const void* tensor_table, const int32_t* block_tensor, int n_tensors, int64_t total_blocks, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, float* step, float ema_decay, int ema_copy, const float* grad_scale,
+                          const float* found_inf, b200sr_stream stream) {
+  if (!tensor_table || !block_tensor || !step || n_tensors < 1 || total_blocks < 1) return fail(B200SR_ERR_INVALID, "bad argument");
+  AdamEmaHyper h;
+  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
+  h.ema_decay = ema_decay; h.ema_copy = ema_copy; h.grad_scale = grad_scale; h.found_inf = found_inf;
+  h.step = step; h.block_tensor = block_tensor;
+  fused_adam_ema_kernel<<<(unsigned)total_blocks, kOptBlock, 0, (cudaStream_t)stream>>>((const OptTensor*)tensor_table, n_tensors, h);
+  CUDA_TRY(cudaGetLastError());
+  adam_step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step, found_inf);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -45,6 +45,8 @@ SIGNATURES = {
     "b200sr_conv3x3_wgrad_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "b200sr_conv3x3_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200sr_fused_adam_ema": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_float, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200sr_last_error": (C.c_char_p, []),
     "b200sr_version": (C.c_int, []),
     "b200sr_debug_set": (None, [C.c_int]),
