@@ -122,6 +122,9 @@ int b200sr_version(void);
 /* timing probes for profiling only (results become wrong): bit0 no epilogue traffic, bit1 no MMAs, bit2 no activation
  * loads, bit3 no weight loads in the conv kernel.  0 = normal operation (default). */
 void b200sr_debug_set(int flags);
+/* bit 6 (64) of the debug flags makes the chain kernel record, per CTA, the cycles each warp role waited on each barrier
+ * kind (12 counters per CTA, see conv_kernel.cuh); this copies the first n counters of the last launch to the host. */
+int b200sr_debug_read_profile(unsigned long long* out_host, int n);
 
 #ifdef __cplusplus
 }

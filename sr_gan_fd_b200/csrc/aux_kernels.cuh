@@ -24,8 +24,9 @@ struct PackSeg {
 
 struct PackOp {
   int row0;        // first packed row
-  int n_total;     // rows per (chunk, dx, dy) block
-  int n_valid;     // rows >= n_valid are zero
+  int n_total;     // output columns of the conv (= n_cols * column groups)
+  int n_cols;      // columns per column group (rows per tap tile)
+  int n_valid;     // output columns >= n_valid are zero
   int num_chunks;  // 64-channel K chunks
   int mode;
   int nseg;
@@ -69,7 +70,10 @@ __device__ __forceinline__ float pack_fetch(const PackOp& op, const float* const
   return 0.f;
 }
 
-// One thread per packed element.  Row layout inside an op: [chunk][dx][dy][n], 64 K-channels per row.
+// One thread per packed element.  Row layout inside an op: [chunk][column group][dx][dy][n in group], 64 K-channels
+// (128 B) per row.  The rows are stored PRE-SWIZZLED: 16-byte chunk j of a row lands at position j ^ (n & 7), i.e. the
+// image is byte-for-byte what a 128B-swizzled TMA load would have produced in shared memory, so the kernels fetch a
+// whole chunk's nine tap tiles with ONE linear bulk copy (cp.async.bulk) instead of nine tensor-map boxes.
 __global__ void pack_weights_kernel(const PackOp* __restrict__ ops, int num_ops, const float* const* __restrict__ params,
                                     __nv_bfloat16* __restrict__ packed, long long total_rows) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -83,11 +87,14 @@ __global__ void pack_weights_kernel(const PackOp* __restrict__ ops, int num_ops,
   }
   const PackOp& op = ops[lo];
   const int r = static_cast<int>(row - op.row0);
-  const int n = r % op.n_total;
-  const int t = r / op.n_total;  // (chunk*3 + dx)*3 + dy
-  const int dy = t % 3, dx = (t / 3) % 3, c = t / 9;
+  const int ng = r % op.n_cols;          // row inside the tap tile
+  const int t = r / op.n_cols;           // ((chunk*CG + cg)*3 + dx)*3 + dy
+  const int cgs = op.n_total / op.n_cols;
+  const int dy = t % 3, dx = (t / 3) % 3, cg = (t / 9) % cgs, c = t / (9 * cgs);
+  const int n = cg * op.n_cols + ng;
   float v = (c < op.num_chunks) ? pack_fetch(op, params, n, c * 64 + kk, dy, dx) : 0.f;
-  packed[idx] = __float2bfloat16_rn(v);
+  const int chunk16 = (kk >> 3) ^ (ng & 7);
+  packed[row * 64 + chunk16 * 8 + (kk & 7)] = __float2bfloat16_rn(v);
 }
 
 // biases: flat fp32 copy (bias_index < 0 -> zeros)

@@ -165,7 +165,6 @@ struct b200sr_plan {
   void* cached_ws = nullptr;
   void* cached_packed = nullptr;
   std::vector<CUtensorMap> maps;
-  WeightMaps wmaps;
   std::vector<Step> layer_steps;      // every conv launch of fwd then bwd, in execution order (= layer list)
   std::vector<LayerDesc> h_layers;
   LayerDesc* d_layers = nullptr;
@@ -200,6 +199,7 @@ struct Builder {
   }
   // packed rows for an op; returns row0
   int add_pack(PackOp op) {
+    if (op.n_cols == 0) op.n_cols = op.n_total > 64 ? 64 : op.n_total;  // column groups of 64 (the upsample convs' four phases)
     op.row0 = (int)P.total_rows;
     P.total_rows += (long long)op.num_chunks * 9 * op.n_total;
     P.pack_ops.push_back(op);
@@ -227,7 +227,7 @@ ConvParams base_conv_params(int n, int h, int w, int num_chunks, int ksteps_last
   p.a_c0 = a_c0; p.a_wrap = a_wrap;
   p.w_row0 = row0; p.n_cols = n_cols; p.n_total = n_total;
   p.col_groups = n_total / n_cols;
-  p.wmap = wmap_index(n_cols);
+  p.w_taps = (n_cols <= 32) ? 9 : 3;
   p.num_stages = conv_pick_stages(n_cols);
   p.epi.alpha = 1.f; p.epi.delta = 1.f; p.epi.beta1 = 1.f; p.epi.beta2 = 1.f;
   p.epi.res_stride = 64; p.epi.of_stride = 64;
@@ -751,10 +751,6 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
     int rc = encode_act_map(&P.maps[i], (char*)wsp + s.off, s.c_valid, s.c_pix, s.n, s.h, s.w, s.box_rows);
     if (rc) return rc;
   }
-  for (int i = 0; i < 4; ++i) {
-    int rc = encode_w_map(&P.wmaps.m[i], packed, P.total_rows, kWmapCols[i]);
-    if (rc) return rc;
-  }
   // device-resident layer list (pointers resolved against this workspace / packed buffer)
   Bases b{wsp, packed, nullptr, nullptr, nullptr};
   P.h_layers.resize(P.layer_steps.size());
@@ -825,7 +821,8 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   int dbg = g_debug;
   unsigned int* ctr = P.d_counters;
   CUDA_TRY(cudaMemsetAsync(ctr, 0, (size_t)ne * sizeof(unsigned int), st));
-  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&P.wmaps, (void*)&ctr, (void*)&y, (void*)&dbg};
+  const uint8_t* pw = (const uint8_t*)b.packed;
+  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&y, (void*)&dbg};
   const void* fn = (const void*)conv3x3_chain_kernel<1>;
   if (ne > 1) {
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
@@ -952,6 +949,10 @@ extern "C" {
 const char* b200sr_last_error(void) { return g_err; }
 int b200sr_version(void) { return 100; }
 void b200sr_debug_set(int flags) { g_debug = flags; }
+int b200sr_debug_read_profile(unsigned long long* out_host, int n) {
+  CUDA_TRY(cudaMemcpyFromSymbol(out_host, g_conv_prof, sizeof(unsigned long long) * (size_t)n));
+  return 0;
+}
 
 int b200sr_plan_create(const b200sr_net_desc* desc, b200sr_plan** out) {
   if (!desc || !out) return fail(B200SR_ERR_INVALID, "null argument");
@@ -1089,7 +1090,7 @@ static int single_conv(int mode, const void* x, int n, int h, int w, int cin, in
   const long long bias_off = align_up(rows * 128, 1024);
   const long long tab_off = bias_off + align_up(cout * 4, 1024);
   PackOp op; memset(&op, 0, sizeof(op));
-  op.row0 = 0; op.n_total = cout; op.n_valid = cout; op.num_chunks = chunks; op.mode = mode; op.nseg = 1;
+  op.row0 = 0; op.n_total = cout; op.n_cols = n_cols; op.n_valid = cout; op.num_chunks = chunks; op.mode = mode; op.nseg = 1;
   if (mode == kPackFwd) op.seg[0] = seg(0, cin, 0, cout, cin, 0, 0, 0);
   else                  op.seg[0] = seg(0, cin, 0, cin, cout, 0, 0, 0);
   BiasOp bo; bo.off = 0; bo.n = cout; bo.b_index = bias ? 1 : -1; bo.n_valid = cout; bo.rep = 0;
@@ -1102,10 +1103,8 @@ static int single_conv(int mode, const void* x, int n, int h, int w, int cin, in
   CUDA_TRY(cudaGetLastError());
   pack_bias_kernel<<<1, 64, 0, st>>>((const BiasOp*)(sc + tab_off + 1024), 1, (const float* const*)(sc + tab_off + 2048), (float*)(sc + bias_off));
   CUDA_TRY(cudaGetLastError());
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA;
   rc = encode_act_map(&tmA, (void*)x, cin, x_stride, n, h, w, kABoxRows);
-  if (rc) return rc;
-  rc = encode_w_map(&tmW, sc, rows, n_cols);
   if (rc) return rc;
   LayerDesc L;
   L.tmA = tmA;
@@ -1114,9 +1113,7 @@ static int single_conv(int mode, const void* x, int n, int h, int w, int cin, in
   L.p.epi.ob_stride = y_stride; L.p.epi.ob_coff = y_coff;
   L.p.epi.bias = (const float*)(sc + bias_off);
   L.p.epi.out_bf16 = (__nv_bfloat16*)y;
-  WeightMaps wm;
-  memset(&wm, 0, sizeof(wm));
-  wm.m[L.p.wmap] = tmW;
+  const uint8_t* pw = (const uint8_t*)sc;
   CUDA_TRY(cudaMemcpyAsync(sc + tab_off + 3072, &L, sizeof(L), cudaMemcpyHostToDevice, st));
   EntryDesc ent; memset(&ent, 0, sizeof(ent));
   ent.layer = 0; ent.tile_lo = 0; ent.tile_hi = L.p.num_tiles; ent.dep = -1; ent.rot = 0;
@@ -1129,7 +1126,7 @@ static int single_conv(int mode, const void* x, int n, int h, int w, int cin, in
   int ne = 1, dbg = g_debug;
   unsigned int* ctr = (unsigned int*)(sc + tab_off + 3072 + 640);
   float* ydyn = nullptr;
-  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&wm, (void*)&ctr, (void*)&ydyn, (void*)&dbg};
+  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&ydyn, (void*)&dbg};
   CUDA_TRY(cudaLaunchKernel((const void*)conv3x3_chain_kernel<1>, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   (void)grid_y;
   return 0;

@@ -78,7 +78,7 @@ struct ConvParams {
   int n_cols;   // UMMA N handled by one work item (16, 32 or 64)
   int n_total;  // n_cols * col_groups
   int col_groups;  // work item w -> tile w / col_groups, column group w % col_groups
-  int wmap;        // which weight tensor map (box rows = n_cols): 0:16 1:32 2:64 3:128
+  int w_taps;      // taps fetched per weight bulk copy: 9 (a whole K chunk, n_cols <= 32) or 3 (one dx column, n_cols = 64)
   int num_stages;
   ConvEpilogue epi;
 };
@@ -211,7 +211,6 @@ struct alignas(128) LayerDesc {
   CUtensorMap tmA;  // activation tensor map of this layer (lives in global memory, read by TMA through a generic address)
   ConvParams p;
 };
-struct WeightMaps { CUtensorMap m[4]; };
 struct alignas(32) EntryDesc {
   int layer;             // index into the layer list handed to the kernel
   int tile_lo, tile_hi;  // pixel tiles of this entry (an image group of the layer)
@@ -223,6 +222,14 @@ struct alignas(32) EntryDesc {
 constexpr int kWGranule = 12288;   // weight ring granule = one (chunk, dx) stage of a 32-column layer (3 taps x 32 x 128 B)
 constexpr int kWGranules = 10;
 constexpr int kNumASlots = 2;
+
+// Software profiler (debug bit 64): cycles each warp role of every CTA spends in each kind of wait, summed over a launch.
+//  [0] producer: dependency wait   [1] producer: A slot free   [2] producer: W granules free   [3] producer: total
+//  [4] MMA: accumulator free       [5] MMA: A tile landed      [6] MMA: W stage landed         [7] MMA: total
+//  [8] epilogue(warp 2): dependency wait + barriers   [9] epilogue: accumulator ready   [10] epilogue: total   [11] items
+__device__ unsigned long long g_conv_prof[160 * 12];
+#define PROF_T0(flag) const long long _t0 = (flag) ? clock64() : 0
+#define PROF_ADD(flag, slot) do { if (flag) prof[slot] += clock64() - _t0; } while (0)
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
@@ -244,7 +251,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;"
 template <int kUnused>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __restrict__ entries, int num_entries,
-                     const __grid_constant__ WeightMaps wmaps, unsigned int* counters, float* y_dyn, int debug) {
+                     const uint8_t* __restrict__ packed_w, unsigned int* counters, float* y_dyn, int debug) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // [ A ring: kNumASlots x 44032 | W ring: kWGranules x 12288 | barriers 256 B | epilogue params 2 x 384 B | epilogue bias 2 x 1 KB ]
@@ -270,7 +277,6 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages (each: two halves x <= 128 columns)
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 4; ++i) prefetch_tensormap(&wmaps.m[i]);
     for (int s = 0; s < 4; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < kWGranules; ++s) { mbar_init(&fullW[s], 1); mbar_init(&emptyW[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
@@ -287,6 +293,9 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     // (whole warp walks the loops so the index math stays warp-uniform; one elected lane issues)
     uint32_t eA_bits = 0, eW_bits = 0;  // phase parity per A slot / W granule (empty barriers)
     int sa = 0, gw = 0;
+    const bool pf = (debug & 64) != 0;
+    long long prof[4] = {0, 0, 0, 0};
+    const long long pstart = pf ? clock64() : 0;
     for (int e = 0; e < num_entries; ++e) {
       const EntryDesc* ed = entries + e;
       const int tile_lo = __ldcg(&ed->tile_lo), tile_hi = __ldcg(&ed->tile_hi), dep = __ldcg(&ed->dep), rot = __ldcg(&ed->rot);
@@ -294,24 +303,26 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const ConvParams* gp = &L->p;
       const int tiles_x = __ldcg(&gp->tiles_x), tiles_y = __ldcg(&gp->tiles_y), num_chunks = __ldcg(&gp->num_chunks);
       const int a_c0 = __ldcg(&gp->a_c0), a_wrap = __ldcg(&gp->a_wrap), w_row0 = __ldcg(&gp->w_row0);
-      const int n_cols = __ldcg(&gp->n_cols), n_total = __ldcg(&gp->n_total), col_groups = __ldcg(&gp->col_groups);
+      const int n_cols = __ldcg(&gp->n_cols), col_groups = __ldcg(&gp->col_groups);
       const CUtensorMap* tmA = &L->tmA;
-      const CUtensorMap* tmW = &wmaps.m[__ldcg(&gp->wmap)];
+      const int w_taps = __ldcg(&gp->w_taps);
       const int tiles_per_img = tiles_x * tiles_y;
       const int num_work = (tile_hi - tile_lo) * col_groups;
-      const int g = (n_cols + 31) >> 5;  // W granules per stage (1 or 2)
-      const int wbytes = 3 * n_cols * 128;
+      const int wbytes = w_taps * n_cols * 128;              // one weight stage = w_taps tap tiles, fetched by ONE bulk copy
+      const int g = (wbytes + kWGranule - 1) / kWGranule;    // W granules per stage
+      const int wsteps = 9 / w_taps;                         // stages per K chunk (1 or 3)
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
       if (v < num_work && dep >= 0) {
+        { PROF_T0(pf);
         if (lane == 0 && !(debug & 16)) {
           wait_entry_done(counters, dep, grid);
           asm volatile("fence.proxy.async.global;" ::: "memory");  // TMA (async proxy) reads after generic-proxy stores
         }
         __syncwarp();
+        PROF_ADD(pf, 0); }
       }
       for (int w = v; w < num_work; w += static_cast<int>(grid)) {
         const int tile = tile_lo + w / col_groups;
-        const int colbase = (w % col_groups) * n_cols;
         const int n = tile / tiles_per_img;
         const int t2 = tile - n * tiles_per_img;
         const int ty = t2 / tiles_x;
@@ -319,7 +330,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const int y0 = ty * kTileH;
         for (int c = 0; c < num_chunks; ++c) {
           const int ac = a_c0 + (c % a_wrap) * 64;
-          mbar_wait(&emptyA[sa], ((eA_bits >> sa) & 1u) ^ 1u);
+          { PROF_T0(pf); mbar_wait(&emptyA[sa], ((eA_bits >> sa) & 1u) ^ 1u); PROF_ADD(pf, 1); }
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(&fullA[sa], kABytes);
             tma_load_4d(smem + sa * kASlot, tmA, &fullA[sa], ac, x0 - 1, y0 - 1, n);
@@ -327,17 +338,15 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           __syncwarp();
           eA_bits ^= (1u << sa);
           if (++sa == kNumASlots) sa = 0;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const int dxi = (d == 0) ? 1 : (d == 1 ? 0 : 2);  // centre column first (see MMA loop)
+          for (int d = 0; d < wsteps; ++d) {
+            // stage d of this chunk: all nine taps (w_taps = 9) or the dx column {1, 0, 2}[d] (centre column first)
+            const int dxi = (w_taps == 9) ? 0 : ((d == 0) ? 1 : (d == 1 ? 0 : 2));
             if (gw + g > kWGranules) gw = 0;
-            for (int j = 0; j < g; ++j) mbar_wait(&emptyW[gw + j], ((eW_bits >> (gw + j)) & 1u) ^ 1u);
+            { PROF_T0(pf); for (int j = 0; j < g; ++j) mbar_wait(&emptyW[gw + j], ((eW_bits >> (gw + j)) & 1u) ^ 1u); PROF_ADD(pf, 2); }
             if (elect_one_sync()) {
               mbar_arrive_expect_tx(&fullW[gw], wbytes);
-#pragma unroll
-              for (int dyi = 0; dyi < 3; ++dyi)
-                tma_load_2d(smemW + gw * kWGranule + dyi * n_cols * 128, tmW, &fullW[gw], 0,
-                            w_row0 + ((c * 3 + dxi) * 3 + dyi) * n_total + colbase);
+              const long long row = w_row0 + (static_cast<long long>((c * col_groups + (w % col_groups)) * 3 + dxi) * 3) * n_cols;
+              bulk_load_1d(smemW + gw * kWGranule, packed_w + row * 128, wbytes, &fullW[gw]);
             }
             __syncwarp();
             for (int j = 0; j < g; ++j) eW_bits ^= (1u << (gw + j));
@@ -345,6 +354,10 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           }
         }
       }
+    }
+    if (pf && lane == 0) {
+      prof[3] = clock64() - pstart;
+      for (int i = 0; i < 4; ++i) g_conv_prof[blockIdx.x * 12 + i] = prof[i];
     }
   } else if (warp == 1) {
     // ================================================== MMA issuer ==================================================
@@ -355,51 +368,61 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     uint32_t fA_bits = 0, fW_bits = 0;  // phase parity per A slot / W granule (full barriers)
     int sa = 0, gw = 0;
     int it = 0;
+    const bool pf = (debug & 64) != 0;
+    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long pstart = pf ? clock64() : 0;
     for (int e = 0; e < num_entries; ++e) {
       const EntryDesc* ed = entries + e;
       const int tile_lo = __ldcg(&ed->tile_lo), tile_hi = __ldcg(&ed->tile_hi), rot = __ldcg(&ed->rot);
       const ConvParams* gp = &(layers + __ldcg(&ed->layer))->p;
       const int num_chunks = __ldcg(&gp->num_chunks), ksteps_last = __ldcg(&gp->ksteps_last);
-      const int n_cols = __ldcg(&gp->n_cols), col_groups = __ldcg(&gp->col_groups);
+      const int n_cols = __ldcg(&gp->n_cols), col_groups = __ldcg(&gp->col_groups), w_taps = __ldcg(&gp->w_taps);
       const int num_work = (tile_hi - tile_lo) * col_groups;
-      const int g = (n_cols + 31) >> 5;
+      const int g = (w_taps * n_cols * 128 + kWGranule - 1) / kWGranule;
+      const int wsteps = 9 / w_taps;
       const uint32_t idesc = make_idesc_bf16(128, n_cols, 0, 0);
       const uint32_t b_dy = static_cast<uint32_t>(n_cols) * 8;  // (n_cols * 128 B) >> 4
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
       for (int w = v; w < num_work; w += static_cast<int>(grid), ++it) {
         const int as = it & 1;
-        mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
+        { PROF_T0(pf); mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1); PROF_ADD(pf, 4); }
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * kAccStride;
         for (int c = 0; c < num_chunks; ++c) {
           const int ksteps = (c == num_chunks - 1) ? ksteps_last : 4;
-          mbar_wait(&fullA[sa], (fA_bits >> sa) & 1u);
+          { PROF_T0(pf); mbar_wait(&fullA[sa], (fA_bits >> sa) & 1u); PROF_ADD(pf, 5); }
           const uint32_t a_lo = smem_desc_lo(smem_u32(smem + sa * kASlot), 16);
-          for (int d = 0; d < 3; ++d) {
-            const int dxi = (d == 0) ? 1 : (d == 1 ? 0 : 2);
+          for (int d = 0; d < wsteps; ++d) {
             if (gw + g > kWGranules) gw = 0;
-            mbar_wait(&fullW[gw], (fW_bits >> gw) & 1u);
+            { PROF_T0(pf); mbar_wait(&fullW[gw], (fW_bits >> gw) & 1u); PROF_ADD(pf, 6); }
             tcgen05_fence_after();
             if (elect_one_sync()) {
-              const uint32_t b_lo = smem_desc_lo(smem_u32(smemW + gw * kWGranule), 16);
-              const uint32_t first = (c | d) ? 1u : 0u;  // very first MMA of the item overwrites the accumulators
+              const uint32_t b_base = smem_desc_lo(smem_u32(smemW + gw * kWGranule), 16);
+              const int ncol_dx = 9 / wsteps / 3;  // dx columns held by this stage: 3 (whole chunk) or 1
+#pragma unroll 1
+              for (int dd = 0; dd < ncol_dx; ++dd) {
+                const int o = (ncol_dx == 3) ? dd : d;                 // position in the centre-first order {1, 0, 2}
+                const int dxi = (o == 0) ? 1 : (o == 1 ? 0 : 2);
+                const uint32_t b_lo = b_base + ((ncol_dx == 3) ? dxi * 3 : 0) * b_dy;
+                const uint32_t first = (c | o) ? 1u : 0u;  // very first MMA of the item overwrites the accumulators
 #pragma unroll
-              for (int t = 0; t < 3; ++t) {
-                const int dyi = (t == 0) ? 1 : (t == 1 ? 0 : 2);  // centre row first
+                for (int t = 0; t < 3; ++t) {
+                  const int dyi = (t == 0) ? 1 : (t == 1 ? 0 : 2);  // centre row first
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if (ks < ksteps && !(debug & 2)) {
-                    // tap (dy,dx) = the haloed tile shifted by (dy*10+dx) rows of 128 B; the two 128-pixel halves
-                    // (patch rows 0-15 / 16-31) reuse the same weight tile
-                    const uint32_t a_tap = a_lo + (dyi * kABoxW + dxi) * 8 + ks * 2;
-                    umma_bf16_ss_lohi2(d_tmem, a_tap, kHiA, b_lo + dyi * b_dy + ks * 2, kHi, idesc, (t == 0 && ks == 0) ? first : 1u);
-                    umma_bf16_ss_lohi2(d_tmem + 128, a_tap + 16 * kABoxW * 8, kHiA, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
-                                       (t == 0 && ks == 0) ? first : 1u);
+                  for (int ks = 0; ks < 4; ++ks) {
+                    if (ks < ksteps && !(debug & 2)) {
+                      // tap (dy,dx) = the haloed tile shifted by (dy*10+dx) rows of 128 B; the two 128-pixel halves
+                      // (patch rows 0-15 / 16-31) reuse the same weight tile
+                      const uint32_t a_tap = a_lo + (dyi * kABoxW + dxi) * 8 + ks * 2;
+                      umma_bf16_ss_lohi2(d_tmem, a_tap, kHiA, b_lo + dyi * b_dy + ks * 2, kHi, idesc, (t == 0 && ks == 0) ? first : 1u);
+                      umma_bf16_ss_lohi2(d_tmem + 128, a_tap + 16 * kABoxW * 8, kHiA, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
+                                         (t == 0 && ks == 0) ? first : 1u);
+                    }
                   }
                 }
               }
               for (int j = 0; j < g; ++j) umma_commit(&emptyW[gw + j]);  // frees the weight granules once these MMAs drained
-              if (d == 2) umma_commit(&emptyA[sa]);                      // ... and the activation tile after its last column
+              if (d == wsteps - 1) umma_commit(&emptyA[sa]);             // ... and the activation tile after its last stage
             }
             __syncwarp();
             fW_bits ^= (1u << gw);
@@ -411,6 +434,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         if (elect_one_sync()) umma_commit(&tfull[as]);  // accumulators ready for the epilogue warps
         __syncwarp();
       }
+    }
+    if (pf && lane == 0) {
+      prof[7] = clock64() - pstart;
+      for (int i = 4; i < 8; ++i) g_conv_prof[blockIdx.x * 12 + i] = prof[i];
+      g_conv_prof[blockIdx.x * 12 + 11] = it;
     }
   } else {
     // =================================================== epilogue ===================================================
@@ -434,8 +462,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     };
     stage_entry(0);
     int it = 0;
+    const bool pf = (debug & 64) != 0;
+    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long pstart = pf ? clock64() : 0;
     for (int e = 0; e < num_entries; ++e) {
-      epi_bar_sync();  // slot (e & 1) is complete and visible; every epilogue thread has left entry e-1
+      { PROF_T0(pf); epi_bar_sync(); PROF_ADD(pf, 8); }  // slot (e & 1) is complete and visible; every epilogue thread has left entry e-1
       if (e + 1 < num_entries) stage_entry(e + 1);
       const ConvParams& p = *reinterpret_cast<const ConvParams*>(sp_base + (e & 1) * 384);
       const EntryDesc& ent = *reinterpret_cast<const EntryDesc*>(sp_base + (e & 1) * 384 + 320);
@@ -445,11 +476,13 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(ent.rot)) % grid);
       if (v < num_work && ent.dep >= 0) {
         // residuals / masks written by the entry we depend on are read before the accumulator is ready: check it too
+        PROF_T0(pf);
         if (et == 0 && !(debug & 16)) {
           wait_entry_done(counters, ent.dep, grid);
           __threadfence();
         }
         epi_bar_sync();
+        PROF_ADD(pf, 8);
       }
       for (int w = v; w < num_work; w += static_cast<int>(grid), ++it) {
         const int tile = ent.tile_lo + w / p.col_groups;
@@ -501,7 +534,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             }
           }
         }
-        mbar_wait(&tfull[as], (it >> 1) & 1);
+        { PROF_T0(pf); mbar_wait(&tfull[as], (it >> 1) & 1); PROF_ADD(pf, 9); }
         tcgen05_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * 128;
 #pragma unroll
@@ -535,11 +568,15 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         if (lane == 0) mbar_arrive(&tempty[as]);
       }
       // announce: this CTA's part of entry e is stored (cumulativity: bar.sync + gpu-scope fence by the signalling thread)
-      epi_bar_sync();
+      { PROF_T0(pf); epi_bar_sync(); PROF_ADD(pf, 8); }
       if (et == 0) {
         __threadfence();
         atomicAdd(counters + e, 1u);
       }
+    }
+    if (pf && threadIdx.x == 64) {
+      prof[10] = clock64() - pstart;
+      for (int i = 8; i < 11; ++i) g_conv_prof[blockIdx.x * 12 + i] = prof[i];
     }
   }
 

@@ -50,6 +50,7 @@ SIGNATURES = {
     "b200sr_last_error": (C.c_char_p, []),
     "b200sr_version": (C.c_int, []),
     "b200sr_debug_set": (None, [C.c_int]),
+    "b200sr_debug_read_profile": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 
