@@ -15,6 +15,7 @@ enum PackMode : int {
 };
 
 struct PackSeg {
+  int n0, nlen;   // packed output-column range [n0, n0 + nlen) served by this segment (nlen = 0: all columns)
   int k0, klen;   // packed K-channel range [k0, k0 + klen) served by this segment
   int w_index;    // index into the parameter pointer table
   int O, I;       // source tensor dims (OIHW)
@@ -41,12 +42,17 @@ __host__ __device__ inline void up_phase_taps(int a, int t, int& lo, int& hi) {
   else        { lo = (t == 0) ? 0 : (t == 1 ? 0 : 2); hi = (t == 0) ? 0 : (t == 1 ? 2 : 3); }
 }
 
-__device__ __forceinline__ float pack_fetch(const PackOp& op, const float* const* params, int n, int k, int ty, int tx) {
-  if (n >= op.n_valid) return 0.f;
+__device__ __forceinline__ float pack_fetch(const PackOp& op, const float* const* params, int n_in, int k, int ty, int tx) {
+  if (n_in >= op.n_valid) return 0.f;
   for (int s = 0; s < op.nseg; ++s) {
     const PackSeg& sg = op.seg[s];
+    int n = n_in;
     const int kl = k - sg.k0;
     if (kl < 0 || kl >= sg.klen) continue;
+    if (sg.nlen > 0) {
+      if (n < sg.n0 || n >= sg.n0 + sg.nlen) continue;
+      n -= sg.n0;
+    }
     const float* w = params[sg.w_index];
     float v = 0.f;
     if (op.mode == kPackFwd) {

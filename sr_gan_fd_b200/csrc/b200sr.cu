@@ -153,6 +153,9 @@ struct b200sr_plan {
   long long o_dyp = 0, o_g3 = 0, o_gt = 0, o_gtb = 0, o_gr = 0, o_gc1 = 0, o_gc2 = 0, o_go1 = 0;
   long long o_dyb[6] = {0, 0, 0, 0, 0, 0};
   std::vector<long long> o_gu;
+  bool reassoc = true;                // dense blocks re-associated by input slice (B200SR_REASSOC=0 selects the per-conv schedule)
+  int groups = 1;                     // image groups that flow through a chain independently
+  int plan_sms = 148;                 // SM count the schedule was laid out for
   long long gw_bytes = 0;
   long long o_gw = 0;                 // staged weight gradients, per conv [tap][ci][co_pad] fp32
   std::vector<long long> gw_off;      // float offsets per conv into the staging buffer
@@ -227,7 +230,8 @@ ConvParams base_conv_params(int n, int h, int w, int num_chunks, int ksteps_last
   p.a_c0 = a_c0; p.a_wrap = a_wrap;
   p.w_row0 = row0; p.n_cols = n_cols; p.n_total = n_total;
   p.col_groups = n_total / n_cols;
-  p.w_taps = (n_cols <= 32) ? 9 : 3;
+  p.w_taps = (9 * n_cols * 128 <= 5 * kWGranule) ? 9 : ((3 * n_cols * 128 <= 5 * kWGranule) ? 3 : 1);  // bytes per weight bulk copy <= 60 KB
+  p.acc_col0 = 0; p.acc_first = 1; p.acc_hold = 0; p.epi_cols = n_cols;
   p.num_stages = conv_pick_stages(n_cols);
   p.epi.alpha = 1.f; p.epi.delta = 1.f; p.epi.beta1 = 1.f; p.epi.beta2 = 1.f;
   p.epi.res_stride = 64; p.epi.of_stride = 64;
@@ -236,7 +240,12 @@ ConvParams base_conv_params(int n, int h, int w, int num_chunks, int ksteps_last
 }
 
 PackSeg seg(int k0, int klen, int w_index, int O, int I, int o_off, int i_off, int part) {
-  PackSeg s; s.k0 = k0; s.klen = klen; s.w_index = w_index; s.O = O; s.I = I; s.o_off = o_off; s.i_off = i_off; s.part = part;
+  PackSeg s; s.n0 = 0; s.nlen = 0; s.k0 = k0; s.klen = klen; s.w_index = w_index; s.O = O; s.I = I; s.o_off = o_off; s.i_off = i_off; s.part = part;
+  return s;
+}
+PackSeg nseg(int n0, int nlen, int k0, int klen, int w_index, int O, int I, int o_off, int i_off) {  // segment limited to output columns [n0, n0+nlen)
+  PackSeg s = seg(k0, klen, w_index, O, I, o_off, i_off, 0);
+  s.n0 = n0; s.nlen = nlen;
   return s;
 }
 }  // namespace
@@ -268,6 +277,25 @@ static int build_plan(b200sr_plan& P) {
   if (d.batch < 1 || d.height < 1 || d.width < 1) return fail(B200SR_ERR_INVALID, "bad geometry");
   P.R = 3 * d.num_blocks;
   P.L = d.n_up;
+  {
+    // Image groups: >= 2 whenever the batch allows (latency hiding between groups).  The re-associated dense block keeps
+    // one work item's partial sums in a CTA's TMEM across five passes, so every group must fit one item per CTA.
+    int dev_count = 0, sms = 0;
+    if (cudaGetDeviceCount(&dev_count) == cudaSuccess && dev_count > 0) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    } else {
+      cudaGetLastError();
+    }
+    if (sms > 0) P.plan_sms = sms;
+    const int tpi = ((d.width + kTileW - 1) / kTileW) * ((d.height + kTileH - 1) / kTileH);
+    P.groups = d.batch >= 2 ? 2 : 1;
+    if (P.reassoc) {
+      int g = P.groups;
+      while (g <= d.batch && ((d.batch + g - 1) / g) * tpi > P.plan_sms) ++g;
+      if (g <= d.batch) P.groups = g; else P.reassoc = false;  // a single image already exceeds one item per CTA
+    }
+  }
   const int R = P.R, L = P.L;
   const bool train = d.training != 0;
   const int N = d.batch, H = d.height, W = d.width;
@@ -379,9 +407,66 @@ static int build_plan(b200sr_plan& P) {
     P.fwd.push_back(s);
   }
   // trunk
+  const bool reassoc = P.reassoc;
   for (int r = 0; r < R; ++r) {
     const int j = r % 3;
     const long long D = dense_off(r);
+    // epilogue of the block's last conv (conv5): residual scalings, fp32 carrier, bf16 shadow into the next dense buffer
+    auto conv5_epilogue = [&](Step& s) {
+      const long long cin_c = (j == 0) ? P.o_tr : (j == 1 ? P.o_c1 : P.o_c2);
+      const long long cout_c = (j == 0) ? P.o_c1 : (j == 1 ? P.o_c2 : P.o_tr);
+      s.cp.epi.alpha = (j == 2) ? 0.04f : 0.2f;
+      s.r1 = ws(cin_c); s.cp.epi.beta1 = (j == 2) ? 0.2f : 1.f;
+      if (j == 2) { s.r2 = ws(P.o_tr); s.cp.epi.beta2 = 1.f; }
+      s.of = ws(cout_c);
+      if (r < R - 1) {
+        s.ob = ws(dense_off(r + 1)); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 0;
+      } else {
+        s.ob = ws(P.o_splt); s.cp.epi.ob_stride = 128; s.cp.epi.ob_coff = 0; s.cp.epi.split_off = 64;
+      }
+    };
+    if (reassoc) {
+      // Dense block RE-ASSOCIATED BY INPUT SLICE: pass q feeds slice q (x, o1..o4) to ALL convs that consume it at once
+      // (N = 192, 160, 128, 96, 64 instead of 32,32,32,32,64); the partial sums stay in TMEM between the passes.
+      for (int q = 0; q < 5; ++q) {
+        const int c_q = (q == 0) ? 0 : 64 + 32 * (q - 1);
+        const int klen = (q == 0) ? 64 : 32;
+        // every pass is two sub-layers over the same input slice: CRITICAL = the columns of conv q+1, which this slice
+        // completes (small N, has the epilogue that produces the next slice) and DEFERRED = the partial sums of the later
+        // convs (large N, no epilogue), which the MMA warp works off while the critical epilogue and the cross-CTA
+        // dependency of the next pass are in flight.
+        for (int part = 0; part < 2; ++part) {
+          const int col_lo = (part == 0) ? 32 * q : 32 * (q + 1);          // accumulator columns [col_lo, col_hi)
+          const int col_hi = (part == 0) ? ((q < 4) ? 32 * (q + 1) : 192) : 192;
+          const int ncols = col_hi - col_lo;
+          if (ncols <= 0) continue;
+          PackOp op; memset(&op, 0, sizeof(op));
+          op.n_total = ncols; op.n_cols = ncols; op.n_valid = ncols; op.num_chunks = 1; op.mode = kPackFwd; op.nseg = 0;
+          for (int k = q + 1; k <= 5; ++k) {
+            const int k_lo = (k < 5) ? 32 * (k - 1) : 128, k_hi = (k < 5) ? 32 * k : 192;  // accumulator columns of conv k
+            if (k_lo < col_lo || k_hi > col_hi) continue;
+            const int ci = conv_index_rdb(r, k);
+            op.seg[op.nseg++] = nseg(k_lo - col_lo, k_hi - k_lo, 0, klen, 2 * ci, (k < 5) ? 32 : 64, 64 + 32 * (k - 1), 0, c_q);
+          }
+          const int row0 = B.add_pack(op);
+          ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, c_q, 1 << 20, row0, ncols, ncols);
+          cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = (part == 0) ? ncols : 0;
+          Step s = conv_step(B.add_map(D, c_q + klen, 192, N, H, W, kABoxRows), cp, 1);
+          if (part == 0) {
+            const int ci_done = conv_index_rdb(r, q + 1);  // the conv that is complete after this pass
+            s.bias = packed_bias(B.add_bias(cp.epi_cols, 2 * ci_done + 1, cp.epi_cols, 0));
+            if (q < 4) {
+              s.cp.epi.act = 1;
+              s.ob = ws(D); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * q;
+            } else {
+              conv5_epilogue(s);
+            }
+          }
+          P.fwd.push_back(s);
+        }
+      }
+      continue;
+    }
     for (int k = 1; k <= 5; ++k) {
       const int ci = conv_index_rdb(r, k);
       const int cin = 64 + 32 * (k - 1), cout = (k < 5) ? 32 : 64;
@@ -396,17 +481,7 @@ static int build_plan(b200sr_plan& P) {
         s.cp.epi.act = 1;
         s.ob = ws(D); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * (k - 1);
       } else {
-        const long long cin_c = (j == 0) ? P.o_tr : (j == 1 ? P.o_c1 : P.o_c2);
-        const long long cout_c = (j == 0) ? P.o_c1 : (j == 1 ? P.o_c2 : P.o_tr);
-        s.cp.epi.alpha = (j == 2) ? 0.04f : 0.2f;
-        s.r1 = ws(cin_c); s.cp.epi.beta1 = (j == 2) ? 0.2f : 1.f;
-        if (j == 2) { s.r2 = ws(P.o_tr); s.cp.epi.beta2 = 1.f; }
-        s.of = ws(cout_c);
-        if (r < R - 1) {
-          s.ob = ws(dense_off(r + 1)); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 0;
-        } else {
-          s.ob = ws(P.o_splt); s.cp.epi.ob_stride = 128; s.cp.epi.ob_coff = 0; s.cp.epi.split_off = 64;
-        }
+        conv5_epilogue(s);
       }
       P.fwd.push_back(s);
     }
@@ -633,6 +708,52 @@ static int build_plan(b200sr_plan& P) {
       const int blk = r / 3;
       const long long DYc = P.o_dyb[3 * (blk & 1) + (2 - j)];
       const long long DYn = (j > 0) ? P.o_dyb[3 * (blk & 1) + (2 - (j - 1))] : P.o_dyb[3 * ((blk + 1) & 1)];
+      // epilogue of the block-input (x) slice: fp32 gradient carriers and the next block's dY5
+      auto xslice_epilogue = [&](Step& s) {
+        if (j == 2) { s.r1 = ws(P.o_gr); s.cp.epi.beta1 = 0.2f; s.of = ws(P.o_gc2); s.cp.epi.delta = 0.2f; }
+        else if (j == 1) { s.r1 = ws(P.o_gc2); s.of = ws(P.o_gc1); s.cp.epi.delta = 0.2f; }
+        else { s.r1 = ws(P.o_gc1); s.r2 = ws(P.o_gr); s.of = ws(P.o_gr); s.cp.epi.delta = 0.04f; }
+        if (r > 0) { s.ob = ws(DYn); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 0; }
+      };
+      if (P.reassoc) {
+        // Mirror image of the forward passes: pass q feeds dY_{5-q} (64 or 32 channels) to ALL input slices its conv
+        // reads; accumulator columns are [o4 | o3 | o2 | o1 | x], so after pass q the leading 32 columns (slice o_{4-q})
+        // are complete and become dY_{4-q} (times the LeakyReLU derivative); the x columns complete last.
+        for (int q = 0; q < 5; ++q) {
+          const int kk = 5 - q;                               // the conv whose output gradient is consumed
+          const int klen = (kk == 5) ? 64 : 32;
+          const int a_c0 = (q == 0) ? 0 : 64 + 32 * (q - 1);   // dY_kk inside [dY5 | dY4 | dY3 | dY2 | dY1]
+          const int ci = conv_index_rdb(r, kk);
+          for (int part = 0; part < 2; ++part) {               // critical (completed slice) / deferred (later slices), as forward
+            const int col_lo = (part == 0) ? 32 * q : 32 * (q + 1);
+            const int col_hi = (part == 0) ? ((q < 4) ? 32 * (q + 1) : 192) : 192;
+            const int ncols = col_hi - col_lo;
+            if (ncols <= 0) continue;
+            PackOp op; memset(&op, 0, sizeof(op));
+            op.n_total = ncols; op.n_cols = ncols; op.n_valid = ncols; op.num_chunks = 1; op.mode = kPackDgrad; op.nseg = 0;
+            for (int sidx = 4 - q; sidx >= 0; --sidx) {          // input slices read by conv kk: o_sidx (sidx >= 1) and x (sidx = 0)
+              const int s_lo = (sidx >= 1) ? 32 * (4 - sidx) : 128, s_hi = (sidx >= 1) ? s_lo + 32 : 192;
+              if (s_lo < col_lo || s_hi > col_hi) continue;
+              op.seg[op.nseg++] = nseg(s_lo - col_lo, s_hi - s_lo, 0, klen, 2 * ci, klen, 64 + 32 * (kk - 1), 0,
+                                       (sidx >= 1) ? 64 + 32 * (sidx - 1) : 0);
+            }
+            const int row0 = B.add_pack(op);
+            ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, a_c0, 1 << 20, row0, ncols, ncols);
+            cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = (part == 0) ? ncols : 0;
+            Step s = conv_step(B.add_map(DYc, a_c0 + klen, 192, N, H, W, kABoxRows), cp, 1);
+            if (part == 0) {
+              if (q < 4) {
+                const int sl = 4 - q;  // completed slice o_sl
+                s.mask = ws(D); s.cp.epi.mask_stride = 192; s.cp.epi.mask_coff = 64 + 32 * (sl - 1);
+                s.ob = ws(DYc); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * q;
+              } else {
+                xslice_epilogue(s);
+              }
+            }
+            emit(s);
+          }
+        }
+      } else
       for (int sl = 4; sl >= 0; --sl) {
         // gradient w.r.t. input slice sl (0: the 64-ch block input x, 1..4: growth outputs o_sl) = sum over consumer convs
         const int c_s = (sl == 0) ? 0 : 64 + 32 * (sl - 1);
@@ -654,10 +775,7 @@ static int build_plan(b200sr_plan& P) {
           s.mask = ws(D); s.cp.epi.mask_stride = 192; s.cp.epi.mask_coff = c_s;
           s.ob = ws(DYc); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * (4 - sl);
         } else {
-          if (j == 2) { s.r1 = ws(P.o_gr); s.cp.epi.beta1 = 0.2f; s.of = ws(P.o_gc2); s.cp.epi.delta = 0.2f; }
-          else if (j == 1) { s.r1 = ws(P.o_gc2); s.of = ws(P.o_gc1); s.cp.epi.delta = 0.2f; }
-          else { s.r1 = ws(P.o_gc1); s.r2 = ws(P.o_gr); s.of = ws(P.o_gr); s.cp.epi.delta = 0.04f; }
-          if (r > 0) { s.ob = ws(DYn); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 0; }
+          xslice_epilogue(s);
         }
         emit(s);
       }
@@ -774,23 +892,43 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
       for (Step& s : steps) {
         if (s.type != ST_CHAIN) continue;
         const int grid = s.chain_grid < g_num_sms ? s.chain_grid : g_num_sms;
-        const int groups = P.d.batch >= 2 ? 2 : 1;
+        const int groups = P.groups;
         s.entry0 = (int)P.h_entries.size();
-        for (int l = 0; l < s.nlayers; ++l) {
+        // emission order: ordinary layers go (layer, group A), (layer, group B); the five pass layers of a dense block go
+        // group-major (A: pass 0..4, then B: pass 0..4) because a block's accumulators occupy the CTA's TMEM for all five
+        std::vector<std::pair<int, int>> order;  // (layer, group)
+        for (int l = 0; l < s.nlayers;) {
+          const ConvParams& cp = P.layer_steps[s.layer0 + l].cp;
+          if (cp.acc_hold && cp.acc_first) {
+            int l1 = l + 1;
+            // a dense block = the run of pass sub-layers up to (not including) the next block's first critical sub-layer
+            while (l1 < s.nlayers && P.layer_steps[s.layer0 + l1].cp.acc_hold &&
+                   !(P.layer_steps[s.layer0 + l1].cp.acc_first && P.layer_steps[s.layer0 + l1].cp.epi_cols > 0)) ++l1;
+            for (int g = 0; g < groups; ++g)
+              for (int ll = l; ll < l1; ++ll) order.push_back({ll, g});
+            l = l1;
+          } else {
+            for (int g = 0; g < groups; ++g) order.push_back({l, g});
+            ++l;
+          }
+        }
+        std::vector<int> index_of((size_t)s.nlayers * groups, -1);
+        for (size_t i = 0; i < order.size(); ++i) index_of[(size_t)order[i].first * groups + order[i].second] = (int)i;
+        for (size_t i = 0; i < order.size(); ++i) {
+          const int l = order[i].first, g = order[i].second;
           const ConvParams& cp = P.layer_steps[s.layer0 + l].cp;
           const int tpi = cp.tiles_x * cp.tiles_y;
-          int work0 = 0;
-          for (int g = 0; g < groups; ++g) {
-            const int img_lo = (int)((long long)P.d.batch * g / groups), img_hi = (int)((long long)P.d.batch * (g + 1) / groups);
-            EntryDesc e; memset(&e, 0, sizeof(e));
-            e.layer = s.layer0 + l;
-            e.tile_lo = img_lo * tpi; e.tile_hi = img_hi * tpi;
-            e.dep = (l > 0) ? ((l - 1) * groups + g) : -1;
-            const int work = (e.tile_hi - e.tile_lo) * cp.col_groups;
-            e.rot = (g == 0) ? 0 : (work0 % grid);  // the second group starts where the first one's last round ended
-            if (g == 0) work0 = work;
-            P.h_entries.push_back(e);
-          }
+          const int img_lo = (int)((long long)P.d.batch * g / groups), img_hi = (int)((long long)P.d.batch * (g + 1) / groups);
+          EntryDesc e; memset(&e, 0, sizeof(e));
+          e.layer = s.layer0 + l;
+          e.tile_lo = img_lo * tpi; e.tile_hi = img_hi * tpi;
+          // dependency = the nearest earlier layer that PRODUCES data (has an epilogue).  A deferred partial-sum layer reads the
+          // same slice as the critical sub-layer right before it, so it inherits that layer's dependency.
+          int lp = (cp.epi_cols == 0) ? l - 2 : l - 1;
+          while (lp >= 0 && P.layer_steps[s.layer0 + lp].cp.epi_cols == 0) --lp;
+          e.dep = (lp >= 0) ? index_of[(size_t)lp * groups + g] : -1;
+          e.rot = (int)(((long long)img_lo * tpi * cp.col_groups) % grid);  // each group starts where the previous one's last round ended
+          P.h_entries.push_back(e);
         }
         s.nentries = (int)P.h_entries.size() - s.entry0;
       }
@@ -958,6 +1096,7 @@ int b200sr_plan_create(const b200sr_net_desc* desc, b200sr_plan** out) {
   if (!desc || !out) return fail(B200SR_ERR_INVALID, "null argument");
   b200sr_plan* p = new b200sr_plan();
   p->d = *desc;
+  if (const char* e = getenv("B200SR_REASSOC")) p->reassoc = atoi(e) != 0;
   int rc = build_plan(*p);
   if (rc) { delete p; return rc; }
   *out = p;

@@ -75,10 +75,18 @@ struct ConvParams {
   int a_c0;         // activation channel coordinate of chunk c: a_c0 + (c % a_wrap) * 64
   int a_wrap;
   int w_row0;   // first row of this conv in the packed weight matrix
-  int n_cols;   // UMMA N handled by one work item (16, 32 or 64)
+  int n_cols;   // UMMA N handled by one work item (multiple of 16, <= 64 for ordinary layers, <= 192 for pass layers)
   int n_total;  // n_cols * col_groups
   int col_groups;  // work item w -> tile w / col_groups, column group w % col_groups
-  int w_taps;      // taps fetched per weight bulk copy: 9 (a whole K chunk, n_cols <= 32) or 3 (one dx column, n_cols = 64)
+  int w_taps;      // taps fetched per weight bulk copy: 9 (a whole K chunk), 3 (one dx column) or 1
+  // accumulator placement.  Ordinary layers: fresh accumulators, double buffered (acc_hold = 0).  Dense-block PASS layers
+  // (acc_hold = 1): the block's 192 accumulator columns live in a fixed TMEM block across five consecutive entries; pass j
+  // adds input slice j's contribution to columns [acc_col0, acc_col0 + n_cols) and its epilogue consumes the leading
+  // epi_cols columns (the conv that just became complete).
+  int acc_col0;
+  int acc_first;   // 1: the first MMA of an item overwrites the accumulators, 0: accumulate onto earlier passes
+  int acc_hold;
+  int epi_cols;
   int num_stages;
   ConvEpilogue epi;
 };
@@ -339,13 +347,17 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           eA_bits ^= (1u << sa);
           if (++sa == kNumASlots) sa = 0;
           for (int d = 0; d < wsteps; ++d) {
-            // stage d of this chunk: all nine taps (w_taps = 9) or the dx column {1, 0, 2}[d] (centre column first)
-            const int dxi = (w_taps == 9) ? 0 : ((d == 0) ? 1 : (d == 1 ? 0 : 2));
+            // stage d of this chunk holds w_taps consecutive taps of the centre-first order: dx in {1,0,2}, dy in {1,0,2}.
+            // Packed rows are [dx][dy][n]; a 9-tap stage is the whole block, a 3-tap stage one dx column, a 1-tap stage one tile.
+            int tap_row;
+            if (w_taps == 9) tap_row = 0;
+            else if (w_taps == 3) tap_row = ((d == 0) ? 1 : (d == 1 ? 0 : 2)) * 3;
+            else { const int o1 = d / 3, o2 = d - o1 * 3; tap_row = ((o1 == 0) ? 1 : (o1 == 1 ? 0 : 2)) * 3 + ((o2 == 0) ? 1 : (o2 == 1 ? 0 : 2)); }
             if (gw + g > kWGranules) gw = 0;
             { PROF_T0(pf); for (int j = 0; j < g; ++j) mbar_wait(&emptyW[gw + j], ((eW_bits >> (gw + j)) & 1u) ^ 1u); PROF_ADD(pf, 2); }
             if (elect_one_sync()) {
               mbar_arrive_expect_tx(&fullW[gw], wbytes);
-              const long long row = w_row0 + (static_cast<long long>((c * col_groups + (w % col_groups)) * 3 + dxi) * 3) * n_cols;
+              const long long row = w_row0 + (static_cast<long long>(c * col_groups + (w % col_groups)) * 9 + tap_row) * n_cols;
               bulk_load_1d(smemW + gw * kWGranule, packed_w + row * 128, wbytes, &fullW[gw]);
             }
             __syncwarp();
@@ -366,6 +378,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     constexpr uint32_t kHi = smem_desc_hi(1024);            // weights: 8-row groups 1024 B apart
     constexpr uint32_t kHiA = smem_desc_hi(kABoxW * 128);   // activations: 8 pixels of a patch row, rows 1280 B apart
     uint32_t fA_bits = 0, fW_bits = 0;  // phase parity per A slot / W granule (full barriers)
+    uint32_t acc_bits = 0;              // phase parity of the two accumulator stages (tempty barriers)
+    int acc_toggle = 0, last_hold = 0;
     int sa = 0, gw = 0;
     int it = 0;
     const bool pf = (debug & 64) != 0;
@@ -377,17 +391,27 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const ConvParams* gp = &(layers + __ldcg(&ed->layer))->p;
       const int num_chunks = __ldcg(&gp->num_chunks), ksteps_last = __ldcg(&gp->ksteps_last);
       const int n_cols = __ldcg(&gp->n_cols), col_groups = __ldcg(&gp->col_groups), w_taps = __ldcg(&gp->w_taps);
+      const int acc_col0 = __ldcg(&gp->acc_col0), acc_first = __ldcg(&gp->acc_first), acc_hold = __ldcg(&gp->acc_hold);
+      const bool has_epi = __ldcg(&gp->epi_cols) > 0;  // deferred partial-sum layers have no epilogue: nothing to hand over
       const int num_work = (tile_hi - tile_lo) * col_groups;
       const int g = (w_taps * n_cols * 128 + kWGranule - 1) / kWGranule;
       const int wsteps = 9 / w_taps;
       const uint32_t idesc = make_idesc_bf16(128, n_cols, 0, 0);
       const uint32_t b_dy = static_cast<uint32_t>(n_cols) * 8;  // (n_cols * 128 B) >> 4
+      const uint32_t half_stride = acc_hold ? 256u : 128u;
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
       for (int w = v; w < num_work; w += static_cast<int>(grid), ++it) {
-        const int as = it & 1;
-        { PROF_T0(pf); mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1); PROF_ADD(pf, 4); }
+        // accumulator stage: pass layers always use the fixed block (stage 0); ordinary layers alternate
+        const int as = acc_hold ? 0 : (acc_toggle & 1);
+        if (!acc_hold) ++acc_toggle;
+        if (acc_hold != last_hold) {
+          // switching between the double-buffered layout and the fixed dense-block layout: both stages must be drained
+          { PROF_T0(pf); mbar_wait(&tempty[as ^ 1], ((acc_bits >> (as ^ 1)) & 1u) ^ 1u); PROF_ADD(pf, 4); }
+          last_hold = acc_hold;
+        }
+        { PROF_T0(pf); mbar_wait(&tempty[as], ((acc_bits >> as) & 1u) ^ 1u); PROF_ADD(pf, 4); }
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        const uint32_t d_tmem = tmem_base + (acc_hold ? 0u : as * kAccStride) + acc_col0;
         for (int c = 0; c < num_chunks; ++c) {
           const int ksteps = (c == num_chunks - 1) ? ksteps_last : 4;
           { PROF_T0(pf); mbar_wait(&fullA[sa], (fA_bits >> sa) & 1u); PROF_ADD(pf, 5); }
@@ -398,26 +422,26 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             tcgen05_fence_after();
             if (elect_one_sync()) {
               const uint32_t b_base = smem_desc_lo(smem_u32(smemW + gw * kWGranule), 16);
-              const int ncol_dx = 9 / wsteps / 3;  // dx columns held by this stage: 3 (whole chunk) or 1
 #pragma unroll 1
-              for (int dd = 0; dd < ncol_dx; ++dd) {
-                const int o = (ncol_dx == 3) ? dd : d;                 // position in the centre-first order {1, 0, 2}
-                const int dxi = (o == 0) ? 1 : (o == 1 ? 0 : 2);
-                const uint32_t b_lo = b_base + ((ncol_dx == 3) ? dxi * 3 : 0) * b_dy;
-                const uint32_t first = (c | o) ? 1u : 0u;  // very first MMA of the item overwrites the accumulators
+              for (int tt = 0; tt < w_taps; ++tt) {
+                // position of this tap in the centre-first order (dx in {1,0,2} outer, dy in {1,0,2} inner)
+                const int pos = d * w_taps + tt;
+                const int o1 = pos / 3, o2 = pos - o1 * 3;
+                const int dxi = (o1 == 0) ? 1 : (o1 == 1 ? 0 : 2);
+                const int dyi = (o2 == 0) ? 1 : (o2 == 1 ? 0 : 2);
+                // tile of this tap inside the stage (rows are packed [dx][dy][n])
+                const int tile_in_stage = (w_taps == 9) ? dxi * 3 + dyi : (w_taps == 3 ? dyi : 0);
+                const uint32_t b_lo = b_base + tile_in_stage * b_dy;
+                const uint32_t first = (acc_first && c == 0 && pos == 0) ? 0u : 1u;  // very first MMA of a fresh item overwrites
+                const uint32_t a_tap = a_lo + (dyi * kABoxW + dxi) * 8;
 #pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                  const int dyi = (t == 0) ? 1 : (t == 1 ? 0 : 2);  // centre row first
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    if (ks < ksteps && !(debug & 2)) {
-                      // tap (dy,dx) = the haloed tile shifted by (dy*10+dx) rows of 128 B; the two 128-pixel halves
-                      // (patch rows 0-15 / 16-31) reuse the same weight tile
-                      const uint32_t a_tap = a_lo + (dyi * kABoxW + dxi) * 8 + ks * 2;
-                      umma_bf16_ss_lohi2(d_tmem, a_tap, kHiA, b_lo + dyi * b_dy + ks * 2, kHi, idesc, (t == 0 && ks == 0) ? first : 1u);
-                      umma_bf16_ss_lohi2(d_tmem + 128, a_tap + 16 * kABoxW * 8, kHiA, b_lo + dyi * b_dy + ks * 2, kHi, idesc,
-                                         (t == 0 && ks == 0) ? first : 1u);
-                    }
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks < ksteps && !(debug & 2)) {
+                    // tap (dy,dx) = the haloed tile shifted by (dy*10+dx) rows of 128 B; the two 128-pixel halves
+                    // (patch rows 0-15 / 16-31) reuse the same weight tile
+                    umma_bf16_ss_lohi2(d_tmem, a_tap + ks * 2, kHiA, b_lo + ks * 2, kHi, idesc, (ks == 0) ? first : 1u);
+                    umma_bf16_ss_lohi2(d_tmem + half_stride, a_tap + 16 * kABoxW * 8 + ks * 2, kHiA, b_lo + ks * 2, kHi, idesc,
+                                       (ks == 0) ? first : 1u);
                   }
                 }
               }
@@ -431,8 +455,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           fA_bits ^= (1u << sa);
           if (++sa == kNumASlots) sa = 0;
         }
-        if (elect_one_sync()) umma_commit(&tfull[as]);  // accumulators ready for the epilogue warps
-        __syncwarp();
+        if (has_epi) {
+          if (elect_one_sync()) umma_commit(&tfull[as]);  // accumulators ready for the epilogue warps
+          __syncwarp();
+          acc_bits ^= (1u << as);
+        }
       }
     }
     if (pf && lane == 0) {
@@ -456,12 +483,14 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       if (et < static_cast<int>(sizeof(ConvParams) / 4)) dst[et] = __ldcg(reinterpret_cast<const uint32_t*>(gp) + et);
       if (et >= 80 && et < 88) dst[et] = __ldcg(reinterpret_cast<const uint32_t*>(ed) + (et - 80));  // EntryDesc at +320 B
       const float* nb = reinterpret_cast<const float*>(__ldcg(reinterpret_cast<const unsigned long long*>(&gp->epi.bias)));
-      const int nt = __ldcg(&gp->n_total);
+      const int nt = __ldcg(&gp->acc_hold) ? __ldcg(&gp->epi_cols) : __ldcg(&gp->n_total);
       float* bdst = sbias_base + (e & 1) * 256;
       for (int i = et; i < nt; i += 256) bdst[i] = nb ? __ldcg(nb + i) : 0.f;
     };
     stage_entry(0);
     int it = 0;
+    uint32_t acc_bits = 0;  // phase parity of the two accumulator stages (tfull barriers)
+    int acc_toggle = 0;
     const bool pf = (debug & 64) != 0;
     long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long pstart = pf ? clock64() : 0;
@@ -474,7 +503,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int tiles_per_img = p.tiles_x * p.tiles_y;
       const int num_work = (ent.tile_hi - ent.tile_lo) * p.col_groups;
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(ent.rot)) % grid);
-      if (v < num_work && ent.dep >= 0) {
+      if (v < num_work && ent.dep >= 0 && p.epi_cols > 0) {
         // residuals / masks written by the entry we depend on are read before the accumulator is ready: check it too
         PROF_T0(pf);
         if (et == 0 && !(debug & 16)) {
@@ -484,7 +513,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         epi_bar_sync();
         PROF_ADD(pf, 8);
       }
-      for (int w = v; w < num_work; w += static_cast<int>(grid), ++it) {
+      for (int w = v; w < ((p.epi_cols > 0) ? num_work : 0); w += static_cast<int>(grid), ++it) {
         const int tile = ent.tile_lo + w / p.col_groups;
         const int colbase = (w % p.col_groups) * p.n_cols;
         const int n = tile / tiles_per_img;
@@ -493,7 +522,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const int x = (t2 - ty * p.tiles_x) * kTileW + (m & 7);
         const int y = ty * kTileH + half * 16 + (m >> 3);
         const bool valid = (x < p.W) && (y < p.H);
-        const int as = it & 1;
+        const int as = p.acc_hold ? 0 : (acc_toggle & 1);
+        if (!p.acc_hold) ++acc_toggle;
         // Operands that do not depend on the accumulator are fetched BEFORE waiting for the MMAs, so their L2 latency
         // hides behind the tensor work: combined fp32 residual (<= 64 columns) and the LeakyReLU-derivative mask words.
         const ConvEpilogue& ep = p.epi;
@@ -508,7 +538,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           const float* r1p = ep.r1 + cbase + (colbase >> 2) * kCarrierChunkStride;
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            if (4 * k < p.n_cols) {
+            if (4 * k < p.epi_cols) {
               const float4 r = __ldcg(reinterpret_cast<const float4*>(r1p + k * kCarrierChunkStride));
               res[4 * k] = ep.beta1 * r.x; res[4 * k + 1] = ep.beta1 * r.y; res[4 * k + 2] = ep.beta1 * r.z; res[4 * k + 3] = ep.beta1 * r.w;
             }
@@ -517,7 +547,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             const float* r2p = ep.r2 + cbase + (colbase >> 2) * kCarrierChunkStride;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-              if (4 * k < p.n_cols) {
+              if (4 * k < p.epi_cols) {
                 const float4 r = __ldcg(reinterpret_cast<const float4*>(r2p + k * kCarrierChunkStride));
                 res[4 * k] += ep.beta2 * r.x; res[4 * k + 1] += ep.beta2 * r.y; res[4 * k + 2] += ep.beta2 * r.z; res[4 * k + 3] += ep.beta2 * r.w;
               }
@@ -528,27 +558,34 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           const uint4* mp = reinterpret_cast<const uint4*>(ep.mask + pix * ep.mask_stride + ep.mask_coff + colbase);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            if (8 * k < p.n_cols) {
+            if (8 * k < p.epi_cols) {
               const uint4 m4 = __ldcg(mp + k);
               maskw[4 * k] = m4.x; maskw[4 * k + 1] = m4.y; maskw[4 * k + 2] = m4.z; maskw[4 * k + 3] = m4.w;
             }
           }
         }
-        { PROF_T0(pf); mbar_wait(&tfull[as], (it >> 1) & 1); PROF_ADD(pf, 9); }
+        { PROF_T0(pf); mbar_wait(&tfull[as], (acc_bits >> as) & 1u); PROF_ADD(pf, 9); }
+        acc_bits ^= (1u << as);
         tcgen05_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * 128;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (p.acc_hold ? 0u : as * kAccStride) +
+                                half * (p.acc_hold ? 256u : 128u) + p.acc_col0;
 #pragma unroll
         for (int gq = 0; gq < 2; ++gq) {
           const int c0 = gq * 32;
-          if (c0 < p.n_cols) {
+          if (c0 < p.epi_cols) {
             float vv[32];
-            const int ncol = (p.n_cols - c0) >= 32 ? 32 : 16;
+            const int ncol = (p.epi_cols - c0) >= 32 ? 32 : 16;
             if (ncol == 32) {
               uint32_t r[32];
               tmem_ld_32x32b_x32(t_addr + c0, r);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) vv[i] = __uint_as_float(r[i]);
+              if (c0 + 32 >= p.epi_cols) {  // last TMEM read of this item: release the accumulator before the global stores
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+              }
             } else {
               uint32_t r[16];
               tmem_ld_32x32b_x16(t_addr + c0, r);
@@ -557,15 +594,15 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
               for (int i = 0; i < 16; ++i) vv[i] = __uint_as_float(r[i]);
 #pragma unroll
               for (int i = 16; i < 32; ++i) vv[i] = 0.f;
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[as]);
             }
             if (pre)
               conv_epilogue_store(p, y_dyn, sbias, has_res ? &res[gq * 32] : nullptr, has_mask ? &maskw[gq * 16] : nullptr, cbase, n, y,
                                   x, colbase + c0, ncol, vv);
           }
         }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
       }
       // announce: this CTA's part of entry e is stored (cumulativity: bar.sync + gpu-scope fence by the signalling thread)
       { PROF_T0(pf); epi_bar_sync(); PROF_ADD(pf, 8); }
