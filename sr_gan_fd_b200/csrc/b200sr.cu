@@ -72,8 +72,8 @@ static int runtime_init() {
 }
 
 // NHWC bf16 activation map: dims (C, W, H, N), box (64, 10 | 8, rows, 1), 128B swizzle, zero OOB fill.
-static int encode_act_map(CUtensorMap* m, void* base, int c_valid, int c_pix, int n, int h, int w, int box_rows) {
-  const int box_w = (box_rows == kABoxRows) ? kABoxW : kTileW;  // conv tiles carry the horizontal halo, wgrad tiles do not
+static int encode_act_map(CUtensorMap* m, void* base, int c_valid, int c_pix, int n, int h, int w, int box_rows, int box_w_in = -1) {
+  const int box_w = box_w_in > 0 ? box_w_in : ((box_rows == kABoxRows) ? kABoxW : kTileW);  // conv tiles carry the horizontal halo, wgrad tiles do not
   cuuint64_t dims[4] = {(cuuint64_t)c_valid, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c_pix * 2, (cuuint64_t)w * c_pix * 2, (cuuint64_t)h * w * c_pix * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
@@ -104,7 +104,7 @@ struct Ref {
 };
 static Ref ws(long long off) { Ref r; r.kind = RK_WS; r.off = off; return r; }
 
-struct ActMapSpec { long long off; int c_valid, c_pix, n, h, w, box_rows; };
+struct ActMapSpec { long long off; int c_valid, c_pix, n, h, w, box_rows, box_w; };
 struct Bases { void* ws; void* packed; void* y; const void* dy; void* grads; };
 
 enum StepType { ST_CONV, ST_CHAIN, ST_WGRAD, ST_BIASGRAD, ST_UNPACK, ST_ADD, ST_MEMSET, ST_INGEST_X, ST_INGEST_DY };
@@ -153,8 +153,11 @@ struct b200sr_plan {
   long long o_dyp = 0, o_g3 = 0, o_gt = 0, o_gtb = 0, o_gr = 0, o_gc1 = 0, o_gc2 = 0, o_go1 = 0;
   long long o_dyb[6] = {0, 0, 0, 0, 0, 0};
   std::vector<long long> o_gu;
-  bool reassoc = true;                // dense blocks re-associated by input slice (B200SR_REASSOC=0 selects the per-conv schedule)
+  bool reassoc = false;               // experimental (B200SR_REASSOC=1): dense blocks re-associated by input slice; default = per-conv schedule
   int groups = 1;                     // image groups that flow through a chain independently
+  bool unit_all = false;              // experimental: every chain layer works on single 8 x 16 units (B200SR_UNIT=1)
+  int groups_env = 0;                 // experimental: force the number of image groups (B200SR_GROUPS)
+  bool split_passes = false;          // experimental: split every pass into a critical and a deferred sub-layer
   int plan_sms = 148;                 // SM count the schedule was laid out for
   long long gw_bytes = 0;
   long long o_gw = 0;                 // staged weight gradients, per conv [tap][ci][co_pad] fp32
@@ -173,6 +176,8 @@ struct b200sr_plan {
   LayerDesc* d_layers = nullptr;
   std::vector<EntryDesc> h_entries;   // (layer, image group) entries of every chain, chain after chain
   EntryDesc* d_entries = nullptr;
+  uint4* d_layer_rec = nullptr;       // constant-memory images of the two tables (copied device -> constant per launch)
+  uint4* d_entry_rec = nullptr;
   unsigned int* d_counters = nullptr; // per-entry completion counters of the chain being launched
 };
 
@@ -191,13 +196,15 @@ struct Builder {
     cursor = align_up(cursor + bytes, 1024);
     return o;
   }
-  int add_map(long long off, int c_valid, int c_pix, int n, int h, int w, int box_rows) {
+  int add_map(long long off, int c_valid, int c_pix, int n, int h, int w, int box_rows, int box_w = -1) {
+    if (P.unit_all && box_rows == kABoxRows) { box_rows = 18; box_w = kABoxW; }
     for (size_t i = 0; i < P.map_specs.size(); ++i) {
       const ActMapSpec& s = P.map_specs[i];
-      if (s.off == off && s.c_valid == c_valid && s.c_pix == c_pix && s.n == n && s.h == h && s.w == w && s.box_rows == box_rows)
+      if (s.off == off && s.c_valid == c_valid && s.c_pix == c_pix && s.n == n && s.h == h && s.w == w && s.box_rows == box_rows &&
+          s.box_w == box_w)
         return (int)i;
     }
-    P.map_specs.push_back({off, c_valid, c_pix, n, h, w, box_rows});
+    P.map_specs.push_back({off, c_valid, c_pix, n, h, w, box_rows, box_w});
     return (int)P.map_specs.size() - 1;
   }
   // packed rows for an op; returns row0
@@ -231,7 +238,7 @@ ConvParams base_conv_params(int n, int h, int w, int num_chunks, int ksteps_last
   p.w_row0 = row0; p.n_cols = n_cols; p.n_total = n_total;
   p.col_groups = n_total / n_cols;
   p.w_taps = (9 * n_cols * 128 <= 5 * kWGranule) ? 9 : ((3 * n_cols * 128 <= 5 * kWGranule) ? 3 : 1);  // bytes per weight bulk copy <= 60 KB
-  p.acc_col0 = 0; p.acc_first = 1; p.acc_hold = 0; p.epi_cols = n_cols;
+  p.acc_col0 = 0; p.acc_first = 1; p.acc_hold = 0; p.epi_cols = n_cols; p.halves = 2;
   p.num_stages = conv_pick_stages(n_cols);
   p.epi.alpha = 1.f; p.epi.delta = 1.f; p.epi.beta1 = 1.f; p.epi.beta2 = 1.f;
   p.epi.res_stride = 64; p.epi.of_stride = 64;
@@ -247,6 +254,12 @@ PackSeg nseg(int n0, int nlen, int k0, int klen, int w_index, int O, int I, int 
   PackSeg s = seg(k0, klen, w_index, O, I, o_off, i_off, 0);
   s.n0 = n0; s.nlen = nlen;
   return s;
+}
+// dense-block pass layers work on single 8 x 16 units (one 128-pixel half per item)
+void make_unit_layer(ConvParams& p) {
+  p.halves = 1;
+  p.tiles_y = (p.H + 15) / 16;
+  p.num_tiles = p.N * p.tiles_x * p.tiles_y;
 }
 }  // namespace
 
@@ -288,13 +301,14 @@ static int build_plan(b200sr_plan& P) {
       cudaGetLastError();
     }
     if (sms > 0) P.plan_sms = sms;
-    const int tpi = ((d.width + kTileW - 1) / kTileW) * ((d.height + kTileH - 1) / kTileH);
+    const int tpi = ((d.width + kTileW - 1) / kTileW) * ((d.height + 15) / 16);  // 8 x 16 units per image (dense-block passes)
     P.groups = d.batch >= 2 ? 2 : 1;
     if (P.reassoc) {
       int g = P.groups;
       while (g <= d.batch && ((d.batch + g - 1) / g) * tpi > P.plan_sms) ++g;
       if (g <= d.batch) P.groups = g; else P.reassoc = false;  // a single image already exceeds one item per CTA
     }
+    if (P.groups_env > 0 && !P.reassoc) P.groups = P.groups_env < d.batch ? P.groups_env : d.batch;
   }
   const int R = P.R, L = P.L;
   const bool train = d.training != 0;
@@ -378,6 +392,7 @@ static int build_plan(b200sr_plan& P) {
     s.amap = amap;
     s.wmap = wmap_index(cp.n_cols);
     s.cp = cp;
+    if (P.unit_all && s.cp.halves == 2) make_unit_layer(s.cp);
     s.grid = dim3(1, grid_y, 1);
     s.smem = 0;
     return s;
@@ -435,9 +450,9 @@ static int build_plan(b200sr_plan& P) {
         // completes (small N, has the epilogue that produces the next slice) and DEFERRED = the partial sums of the later
         // convs (large N, no epilogue), which the MMA warp works off while the critical epilogue and the cross-CTA
         // dependency of the next pass are in flight.
-        for (int part = 0; part < 2; ++part) {
+        for (int part = 0; part < (P.split_passes ? 2 : 1); ++part) {
           const int col_lo = (part == 0) ? 32 * q : 32 * (q + 1);          // accumulator columns [col_lo, col_hi)
-          const int col_hi = (part == 0) ? ((q < 4) ? 32 * (q + 1) : 192) : 192;
+          const int col_hi = !P.split_passes ? 192 : ((part == 0) ? ((q < 4) ? 32 * (q + 1) : 192) : 192);
           const int ncols = col_hi - col_lo;
           if (ncols <= 0) continue;
           PackOp op; memset(&op, 0, sizeof(op));
@@ -450,8 +465,9 @@ static int build_plan(b200sr_plan& P) {
           }
           const int row0 = B.add_pack(op);
           ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, c_q, 1 << 20, row0, ncols, ncols);
-          cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = (part == 0) ? ncols : 0;
-          Step s = conv_step(B.add_map(D, c_q + klen, 192, N, H, W, kABoxRows), cp, 1);
+          cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = (part == 0) ? ((q < 4) ? 32 : 64) : 0;
+          make_unit_layer(cp);
+          Step s = conv_step(B.add_map(D, c_q + klen, 192, N, H, W, 18, kABoxW), cp, 1);
           if (part == 0) {
             const int ci_done = conv_index_rdb(r, q + 1);  // the conv that is complete after this pass
             s.bias = packed_bias(B.add_bias(cp.epi_cols, 2 * ci_done + 1, cp.epi_cols, 0));
@@ -724,9 +740,9 @@ static int build_plan(b200sr_plan& P) {
           const int klen = (kk == 5) ? 64 : 32;
           const int a_c0 = (q == 0) ? 0 : 64 + 32 * (q - 1);   // dY_kk inside [dY5 | dY4 | dY3 | dY2 | dY1]
           const int ci = conv_index_rdb(r, kk);
-          for (int part = 0; part < 2; ++part) {               // critical (completed slice) / deferred (later slices), as forward
+          for (int part = 0; part < (P.split_passes ? 2 : 1); ++part) {  // optional critical / deferred split, as forward
             const int col_lo = (part == 0) ? 32 * q : 32 * (q + 1);
-            const int col_hi = (part == 0) ? ((q < 4) ? 32 * (q + 1) : 192) : 192;
+            const int col_hi = !P.split_passes ? 192 : ((part == 0) ? ((q < 4) ? 32 * (q + 1) : 192) : 192);
             const int ncols = col_hi - col_lo;
             if (ncols <= 0) continue;
             PackOp op; memset(&op, 0, sizeof(op));
@@ -739,8 +755,9 @@ static int build_plan(b200sr_plan& P) {
             }
             const int row0 = B.add_pack(op);
             ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, a_c0, 1 << 20, row0, ncols, ncols);
-            cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = (part == 0) ? ncols : 0;
-            Step s = conv_step(B.add_map(DYc, a_c0 + klen, 192, N, H, W, kABoxRows), cp, 1);
+            cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = (part == 0) ? ((q < 4) ? 32 : 64) : 0;
+            make_unit_layer(cp);
+            Step s = conv_step(B.add_map(DYc, a_c0 + klen, 192, N, H, W, 18, kABoxW), cp, 1);
             if (part == 0) {
               if (q < 4) {
                 const int sl = 4 - q;  // completed slice o_sl
@@ -866,7 +883,7 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
   P.maps.resize(P.map_specs.size());
   for (size_t i = 0; i < P.map_specs.size(); ++i) {
     const ActMapSpec& s = P.map_specs[i];
-    int rc = encode_act_map(&P.maps[i], (char*)wsp + s.off, s.c_valid, s.c_pix, s.n, s.h, s.w, s.box_rows);
+    int rc = encode_act_map(&P.maps[i], (char*)wsp + s.off, s.c_valid, s.c_pix, s.n, s.h, s.w, s.box_rows, s.box_w);
     if (rc) return rc;
   }
   // device-resident layer list (pointers resolved against this workspace / packed buffer)
@@ -904,8 +921,10 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
             // a dense block = the run of pass sub-layers up to (not including) the next block's first critical sub-layer
             while (l1 < s.nlayers && P.layer_steps[s.layer0 + l1].cp.acc_hold &&
                    !(P.layer_steps[s.layer0 + l1].cp.acc_first && P.layer_steps[s.layer0 + l1].cp.epi_cols > 0)) ++l1;
-            for (int g = 0; g < groups; ++g)
-              for (int ll = l; ll < l1; ++ll) order.push_back({ll, g});
+            // two groups are resident in a CTA's TMEM at a time: interleave them pass by pass, pair after pair
+            for (int g0 = 0; g0 < groups; g0 += 2)
+              for (int ll = l; ll < l1; ++ll)
+                for (int g = g0; g < g0 + 2 && g < groups; ++g) order.push_back({ll, g});
             l = l1;
           } else {
             for (int g = 0; g < groups; ++g) order.push_back({l, g});
@@ -927,7 +946,8 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
           int lp = (cp.epi_cols == 0) ? l - 2 : l - 1;
           while (lp >= 0 && P.layer_steps[s.layer0 + lp].cp.epi_cols == 0) --lp;
           e.dep = (lp >= 0) ? index_of[(size_t)lp * groups + g] : -1;
-          e.rot = (int)(((long long)img_lo * tpi * cp.col_groups) % grid);  // each group starts where the previous one's last round ended
+          e.rot = (int)(((long long)img_lo * tpi * cp.col_groups) % grid);
+          e.slot = g & 1;  // each group starts where the previous one's last round ended
           P.h_entries.push_back(e);
         }
         s.nentries = (int)P.h_entries.size() - s.entry0;
@@ -941,6 +961,14 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
     CUDA_TRY(cudaMalloc(&P.d_entries, P.h_entries.size() * sizeof(EntryDesc)));
     CUDA_TRY(cudaMalloc(&P.d_counters, 16384));
     CUDA_TRY(cudaMemcpyAsync(P.d_entries, P.h_entries.data(), P.h_entries.size() * sizeof(EntryDesc), cudaMemcpyHostToDevice, st));
+    std::vector<uint4> lrec(P.h_layers.size() * 2), erec(P.h_entries.size());
+    for (size_t i = 0; i < P.h_layers.size(); ++i) make_layer_rec(P.h_layers[i].p, &lrec[2 * i], packed);
+    for (size_t i = 0; i < P.h_entries.size(); ++i) erec[i] = make_entry_rec(P.h_entries[i]);
+    CUDA_TRY(cudaMalloc(&P.d_layer_rec, lrec.size() * sizeof(uint4)));
+    CUDA_TRY(cudaMalloc(&P.d_entry_rec, erec.size() * sizeof(uint4)));
+    CUDA_TRY(cudaMemcpyAsync(P.d_layer_rec, lrec.data(), lrec.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(P.d_entry_rec, erec.data(), erec.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // lrec / erec are pageable host vectors that die at scope exit
   }
   CUDA_TRY(cudaMemcpyAsync(P.d_layers, P.h_layers.data(), P.h_layers.size() * sizeof(LayerDesc), cudaMemcpyHostToDevice, st));
   P.cached_ws = wsp;
@@ -951,7 +979,12 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
 static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStream_t st) {
   int grid = s.chain_grid < g_num_sms ? s.chain_grid : g_num_sms;
   if (grid < 1) grid = 1;
-  if (s.nentries * (int)sizeof(unsigned int) > 16384) return fail(B200SR_ERR_INVALID, "chain too long (%d entries)", s.nentries);
+  if (s.nentries > kMaxChainEntries || s.nlayers > kMaxChainLayers)
+    return fail(B200SR_ERR_INVALID, "chain too long (%d entries, %d layers)", s.nentries, s.nlayers);
+  // the producer / MMA warps read their parameters from constant memory: load this chain's slice (stream ordered)
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_layer_rec, P.d_layer_rec + 2 * (size_t)s.layer0, (size_t)s.nlayers * 2 * sizeof(uint4), 0, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_entry_rec, P.d_entry_rec + s.entry0, (size_t)s.nentries * sizeof(uint4), 0, cudaMemcpyDeviceToDevice, st));
+  int layer0 = s.layer0;
   const LayerDesc* layers = P.d_layers;
   const EntryDesc* entries = P.d_entries + s.entry0;
   int ne = s.nentries;
@@ -960,7 +993,7 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   unsigned int* ctr = P.d_counters;
   CUDA_TRY(cudaMemsetAsync(ctr, 0, (size_t)ne * sizeof(unsigned int), st));
   const uint8_t* pw = (const uint8_t*)b.packed;
-  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&y, (void*)&dbg};
+  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&y, (void*)&dbg, (void*)&layer0};
   const void* fn = (const void*)conv3x3_chain_kernel<1>;
   if (ne > 1) {
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
@@ -1097,6 +1130,9 @@ int b200sr_plan_create(const b200sr_net_desc* desc, b200sr_plan** out) {
   b200sr_plan* p = new b200sr_plan();
   p->d = *desc;
   if (const char* e = getenv("B200SR_REASSOC")) p->reassoc = atoi(e) != 0;
+  if (const char* e = getenv("B200SR_SPLIT")) p->split_passes = atoi(e) != 0;
+  if (const char* e = getenv("B200SR_UNIT")) p->unit_all = atoi(e) != 0;
+  if (const char* e = getenv("B200SR_GROUPS")) p->groups_env = atoi(e);
   int rc = build_plan(*p);
   if (rc) { delete p; return rc; }
   *out = p;
@@ -1111,6 +1147,8 @@ void b200sr_plan_destroy(b200sr_plan* p) {
   if (p->d_unpack_ops) cudaFree(p->d_unpack_ops);
   if (p->d_layers) cudaFree(p->d_layers);
   if (p->d_entries) cudaFree(p->d_entries);
+  if (p->d_layer_rec) cudaFree(p->d_layer_rec);
+  if (p->d_entry_rec) cudaFree(p->d_entry_rec);
   if (p->d_counters) cudaFree(p->d_counters);
   delete p;
 }
@@ -1265,7 +1303,12 @@ static int single_conv(int mode, const void* x, int n, int h, int w, int cin, in
   int ne = 1, dbg = g_debug;
   unsigned int* ctr = (unsigned int*)(sc + tab_off + 3072 + 640);
   float* ydyn = nullptr;
-  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&ydyn, (void*)&dbg};
+  uint4 lrec[2], erec = make_entry_rec(ent);
+  make_layer_rec(L.p, lrec, sc);
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_layer_rec, lrec, sizeof(lrec), 0, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_entry_rec, &erec, sizeof(erec), 0, cudaMemcpyHostToDevice, st));
+  int layer0 = 0;
+  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&ydyn, (void*)&dbg, (void*)&layer0};
   CUDA_TRY(cudaLaunchKernel((const void*)conv3x3_chain_kernel<1>, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   (void)grid_y;
   return 0;

@@ -14,7 +14,7 @@
 // TMA wrote; the descriptor's base_offset field must stay 0.)  Weights are pre-packed per (chunk, dx, dy) as
 // [cout][64] K-major bf16 rows and stream through their own smem ring, three taps (one dx column) per slot.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// Warp roles (352 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warp 10 = signaller,
 // warps 2..5 / 6..9 = epilogue of the upper / lower 128-pixel half (TMEM -> registers -> fused bias / LeakyReLU /
 // mask / residuals -> global).  Accumulators are double buffered in TMEM so the epilogue of item i overlaps the MMAs
 // of item i+1 (persistent CTAs).
@@ -31,7 +31,7 @@ constexpr int kABytes = kABoxRows * kABoxW * 128;       // 43520 B: one haloed a
 constexpr int kASlot = 44032;                           // A-ring slot (1024-byte multiple)
 constexpr int kMaxAStages = 4;
 constexpr int kMaxWStages = 6;
-constexpr int kConvThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of the upper 128-pixel half, warps 6-9 of the lower half
+constexpr int kConvThreads = 352;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of the upper 128-pixel half, warps 6-9 of the lower half
 constexpr int kMaxStages = 8;
 
 enum StoreMode : int {
@@ -83,6 +83,7 @@ struct ConvParams {
   // (acc_hold = 1): the block's 192 accumulator columns live in a fixed TMEM block across five consecutive entries; pass j
   // adds input slice j's contribution to columns [acc_col0, acc_col0 + n_cols) and its epilogue consumes the leading
   // epi_cols columns (the conv that just became complete).
+  int halves;      // 128-pixel halves per work item: 2 (8 x 32 patch, ordinary layers) or 1 (8 x 16 unit, dense-block passes)
   int acc_col0;
   int acc_first;   // 1: the first MMA of an item overwrites the accumulators, 0: accumulate onto earlier passes
   int acc_hold;
@@ -224,8 +225,41 @@ struct alignas(32) EntryDesc {
   int tile_lo, tile_hi;  // pixel tiles of this entry (an image group of the layer)
   int dep;               // entry whose completion gates this entry's input reads (-1: inputs exist before the launch)
   int rot;               // CTA rotation: virtual CTA v = (blockIdx.x - rot) mod gridDim.x takes items v, v + gridDim.x, ...
-  int pad[3];
+  int slot;              // dense-block passes: which of the CTA's two resident accumulator blocks this image group uses
+  int pad[2];
 };
+
+// Compact per-layer / per-entry records for the TMA-producer and MMA-issuer warps, kept in CONSTANT memory: loads with a
+// warp-uniform index go through the uniform datapath, so everything derived from them (TMEM addresses, instruction
+// descriptors, loop bounds) stays in uniform registers and tcgen05.mma issues back to back without R2UR round trips.
+// The host copies the slice of the chain being launched into these tables right before the launch (stream ordered).
+constexpr int kMaxChainLayers = 768;
+constexpr int kMaxChainEntries = 2048;
+// layer record A: x = n_cols | chunks<<10 | ksteps_last<<14 | halves<<17 | w_taps<<19 | col_groups<<23
+//                 y = acc_col0 | acc_first<<8 | acc_hold<<9 | has_epi<<10      z = w_row0      w = a_c0
+// layer record B: x = tiles_x | tiles_y<<16      y = a_wrap      z = bias byte offset in the packed buffer + 1 (0: none)      w = bias floats
+// entry record  : x = layer (absolute) | slot<<20      y = tile_lo      z = tile_hi      w = rot | (dep+1)<<16
+__constant__ uint4 c_layer_rec[kMaxChainLayers * 2];
+__constant__ uint4 c_entry_rec[kMaxChainEntries];
+inline void make_layer_rec(const ConvParams& p, uint4 out[2], const void* packed_base) {
+  out[0].x = static_cast<uint32_t>(p.n_cols) | (p.num_chunks << 10) | (p.ksteps_last << 14) | (p.halves << 17) | (p.w_taps << 19) | (p.col_groups << 23);
+  out[0].y = static_cast<uint32_t>(p.acc_col0) | ((p.acc_first ? 1u : 0u) << 8) | ((p.acc_hold ? 1u : 0u) << 9) | ((p.epi_cols > 0 ? 1u : 0u) << 10);
+  out[0].z = static_cast<uint32_t>(p.w_row0);
+  out[0].w = static_cast<uint32_t>(p.a_c0);
+  out[1].x = static_cast<uint32_t>(p.tiles_x) | (static_cast<uint32_t>(p.tiles_y) << 16);
+  out[1].y = static_cast<uint32_t>(p.a_wrap);
+  out[1].z = p.epi.bias ? static_cast<uint32_t>(reinterpret_cast<const char*>(p.epi.bias) - static_cast<const char*>(packed_base)) + 1u : 0u;
+  out[1].w = static_cast<uint32_t>(p.acc_hold ? p.epi_cols : p.n_total);
+}
+inline uint4 make_entry_rec(const EntryDesc& e) {
+  uint4 r;
+  r.x = static_cast<uint32_t>(e.layer) | (static_cast<uint32_t>(e.slot) << 20);
+  r.y = static_cast<uint32_t>(e.tile_lo);
+  r.z = static_cast<uint32_t>(e.tile_hi);
+  r.w = static_cast<uint32_t>(e.rot) | (static_cast<uint32_t>(e.dep + 1) << 16);
+  return r;
+}
+
 
 constexpr int kWGranule = 12288;   // weight ring granule = one (chunk, dx) stage of a 32-column layer (3 taps x 32 x 128 B)
 constexpr int kWGranules = 10;
@@ -256,13 +290,39 @@ __device__ __forceinline__ void wait_entry_done(const unsigned int* counters, in
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
 
+// One weight stage worth of tcgen05.mma, fully unrolled with compile-time tap offsets so that consecutive MMAs differ
+// only by immediates added to uniform registers.  TAPS = taps in the stage (9: whole 3x3, centre first; 3: the three
+// dy of one dx column -- a_lo / b_base already point at that column; 1: a single tap), HALVES = 128-pixel halves of
+// the work item (the second half reuses the weight tile), KSTEPS = 16-channel K steps of this chunk.
+template <int TAPS, int HALVES, int KSTEPS>
+__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a_lo, uint32_t b_base, uint32_t b_dy, uint32_t idesc, uint32_t first) {
+  constexpr uint32_t kHi = smem_desc_hi(1024);            // weights: 8-row groups 1024 B apart
+  constexpr uint32_t kHiA = smem_desc_hi(kABoxW * 128);   // activations: 8 pixels of a patch row, rows 1280 B apart
+  constexpr int ord[3] = {1, 0, 2};
+#pragma unroll
+  for (int tt = 0; tt < TAPS; ++tt) {
+    const int dxi = (TAPS == 9) ? ord[tt / 3] : 0;   // TAPS 3 / 1: the caller folded dx (and dy) into a_lo
+    const int dyi = (TAPS == 1) ? 0 : ord[tt % 3];
+    const int tile_in_stage = (TAPS == 9) ? dxi * 3 + dyi : (TAPS == 3 ? dyi : 0);  // rows are packed [dx][dy][n]
+    const uint32_t b_lo = b_base + tile_in_stage * b_dy;
+    const uint32_t a_tap = a_lo + (dyi * kABoxW + dxi) * 8;  // tap (dy,dx) = the haloed tile shifted by dy*10+dx rows of 128 B
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const uint32_t acc = (tt == 0 && ks == 0) ? first : 1u;
+      umma_bf16_ss_lohi2(d_tmem, a_tap + ks * 2, kHiA, b_lo + ks * 2, kHi, idesc, acc);
+      if (HALVES == 2) umma_bf16_ss_lohi2(d_tmem + 128, a_tap + 16 * kABoxW * 8 + ks * 2, kHiA, b_lo + ks * 2, kHi, idesc, acc);
+    }
+  }
+}
+
 template <int kUnused>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __restrict__ entries, int num_entries,
-                     const uint8_t* __restrict__ packed_w, unsigned int* counters, float* y_dyn, int debug) {
+                     const uint8_t* __restrict__ packed_w, unsigned int* counters, float* y_dyn, int debug, int layer0) {
+  // `entries` points at the first entry of THIS chain; c_entry_rec[0..num_entries) / c_layer_rec[2 * (layer - layer0)] mirror it
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // [ A ring: kNumASlots x 44032 | W ring: kWGranules x 12288 | barriers 256 B | epilogue params 2 x 384 B | epilogue bias 2 x 1 KB ]
+  // [ A ring: kNumASlots x 44032 | W ring: kWGranules x 12288 | barriers 512 B | flags | epilogue params 4 x 384 B | epilogue bias 4 x 1 KB ]
   uint8_t* smemW = smem + kNumASlots * kASlot;
   uint8_t* fixed = smemW + kWGranules * kWGranule;
   uint64_t* bars = reinterpret_cast<uint64_t*>(fixed);
@@ -270,13 +330,17 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   uint64_t* emptyA = bars + 4;   // [4]
   uint64_t* fullW = bars + 8;    // [10]
   uint64_t* emptyW = bars + 18;  // [10]
-  uint64_t* tfull = bars + 28;
-  uint64_t* tempty = bars + 30;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 3072);
-  uint8_t* sp_base = fixed + 256;
-  float* sbias_base = reinterpret_cast<float*>(fixed + 1024);
-  static_assert(sizeof(ConvParams) <= 320, "ConvParams + EntryDesc must fit the 384-byte smem slot");
-  static_assert(kNumASlots * kASlot + kWGranules * kWGranule + 3072 + 64 + 1024 <= conv_smem_bytes(1), "smem budget");
+  uint64_t* tfull = bars + 28;   // [2]
+  uint64_t* tempty = bars + 30;  // [2]
+  uint64_t* sig = bars + 32;     // [2] epilogue warps -> signaller warp: "my stores for entry e are issued"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 512);
+  volatile uint32_t* dep_flag = reinterpret_cast<volatile uint32_t*>(fixed + 516);  // producer -> epilogue: e + 1 once entry e's dependency is done
+  volatile uint32_t* sig_done = reinterpret_cast<volatile uint32_t*>(fixed + 520);  // signaller -> epilogue: entries announced so far
+  uint8_t* sp_base = fixed + 1024;                                  // 4 x 384 B
+  float* sbias_base = reinterpret_cast<float*>(fixed + 3072);       // 4 x 1 KB
+  constexpr int kFixedBytes = 3072 + 4096;
+  static_assert(sizeof(ConvParams) <= 384 && sizeof(ConvParams) % 16 == 0, "ConvParams must fit the 384-byte smem slot in 16-byte pieces");
+  static_assert(kNumASlots * kASlot + kWGranules * kWGranule + kFixedBytes + 1024 <= conv_smem_bytes(1), "smem budget");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -287,7 +351,9 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 4; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < kWGranules; ++s) { mbar_init(&fullW[s], 1); mbar_init(&emptyW[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); mbar_init(&sig[a], 8); }
+    *dep_flag = 0;
+    *sig_done = 0;
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_imm<kTmemCols>(tmem_slot);
@@ -305,15 +371,17 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     long long prof[4] = {0, 0, 0, 0};
     const long long pstart = pf ? clock64() : 0;
     for (int e = 0; e < num_entries; ++e) {
-      const EntryDesc* ed = entries + e;
-      const int tile_lo = __ldcg(&ed->tile_lo), tile_hi = __ldcg(&ed->tile_hi), dep = __ldcg(&ed->dep), rot = __ldcg(&ed->rot);
-      const LayerDesc* L = layers + __ldcg(&ed->layer);
-      const ConvParams* gp = &L->p;
-      const int tiles_x = __ldcg(&gp->tiles_x), tiles_y = __ldcg(&gp->tiles_y), num_chunks = __ldcg(&gp->num_chunks);
-      const int a_c0 = __ldcg(&gp->a_c0), a_wrap = __ldcg(&gp->a_wrap), w_row0 = __ldcg(&gp->w_row0);
-      const int n_cols = __ldcg(&gp->n_cols), col_groups = __ldcg(&gp->col_groups);
-      const CUtensorMap* tmA = &L->tmA;
-      const int w_taps = __ldcg(&gp->w_taps);
+      const uint4 er = c_entry_rec[e];
+      const int li = static_cast<int>(er.x & 0xFFFFF);
+      const int tile_lo = static_cast<int>(er.y), tile_hi = static_cast<int>(er.z);
+      const int rot = static_cast<int>(er.w & 0xFFFF), dep = static_cast<int>(er.w >> 16) - 1;
+      const uint4 la = c_layer_rec[(li - layer0) * 2], lb = c_layer_rec[(li - layer0) * 2 + 1];
+      const int n_cols = la.x & 0x3FF, num_chunks = (la.x >> 10) & 0xF, w_taps = (la.x >> 19) & 0xF, col_groups = (la.x >> 23) & 0x1F;
+      const int tile_h = 16 * static_cast<int>((la.x >> 17) & 0x3);
+      const int w_row0 = static_cast<int>(la.z), a_c0 = static_cast<int>(la.w), a_wrap = static_cast<int>(lb.y);
+      const int tiles_x = static_cast<int>(lb.x & 0xFFFF), tiles_y = static_cast<int>(lb.x >> 16);
+      const int a_bytes = (tile_h + 2) * kABoxW * 128;
+      const CUtensorMap* tmA = &layers[li].tmA;
       const int tiles_per_img = tiles_x * tiles_y;
       const int num_work = (tile_hi - tile_lo) * col_groups;
       const int wbytes = w_taps * n_cols * 128;              // one weight stage = w_taps tap tiles, fetched by ONE bulk copy
@@ -322,9 +390,12 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
       if (v < num_work && dep >= 0) {
         { PROF_T0(pf);
-        if (lane == 0 && !(debug & 16)) {
-          wait_entry_done(counters, dep, grid);
+        if (lane == 0) {
+          if (!(debug & 16)) wait_entry_done(counters, dep, grid);
           asm volatile("fence.proxy.async.global;" ::: "memory");  // TMA (async proxy) reads after generic-proxy stores
+          // tell this CTA's epilogue warps (they read residual carriers written by earlier entries): acquire.gpu above,
+          // release.cta here, acquire.cta on their side -- causality order is transitive
+          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(dep_flag))), "r"(e + 1) : "memory");
         }
         __syncwarp();
         PROF_ADD(pf, 0); }
@@ -335,12 +406,12 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const int t2 = tile - n * tiles_per_img;
         const int ty = t2 / tiles_x;
         const int x0 = (t2 - ty * tiles_x) * kTileW;
-        const int y0 = ty * kTileH;
+        const int y0 = ty * tile_h;
         for (int c = 0; c < num_chunks; ++c) {
           const int ac = a_c0 + (c % a_wrap) * 64;
           { PROF_T0(pf); mbar_wait(&emptyA[sa], ((eA_bits >> sa) & 1u) ^ 1u); PROF_ADD(pf, 1); }
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&fullA[sa], kABytes);
+            mbar_arrive_expect_tx(&fullA[sa], a_bytes);
             tma_load_4d(smem + sa * kASlot, tmA, &fullA[sa], ac, x0 - 1, y0 - 1, n);
           }
           __syncwarp();
@@ -386,23 +457,25 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long pstart = pf ? clock64() : 0;
     for (int e = 0; e < num_entries; ++e) {
-      const EntryDesc* ed = entries + e;
-      const int tile_lo = __ldcg(&ed->tile_lo), tile_hi = __ldcg(&ed->tile_hi), rot = __ldcg(&ed->rot);
-      const ConvParams* gp = &(layers + __ldcg(&ed->layer))->p;
-      const int num_chunks = __ldcg(&gp->num_chunks), ksteps_last = __ldcg(&gp->ksteps_last);
-      const int n_cols = __ldcg(&gp->n_cols), col_groups = __ldcg(&gp->col_groups), w_taps = __ldcg(&gp->w_taps);
-      const int acc_col0 = __ldcg(&gp->acc_col0), acc_first = __ldcg(&gp->acc_first), acc_hold = __ldcg(&gp->acc_hold);
-      const bool has_epi = __ldcg(&gp->epi_cols) > 0;  // deferred partial-sum layers have no epilogue: nothing to hand over
+      const long long _tp = pf ? clock64() : 0;
+      const uint4 er = c_entry_rec[e];
+      const int li = static_cast<int>(er.x & 0xFFFFF), slot = static_cast<int>(er.x >> 20);
+      const int tile_lo = static_cast<int>(er.y), tile_hi = static_cast<int>(er.z), rot = static_cast<int>(er.w & 0xFFFF);
+      const uint4 la = c_layer_rec[(li - layer0) * 2];
+      const int n_cols = la.x & 0x3FF, num_chunks = (la.x >> 10) & 0xF, ksteps_last = (la.x >> 14) & 0x7, halves = (la.x >> 17) & 0x3;
+      const int w_taps = (la.x >> 19) & 0xF, col_groups = (la.x >> 23) & 0x1F;
+      const int acc_col0 = la.y & 0xFF, acc_first = (la.y >> 8) & 1, acc_hold = (la.y >> 9) & 1;
+      const bool has_epi = ((la.y >> 10) & 1) != 0;  // deferred partial-sum layers have no epilogue: nothing to hand over
       const int num_work = (tile_hi - tile_lo) * col_groups;
       const int g = (w_taps * n_cols * 128 + kWGranule - 1) / kWGranule;
       const int wsteps = 9 / w_taps;
       const uint32_t idesc = make_idesc_bf16(128, n_cols, 0, 0);
       const uint32_t b_dy = static_cast<uint32_t>(n_cols) * 8;  // (n_cols * 128 B) >> 4
-      const uint32_t half_stride = acc_hold ? 256u : 128u;
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
+      if (pf) prof[8] += clock64() - _tp + (v == 0x7fffffff ? n_cols + idesc : 0);  // entry parameter fetch (forces the loads to be complete)
       for (int w = v; w < num_work; w += static_cast<int>(grid), ++it) {
-        // accumulator stage: pass layers always use the fixed block (stage 0); ordinary layers alternate
-        const int as = acc_hold ? 0 : (acc_toggle & 1);
+        // accumulator stage: a pass layer uses its image group's resident block; ordinary layers alternate
+        const int as = acc_hold ? slot : (acc_toggle & 1);
         if (!acc_hold) ++acc_toggle;
         if (acc_hold != last_hold) {
           // switching between the double-buffered layout and the fixed dense-block layout: both stages must be drained
@@ -411,7 +484,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         }
         { PROF_T0(pf); mbar_wait(&tempty[as], ((acc_bits >> as) & 1u) ^ 1u); PROF_ADD(pf, 4); }
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (acc_hold ? 0u : as * kAccStride) + acc_col0;
+        const uint32_t d_tmem = tmem_base + as * kAccStride + acc_col0;
         for (int c = 0; c < num_chunks; ++c) {
           const int ksteps = (c == num_chunks - 1) ? ksteps_last : 4;
           { PROF_T0(pf); mbar_wait(&fullA[sa], (fA_bits >> sa) & 1u); PROF_ADD(pf, 5); }
@@ -420,35 +493,35 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             if (gw + g > kWGranules) gw = 0;
             { PROF_T0(pf); mbar_wait(&fullW[gw], (fW_bits >> gw) & 1u); PROF_ADD(pf, 6); }
             tcgen05_fence_after();
+            const long long _ti = pf ? clock64() : 0;
             if (elect_one_sync()) {
               const uint32_t b_base = smem_desc_lo(smem_u32(smemW + gw * kWGranule), 16);
-#pragma unroll 1
-              for (int tt = 0; tt < w_taps; ++tt) {
-                // position of this tap in the centre-first order (dx in {1,0,2} outer, dy in {1,0,2} inner)
-                const int pos = d * w_taps + tt;
-                const int o1 = pos / 3, o2 = pos - o1 * 3;
-                const int dxi = (o1 == 0) ? 1 : (o1 == 1 ? 0 : 2);
-                const int dyi = (o2 == 0) ? 1 : (o2 == 1 ? 0 : 2);
-                // tile of this tap inside the stage (rows are packed [dx][dy][n])
-                const int tile_in_stage = (w_taps == 9) ? dxi * 3 + dyi : (w_taps == 3 ? dyi : 0);
-                const uint32_t b_lo = b_base + tile_in_stage * b_dy;
-                const uint32_t first = (acc_first && c == 0 && pos == 0) ? 0u : 1u;  // very first MMA of a fresh item overwrites
-                const uint32_t a_tap = a_lo + (dyi * kABoxW + dxi) * 8;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if (ks < ksteps && !(debug & 2)) {
-                    // tap (dy,dx) = the haloed tile shifted by (dy*10+dx) rows of 128 B; the two 128-pixel halves
-                    // (patch rows 0-15 / 16-31) reuse the same weight tile
-                    umma_bf16_ss_lohi2(d_tmem, a_tap + ks * 2, kHiA, b_lo + ks * 2, kHi, idesc, (ks == 0) ? first : 1u);
-                    umma_bf16_ss_lohi2(d_tmem + half_stride, a_tap + 16 * kABoxW * 8 + ks * 2, kHiA, b_lo + ks * 2, kHi, idesc,
-                                       (ks == 0) ? first : 1u);
-                  }
+              // centre-first tap order: stage d of a 3-tap layer is the dx column {1,0,2}[d], of a 1-tap layer tap (dx,dy) = ({1,0,2}[d/3], {1,0,2}[d%3])
+              const int o1 = (w_taps == 1) ? d / 3 : d, o2 = d - (d / 3) * 3;
+              const int dxi = (o1 == 0) ? 1 : (o1 == 1 ? 0 : 2);
+              const int dyi = (o2 == 0) ? 1 : (o2 == 1 ? 0 : 2);
+              const uint32_t first = (acc_first && c == 0 && d == 0) ? 0u : 1u;  // very first MMA of a fresh item overwrites
+              if (!(debug & 2)) {
+                const uint32_t a1 = a_lo + (w_taps == 9 ? 0 : dxi * 8) + (w_taps == 1 ? dyi * kABoxW * 8 : 0);
+#define B200SR_ISSUE_K(T, H)                                                                       \
+  switch (ksteps) {                                                                                \
+    case 4: issue_stage<T, H, 4>(d_tmem, a1, b_base, b_dy, idesc, first); break;                    \
+    case 3: issue_stage<T, H, 3>(d_tmem, a1, b_base, b_dy, idesc, first); break;                    \
+    case 2: issue_stage<T, H, 2>(d_tmem, a1, b_base, b_dy, idesc, first); break;                    \
+    default: issue_stage<T, H, 1>(d_tmem, a1, b_base, b_dy, idesc, first); break;                   \
+  }
+                if (halves == 2) {
+                  if (w_taps == 9) { B200SR_ISSUE_K(9, 2) } else if (w_taps == 3) { B200SR_ISSUE_K(3, 2) } else { B200SR_ISSUE_K(1, 2) }
+                } else {
+                  if (w_taps == 9) { B200SR_ISSUE_K(9, 1) } else if (w_taps == 3) { B200SR_ISSUE_K(3, 1) } else { B200SR_ISSUE_K(1, 1) }
                 }
+#undef B200SR_ISSUE_K
               }
               for (int j = 0; j < g; ++j) umma_commit(&emptyW[gw + j]);  // frees the weight granules once these MMAs drained
               if (d == wsteps - 1) umma_commit(&emptyA[sa]);             // ... and the activation tile after its last stage
             }
             __syncwarp();
+            if (pf) prof[9] += clock64() - _ti;  // MMA issue block
             fW_bits ^= (1u << gw);
             gw += g;
           }
@@ -466,6 +539,22 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       prof[7] = clock64() - pstart;
       for (int i = 4; i < 8; ++i) g_conv_prof[blockIdx.x * 12 + i] = prof[i];
       g_conv_prof[blockIdx.x * 12 + 11] = it;
+      g_conv_prof[160 * 12 - 320 + blockIdx.x * 2] = prof[8];
+      g_conv_prof[160 * 12 - 320 + blockIdx.x * 2 + 1] = prof[9];
+    }
+  } else if (warp == 10) {
+    // =================================================== signaller ==================================================
+    // Announces "this CTA's part of entry e is stored" on the entry's completion counter.  The gpu-scope fence (which
+    // has to wait for the epilogue warps' stores to reach L2) runs here, off the epilogue's serial path; the mbarrier
+    // hand-over (release.cta arrive / acquire.cta wait) plus fence cumulativity orders those stores before the atomic.
+    for (int e = 0; e < num_entries; ++e) {
+      mbar_wait(&sig[e & 1], (e >> 1) & 1);
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(counters + e, 1u);
+        *sig_done = e + 1;
+      }
+      __syncwarp();
     }
   } else {
     // =================================================== epilogue ===================================================
@@ -476,18 +565,30 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     const int m = q * 32 + lane;
     const int half = (warp >= 6) ? 1 : 0;
     const int et = threadIdx.x - 64;  // 0..255
+    // Stage entry e's layer parameters + bias into ring slot (e & 3) with cp.async: no register round trip, so the L2
+    // latency never sits on this role's serial path (entries are staged two ahead).  What to fetch comes from the
+    // constant-memory records.
     auto stage_entry = [&](int e) {
-      const EntryDesc* ed = entries + e;
-      const ConvParams* gp = &(layers + __ldcg(&ed->layer))->p;
-      uint32_t* dst = reinterpret_cast<uint32_t*>(sp_base + (e & 1) * 384);
-      if (et < static_cast<int>(sizeof(ConvParams) / 4)) dst[et] = __ldcg(reinterpret_cast<const uint32_t*>(gp) + et);
-      if (et >= 80 && et < 88) dst[et] = __ldcg(reinterpret_cast<const uint32_t*>(ed) + (et - 80));  // EntryDesc at +320 B
-      const float* nb = reinterpret_cast<const float*>(__ldcg(reinterpret_cast<const unsigned long long*>(&gp->epi.bias)));
-      const int nt = __ldcg(&gp->acc_hold) ? __ldcg(&gp->epi_cols) : __ldcg(&gp->n_total);
-      float* bdst = sbias_base + (e & 1) * 256;
-      for (int i = et; i < nt; i += 256) bdst[i] = nb ? __ldcg(nb + i) : 0.f;
+      if (e < num_entries) {
+        const int li = static_cast<int>(c_entry_rec[e].x & 0xFFFFF);
+        const uint4 lb = c_layer_rec[(li - layer0) * 2 + 1];
+        const int nt = static_cast<int>(lb.w);      // bias floats the epilogue reads
+        const uint32_t boff = lb.z;                 // bias byte offset from the packed buffer + 1 (0: no bias)
+        if (et < static_cast<int>(sizeof(ConvParams) / 16)) {
+          cp_async_16(sp_base + (e & 3) * 384 + et * 16, reinterpret_cast<const uint8_t*>(&layers[li].p) + et * 16);
+        } else if (et >= 64 && et < 128) {
+          const int i = et - 64;
+          if (4 * i < nt) {
+            uint8_t* dst = reinterpret_cast<uint8_t*>(sbias_base + (e & 3) * 256) + i * 16;
+            if (boff) cp_async_16(dst, packed_w + (boff - 1) + i * 16);
+            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      cp_async_commit();
     };
     stage_entry(0);
+    stage_entry(1);
     int it = 0;
     uint32_t acc_bits = 0;  // phase parity of the two accumulator stages (tfull barriers)
     int acc_toggle = 0;
@@ -495,41 +596,51 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long pstart = pf ? clock64() : 0;
     for (int e = 0; e < num_entries; ++e) {
-      { PROF_T0(pf); epi_bar_sync(); PROF_ADD(pf, 8); }  // slot (e & 1) is complete and visible; every epilogue thread has left entry e-1
-      if (e + 1 < num_entries) stage_entry(e + 1);
-      const ConvParams& p = *reinterpret_cast<const ConvParams*>(sp_base + (e & 1) * 384);
-      const EntryDesc& ent = *reinterpret_cast<const EntryDesc*>(sp_base + (e & 1) * 384 + 320);
-      const float* sbias = sbias_base + (e & 1) * 256;
+      { PROF_T0(pf);
+      cp_async_wait_group<1>();  // this thread's pieces of slot e have landed (only the group of e + 1 may be pending)
+      if (et == 0) while (static_cast<int>(*sig_done) < e - 1) {}  // sig[e & 1] must have been consumed for entry e - 2
+      epi_bar_sync();            // ... and everybody else's; every epilogue thread has left entry e - 1
+      PROF_ADD(pf, 8); }
+      stage_entry(e + 2);        // ring slot (e + 2) & 3 was last read in entry e - 2
+      const ConvParams& p = *reinterpret_cast<const ConvParams*>(sp_base + (e & 3) * 384);
+      const uint4 er = c_entry_rec[e];
+      const int ent_tile_lo = static_cast<int>(er.y), ent_tile_hi = static_cast<int>(er.z);
+      const int ent_rot = static_cast<int>(er.w & 0xFFFF), ent_dep = static_cast<int>(er.w >> 16) - 1, ent_slot = static_cast<int>(er.x >> 20);
+      const float* sbias = sbias_base + (e & 3) * 256;
       const int tiles_per_img = p.tiles_x * p.tiles_y;
-      const int num_work = (ent.tile_hi - ent.tile_lo) * p.col_groups;
-      const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(ent.rot)) % grid);
-      if (v < num_work && ent.dep >= 0 && p.epi_cols > 0) {
-        // residuals / masks written by the entry we depend on are read before the accumulator is ready: check it too
+      const int num_work = (ent_tile_hi - ent_tile_lo) * p.col_groups;
+      const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(ent_rot)) % grid);
+      if (v < num_work && ent_dep >= 0 && p.epi_cols > 0) {
+        // residuals written by earlier entries are read before the accumulator is ready: wait until the producer warp has
+        // seen this entry's dependency complete (it must anyway before it can load the entry's activations)
         PROF_T0(pf);
-        if (et == 0 && !(debug & 16)) {
-          wait_entry_done(counters, ent.dep, grid);
-          __threadfence();
-        }
-        epi_bar_sync();
+        uint32_t seen;
+        do {
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(const_cast<uint32_t*>(dep_flag))) : "memory");
+        } while (static_cast<int>(seen) < e + 1);
         PROF_ADD(pf, 8);
       }
       for (int w = v; w < ((p.epi_cols > 0) ? num_work : 0); w += static_cast<int>(grid), ++it) {
-        const int tile = ent.tile_lo + w / p.col_groups;
+        const int tile = ent_tile_lo + w / p.col_groups;
         const int colbase = (w % p.col_groups) * p.n_cols;
         const int n = tile / tiles_per_img;
         const int t2 = tile - n * tiles_per_img;
         const int ty = t2 / p.tiles_x;
         const int x = (t2 - ty * p.tiles_x) * kTileW + (m & 7);
-        const int y = ty * kTileH + half * 16 + (m >> 3);
+        // two-half items: this warp set owns half `half`; single-unit items: both warp sets see the same 128 pixels and
+        // split the columns (set 0: columns 0-31, set 1: columns 32-63 if the epilogue has that many)
+        const int y = (p.halves == 2) ? ty * 32 + half * 16 + (m >> 3) : ty * 16 + (m >> 3);
         const bool valid = (x < p.W) && (y < p.H);
-        const int as = p.acc_hold ? 0 : (acc_toggle & 1);
+        const int as = p.acc_hold ? ent_slot : (acc_toggle & 1);
         if (!p.acc_hold) ++acc_toggle;
         // Operands that do not depend on the accumulator are fetched BEFORE waiting for the MMAs, so their L2 latency
         // hides behind the tensor work: combined fp32 residual (<= 64 columns) and the LeakyReLU-derivative mask words.
         const ConvEpilogue& ep = p.epi;
         const bool pre = valid && !(debug & 1);
         const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
-        const long long cbase = carrier_base(tile, half, m);
+        // fp32 carriers are tile-blocked over 8 x 32 patches: a 16-row unit is half (ty & 1) of patch (n, ty / 2, tx)
+        const long long cbase = (p.halves == 2) ? carrier_base(tile, half, m)
+                                                : carrier_base((n * ((p.H + 31) / 32) + (ty >> 1)) * p.tiles_x + (t2 - ty * p.tiles_x), ty & 1, m);
         float res[64];
         uint32_t maskw[32];
         const bool has_res = (ep.r1 != nullptr);
@@ -567,12 +678,13 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         { PROF_T0(pf); mbar_wait(&tfull[as], (acc_bits >> as) & 1u); PROF_ADD(pf, 9); }
         acc_bits ^= (1u << as);
         tcgen05_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (p.acc_hold ? 0u : as * kAccStride) +
-                                half * (p.acc_hold ? 256u : 128u) + p.acc_col0;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + ((p.halves == 2) ? half * 128u : 0u) +
+                                p.acc_col0;
+        bool released = false;
 #pragma unroll
         for (int gq = 0; gq < 2; ++gq) {
           const int c0 = gq * 32;
-          if (c0 < p.epi_cols) {
+          if (c0 < p.epi_cols && (p.halves == 2 || gq == half)) {
             float vv[32];
             const int ncol = (p.epi_cols - c0) >= 32 ? 32 : 16;
             if (ncol == 32) {
@@ -581,10 +693,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) vv[i] = __uint_as_float(r[i]);
-              if (c0 + 32 >= p.epi_cols) {  // last TMEM read of this item: release the accumulator before the global stores
+              if (c0 + 32 >= p.epi_cols || p.halves == 1) {  // last TMEM read of this warp set: release the accumulator before the global stores
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
+                released = true;
               }
             } else {
               uint32_t r[16];
@@ -597,19 +710,21 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
               tcgen05_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty[as]);
+              released = true;
             }
             if (pre)
               conv_epilogue_store(p, y_dyn, sbias, has_res ? &res[gq * 32] : nullptr, has_mask ? &maskw[gq * 16] : nullptr, cbase, n, y,
                                   x, colbase + c0, ncol, vv);
           }
         }
+        if (!released) {  // a warp set with no columns of its own still takes part in the accumulator hand-back
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[as]);
+        }
       }
-      // announce: this CTA's part of entry e is stored (cumulativity: bar.sync + gpu-scope fence by the signalling thread)
-      { PROF_T0(pf); epi_bar_sync(); PROF_ADD(pf, 8); }
-      if (et == 0) {
-        __threadfence();
-        atomicAdd(counters + e, 1u);
-      }
+      // this warp's stores for entry e are issued: hand the announcement to the signaller warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sig[e & 1]);
     }
     if (pf && threadIdx.x == 64) {
       prof[10] = clock64() - pstart;

@@ -14,9 +14,11 @@ with torch.no_grad():
     L.b200sr_debug_set(64)
     net(lr); torch.cuda.synchronize()
     L.b200sr_debug_set(0)
-buf = (C.c_ulonglong * (148 * 12))()
-lib.check(L.b200sr_debug_read_profile(buf, 148 * 12))
-a = np.array(buf, dtype=np.float64).reshape(148, 12)
+buf = (C.c_ulonglong * (160 * 12))()
+lib.check(L.b200sr_debug_read_profile(buf, 160 * 12))
+full = np.array(buf, dtype=np.float64)
+a = full[:148 * 12].reshape(148, 12)
+extra = full[160 * 12 - 320: 160 * 12 - 320 + 296].reshape(148, 2)
 names = ["prod: dependency wait", "prod: wait A slot free", "prod: wait W granules free", "prod: TOTAL",
          "mma: wait accumulator free", "mma: wait A tile landed", "mma: wait W stage landed", "mma: TOTAL",
          "epi: dependency wait + barriers", "epi: wait accumulator ready", "epi: TOTAL", "items per CTA"]
@@ -26,3 +28,5 @@ for i, n in enumerate(names):
     col = a[:, i]
     if i == 11: print(f"{n:34s} {col.mean():9.1f} {col.min():9.0f} {col.max():9.0f}")
     else: print(f"{n:34s} {col.mean()/clk*1e3:9.3f} {col.min()/clk*1e3:9.3f} {col.max()/clk*1e3:9.3f}")
+print(f"{'mma: entry parameter fetch':34s} {extra[:,0].mean()/clk*1e3:9.3f}")
+print(f"{'mma: issue blocks (elect..commit)':34s} {extra[:,1].mean()/clk*1e3:9.3f}")
