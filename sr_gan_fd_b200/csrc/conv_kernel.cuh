@@ -105,18 +105,50 @@ constexpr long long kCarrierBytesPerTile = 2LL * 16 * 128 * 16;  // 65536
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 
+// Store 64 contiguous bytes per lane (h[16] -> row pointer `row`) so that each warp-wide store instruction covers
+// whole 64-byte runs: the four lanes of a quad first transpose their 4 x 4 grid of 16-byte pieces with two rounds of
+// shuffles, then instruction i writes piece (lane & 3) of the quad's i-th row.  A warp store touches 8 rows x 64 B
+// instead of 32 rows x 16 B (4x fewer L1 wavefronts).  All 32 lanes must call this; `ok` guards the lane's own row.
+__device__ __forceinline__ void store_rows_quad(uint32_t (&h)[16], void* row, bool ok, int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+  for (int c = 0; c < 4; c += 2) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t send = b0 ? h[4 * c + k] : h[4 * (c + 1) + k];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+      if (b0) h[4 * c + k] = recv; else h[4 * (c + 1) + k] = recv;
+    }
+  }
+#pragma unroll
+  for (int sidx = 0; sidx < 2; ++sidx) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t send = b1 ? h[4 * sidx + k] : h[4 * (sidx + 2) + k];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
+      if (b1) h[4 * sidx + k] = recv; else h[4 * (sidx + 2) + k] = recv;
+    }
+  }
+  const unsigned long long mine = reinterpret_cast<unsigned long long>(row);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int src = (lane & ~3) + i;
+    const unsigned long long r = __shfl_sync(0xffffffffu, mine, src);
+    const int rok = __shfl_sync(0xffffffffu, ok ? 1 : 0, src);
+    if (rok) st_global_v4(reinterpret_cast<uint8_t*>(r) + (lane & 3) * 16, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Epilogue for one pixel and 32 (or 16) consecutive accumulator columns held in registers.
 //   sbias : this layer's bias vector staged in shared memory (indexed by global column)
 //   res   : beta1*r1 + beta2*r2 for these 32 columns, prefetched before the accumulator was ready (or nullptr)
 //   maskw : 16 words = 32 bf16 saved activations for the LeakyReLU-derivative mask, prefetched (or nullptr)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, float* y_dyn, const float* sbias, const float* res,
-                                                    const uint32_t* maskw, long long cbase, int n, int y, int x, int col0,
-                                                    int ncol, float (&v)[32]) {
-  const ConvEpilogue& e = p.epi;
-  const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
-  // 1. bias + scale (+ activation)
+struct HW { int H, W; bool nostore; };
+// Part 1 (registers only): bias + scale, LeakyReLU, LeakyReLU-derivative mask, fp32 residuals.
+__device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const float* sbias, const float (&res)[32], bool has_res,
+                                                   const uint32_t (&maskw)[16], bool has_mask, int col0, int ncol, float (&v)[32]) {
   if (ncol == 32) {
     const float4* b4 = reinterpret_cast<const float4*>(sbias + col0);
 #pragma unroll
@@ -133,7 +165,26 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, float* 
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);  // LeakyReLU(0.2)
   }
+  if (has_mask) {  // LeakyReLU derivative from the saved forward activation
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[2 * j] *= (bf16_lo_to_f32(maskw[j]) > 0.f) ? 1.f : 0.2f;
+      v[2 * j + 1] *= (bf16_hi_to_f32(maskw[j]) > 0.f) ? 1.f : 0.2f;
+    }
+  }
+  if (has_res) {  // fp32 residuals (already combined)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += res[i];
+  }
+}
+
+// Part 2: stores.  Called by all 32 lanes of the warp (the bf16 store shuffles); `ok` = this lane's pixel exists and
+// stores are enabled.
+__device__ __forceinline__ void conv_epilogue_write(const HW p, const ConvEpilogue& e, float* y_dyn, long long cbase, int n, int y, int x,
+                                                    int col0, float (&v)[32], bool ok, int lane) {
+  const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
   if (e.store_mode == kStoreFinal) {
+    if (!ok) return;
     const long long plane = static_cast<long long>(p.H) * p.W;
     const long long base = static_cast<long long>(n) * e.n_valid * plane + static_cast<long long>(y) * p.W + x;
 #pragma unroll
@@ -141,37 +192,22 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, float* 
       if (i < e.n_valid) {
         float pre = v[i];
         float cl = fminf(fmaxf(pre, 0.f), 1.f);
-        y_dyn[base + i * plane] = cl;  // the generator output tensor is passed per launch, not baked into the layer list
-        if (e.clamp_mask) e.clamp_mask[base + i * plane] = (pre >= 0.f && pre <= 1.f) ? 1 : 0;
+        st_global_f32(y_dyn + base + i * plane, cl);  // the generator output tensor is passed per launch, not baked into the layer list
+        if (e.clamp_mask) st_global_u8(e.clamp_mask + base + i * plane, (pre >= 0.f && pre <= 1.f) ? 1u : 0u);
       }
     }
     return;
   }
-  // 2. LeakyReLU derivative mask from the saved forward activation
-  if (maskw) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      v[2 * j] *= (bf16_lo_to_f32(maskw[j]) > 0.f) ? 1.f : 0.2f;
-      v[2 * j + 1] *= (bf16_hi_to_f32(maskw[j]) > 0.f) ? 1.f : 0.2f;
-    }
-  }
-  // 3. fp32 residuals (already combined)
-  if (res) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += res[i];
-  }
   // 4. fp32 outputs (same lattice position)
-  if (e.out_f32) {
+  if (e.out_f32 && ok) {
     float* op = e.out_f32 + cbase + (col0 >> 2) * kCarrierChunkStride;
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      *reinterpret_cast<float4*>(op + q * kCarrierChunkStride) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 8; ++q) st_global_v4f(op + q * kCarrierChunkStride, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
-  if (e.out_f32_b) {
+  if (e.out_f32_b && ok) {
     float* op = e.out_f32_b + cbase + (col0 >> 2) * kCarrierChunkStride;
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      *reinterpret_cast<float4*>(op + q * kCarrierChunkStride) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 8; ++q) st_global_v4f(op + q * kCarrierChunkStride, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
   // 5. bf16 output (optionally hi/lo split), with the pixel (un)shuffle folded into the address
   if (e.out_bf16) {
@@ -192,18 +228,14 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, float* 
     uint32_t hi[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1]);
-    uint4* op = reinterpret_cast<uint4*>(ob);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) op[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+    uint32_t lo[16];
     if (e.split_off > 0) {
-      uint32_t lo[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         lo[j] = pack_bf16x2(e.delta * v[2 * j] - bf16_lo_to_f32(hi[j]), e.delta * v[2 * j + 1] - bf16_hi_to_f32(hi[j]));
-      uint4* lp = reinterpret_cast<uint4*>(ob + e.split_off);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) lp[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
     }
+    store_rows_quad(hi, ob, ok && !p.nostore, lane);
+    if (e.split_off > 0) store_rows_quad(lo, ob + e.split_off, ok && !p.nostore, lane);
   }
 }
 
@@ -269,7 +301,23 @@ constexpr int kNumASlots = 2;
 //  [0] producer: dependency wait   [1] producer: A slot free   [2] producer: W granules free   [3] producer: total
 //  [4] MMA: accumulator free       [5] MMA: A tile landed      [6] MMA: W stage landed         [7] MMA: total
 //  [8] epilogue(warp 2): dependency wait + barriers   [9] epilogue: accumulator ready   [10] epilogue: total   [11] items
-__device__ unsigned long long g_conv_prof[160 * 12];
+constexpr int kTlEntries = 256, kTlFirst = 300, kTlCtas = 4, kTlStride = 37;
+__device__ unsigned long long g_conv_prof[160 * 12 + kTlCtas * kTlEntries * 16];
+// debug bit 128: per-entry event timeline (globaltimer ns) of CTAs 0, 37, 74, 111 for entries [kTlFirst, kTlFirst + kTlEntries):
+//  0 producer reaches the entry   1 producer: dependency seen done   2 MMA: accumulator free, entry's first item starts
+//  3 MMA: first A tile landed     4 MMA: last MMA issued (tfull commit)   5 epilogue: accumulator ready
+//  6 epilogue: stores issued      7 signaller: counter bumped    8 epilogue: entry start (after bar)   9 epilogue: dependency flag seen
+//  10 epilogue: first TMEM load returned   11 signaller: epilogue warps arrived
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL_MARK(ev)                                                                                                   \
+  do {                                                                                                                \
+    if (tl && e >= kTlFirst && e < kTlFirst + kTlEntries)                                                              \
+      g_conv_prof[160 * 12 + ((blockIdx.x / kTlStride) * kTlEntries + (e - kTlFirst)) * 16 + (ev)] = globaltimer_ns();   \
+  } while (0)
 #define PROF_T0(flag) const long long _t0 = (flag) ? clock64() : 0
 #define PROF_ADD(flag, slot) do { if (flag) prof[slot] += clock64() - _t0; } while (0)
 
@@ -321,7 +369,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
                      const uint8_t* __restrict__ packed_w, unsigned int* counters, float* y_dyn, int debug, int layer0) {
   // `entries` points at the first entry of THIS chain; c_entry_rec[0..num_entries) / c_layer_rec[2 * (layer - layer0)] mirror it
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, still provably a shared-memory pointer
   // [ A ring: kNumASlots x 44032 | W ring: kWGranules x 12288 | barriers 512 B | flags | epilogue params 4 x 384 B | epilogue bias 4 x 1 KB ]
   uint8_t* smemW = smem + kNumASlots * kASlot;
   uint8_t* fixed = smemW + kWGranules * kWGranule;
@@ -361,6 +409,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool tl = (debug & 128) && (blockIdx.x % kTlStride == 0) && (blockIdx.x / kTlStride < kTlCtas) && (lane == 0);
 
   if (warp == 0) {
     // ================================================= TMA producer =================================================
@@ -388,10 +437,17 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int g = (wbytes + kWGranule - 1) / kWGranule;    // W granules per stage
       const int wsteps = 9 / w_taps;                         // stages per K chunk (1 or 3)
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
+      TL_MARK(0);
       if (v < num_work && dep >= 0) {
         { PROF_T0(pf);
         if (lane == 0) {
-          if (!(debug & 16)) wait_entry_done(counters, dep, grid);
+          if (!(debug & 16)) {
+            // only the CTAs that had work in the dependency announce it
+            const uint4 dr = c_entry_rec[dep];
+            const uint32_t dcg = (c_layer_rec[(static_cast<int>(dr.x & 0xFFFFF) - layer0) * 2].x >> 23) & 0x1F;
+            const unsigned int dwork = (dr.z - dr.y) * dcg;
+            wait_entry_done(counters, dep, dwork < grid ? dwork : grid);
+          }
           asm volatile("fence.proxy.async.global;" ::: "memory");  // TMA (async proxy) reads after generic-proxy stores
           // tell this CTA's epilogue warps (they read residual carriers written by earlier entries): acquire.gpu above,
           // release.cta here, acquire.cta on their side -- causality order is transitive
@@ -400,6 +456,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         __syncwarp();
         PROF_ADD(pf, 0); }
       }
+      TL_MARK(1);
       for (int w = v; w < num_work; w += static_cast<int>(grid)) {
         const int tile = tile_lo + w / col_groups;
         const int n = tile / tiles_per_img;
@@ -411,8 +468,12 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           const int ac = a_c0 + (c % a_wrap) * 64;
           { PROF_T0(pf); mbar_wait(&emptyA[sa], ((eA_bits >> sa) & 1u) ^ 1u); PROF_ADD(pf, 1); }
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&fullA[sa], a_bytes);
-            tma_load_4d(smem + sa * kASlot, tmA, &fullA[sa], ac, x0 - 1, y0 - 1, n);
+            if (debug & 4) {  // experiment: no loads at all (MMAs run on whatever is in smem)
+              mbar_arrive(&fullA[sa]);
+            } else {
+              mbar_arrive_expect_tx(&fullA[sa], a_bytes);
+              tma_load_4d(smem + sa * kASlot, tmA, &fullA[sa], ac, x0 - 1, y0 - 1, n);
+            }
           }
           __syncwarp();
           eA_bits ^= (1u << sa);
@@ -427,9 +488,13 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             if (gw + g > kWGranules) gw = 0;
             { PROF_T0(pf); for (int j = 0; j < g; ++j) mbar_wait(&emptyW[gw + j], ((eW_bits >> (gw + j)) & 1u) ^ 1u); PROF_ADD(pf, 2); }
             if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&fullW[gw], wbytes);
-              const long long row = w_row0 + (static_cast<long long>(c * col_groups + (w % col_groups)) * 9 + tap_row) * n_cols;
-              bulk_load_1d(smemW + gw * kWGranule, packed_w + row * 128, wbytes, &fullW[gw]);
+              if (debug & 4) {
+                mbar_arrive(&fullW[gw]);
+              } else {
+                mbar_arrive_expect_tx(&fullW[gw], wbytes);
+                const long long row = w_row0 + (static_cast<long long>(c * col_groups + (w % col_groups)) * 9 + tap_row) * n_cols;
+                bulk_load_1d(smemW + gw * kWGranule, packed_w + row * 128, wbytes, &fullW[gw]);
+              }
             }
             __syncwarp();
             for (int j = 0; j < g; ++j) eW_bits ^= (1u << (gw + j));
@@ -484,10 +549,12 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         }
         { PROF_T0(pf); mbar_wait(&tempty[as], ((acc_bits >> as) & 1u) ^ 1u); PROF_ADD(pf, 4); }
         tcgen05_fence_after();
+        TL_MARK(2);
         const uint32_t d_tmem = tmem_base + as * kAccStride + acc_col0;
         for (int c = 0; c < num_chunks; ++c) {
           const int ksteps = (c == num_chunks - 1) ? ksteps_last : 4;
           { PROF_T0(pf); mbar_wait(&fullA[sa], (fA_bits >> sa) & 1u); PROF_ADD(pf, 5); }
+          if (c == 0) TL_MARK(3);
           const uint32_t a_lo = smem_desc_lo(smem_u32(smem + sa * kASlot), 16);
           for (int d = 0; d < wsteps; ++d) {
             if (gw + g > kWGranules) gw = 0;
@@ -531,6 +598,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         if (has_epi) {
           if (elect_one_sync()) umma_commit(&tfull[as]);  // accumulators ready for the epilogue warps
           __syncwarp();
+          TL_MARK(4);
           acc_bits ^= (1u << as);
         }
       }
@@ -548,12 +616,20 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     // has to wait for the epilogue warps' stores to reach L2) runs here, off the epilogue's serial path; the mbarrier
     // hand-over (release.cta arrive / acquire.cta wait) plus fence cumulativity orders those stores before the atomic.
     for (int e = 0; e < num_entries; ++e) {
+      const uint4 er = c_entry_rec[e];
+      const uint32_t cg = (c_layer_rec[(static_cast<int>(er.x & 0xFFFFF) - layer0) * 2].x >> 23) & 0x1F;
+      const unsigned int num_work = (er.z - er.y) * cg;
+      const unsigned int v = (blockIdx.x + grid - (er.w & 0xFFFF)) % grid;
       mbar_wait(&sig[e & 1], (e >> 1) & 1);
+      TL_MARK(11);
       if (lane == 0) {
-        __threadfence();
-        atomicAdd(counters + e, 1u);
+        if (v < num_work) {  // CTAs without work in this entry have nothing to publish and are not counted
+          __threadfence();
+          atomicAdd(counters + e, 1u);
+        }
         *sig_done = e + 1;
       }
+      TL_MARK(7);
       __syncwarp();
     }
   } else {
@@ -601,8 +677,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       if (et == 0) while (static_cast<int>(*sig_done) < e - 1) {}  // sig[e & 1] must have been consumed for entry e - 2
       epi_bar_sync();            // ... and everybody else's; every epilogue thread has left entry e - 1
       PROF_ADD(pf, 8); }
+      if (warp == 2) TL_MARK(8);
       stage_entry(e + 2);        // ring slot (e + 2) & 3 was last read in entry e - 2
       const ConvParams& p = *reinterpret_cast<const ConvParams*>(sp_base + (e & 3) * 384);
+      const ConvEpilogue& ep = p.epi;
+      const HW hw{p.H, p.W, (debug & 8) != 0};
       const uint4 er = c_entry_rec[e];
       const int ent_tile_lo = static_cast<int>(er.y), ent_tile_hi = static_cast<int>(er.z);
       const int ent_rot = static_cast<int>(er.w & 0xFFFF), ent_dep = static_cast<int>(er.w >> 16) - 1, ent_slot = static_cast<int>(er.x >> 20);
@@ -620,6 +699,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         } while (static_cast<int>(seen) < e + 1);
         PROF_ADD(pf, 8);
       }
+      if (warp == 2) TL_MARK(9);
       for (int w = v; w < ((p.epi_cols > 0) ? num_work : 0); w += static_cast<int>(grid), ++it) {
         const int tile = ent_tile_lo + w / p.col_groups;
         const int colbase = (w % p.col_groups) * p.n_cols;
@@ -635,47 +715,46 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         if (!p.acc_hold) ++acc_toggle;
         // Operands that do not depend on the accumulator are fetched BEFORE waiting for the MMAs, so their L2 latency
         // hides behind the tensor work: combined fp32 residual (<= 64 columns) and the LeakyReLU-derivative mask words.
-        const ConvEpilogue& ep = p.epi;
         const bool pre = valid && !(debug & 1);
         const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
         // fp32 carriers are tile-blocked over 8 x 32 patches: a 16-row unit is half (ty & 1) of patch (n, ty / 2, tx)
         const long long cbase = (p.halves == 2) ? carrier_base(tile, half, m)
                                                 : carrier_base((n * ((p.H + 31) / 32) + (ty >> 1)) * p.tiles_x + (t2 - ty * p.tiles_x), ty & 1, m);
-        float res[64];
-        uint32_t maskw[32];
+        float res[32];
+        uint32_t maskw[16];
         const bool has_res = (ep.r1 != nullptr);
         const bool has_mask = (ep.mask != nullptr);
-        if (pre && has_res) {
-          const float* r1p = ep.r1 + cbase + (colbase >> 2) * kCarrierChunkStride;
+        // residuals + mask words of 32 columns (only that many are held in registers at a time)
+        auto prefetch_cols = [&](int c0) {
+          if (pre && has_res) {
+            const float* r1p = ep.r1 + cbase + ((colbase + c0) >> 2) * kCarrierChunkStride;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            if (4 * k < p.epi_cols) {
+            for (int k = 0; k < 8; ++k) {
               const float4 r = __ldcg(reinterpret_cast<const float4*>(r1p + k * kCarrierChunkStride));
               res[4 * k] = ep.beta1 * r.x; res[4 * k + 1] = ep.beta1 * r.y; res[4 * k + 2] = ep.beta1 * r.z; res[4 * k + 3] = ep.beta1 * r.w;
             }
-          }
-          if (ep.r2) {
-            const float* r2p = ep.r2 + cbase + (colbase >> 2) * kCarrierChunkStride;
+            if (ep.r2) {
+              const float* r2p = ep.r2 + cbase + ((colbase + c0) >> 2) * kCarrierChunkStride;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              if (4 * k < p.epi_cols) {
+              for (int k = 0; k < 8; ++k) {
                 const float4 r = __ldcg(reinterpret_cast<const float4*>(r2p + k * kCarrierChunkStride));
                 res[4 * k] += ep.beta2 * r.x; res[4 * k + 1] += ep.beta2 * r.y; res[4 * k + 2] += ep.beta2 * r.z; res[4 * k + 3] += ep.beta2 * r.w;
               }
             }
           }
-        }
-        if (pre && has_mask) {
-          const uint4* mp = reinterpret_cast<const uint4*>(ep.mask + pix * ep.mask_stride + ep.mask_coff + colbase);
+          if (pre && has_mask) {
+            const uint4* mp = reinterpret_cast<const uint4*>(ep.mask + pix * ep.mask_stride + ep.mask_coff + colbase + c0);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (8 * k < p.epi_cols) {
+            for (int k = 0; k < 4; ++k) {
               const uint4 m4 = __ldcg(mp + k);
               maskw[4 * k] = m4.x; maskw[4 * k + 1] = m4.y; maskw[4 * k + 2] = m4.z; maskw[4 * k + 3] = m4.w;
             }
           }
-        }
+        };
+        const int first_c0 = (p.halves == 2) ? 0 : half * 32;  // single-unit items: warp set `half` owns columns [32 half, 32 half + 32)
+        if (first_c0 < p.epi_cols) prefetch_cols(first_c0);
         { PROF_T0(pf); mbar_wait(&tfull[as], (acc_bits >> as) & 1u); PROF_ADD(pf, 9); }
+        if (warp == 2) TL_MARK(5);
         acc_bits ^= (1u << as);
         tcgen05_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + ((p.halves == 2) ? half * 128u : 0u) +
@@ -691,6 +770,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
               uint32_t r[32];
               tmem_ld_32x32b_x32(t_addr + c0, r);
               tmem_ld_wait();
+              if (warp == 2 && gq == 0) TL_MARK(10);
 #pragma unroll
               for (int i = 0; i < 32; ++i) vv[i] = __uint_as_float(r[i]);
               if (c0 + 32 >= p.epi_cols || p.halves == 1) {  // last TMEM read of this warp set: release the accumulator before the global stores
@@ -712,9 +792,12 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
               if (lane == 0) mbar_arrive(&tempty[as]);
               released = true;
             }
-            if (pre)
-              conv_epilogue_store(p, y_dyn, sbias, has_res ? &res[gq * 32] : nullptr, has_mask ? &maskw[gq * 16] : nullptr, cbase, n, y,
-                                  x, colbase + c0, ncol, vv);
+            if (warp == 2 && gq == 0) TL_MARK(12);
+            conv_epilogue_math(ep, sbias, res, has_res, maskw, has_mask, colbase + c0, ncol, vv);
+            // the residual / mask registers are free again: fetch the second 32 columns' while the first are stored
+            if (gq == 0 && p.halves == 2 && 32 < p.epi_cols) prefetch_cols(32);
+            conv_epilogue_write(hw, ep, y_dyn, cbase, n, y, x, colbase + c0, vv, pre, lane);
+            if (warp == 2 && gq == 0) TL_MARK(13);
           }
         }
         if (!released) {  // a warp set with no columns of its own still takes part in the accumulator hand-back
@@ -724,6 +807,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       }
       // this warp's stores for entry e are issued: hand the announcement to the signaller warp
       __syncwarp();
+      if (warp == 2) TL_MARK(6);
       if (lane == 0) mbar_arrive(&sig[e & 1]);
     }
     if (pf && threadIdx.x == 64) {

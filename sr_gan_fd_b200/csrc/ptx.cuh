@@ -155,6 +155,18 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// Global stores as inline PTX WITHOUT a memory clobber: the epilogue's output pointers come out of a parameter block in
+// shared memory, so with ordinary C++ stores the compiler has to assume they alias that block and re-reads it after
+// every store (a chain of dependent shared-memory loads).  Ordering against the completion signal is provided by the
+// __syncwarp / mbarrier arrive (both "memory" clobbers) that follow the stores.
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+__device__ __forceinline__ void st_global_v4f(void* p, float a, float b, float c, float d) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
+}
+__device__ __forceinline__ void st_global_f32(void* p, float a) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(a)); }
+__device__ __forceinline__ void st_global_u8(void* p, uint32_t a) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(a)); }
 // hi / lo words of a 128B-swizzle descriptor
 __host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {

@@ -5,7 +5,8 @@
 #include "../sr_gan_fd_b200/csrc/ptx.cuh"
 using namespace b200sr;
 
-__global__ void __launch_bounds__(128, 1) mma_probe(int n_cols, int reps, int a_off_rows, int sbo_a, long long* out_cycles, int commits_per_16) {
+template <int d_rot>
+__global__ void __launch_bounds__(128, 1) mma_probe(int n_cols, int reps, int a_off_rows, int sbo_a, long long* out_cycles, int commits_per_16, int d_stride = 128) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 200 * 1024);
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe(int n_cols, int reps, int a_
     for (int r = 0; r < reps; r += 16) {
 #pragma unroll
       for (int u = 0; u < 16; ++u)  // 4 taps x 4 k-steps, constant offsets -> one add per operand at most
-        umma_bf16_ss_lohi2(tmem, a_lo + (u >> 2) * 80 + (u & 3) * 2, hiA, b_lo + (u >> 2) * 512 + (u & 3) * 2, hiB, idesc, 1u);
+        umma_bf16_ss_lohi2(tmem + (u % d_rot) * d_stride, a_lo + (u >> 2) * 80 + (u & 3) * 2, hiA, b_lo + (u >> 2) * 512 + (u & 3) * 2, hiB, idesc, 1u);
       for (int c = 0; c < commits_per_16; ++c) umma_commit(scratch_bar);
     }
     umma_commit(bar);
@@ -43,20 +44,37 @@ __global__ void __launch_bounds__(128, 1) mma_probe(int n_cols, int reps, int a_
 
 int main() {
   long long* d; cudaMalloc(&d, 8);
-  cudaFuncSetAttribute(mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+  cudaFuncSetAttribute(mma_probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+  cudaFuncSetAttribute(mma_probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+  cudaFuncSetAttribute(mma_probe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
   int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int reps = 4096;
-  for (int commits : {0, 1, 2, 4, 8, 16}) {
+  for (int commits : {0, 2}) {
     for (int n : {32, 96, 192}) {
       long long cyc = 0;
       for (int it = 0; it < 2; ++it) {
-        mma_probe<<<sms, 128, 210 * 1024>>>(n, reps, 0, 1280, d, commits);
+        mma_probe<1><<<sms, 128, 210 * 1024>>>(n, reps, 0, 1280, d, commits);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("CUDA error %s (n=%d)\n", cudaGetErrorString(e), n); return 1; }
         cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
       }
       const double per = (double)cyc / reps;
       printf("%2d commits per 16 MMAs, N=%3d : %6.1f cycles per MMA (ideal %5.1f)\n", commits, n, per, n / 2.0);
+    }
+  }
+  // independent accumulators: rotate the destination among d_rot TMEM column blocks
+  for (int rot : {1, 2, 4}) {
+    for (int n : {16, 32, 64, 128}) {
+      long long cyc = 0;
+      for (int it = 0; it < 2; ++it) {
+        if (rot == 1) mma_probe<1><<<sms, 128, 210 * 1024>>>(n, reps, 0, 1280, d, 0, 128);
+        else if (rot == 2) mma_probe<2><<<sms, 128, 210 * 1024>>>(n, reps, 0, 1280, d, 0, 128);
+        else mma_probe<4><<<sms, 128, 210 * 1024>>>(n, reps, 0, 1280, d, 0, 128);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error %s (n=%d)\n", cudaGetErrorString(e), n); return 1; }
+        cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+      }
+      printf("%d accumulators in rotation, N=%3d : %6.1f cycles per MMA (ideal %5.1f)\n", rot, n, (double)cyc / reps, n / 2.0);
     }
   }
   return 0;
