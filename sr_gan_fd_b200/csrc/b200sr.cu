@@ -153,8 +153,9 @@ struct b200sr_plan {
   long long o_dyp = 0, o_g3 = 0, o_gt = 0, o_gtb = 0, o_gr = 0, o_gc1 = 0, o_gc2 = 0, o_go1 = 0;
   long long o_dyb[6] = {0, 0, 0, 0, 0, 0};
   std::vector<long long> o_gu;
-  bool reassoc = false;               // experimental (B200SR_REASSOC=1): dense blocks re-associated by input slice; default = per-conv schedule
+  bool reassoc = true;                // dense blocks re-associated by input slice (B200SR_REASSOC=0: per-conv schedule, 1: all five convs resident, 2 = default: windowed)
   int groups = 1;                     // image groups that flow through a chain independently
+  bool window = true;                 // with reassoc: only convs 1-4 (128 columns per 128-pixel half) stay resident, conv5 is an ordinary N=64 layer
   bool unit_all = false;              // experimental: every chain layer works on single 8 x 16 units (B200SR_UNIT=1)
   int groups_env = 0;                 // experimental: force the number of image groups (B200SR_GROUPS)
   bool split_passes = false;          // experimental: split every pass into a critical and a deferred sub-layer
@@ -238,6 +239,7 @@ ConvParams base_conv_params(int n, int h, int w, int num_chunks, int ksteps_last
   p.w_row0 = row0; p.n_cols = n_cols; p.n_total = n_total;
   p.col_groups = n_total / n_cols;
   p.w_taps = (9 * n_cols * 128 <= 5 * kWGranule) ? 9 : ((3 * n_cols * 128 <= 5 * kWGranule) ? 3 : 1);  // bytes per weight bulk copy <= 60 KB
+  if (const char* e = getenv("B200SR_WTAPS")) { const int m = atoi(e); if (m == 3 && p.w_taps == 9) p.w_taps = 3; }  // experiment
   p.acc_col0 = 0; p.acc_first = 1; p.acc_hold = 0; p.epi_cols = n_cols; p.halves = 2;
   p.num_stages = conv_pick_stages(n_cols);
   p.epi.alpha = 1.f; p.epi.delta = 1.f; p.epi.beta1 = 1.f; p.epi.beta2 = 1.f;
@@ -301,7 +303,7 @@ static int build_plan(b200sr_plan& P) {
       cudaGetLastError();
     }
     if (sms > 0) P.plan_sms = sms;
-    const int tpi = ((d.width + kTileW - 1) / kTileW) * ((d.height + 15) / 16);  // 8 x 16 units per image (dense-block passes)
+    const int tpi = ((d.width + kTileW - 1) / kTileW) * (P.window ? (d.height + 31) / 32 : (d.height + 15) / 16);  // resident items per image (8 x 16 units, window mode: 8 x 32)
     P.groups = d.batch >= 2 ? 2 : 1;
     if (P.reassoc) {
       int g = P.groups;
@@ -440,6 +442,44 @@ static int build_plan(b200sr_plan& P) {
         s.ob = ws(P.o_splt); s.cp.epi.ob_stride = 128; s.cp.epi.ob_coff = 0; s.cp.epi.split_off = 64;
       }
     };
+    if (reassoc && P.window) {
+      // WINDOWED re-association: passes 0..3 feed slice q (x, o1, o2, o3) to convs q+1..4 at once (N = 128, 96, 64, 32);
+      // their partial sums (4 x 32 columns per 128-pixel half, so 8 x 32-pixel items and two resident image groups still
+      // fit the 512 TMEM columns) stay in TMEM between the passes.  conv5 (N = 64, K = 192) runs as an ordinary layer in the
+      // same accumulator slot.  An SS tcgen05.mma costs ~(32 + N/4) cycles (shared-memory operand reads), so a pass with
+      // N = 128 does four convs' worth of work in 1.6x the time of one.
+      for (int q = 0; q < 4; ++q) {
+        const int c_q = (q == 0) ? 0 : 64 + 32 * (q - 1);
+        const int klen = (q == 0) ? 64 : 32;
+        const int col_lo = 32 * q, ncols = 128 - col_lo;
+        PackOp op; memset(&op, 0, sizeof(op));
+        op.n_total = ncols; op.n_cols = ncols; op.n_valid = ncols; op.num_chunks = 1; op.mode = kPackFwd; op.nseg = 0;
+        for (int k = q + 1; k <= 4; ++k)
+          op.seg[op.nseg++] = nseg(32 * (k - 1) - col_lo, 32, 0, klen, 2 * conv_index_rdb(r, k), 32, 64 + 32 * (k - 1), 0, c_q);
+        const int row0 = B.add_pack(op);
+        ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, c_q, 1 << 20, row0, ncols, ncols);
+        cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = 32;
+        Step s = conv_step(B.add_map(D, c_q + klen, 192, N, H, W, kABoxRows), cp, 1);
+        s.bias = packed_bias(B.add_bias(32, 2 * conv_index_rdb(r, q + 1) + 1, 32, 0));
+        s.cp.epi.act = 1;
+        s.ob = ws(D); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * q;
+        P.fwd.push_back(s);
+      }
+      {
+        const int ci = conv_index_rdb(r, 5);
+        PackOp op; memset(&op, 0, sizeof(op));
+        op.n_total = 64; op.n_valid = 64; op.num_chunks = 3; op.mode = kPackFwd; op.nseg = 1;
+        op.seg[0] = seg(0, 192, 2 * ci, 64, 192, 0, 0, 0);
+        const int row0 = B.add_pack(op);
+        ConvParams cp = base_conv_params(N, H, W, 3, 4, 0, 1 << 20, row0, 64, 64);
+        cp.acc_hold = 1; cp.acc_first = 1; cp.acc_col0 = 0; cp.epi_cols = 64;
+        Step s = conv_step(B.add_map(D, 192, 192, N, H, W, kABoxRows), cp, 1);
+        s.bias = packed_bias(B.add_bias(64, 2 * ci + 1, 64, 0));
+        conv5_epilogue(s);
+        P.fwd.push_back(s);
+      }
+      continue;
+    }
     if (reassoc) {
       // Dense block RE-ASSOCIATED BY INPUT SLICE: pass q feeds slice q (x, o1..o4) to ALL convs that consume it at once
       // (N = 192, 160, 128, 96, 64 instead of 32,32,32,32,64); the partial sums stay in TMEM between the passes.
@@ -731,7 +771,45 @@ static int build_plan(b200sr_plan& P) {
         else { s.r1 = ws(P.o_gc1); s.r2 = ws(P.o_gr); s.of = ws(P.o_gr); s.cp.epi.delta = 0.04f; }
         if (r > 0) { s.ob = ws(DYn); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 0; }
       };
-      if (P.reassoc) {
+      if (P.reassoc && P.window) {
+        // Mirror image of the windowed forward: passes 0..3 feed dY_{5-q} to the growth slices o_{4-q}..o_1 it reads
+        // (accumulator columns [o4 | o3 | o2 | o1], N = 128, 96, 64, 32); the block-input slice x (N = 64, K = 192) is an
+        // ordinary layer in the same accumulator slot.
+        for (int q = 0; q < 4; ++q) {
+          const int kk = 5 - q;
+          const int klen = (kk == 5) ? 64 : 32;
+          const int a_c0 = (q == 0) ? 0 : 64 + 32 * (q - 1);
+          const int ci = conv_index_rdb(r, kk);
+          const int col_lo = 32 * q, ncols = 128 - col_lo;
+          PackOp op; memset(&op, 0, sizeof(op));
+          op.n_total = ncols; op.n_cols = ncols; op.n_valid = ncols; op.num_chunks = 1; op.mode = kPackDgrad; op.nseg = 0;
+          for (int sidx = 4 - q; sidx >= 1; --sidx)
+            op.seg[op.nseg++] = nseg(32 * (4 - sidx) - col_lo, 32, 0, klen, 2 * ci, klen, 64 + 32 * (kk - 1), 0, 64 + 32 * (sidx - 1));
+          const int row0 = B.add_pack(op);
+          ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, a_c0, 1 << 20, row0, ncols, ncols);
+          cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = 32;
+          Step s = conv_step(B.add_map(DYc, a_c0 + klen, 192, N, H, W, kABoxRows), cp, 1);
+          const int sl = 4 - q;  // completed slice o_sl
+          s.mask = ws(D); s.cp.epi.mask_stride = 192; s.cp.epi.mask_coff = 64 + 32 * (sl - 1);
+          s.ob = ws(DYc); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * q;
+          emit(s);
+        }
+        {
+          PackOp op; memset(&op, 0, sizeof(op));
+          op.n_total = 64; op.n_valid = 64; op.num_chunks = 3; op.mode = kPackDgrad; op.nseg = 0;
+          for (int k = 5; k > 0; --k) {
+            const int k0 = (k == 5) ? 0 : 64 + 32 * (4 - k);
+            const int klen = (k == 5) ? 64 : 32;
+            op.seg[op.nseg++] = seg(k0, klen, 2 * conv_index_rdb(r, k), klen, 64 + 32 * (k - 1), 0, 0, 0);
+          }
+          const int row0 = B.add_pack(op);
+          ConvParams cp = base_conv_params(N, H, W, 3, 4, 0, 1 << 20, row0, 64, 64);
+          cp.acc_hold = 1; cp.acc_first = 1; cp.acc_col0 = 0; cp.epi_cols = 64;
+          Step s = conv_step(B.add_map(DYc, 192, 192, N, H, W, kABoxRows), cp, 1);
+          xslice_epilogue(s);
+          emit(s);
+        }
+      } else if (P.reassoc) {
         // Mirror image of the forward passes: pass q feeds dY_{5-q} (64 or 32 channels) to ALL input slices its conv
         // reads; accumulator columns are [o4 | o3 | o2 | o1 | x], so after pass q the leading 32 columns (slice o_{4-q})
         // are complete and become dY_{4-q} (times the LeakyReLU derivative); the x columns complete last.
@@ -1129,7 +1207,7 @@ int b200sr_plan_create(const b200sr_net_desc* desc, b200sr_plan** out) {
   if (!desc || !out) return fail(B200SR_ERR_INVALID, "null argument");
   b200sr_plan* p = new b200sr_plan();
   p->d = *desc;
-  if (const char* e = getenv("B200SR_REASSOC")) p->reassoc = atoi(e) != 0;
+  if (const char* e = getenv("B200SR_REASSOC")) { p->reassoc = atoi(e) != 0; p->window = atoi(e) == 2; }
   if (const char* e = getenv("B200SR_SPLIT")) p->split_passes = atoi(e) != 0;
   if (const char* e = getenv("B200SR_UNIT")) p->unit_all = atoi(e) != 0;
   if (const char* e = getenv("B200SR_GROUPS")) p->groups_env = atoi(e);

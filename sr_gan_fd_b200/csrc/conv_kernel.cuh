@@ -384,6 +384,10 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 512);
   volatile uint32_t* dep_flag = reinterpret_cast<volatile uint32_t*>(fixed + 516);  // producer -> epilogue: e + 1 once entry e's dependency is done
   volatile uint32_t* sig_done = reinterpret_cast<volatile uint32_t*>(fixed + 520);  // signaller -> epilogue: entries announced so far
+  // producer-private bookkeeping of the weight-stage FIFO (see the producer role)
+  volatile uint32_t* gran_seq = reinterpret_cast<volatile uint32_t*>(fixed + 576);   // [10] 1 + sequence number of the last stage that used the granule
+  volatile uint32_t* stage_bar = reinterpret_cast<volatile uint32_t*>(fixed + 640);  // [16] first granule (= barrier index) of stage seq & 15
+  volatile uint32_t* a_seq = reinterpret_cast<volatile uint32_t*>(fixed + 704);      // [4]  1 + sequence number of the last stage that read the A slot
   uint8_t* sp_base = fixed + 1024;                                  // 4 x 384 B
   float* sbias_base = reinterpret_cast<float*>(fixed + 3072);       // 4 x 1 KB
   constexpr int kFixedBytes = 3072 + 4096;
@@ -402,6 +406,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); mbar_init(&sig[a], 8); }
     *dep_flag = 0;
     *sig_done = 0;
+    for (int i = 0; i < kWGranules; ++i) gran_seq[i] = 0;
+    for (int i = 0; i < 4; ++i) a_seq[i] = 0;
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_imm<kTmemCols>(tmem_slot);
@@ -414,7 +420,19 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   if (warp == 0) {
     // ================================================= TMA producer =================================================
     // (whole warp walks the loops so the index math stays warp-uniform; one elected lane issues)
-    uint32_t eA_bits = 0, eW_bits = 0;  // phase parity per A slot / W granule (empty barriers)
+    // Weight stages form one FIFO: the MMA warp commits ONCE per stage (to the barrier of the stage's first granule; a
+    // tcgen05.commit costs about as much tensor-pipe time as 1.5 MMAs) and stages complete in issue order, so "granule
+    // free" and "A slot free" both reduce to "stage number s has completed".  `confirmed` stages have been waited for.
+    uint32_t cW_bits = 0;               // next phase parity to wait for, per stage barrier
+    uint32_t issued = 0, confirmed = 0;
+    auto ensure_stage = [&](uint32_t seq_p1) {
+      while (confirmed < seq_p1) {
+        const uint32_t j = stage_bar[confirmed & 15];
+        mbar_wait(&emptyW[j], (cW_bits >> j) & 1u);
+        cW_bits ^= (1u << j);
+        ++confirmed;
+      }
+    };
     int sa = 0, gw = 0;
     const bool pf = (debug & 64) != 0;
     long long prof[4] = {0, 0, 0, 0};
@@ -438,25 +456,34 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int wsteps = 9 / w_taps;                         // stages per K chunk (1 or 3)
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
       TL_MARK(0);
-      if (v < num_work && dep >= 0) {
-        { PROF_T0(pf);
+      // The entry's inputs may only be read once the entry it depends on is complete on every CTA that worked on it.  The
+      // wait sits AFTER the first weight stage has been requested (weights do not depend on the previous layer), right
+      // before the first activation load.
+      unsigned int dep_need = 0;
+      if (dep >= 0) {  // only the CTAs that had work in the dependency announce it
+        const uint4 dr = c_entry_rec[dep];
+        const uint32_t dcg = (c_layer_rec[(static_cast<int>(dr.x & 0xFFFFF) - layer0) * 2].x >> 23) & 0x1F;
+        const unsigned int dwork = (dr.z - dr.y) * dcg;
+        dep_need = dwork < grid ? dwork : grid;
+      }
+      auto dependency_ready = [&]() -> bool {  // one non-blocking look at the counter
+        unsigned int seen = 0;
+        if (lane == 0) seen = (debug & 16) ? dep_need : ld_acquire_gpu(counters + dep);
+        return __shfl_sync(0xffffffffu, seen, 0) >= dep_need;
+      };
+      auto dependency_wait = [&]() {
+        PROF_T0(pf);
         if (lane == 0) {
-          if (!(debug & 16)) {
-            // only the CTAs that had work in the dependency announce it
-            const uint4 dr = c_entry_rec[dep];
-            const uint32_t dcg = (c_layer_rec[(static_cast<int>(dr.x & 0xFFFFF) - layer0) * 2].x >> 23) & 0x1F;
-            const unsigned int dwork = (dr.z - dr.y) * dcg;
-            wait_entry_done(counters, dep, dwork < grid ? dwork : grid);
-          }
+          if (!(debug & 16)) wait_entry_done(counters, dep, dep_need);
           asm volatile("fence.proxy.async.global;" ::: "memory");  // TMA (async proxy) reads after generic-proxy stores
           // tell this CTA's epilogue warps (they read residual carriers written by earlier entries): acquire.gpu above,
           // release.cta here, acquire.cta on their side -- causality order is transitive
           asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(dep_flag))), "r"(e + 1) : "memory");
         }
         __syncwarp();
-        PROF_ADD(pf, 0); }
-      }
-      TL_MARK(1);
+        PROF_ADD(pf, 0);
+        TL_MARK(1);
+      };
       for (int w = v; w < num_work; w += static_cast<int>(grid)) {
         const int tile = tile_lo + w / col_groups;
         const int n = tile / tiles_per_img;
@@ -466,18 +493,27 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const int y0 = ty * tile_h;
         for (int c = 0; c < num_chunks; ++c) {
           const int ac = a_c0 + (c % a_wrap) * 64;
-          { PROF_T0(pf); mbar_wait(&emptyA[sa], ((eA_bits >> sa) & 1u) ^ 1u); PROF_ADD(pf, 1); }
-          if (elect_one_sync()) {
-            if (debug & 4) {  // experiment: no loads at all (MMAs run on whatever is in smem)
-              mbar_arrive(&fullA[sa]);
-            } else {
-              mbar_arrive_expect_tx(&fullA[sa], a_bytes);
-              tma_load_4d(smem + sa * kASlot, tmA, &fullA[sa], ac, x0 - 1, y0 - 1, n);
-            }
-          }
-          __syncwarp();
-          eA_bits ^= (1u << sa);
+          { PROF_T0(pf); ensure_stage(a_seq[sa]); PROF_ADD(pf, 1); }  // activation slot free (waits on older stages only)
+          const int sa_used = sa;
           if (++sa == kNumASlots) sa = 0;
+          auto load_activations = [&]() {
+            if (elect_one_sync()) {
+              if (debug & 4) {  // experiment: no loads at all (MMAs run on whatever is in smem)
+                mbar_arrive(&fullA[sa_used]);
+              } else {
+                mbar_arrive_expect_tx(&fullA[sa_used], a_bytes);
+                tma_load_4d(smem + sa_used * kASlot, tmA, &fullA[sa_used], ac, x0 - 1, y0 - 1, n);
+              }
+            }
+            __syncwarp();
+          };
+          // Chunk 0 of an item: weight stages are requested BEFORE the activations as long as the dependency is still
+          // open (weights do not depend on the previous layer) and as long as the ring has room without waiting on one of
+          // this item's own stages (those cannot complete before the activations arrive).
+          bool a_done = (c != 0);
+          if (c != 0) load_activations();
+          const uint32_t item_first = issued + 1;
+          const bool gated = (c == 0 && w == v && dep >= 0);  // the entry's first activation load waits for the dependency
           for (int d = 0; d < wsteps; ++d) {
             // stage d of this chunk holds w_taps consecutive taps of the centre-first order: dx in {1,0,2}, dy in {1,0,2}.
             // Packed rows are [dx][dy][n]; a 9-tap stage is the whole block, a 3-tap stage one dx column, a 1-tap stage one tile.
@@ -486,7 +522,16 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             else if (w_taps == 3) tap_row = ((d == 0) ? 1 : (d == 1 ? 0 : 2)) * 3;
             else { const int o1 = d / 3, o2 = d - o1 * 3; tap_row = ((o1 == 0) ? 1 : (o1 == 1 ? 0 : 2)) * 3 + ((o2 == 0) ? 1 : (o2 == 1 ? 0 : 2)); }
             if (gw + g > kWGranules) gw = 0;
-            { PROF_T0(pf); for (int j = 0; j < g; ++j) mbar_wait(&emptyW[gw + j], ((eW_bits >> (gw + j)) & 1u) ^ 1u); PROF_ADD(pf, 2); }
+            { PROF_T0(pf);
+            uint32_t need = 0;
+            for (int j = 0; j < g; ++j) { const uint32_t q = gran_seq[gw + j]; need = q > need ? q : need; }
+            if (!a_done && (d > 0)) {  // (measured: polling the dependency to squeeze more weight stages in front of it does not pay)
+              if (gated) dependency_wait();
+              load_activations();
+              a_done = true;
+            }
+            ensure_stage(need);
+            PROF_ADD(pf, 2); }
             if (elect_one_sync()) {
               if (debug & 4) {
                 mbar_arrive(&fullW[gw]);
@@ -497,8 +542,18 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
               }
             }
             __syncwarp();
-            for (int j = 0; j < g; ++j) eW_bits ^= (1u << (gw + j));
+            if (lane == 0) {
+              for (int j = 0; j < g; ++j) gran_seq[gw + j] = issued + 1;
+              stage_bar[issued & 15] = gw;
+              if (d == wsteps - 1) a_seq[sa_used] = issued + 1;  // the chunk's last stage also releases its activation tile
+            }
+            __syncwarp();
+            ++issued;
             gw += g;
+          }
+          if (!a_done) {
+            if (gated) dependency_wait();
+            load_activations();
           }
         }
       }
@@ -558,18 +613,20 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           const uint32_t a_lo = smem_desc_lo(smem_u32(smem + sa * kASlot), 16);
           for (int d = 0; d < wsteps; ++d) {
             if (gw + g > kWGranules) gw = 0;
+            // stage set-up first, so that little more than the first tcgen05.mma follows the wait
+            const uint32_t b_base = smem_desc_lo(smem_u32(smemW + gw * kWGranule), 16);
+            // centre-first tap order: stage d of a 3-tap layer is the dx column {1,0,2}[d], of a 1-tap layer tap (dx,dy) = ({1,0,2}[d/3], {1,0,2}[d%3])
+            const int o1 = (w_taps == 1) ? d / 3 : d, o2 = d - (d / 3) * 3;
+            const int dxi = (o1 == 0) ? 1 : (o1 == 1 ? 0 : 2);
+            const int dyi = (o2 == 0) ? 1 : (o2 == 1 ? 0 : 2);
+            const uint32_t first = (acc_first && c == 0 && d == 0) ? 0u : 1u;  // very first MMA of a fresh item overwrites
+            const uint32_t a1 = a_lo + (w_taps == 9 ? 0 : dxi * 8) + (w_taps == 1 ? dyi * kABoxW * 8 : 0);
             { PROF_T0(pf); mbar_wait(&fullW[gw], (fW_bits >> gw) & 1u); PROF_ADD(pf, 6); }
-            tcgen05_fence_after();
+            // (no tcgen05 fence here: the mbarrier wait orders the TMA writes before the MMAs that read them; looking up the
+            //  next stage's barrier ahead of time was measured and does not help)
             const long long _ti = pf ? clock64() : 0;
             if (elect_one_sync()) {
-              const uint32_t b_base = smem_desc_lo(smem_u32(smemW + gw * kWGranule), 16);
-              // centre-first tap order: stage d of a 3-tap layer is the dx column {1,0,2}[d], of a 1-tap layer tap (dx,dy) = ({1,0,2}[d/3], {1,0,2}[d%3])
-              const int o1 = (w_taps == 1) ? d / 3 : d, o2 = d - (d / 3) * 3;
-              const int dxi = (o1 == 0) ? 1 : (o1 == 1 ? 0 : 2);
-              const int dyi = (o2 == 0) ? 1 : (o2 == 1 ? 0 : 2);
-              const uint32_t first = (acc_first && c == 0 && d == 0) ? 0u : 1u;  // very first MMA of a fresh item overwrites
               if (!(debug & 2)) {
-                const uint32_t a1 = a_lo + (w_taps == 9 ? 0 : dxi * 8) + (w_taps == 1 ? dyi * kABoxW * 8 : 0);
 #define B200SR_ISSUE_K(T, H)                                                                       \
   switch (ksteps) {                                                                                \
     case 4: issue_stage<T, H, 4>(d_tmem, a1, b_base, b_dy, idesc, first); break;                    \
@@ -584,8 +641,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
                 }
 #undef B200SR_ISSUE_K
               }
-              for (int j = 0; j < g; ++j) umma_commit(&emptyW[gw + j]);  // frees the weight granules once these MMAs drained
-              if (d == wsteps - 1) umma_commit(&emptyA[sa]);             // ... and the activation tile after its last stage
+              umma_commit(&emptyW[gw]);  // one commit per stage: frees its weight granules and (last stage of a chunk) the activation tile
             }
             __syncwarp();
             if (pf) prof[9] += clock64() - _ti;  // MMA issue block
@@ -615,6 +671,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     // Announces "this CTA's part of entry e is stored" on the entry's completion counter.  The gpu-scope fence (which
     // has to wait for the epilogue warps' stores to reach L2) runs here, off the epilogue's serial path; the mbarrier
     // hand-over (release.cta arrive / acquire.cta wait) plus fence cumulativity orders those stores before the atomic.
+    const long long sc0 = clock64();
+    const unsigned long long sg0 = globaltimer_ns();
     for (int e = 0; e < num_entries; ++e) {
       const uint4 er = c_entry_rec[e];
       const uint32_t cg = (c_layer_rec[(static_cast<int>(er.x & 0xFFFFF) - layer0) * 2].x >> 23) & 0x1F;
@@ -631,6 +689,10 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       }
       TL_MARK(7);
       __syncwarp();
+    }
+    if ((debug & 128) && blockIdx.x == 0 && lane == 0 && num_entries > 100) {  // SM clock actually sustained: cycles and ns of the whole launch
+      g_conv_prof[160 * 12 - 16] = clock64() - sc0;
+      g_conv_prof[160 * 12 - 15] = globaltimer_ns() - sg0;
     }
   } else {
     // =================================================== epilogue ===================================================

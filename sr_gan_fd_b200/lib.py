@@ -60,11 +60,12 @@ def load() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("B200SR_LIB", LIB_PATH)  # developer A/B switch: another build of the same library
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -m sr_gan_fd_b200.build` (needs nvcc). "
+                f"{path} is missing: build it with `python -m sr_gan_fd_b200.build` (needs nvcc). "
                 "The B200 generator path has no PyTorch fallback.")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res

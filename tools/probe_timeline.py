@@ -18,7 +18,9 @@ with torch.no_grad():
 n = 160 * 12 + NC * NE * 16
 buf = (C.c_ulonglong * n)()
 lib.check(L.b200sr_debug_read_profile(buf, n))
-t = np.array(buf, dtype=np.float64)[160 * 12:].reshape(NC, NE, 16)
+full = np.array(buf, dtype=np.float64)
+print(f"sustained SM clock during the launch: {full[160*12-16] / full[160*12-15] * 1e3:.0f} MHz ({full[160*12-15]/1e6:.3f} ms)")
+t = full[160 * 12:].reshape(NC, NE, 16)
 t0 = t[t > 0].min()
 t = np.where(t > 0, (t - t0) / 1e3, np.nan)  # us
 names = ["prod@", "depOK", "mma0", "Aland", "mmaEnd", "accRdy", "stored", "signal", "epi@", "epiDep", "tmemLd", "sigArr", "preSt", "postSt", "-", "-"]
