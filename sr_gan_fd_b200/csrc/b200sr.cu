@@ -47,6 +47,9 @@ static int g_num_sms = 0;
 static bool g_attr_set = false;
 static int g_ctas_per_sm = 1;
 static int g_debug = 0;  // timing probes only (b200sr_debug_set)
+// Neighbour-tile dependencies (B200SR_NBSYNC=1) are correct but measured no faster than the per-entry counters on config 2
+// (the chain is bound by per-layer latencies every CTA sees alike, not by skew between CTAs): opt-in.
+static const bool g_no_neighbour_sync = [] { const char* e = getenv("B200SR_NBSYNC"); return !(e && atoi(e) == 1); }();
 
 static int runtime_init() {
   if (!g_encode) {
@@ -179,7 +182,8 @@ struct b200sr_plan {
   EntryDesc* d_entries = nullptr;
   uint4* d_layer_rec = nullptr;       // constant-memory images of the two tables (copied device -> constant per launch)
   uint4* d_entry_rec = nullptr;
-  unsigned int* d_counters = nullptr; // per-entry completion counters of the chain being launched
+  unsigned int* d_counters = nullptr; // per-entry completion counters of the chain being launched, followed by the per-item flags
+  size_t counters_bytes = 0;          // 16 KB of counters + the largest chain's (entries x items) flag matrix
 };
 
 static int wmap_index(int n_cols) { return n_cols == 16 ? 0 : n_cols == 32 ? 1 : n_cols == 64 ? 2 : 3; }
@@ -1026,6 +1030,16 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
           e.dep = (lp >= 0) ? index_of[(size_t)lp * groups + g] : -1;
           e.rot = (int)(((long long)img_lo * tpi * cp.col_groups) % grid);
           e.slot = g & 1;  // each group starts where the previous one's last round ended
+          // Neighbour-tile dependency: when this layer and the one it depends on tile the same lattice the same way (one
+          // item per tile), an item only needs the 3 x 3 neighbourhood of its tile to be finished in the dependency --
+          // not all of it -- and waits on per-item flags instead of the entry's counter.
+          e.pad[0] = 0;
+          if (lp >= 0 && !g_no_neighbour_sync) {
+            const ConvParams& dp = P.layer_steps[s.layer0 + lp].cp;
+            if (dp.N == cp.N && dp.H == cp.H && dp.W == cp.W && dp.halves == cp.halves && dp.tiles_x == cp.tiles_x &&
+                dp.tiles_y == cp.tiles_y && dp.col_groups == 1 && cp.col_groups == 1 && dp.epi.store_mode == kStorePix)
+              e.pad[0] = 1;
+          }
           P.h_entries.push_back(e);
         }
         s.nentries = (int)P.h_entries.size() - s.entry0;
@@ -1037,7 +1051,15 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
   if (!P.d_layers) {
     CUDA_TRY(cudaMalloc(&P.d_layers, P.h_layers.size() * sizeof(LayerDesc)));
     CUDA_TRY(cudaMalloc(&P.d_entries, P.h_entries.size() * sizeof(EntryDesc)));
-    CUDA_TRY(cudaMalloc(&P.d_counters, 16384));
+    // completion counters (16 KB) followed by the per-item "done" flags of the largest chain (entries x items, one word each)
+    size_t flag_words = 0;
+    auto scan = [&](const std::vector<Step>& steps) {
+      for (const Step& s : steps)
+        if (s.type == ST_CHAIN) { const size_t wds = (size_t)s.nentries * (size_t)s.chain_grid; if (wds > flag_words) flag_words = wds; }
+    };
+    scan(P.fwd); scan(P.bwd);
+    P.counters_bytes = 16384 + flag_words * sizeof(unsigned int);
+    CUDA_TRY(cudaMalloc(&P.d_counters, P.counters_bytes));
     CUDA_TRY(cudaMemcpyAsync(P.d_entries, P.h_entries.data(), P.h_entries.size() * sizeof(EntryDesc), cudaMemcpyHostToDevice, st));
     std::vector<uint4> lrec(P.h_layers.size() * 2), erec(P.h_entries.size());
     for (size_t i = 0; i < P.h_layers.size(); ++i) make_layer_rec(P.h_layers[i].p, &lrec[2 * i], packed);
@@ -1069,9 +1091,11 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   float* y = (float*)b.y;
   int dbg = g_debug;
   unsigned int* ctr = P.d_counters;
-  CUDA_TRY(cudaMemsetAsync(ctr, 0, (size_t)ne * sizeof(unsigned int), st));
+  unsigned int* flags = P.d_counters + 4096;
+  int flag_stride = s.chain_grid;  // items of the chain's largest entry
+  CUDA_TRY(cudaMemsetAsync(ctr, 0, 16384 + (size_t)ne * (size_t)flag_stride * sizeof(unsigned int), st));
   const uint8_t* pw = (const uint8_t*)b.packed;
-  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&y, (void*)&dbg, (void*)&layer0};
+  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&y, (void*)&dbg, (void*)&layer0, (void*)&flags, (void*)&flag_stride};
   const void* fn = (const void*)conv3x3_chain_kernel<1>;
   if (ne > 1) {
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
@@ -1386,7 +1410,9 @@ static int single_conv(int mode, const void* x, int n, int h, int w, int cin, in
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_layer_rec, lrec, sizeof(lrec), 0, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_entry_rec, &erec, sizeof(erec), 0, cudaMemcpyHostToDevice, st));
   int layer0 = 0;
-  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&ydyn, (void*)&dbg, (void*)&layer0};
+  unsigned int* flags = nullptr;  // a single layer has no dependencies
+  int flag_stride = 0;
+  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&ydyn, (void*)&dbg, (void*)&layer0, (void*)&flags, (void*)&flag_stride};
   CUDA_TRY(cudaLaunchKernel((const void*)conv3x3_chain_kernel<1>, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   (void)grid_y;
   return 0;

@@ -258,7 +258,7 @@ struct alignas(32) EntryDesc {
   int dep;               // entry whose completion gates this entry's input reads (-1: inputs exist before the launch)
   int rot;               // CTA rotation: virtual CTA v = (blockIdx.x - rot) mod gridDim.x takes items v, v + gridDim.x, ...
   int slot;              // dense-block passes: which of the CTA's two resident accumulator blocks this image group uses
-  int pad[2];
+  int pad[2];            // pad[0] = 1: wait on the per-item flags of the dependency's 3 x 3 tile neighbourhood instead of its counter
 };
 
 // Compact per-layer / per-entry records for the TMA-producer and MMA-issuer warps, kept in CONSTANT memory: loads with a
@@ -270,7 +270,7 @@ constexpr int kMaxChainEntries = 2048;
 // layer record A: x = n_cols | chunks<<10 | ksteps_last<<14 | halves<<17 | w_taps<<19 | col_groups<<23
 //                 y = acc_col0 | acc_first<<8 | acc_hold<<9 | has_epi<<10      z = w_row0      w = a_c0
 // layer record B: x = tiles_x | tiles_y<<16      y = a_wrap      z = bias byte offset in the packed buffer + 1 (0: none)      w = bias floats
-// entry record  : x = layer (absolute) | slot<<20      y = tile_lo      z = tile_hi      w = rot | (dep+1)<<16
+// entry record  : x = layer (absolute) | slot<<20 | neighbour_sync<<21      y = tile_lo      z = tile_hi      w = rot | (dep+1)<<16
 __constant__ uint4 c_layer_rec[kMaxChainLayers * 2];
 __constant__ uint4 c_entry_rec[kMaxChainEntries];
 inline void make_layer_rec(const ConvParams& p, uint4 out[2], const void* packed_base) {
@@ -285,7 +285,7 @@ inline void make_layer_rec(const ConvParams& p, uint4 out[2], const void* packed
 }
 inline uint4 make_entry_rec(const EntryDesc& e) {
   uint4 r;
-  r.x = static_cast<uint32_t>(e.layer) | (static_cast<uint32_t>(e.slot) << 20);
+  r.x = static_cast<uint32_t>(e.layer) | (static_cast<uint32_t>(e.slot & 1) << 20) | (static_cast<uint32_t>(e.pad[0] & 1) << 21);
   r.y = static_cast<uint32_t>(e.tile_lo);
   r.z = static_cast<uint32_t>(e.tile_hi);
   r.w = static_cast<uint32_t>(e.rot) | (static_cast<uint32_t>(e.dep + 1) << 16);
@@ -366,7 +366,8 @@ __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a_lo, uint
 template <int kUnused>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __restrict__ entries, int num_entries,
-                     const uint8_t* __restrict__ packed_w, unsigned int* counters, float* y_dyn, int debug, int layer0) {
+                     const uint8_t* __restrict__ packed_w, unsigned int* counters, float* y_dyn, int debug, int layer0,
+                     unsigned int* item_flags, int flag_stride) {
   // `entries` points at the first entry of THIS chain; c_entry_rec[0..num_entries) / c_layer_rec[2 * (layer - layer0)] mirror it
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, still provably a shared-memory pointer
@@ -440,6 +441,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     for (int e = 0; e < num_entries; ++e) {
       const uint4 er = c_entry_rec[e];
       const int li = static_cast<int>(er.x & 0xFFFFF);
+      const bool nb_sync = ((er.x >> 21) & 1) != 0;  // wait per item on the dependency's 3 x 3 tile neighbourhood
       const int tile_lo = static_cast<int>(er.y), tile_hi = static_cast<int>(er.z);
       const int rot = static_cast<int>(er.w & 0xFFFF), dep = static_cast<int>(er.w >> 16) - 1;
       const uint4 la = c_layer_rec[(li - layer0) * 2], lb = c_layer_rec[(li - layer0) * 2 + 1];
@@ -471,10 +473,27 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         if (lane == 0) seen = (debug & 16) ? dep_need : ld_acquire_gpu(counters + dep);
         return __shfl_sync(0xffffffffu, seen, 0) >= dep_need;
       };
-      auto dependency_wait = [&]() {
+      // (a) whole-entry form: the dependency's counter shows every CTA that worked on it
+      // (b) neighbour form (same tiling in both layers): the flags of the <= 9 items around item w0 of the dependency
+      auto dependency_wait = [&](int w0, int ty, int tx) {
         PROF_T0(pf);
+        if (nb_sync && !(debug & 16)) {
+          const int dy = lane / 3 - 1, dx = lane % 3 - 1;
+          const bool look = lane < 9 && ty + dy >= 0 && ty + dy < tiles_y && tx + dx >= 0 && tx + dx < tiles_x;
+          const unsigned int* f = item_flags + static_cast<long long>(dep) * flag_stride + (w0 + dy * tiles_x + dx);
+          const long long t0 = clock64();
+          bool ok = !look;
+          while (true) {
+            if (!ok) ok = ld_acquire_gpu(f) != 0;
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (clock64() - t0 > 4000000000LL) {
+              if (lane == 0) printf("b200sr: neighbour dependency timeout (block %d entry %d item %d)\n", blockIdx.x, e, w0);
+              __trap();
+            }
+          }
+        }
         if (lane == 0) {
-          if (!(debug & 16)) wait_entry_done(counters, dep, dep_need);
+          if (!nb_sync && !(debug & 16)) wait_entry_done(counters, dep, dep_need);
           asm volatile("fence.proxy.async.global;" ::: "memory");  // TMA (async proxy) reads after generic-proxy stores
           // tell this CTA's epilogue warps (they read residual carriers written by earlier entries): acquire.gpu above,
           // release.cta here, acquire.cta on their side -- causality order is transitive
@@ -513,7 +532,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           bool a_done = (c != 0);
           if (c != 0) load_activations();
           const uint32_t item_first = issued + 1;
-          const bool gated = (c == 0 && w == v && dep >= 0);  // the entry's first activation load waits for the dependency
+          // the entry's first activation load waits for the dependency (neighbour form: every item's first load)
+          const bool gated = (c == 0 && dep >= 0 && (w == v || nb_sync));
           for (int d = 0; d < wsteps; ++d) {
             // stage d of this chunk holds w_taps consecutive taps of the centre-first order: dx in {1,0,2}, dy in {1,0,2}.
             // Packed rows are [dx][dy][n]; a 9-tap stage is the whole block, a 3-tap stage one dx column, a 1-tap stage one tile.
@@ -526,7 +546,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             uint32_t need = 0;
             for (int j = 0; j < g; ++j) { const uint32_t q = gran_seq[gw + j]; need = q > need ? q : need; }
             if (!a_done && (d > 0)) {  // (measured: polling the dependency to squeeze more weight stages in front of it does not pay)
-              if (gated) dependency_wait();
+              if (gated) dependency_wait(w, ty, x0 / kTileW);
               load_activations();
               a_done = true;
             }
@@ -552,7 +572,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             gw += g;
           }
           if (!a_done) {
-            if (gated) dependency_wait();
+            if (gated) dependency_wait(w, ty, x0 / kTileW);
             load_activations();
           }
         }
@@ -579,7 +599,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     for (int e = 0; e < num_entries; ++e) {
       const long long _tp = pf ? clock64() : 0;
       const uint4 er = c_entry_rec[e];
-      const int li = static_cast<int>(er.x & 0xFFFFF), slot = static_cast<int>(er.x >> 20);
+      const int li = static_cast<int>(er.x & 0xFFFFF), slot = static_cast<int>((er.x >> 20) & 1);
       const int tile_lo = static_cast<int>(er.y), tile_hi = static_cast<int>(er.z), rot = static_cast<int>(er.w & 0xFFFF);
       const uint4 la = c_layer_rec[(li - layer0) * 2];
       const int n_cols = la.x & 0x3FF, num_chunks = (la.x >> 10) & 0xF, ksteps_last = (la.x >> 14) & 0x7, halves = (la.x >> 17) & 0x3;
@@ -683,6 +703,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       if (lane == 0) {
         if (v < num_work) {  // CTAs without work in this entry have nothing to publish and are not counted
           __threadfence();
+          if (item_flags)
+            for (unsigned int w = v; w < num_work; w += grid) item_flags[static_cast<long long>(e) * flag_stride + w] = 1u;
           atomicAdd(counters + e, 1u);
         }
         *sig_done = e + 1;
@@ -746,7 +768,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const HW hw{p.H, p.W, (debug & 8) != 0};
       const uint4 er = c_entry_rec[e];
       const int ent_tile_lo = static_cast<int>(er.y), ent_tile_hi = static_cast<int>(er.z);
-      const int ent_rot = static_cast<int>(er.w & 0xFFFF), ent_dep = static_cast<int>(er.w >> 16) - 1, ent_slot = static_cast<int>(er.x >> 20);
+      const int ent_rot = static_cast<int>(er.w & 0xFFFF), ent_dep = static_cast<int>(er.w >> 16) - 1, ent_slot = static_cast<int>((er.x >> 20) & 1);
       const float* sbias = sbias_base + (e & 3) * 256;
       const int tiles_per_img = p.tiles_x * p.tiles_y;
       const int num_work = (ent_tile_hi - ent_tile_lo) * p.col_groups;
