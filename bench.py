@@ -284,7 +284,9 @@ def run_b200(args):
                      "peak_source": how, "traffic": traffic, "ms_forward": ms_fwd},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(lr_host.numel() * 4 + gt_host.numel() * 4), "d2h_bytes_per_step": 4},
-        "gpu_launches": int((plan.launches_fwd + plan.launches_bwd) * args.steps),
+        # kernels of libb200sr.so launched inside the timed region (chain / wgrad / bias-grad / ingest / unpack / add); with the
+        # data-parallel bucket hook (N > 1) the gradient unpack runs once per bucket instead of once per step
+        "gpu_launches": int((plan.launches_fwd + (plan.launches_bwd_bucketed if world > 1 else plan.launches_bwd)) * args.steps),
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -71,7 +71,8 @@ int32_t b200sr_num_params(const b200sr_plan* plan);
 int64_t b200sr_param_numel(const b200sr_plan* plan);
 /* algorithmic FLOPs (2 x MACs of the reference graph) of one forward / one backward at the plan's geometry */
 double b200sr_flops(const b200sr_plan* plan, int backward);
-/* number of kernel launches one forward / backward enqueues */
+/* number of kernel launches one forward (backward = 0) / backward enqueues; backward = 1: no gradient-bucket callback
+ * (one merged gradient unpack), backward = 2: with a callback (one unpack launch per bucket) */
 int32_t b200sr_num_launches(const b200sr_plan* plan, int backward);
 
 /* params: host array of b200sr_num_params() device pointers, fp32, state_dict order (conv1.weight, conv1.bias,

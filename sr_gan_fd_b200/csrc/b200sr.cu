@@ -1282,8 +1282,11 @@ double b200sr_flops(const b200sr_plan* p, int backward) {
 int32_t b200sr_num_launches(const b200sr_plan* p, int backward) {
   if (!p) return 0;
   const std::vector<Step>& v = backward ? p->bwd : p->fwd;
-  int n = 0;
-  for (const Step& s : v) n += (s.type != ST_MEMSET);
+  // kernel launches of one pass.  backward = 1: no gradient-bucket callback, the per-bucket unpack steps collapse into one
+  // launch; backward = 2: with a callback (data-parallel training), one unpack launch per bucket.
+  int n = 0, unpacks = 0;
+  for (const Step& s : v) { n += (s.type != ST_MEMSET); unpacks += (s.type == ST_UNPACK); }
+  if (backward == 1 && unpacks > 1) n -= unpacks - 1;
   return n;
 }
 

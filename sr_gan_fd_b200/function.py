@@ -39,6 +39,7 @@ class _Plan:
         self.flops_bwd = float(lib.b200sr_flops(handle, 1))
         self.launches_fwd = int(lib.b200sr_num_launches(handle, 0))
         self.launches_bwd = int(lib.b200sr_num_launches(handle, 1)) if training else 0
+        self.launches_bwd_bucketed = int(lib.b200sr_num_launches(handle, 2)) if training else 0
 
     def __del__(self):
         try:
