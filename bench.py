@@ -182,24 +182,35 @@ def run_b200(args):
     # copied host->device on a side stream while the current step computes; every step still moves its own inputs from
     # pinned host memory inside the timed region and reads its loss back to the host.
     copy_stream = torch.cuda.Stream(device=dev)
-    staged = {}
+    # two pre-allocated device staging pairs (no allocator traffic in the loop): the copy into pair 1-i is ordered after the
+    # step that last read it (event) and runs while step i computes
+    stage = [(torch.empty_like(lr_dev), torch.empty_like(gt_dev)) for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    state = {"i": 0, "primed": False}
 
-    def prefetch():
+    def prefetch(i):
         with torch.cuda.stream(copy_stream):
-            staged["lr"] = lr_host.to(dev, non_blocking=True)
-            staged["gt"] = gt_host.to(dev, non_blocking=True)
+            copy_stream.wait_event(consumed[i])
+            stage[i][0].copy_(lr_host, non_blocking=True)
+            stage[i][1].copy_(gt_host, non_blocking=True)
+            copied[i].record(copy_stream)
 
     def step_e2e():
-        if not staged:
-            prefetch()
-        torch.cuda.current_stream().wait_stream(copy_stream)
-        lr, gt = staged["lr"], staged["gt"]
-        lr.record_stream(torch.cuda.current_stream())
-        gt.record_stream(torch.cuda.current_stream())
-        prefetch()  # next step's inputs, overlapped with this step's compute
+        i = state["i"]
+        if not state["primed"]:
+            consumed[0].record(); consumed[1].record()
+            prefetch(i)
+            state["primed"] = True
+        cur = torch.cuda.current_stream()
+        cur.wait_event(copied[i])
+        lr, gt = stage[i]
+        prefetch(1 - i)  # next step's inputs, overlapped with this step's compute
         net.zero_grad(set_to_none=True)
         loss = F.l1_loss(net(lr), gt)
         loss.backward()
+        consumed[i].record(cur)
+        state["i"] = 1 - i
         return loss.item()  # device -> host read of the step's result
 
     def barrier():

@@ -64,6 +64,12 @@ class GeneratorRuntime:
         # optional hook(flat_grads) called once backward has enqueued all of its kernels
         self.grad_done_hook: Optional[Callable[[torch.Tensor], None]] = None
         self.last_plan: Optional[_Plan] = None
+        # host fast path: the conv modules in state_dict order, and what was already validated about their parameters
+        self.convs = None
+        self.checked_ptrs = None
+        self.param_shapes = None
+        self.param_numels = None
+        self.cur_key = None
 
     def plan(self, desc: dict, device: torch.device, batch: int, height: int, width: int, training: bool) -> _Plan:
         key = (device.index, batch, height, width, training)
@@ -78,9 +84,10 @@ class GeneratorRuntime:
         self.last_plan = p
         return p
 
-    def packed_weights(self, plan: _Plan, params: List[torch.Tensor], stream: int) -> torch.Tensor:
+    def packed_weights(self, plan: _Plan, params: List[torch.Tensor], stream: int, key=None) -> torch.Tensor:
         t = plan.training
-        key = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        if key is None:
+            key = (tuple([p._version for p in params]), tuple([p.data_ptr() for p in params]))
         buf = self.packed.get(t)
         if buf is not None and buf.device == params[0].device and self.packed_key.get(t) == key:
             return buf
@@ -106,7 +113,7 @@ class _RRDBNetFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
             plan = rt.plan(desc, x.device, n, h, w, training)
-            packed = rt.packed_weights(plan, [p.detach() for p in params], stream)
+            packed = rt.packed_weights(plan, params, stream, rt.cur_key)
             workspace = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=x.device)
             y = torch.empty((n, plan.out_channels, h * plan.scale, w * plan.scale), dtype=torch.float32, device=x.device)
             strides = (C.c_int64 * 4)(*x.stride())
@@ -119,7 +126,6 @@ class _RRDBNetFn(torch.autograd.Function):
             ctx.workspace = workspace
             ctx.packed = packed
             ctx.pack_serial = rt.pack_serial[True]
-            ctx.param_shapes = [tuple(p.shape) for p in params]
             ctx.x_keepalive = x
         return y
 
@@ -148,14 +154,9 @@ class _RRDBNetFn(torch.autograd.Function):
                 rt.grad_done_hook(flat)
         ctx.workspace = None
         ctx.x_keepalive = None
-        grads = []
-        off = 0
-        for i, shp in enumerate(ctx.param_shapes):
-            numel = 1
-            for s in shp:
-                numel *= s
-            grads.append(flat[off:off + numel].view(shp) if ctx.needs_input_grad[3 + i] else None)
-            off += numel
+        need = ctx.needs_input_grad
+        pieces = flat.split(rt.param_numels)  # one call: 702 views of the flat gradient buffer, state_dict order
+        grads = [t.view(shp) if need[3 + i] else None for i, (t, shp) in enumerate(zip(pieces, rt.param_shapes))]
         return (None, None, None, *grads)
 
 
@@ -169,13 +170,26 @@ def generator_forward(module, x: torch.Tensor) -> torch.Tensor:
         raise RuntimeError(f"expected NCHW input, got shape {tuple(x.shape)}")
     if x.dtype not in _DTYPES:
         x = x.float()
+    rt = module._runtime()
+    if rt.convs is None:
+        rt.convs = module._conv_list()
     params = []
-    for conv in module._conv_list():
-        params.append(conv.weight)
-        params.append(conv.bias)
-    for p in params:
-        if p.dtype != torch.float32 or not p.is_contiguous() or p.device != x.device:
-            raise RuntimeError("generator parameters must be contiguous fp32 tensors on the input's device")
+    add = params.append
+    for conv in rt.convs:  # read through _parameters so that re-assigned Parameters are picked up
+        pd = conv._parameters
+        add(pd["weight"])
+        add(pd["bias"])
+    ptrs = tuple([p.data_ptr() for p in params])
+    if ptrs != rt.checked_ptrs:  # dtype / layout can only change together with the storage
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.device != x.device:
+                raise RuntimeError("generator parameters must be contiguous fp32 tensors on the input's device")
+        rt.checked_ptrs = ptrs
+        rt.param_shapes = [tuple(p.shape) for p in params]
+        rt.param_numels = [p.numel() for p in params]
+    elif params[0].device != x.device:
+        raise RuntimeError("generator parameters must be contiguous fp32 tensors on the input's device")
+    rt.cur_key = (tuple([p._version for p in params]), ptrs)
     training = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     if x.requires_grad and training:
         raise NotImplementedError("gradient w.r.t. the LR input is not produced by the B200 generator path")

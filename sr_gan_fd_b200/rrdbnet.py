@@ -109,6 +109,20 @@ class _GeneratorBase(nn.Module):
             new.__dict__[k] = copy.deepcopy(v, memo)
         return new
 
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """Same contract as ``nn.Module.zero_grad``; the ``set_to_none`` path skips the generic per-parameter work (the
+        training loop calls this every step, ESRGAN/train_rrdbnet.py:255, and the gradients are views of one flat buffer)."""
+        if not set_to_none:
+            return super().zero_grad(set_to_none=False)
+        rt = self._runtime()
+        if rt.convs is None:
+            rt.convs = self._conv_list()  # every parameter of the generator belongs to one of these convs
+        for conv in rt.convs:
+            pd = conv._parameters
+            pd["weight"].grad = None
+            if pd["bias"] is not None:
+                pd["bias"].grad = None
+
     def _conv_list(self) -> List[nn.Conv2d]:
         convs = [self.conv1]
         for rrdb in self.trunk:
