@@ -363,6 +363,33 @@ __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a_lo, uint
   }
 }
 
+// All weight stages of one K chunk (TAPS taps per stage -> 9 / TAPS stages), fully specialised: per stage nothing but the
+// barrier wait, the unrolled MMAs, one commit and the ring bookkeeping.  Executed by the whole MMA warp (uniform).
+template <int TAPS, int HALVES, int KSTEPS>
+__device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_lo, uint32_t smemW_addr, uint32_t b_dy, uint32_t idesc, bool fresh,
+                                            int g, int& gw, uint32_t& fW_bits, uint64_t* fullW, uint64_t* emptyW, bool no_mma) {
+  constexpr int kStages = 9 / TAPS;
+  constexpr int ord[3] = {1, 0, 2};
+#pragma unroll
+  for (int d = 0; d < kStages; ++d) {
+    if (gw + g > kWGranules) gw = 0;
+    // centre-first tap order: stage d of a 3-tap layer is the dx column {1,0,2}[d], of a 1-tap layer tap (dx,dy) = ({1,0,2}[d/3], {1,0,2}[d%3])
+    const int dxi = (TAPS == 9) ? 0 : ord[(TAPS == 1) ? d / 3 : d];
+    const int dyi = (TAPS == 1) ? ord[d % 3] : 0;
+    const uint32_t a1 = a_lo + (dyi * kABoxW + dxi) * 8;
+    const uint32_t b_base = ((smemW_addr + gw * kWGranule) >> 4 & 0x3FFFu) | (1u << 16);  // smem_desc_lo(addr, 16)
+    mbar_wait(&fullW[gw], (fW_bits >> gw) & 1u);
+    // (no tcgen05 fence here: the mbarrier wait orders the TMA writes before the MMAs that read them)
+    if (elect_one_sync()) {
+      if (!no_mma) issue_stage<TAPS, HALVES, KSTEPS>(d_tmem, a1, b_base, b_dy, idesc, (fresh && d == 0) ? 0u : 1u);
+      umma_commit(&emptyW[gw]);  // one commit per stage: frees its weight granules and (last stage of a chunk) the activation tile
+    }
+    __syncwarp();
+    fW_bits ^= (1u << gw);
+    gw += g;
+  }
+}
+
 template <int kUnused>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __restrict__ entries, int num_entries,
@@ -626,48 +653,31 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         tcgen05_fence_after();
         TL_MARK(2);
         const uint32_t d_tmem = tmem_base + as * kAccStride + acc_col0;
+        const uint32_t smemW_addr = smem_u32(smemW);
+        const bool no_mma = (debug & 2) != 0;
         for (int c = 0; c < num_chunks; ++c) {
           const int ksteps = (c == num_chunks - 1) ? ksteps_last : 4;
           { PROF_T0(pf); mbar_wait(&fullA[sa], (fA_bits >> sa) & 1u); PROF_ADD(pf, 5); }
           if (c == 0) TL_MARK(3);
           const uint32_t a_lo = smem_desc_lo(smem_u32(smem + sa * kASlot), 16);
-          for (int d = 0; d < wsteps; ++d) {
-            if (gw + g > kWGranules) gw = 0;
-            // stage set-up first, so that little more than the first tcgen05.mma follows the wait
-            const uint32_t b_base = smem_desc_lo(smem_u32(smemW + gw * kWGranule), 16);
-            // centre-first tap order: stage d of a 3-tap layer is the dx column {1,0,2}[d], of a 1-tap layer tap (dx,dy) = ({1,0,2}[d/3], {1,0,2}[d%3])
-            const int o1 = (w_taps == 1) ? d / 3 : d, o2 = d - (d / 3) * 3;
-            const int dxi = (o1 == 0) ? 1 : (o1 == 1 ? 0 : 2);
-            const int dyi = (o2 == 0) ? 1 : (o2 == 1 ? 0 : 2);
-            const uint32_t first = (acc_first && c == 0 && d == 0) ? 0u : 1u;  // very first MMA of a fresh item overwrites
-            const uint32_t a1 = a_lo + (w_taps == 9 ? 0 : dxi * 8) + (w_taps == 1 ? dyi * kABoxW * 8 : 0);
-            { PROF_T0(pf); mbar_wait(&fullW[gw], (fW_bits >> gw) & 1u); PROF_ADD(pf, 6); }
-            // (no tcgen05 fence here: the mbarrier wait orders the TMA writes before the MMAs that read them; looking up the
-            //  next stage's barrier ahead of time was measured and does not help)
-            const long long _ti = pf ? clock64() : 0;
-            if (elect_one_sync()) {
-              if (!(debug & 2)) {
-#define B200SR_ISSUE_K(T, H)                                                                       \
-  switch (ksteps) {                                                                                \
-    case 4: issue_stage<T, H, 4>(d_tmem, a1, b_base, b_dy, idesc, first); break;                    \
-    case 3: issue_stage<T, H, 3>(d_tmem, a1, b_base, b_dy, idesc, first); break;                    \
-    case 2: issue_stage<T, H, 2>(d_tmem, a1, b_base, b_dy, idesc, first); break;                    \
-    default: issue_stage<T, H, 1>(d_tmem, a1, b_base, b_dy, idesc, first); break;                   \
+          const bool fresh = acc_first && c == 0;  // the very first MMA of a fresh item overwrites the accumulators
+          const long long _ti = pf ? clock64() : 0;
+#define B200SR_CHUNK(T, H, K) issue_chunk<T, H, K>(d_tmem, a_lo, smemW_addr, b_dy, idesc, fresh, g, gw, fW_bits, fullW, emptyW, no_mma)
+#define B200SR_CHUNK_K(T, H)                                   \
+  switch (ksteps) {                                            \
+    case 4: B200SR_CHUNK(T, H, 4); break;                      \
+    case 3: B200SR_CHUNK(T, H, 3); break;                      \
+    case 2: B200SR_CHUNK(T, H, 2); break;                      \
+    default: B200SR_CHUNK(T, H, 1); break;                     \
   }
-                if (halves == 2) {
-                  if (w_taps == 9) { B200SR_ISSUE_K(9, 2) } else if (w_taps == 3) { B200SR_ISSUE_K(3, 2) } else { B200SR_ISSUE_K(1, 2) }
-                } else {
-                  if (w_taps == 9) { B200SR_ISSUE_K(9, 1) } else if (w_taps == 3) { B200SR_ISSUE_K(3, 1) } else { B200SR_ISSUE_K(1, 1) }
-                }
-#undef B200SR_ISSUE_K
-              }
-              umma_commit(&emptyW[gw]);  // one commit per stage: frees its weight granules and (last stage of a chunk) the activation tile
-            }
-            __syncwarp();
-            if (pf) prof[9] += clock64() - _ti;  // MMA issue block
-            fW_bits ^= (1u << gw);
-            gw += g;
+          if (halves == 2) {
+            if (w_taps == 9) { B200SR_CHUNK_K(9, 2) } else if (w_taps == 3) { B200SR_CHUNK_K(3, 2) } else { B200SR_CHUNK_K(1, 2) }
+          } else {
+            if (w_taps == 9) { B200SR_CHUNK_K(9, 1) } else if (w_taps == 3) { B200SR_CHUNK_K(3, 1) } else { B200SR_CHUNK_K(1, 1) }
           }
+#undef B200SR_CHUNK_K
+#undef B200SR_CHUNK
+          if (pf) prof[9] += clock64() - _ti;  // MMA issue incl. the weight-stage waits of this chunk
           fA_bits ^= (1u << sa);
           if (++sa == kNumASlots) sa = 0;
         }
