@@ -615,9 +615,10 @@ static int build_plan(b200sr_plan& P) {
       wb.tiles_x = (w + kTileW - 1) / kTileW; wb.tiles_y = (h + kWgTileH - 1) / kWgTileH; wb.num_tiles = n * wb.tiles_x * wb.tiles_y;
       return s;
     };
-    auto add_problem = [&](Step& s, int a_c0, int b_c0, int n_cols, int bias_mode) {
+    auto add_problem = [&](Step& s, int a_c0, int b_c0, int n_cols, int bias_mode, int a_blocks = 2) {
       WgradParams& wp = s.wb.prob[s.wb.num_problems++];
       wp.a_c0 = a_c0; wp.b_c0 = b_c0; wp.n_cols = n_cols; wp.n_blocks = (n_cols + 63) / 64; wp.bias_mode = bias_mode;
+      wp.a_blocks = a_blocks;
       return s.wb.num_problems - 1;
     };
     auto add_seg = [&](Step& s, int cb, int ce, Ref out, int ci_total, int ci0, int co_pad) {  // to the LAST problem added
@@ -631,7 +632,7 @@ static int build_plan(b200sr_plan& P) {
     auto wgrad_step = [&](long long x_off, int x_cvalid, int x_cpix, long long dy_off, int dy_cvalid, int dy_cpix, int n, int h, int w,
                           int a_c0, int b_c0, int n_cols) {  // single-problem launch
       Step s = wgrad_batch(x_off, x_cvalid, x_cpix, dy_off, dy_cvalid, dy_cpix, n, h, w);
-      add_problem(s, a_c0, b_c0, n_cols, 0);
+      add_problem(s, a_c0, b_c0, n_cols, 0, (x_cvalid - a_c0 > 64) ? 2 : 1);
       return s;
     };
     auto biasgrad_step = [&](long long g_off, long long npix, int stride, int c0, int ncols) {
@@ -887,10 +888,10 @@ static int build_plan(b200sr_plan& P) {
         add_seg(wg, 64, 96, wref(conv_index_rdb(r, 4)), 160, 0, 32);
         add_seg(wg, 96, 128, wref(conv_index_rdb(r, 3)), 128, 0, 32);
         add_seg(wg, 128, 160, wref(conv_index_rdb(r, 2)), 96, 0, 32);
-        add_problem(wg, 128, 0, 96, 0);  // o3, o4 rows x [dY5|dY4]
+        add_problem(wg, 128, 0, 96, 0, 1);  // o3, o4 rows (64 channels: one X box) x [dY5|dY4]
         add_seg(wg, 0, 64, wref(conv_index_rdb(r, 5)), 192, 128, 64);
         add_seg(wg, 64, 96, wref(conv_index_rdb(r, 4)), 160, 128, 32);
-        add_problem(wg, 0, 160, 32, 0);  // x rows x dY1 (conv1)
+        add_problem(wg, 0, 160, 32, 0, 1);  // x rows (one X box) x dY1 (conv1)
         add_seg(wg, 0, 32, wref(conv_index_rdb(r, 1)), 64, 0, 32);
         add_problem(wg, 0, 0, 192, 1);   // bias gradients: column sums of [dY5|dY4|dY3|dY2|dY1]
         add_seg(wg, 0, 64, bref(conv_index_rdb(r, 5)), 1, 0, 64);
@@ -1457,7 +1458,7 @@ int b200sr_conv3x3_wgrad(const void* x, int n, int h, int w_, int cin, int x_str
   wb.tiles_x = (w_ + kTileW - 1) / kTileW; wb.tiles_y = (h + kWgTileH - 1) / kWgTileH; wb.num_tiles = n * wb.tiles_x * wb.tiles_y;
   wb.num_problems = 1;
   WgradParams& wp = wb.prob[0];
-  wp.a_c0 = 0; wp.b_c0 = 0; wp.n_cols = cout; wp.n_blocks = (cout + 63) / 64;
+  wp.a_c0 = 0; wp.b_c0 = 0; wp.n_cols = cout; wp.n_blocks = (cout + 63) / 64; wp.a_blocks = (cin > 64) ? 2 : 1;
   wp.num_seg = 1;
   wp.seg[0].col_begin = 0; wp.seg[0].col_end = cout; wp.seg[0].out = staging; wp.seg[0].ci_total = cin; wp.seg[0].ci0 = 0; wp.seg[0].co_pad = cout;
   int splits = g_num_sms / 3;

@@ -44,6 +44,7 @@ struct WgradParams {
   int b_c0;      // first dY channel (accumulator column 0)
   int n_cols;    // UMMA N (multiple of 16, <= 160; bias problem: <= 256)
   int n_blocks;  // ceil(n_cols / 64) dY boxes per tile
+  int a_blocks;  // X boxes loaded per tile: 2 (128 input channels) or 1 (only accumulator rows 0..63 are kept)
   int bias_mode; // 1: A = all ones, one accumulator, no X loads, no taps: column sums of dY
   int splits;    // pixel-tile splits of this problem (CTAs = splits * (bias_mode ? 1 : 3))
   int num_seg;
@@ -59,7 +60,7 @@ struct WgradBatch {
 };
 
 __host__ __device__ inline int wgrad_stage_bytes(const WgradParams& p) {
-  return (p.bias_mode ? 0 : 2 * kWgXBytes) + p.n_blocks * kWgBBytes;
+  return (p.bias_mode ? 0 : p.a_blocks * kWgXBytes) + p.n_blocks * kWgBBytes;
 }
 constexpr int kWgSmemBytes = 227 * 1024;
 
@@ -90,7 +91,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int stage_bytes = wgrad_stage_bytes(p);
   int S = kRing / stage_bytes;
   if (S > 4) S = 4;
-  const int b_off = p.bias_mode ? 0 : 2 * kWgXBytes;
+  const int b_off = p.bias_mode ? 0 : p.a_blocks * kWgXBytes;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmX);
@@ -129,7 +130,9 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         mbar_arrive_expect_tx(&full[s], stage_bytes);
         if (!p.bias_mode) {
           tma_load_4d(st, &tmX, &full[s], p.a_c0, x0 + dxi - 1, y0 - 1, n);
-          tma_load_4d(st + kWgXBytes, &tmX, &full[s], p.a_c0 + 64, x0 + dxi - 1, y0 - 1, n);
+          // with one X box the MMA's rows 64..127 read whatever follows in the stage (finite bf16 data); those accumulator
+          // rows are never flushed
+          if (p.a_blocks == 2) tma_load_4d(st + kWgXBytes, &tmX, &full[s], p.a_c0 + 64, x0 + dxi - 1, y0 - 1, n);
         }
         for (int j = 0; j < p.n_blocks; ++j)
           tma_load_4d(st + b_off + j * kWgBBytes, &tmDY, &full[s], p.b_c0 + 64 * j, x0, y0, n);
