@@ -68,6 +68,7 @@ static int runtime_init() {
   }
   if (!g_attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
+    CUDA_TRY(cudaFuncSetAttribute(wgrad3x3_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     g_attr_set = true;
   }
@@ -123,7 +124,7 @@ struct Step {
   int layer0 = 0, nlayers = 0, chain_grid = 0;  // ST_CHAIN: range of the plan's layer list
   int entry0 = 0, nentries = 0;                 // ... and of its entry list (filled when the device tables are built)
   // wgrad
-  int xmap = -1, dymap = -1;
+  int xmap = -1, dymap = -1, xmap_c = -1;  // xmap_c: X map with a 10-pixel-wide haloed box (cluster-multicast wgrad)
   WgradBatch wb;
   Ref seg_out[5];                 // bias-grad kernel outputs
   Ref wseg_out[kWgMaxProblems][5];  // wgrad batch outputs
@@ -609,6 +610,7 @@ static int build_plan(b200sr_plan& P) {
     auto wgrad_batch = [&](long long x_off, int x_cvalid, int x_cpix, long long dy_off, int dy_cvalid, int dy_cpix, int n, int h, int w) {
       Step s; s.type = ST_WGRAD;
       s.xmap = B.add_map(x_off, x_cvalid, x_cpix, n, h, w, kWgXRows);
+      s.xmap_c = B.add_map(x_off, x_cvalid, x_cpix, n, h, w, kWgXRows, kABoxW);
       s.dymap = B.add_map(dy_off, dy_cvalid, dy_cpix, n, h, w, kWgTileH);
       WgradBatch& wb = s.wb; memset(&wb, 0, sizeof(wb));
       wb.N = n; wb.H = h; wb.W = w;
@@ -1106,6 +1108,74 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   return 0;
 }
 
+// Cluster-multicast launch: clusters of 3 CTAs (the three horizontal taps of one pixel split) share every load.
+// Opt-in (B200SR_WGRAD_CLUSTER=1): parity-green, cuts the L2 reads 3x, but measured slower (15.65 vs 14.9 ms/step): only
+// 45 clusters of 3 are co-resident (135 of 148 SMs) and the main loop is bound by shared-memory bandwidth (MMA operand
+// reads 125 B/clk + TMA fills 49 B/clk against 128 B/clk), which multicast does not change.
+static const bool g_wgrad_cluster = [] { const char* e = getenv("B200SR_WGRAD_CLUSTER"); return e && atoi(e) == 1; }();
+static int launch_wgrad_cluster(const Step& s, const CUtensorMap& tmXc, const CUtensorMap& tmDY, const Bases& b, cudaStream_t st) {
+  WgradBatch wb = s.wb;
+  double work[kWgMaxProblems], total = 0;
+  for (int j = 0; j < wb.num_problems; ++j) {
+    WgradParams& wp = wb.prob[j];
+    for (int i = 0; i < wp.num_seg; ++i) wp.seg[i].out = (float*)resolve(s.wseg_out[j][i], b);
+    const int nacc = wp.bias_mode ? 1 : 3;
+    const double mma = nacc * 8.0 * (32.0 + wp.n_cols / 4.0 > wp.n_cols / 2.0 ? 32.0 + wp.n_cols / 4.0 : wp.n_cols / 2.0);
+    const double ld = wgrad_cluster_tx_bytes(wp) / 64.0;  // shared-memory fill rate of one SM
+    work[j] = (mma > ld ? mma : ld) * nacc;
+    total += work[j];
+  }
+  // one wave of 3-CTA clusters: how many are co-resident depends on the GPC layout, ask the runtime once
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaLaunchConfig_t qc; memset(&qc, 0, sizeof(qc));
+    qc.gridDim = dim3(3 * 64); qc.blockDim = dim3(kWgThreads); qc.dynamicSmemBytes = kWgSmemBytes;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 3; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa; qc.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, wgrad3x3_cluster_kernel, &qc) != cudaSuccess || n < 1) { cudaGetLastError(); n = g_num_sms / 3 - 4; }
+    max_clusters = n;
+    if (getenv("B200SR_VERBOSE")) fprintf(stderr, "b200sr: wgrad clusters of 3 co-resident: %d\n", n);
+  }
+  const int clusters = max_clusters;
+  int cl_of[kWgMaxProblems], cl_sum = 0, largest = 0;
+  for (int j = 0; j < wb.num_problems; ++j) {
+    cl_of[j] = (int)(clusters * work[j] / total);  // round down, then hand the remainder to the largest problem
+    if (cl_of[j] < 1) cl_of[j] = 1;
+    cl_sum += cl_of[j];
+    if (work[j] > work[largest]) largest = j;
+  }
+  if (cl_sum < clusters) cl_of[largest] += clusters - cl_sum;
+  int ctas = 0;
+  for (int j = 0; j < wb.num_problems; ++j) {
+    WgradParams& wp = wb.prob[j];
+    int cl = cl_of[j];  // clusters of this problem
+    if (wp.bias_mode) {                   // three independent CTAs per cluster, each its own split
+      int splits = cl * 3;
+      while (splits > wb.num_tiles && splits > 3) splits -= 3;
+      wp.splits = splits;
+      wb.cta_begin[j] = ctas;
+      ctas += splits;
+    } else {
+      if (cl > wb.num_tiles) cl = wb.num_tiles;
+      wp.splits = cl;
+      wb.cta_begin[j] = ctas;
+      ctas += cl * 3;
+    }
+  }
+  wb.cta_begin[wb.num_problems] = ctas;
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(kWgThreads); cfg.dynamicSmemBytes = kWgSmemBytes; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 3; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, wgrad3x3_cluster_kernel, tmXc, tmDY, wb));
+  return 0;
+}
+
 static int launch_wgrad(const Step& s, const CUtensorMap& tmX, const CUtensorMap& tmDY, const Bases& b, cudaStream_t st) {
   WgradBatch wb = s.wb;
   // deal the CTAs of one wave out in proportion to each problem's cost (max of tensor cycles and L2->SM bytes / 42 B per clock)
@@ -1149,7 +1219,8 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         break;
       }
       case ST_WGRAD: {
-        int rc = launch_wgrad(s, P.maps[s.xmap], P.maps[s.dymap], b, st);
+        int rc = (g_wgrad_cluster && s.xmap_c >= 0) ? launch_wgrad_cluster(s, P.maps[s.xmap_c], P.maps[s.dymap], b, st)
+                                                    : launch_wgrad(s, P.maps[s.xmap], P.maps[s.dymap], b, st);
         if (rc) return rc;
         break;
       }
