@@ -66,6 +66,9 @@ void b200sr_plan_destroy(b200sr_plan* plan);
 /* sizes (bytes) of the caller-allocated buffers */
 size_t b200sr_workspace_bytes(const b200sr_plan* plan);
 size_t b200sr_packed_bytes(const b200sr_plan* plan);
+/* identifies the layout of the packed-weight buffer: plans of one network may pack differently (the dense-block schedule
+ * depends on the geometry); a packed buffer may be shared between plans only if their ids are equal */
+uint64_t b200sr_pack_layout_id(const b200sr_plan* plan);
 /* number of parameter tensors (2 per conv: weight, bias) and total fp32 elements, in state_dict order */
 int32_t b200sr_num_params(const b200sr_plan* plan);
 int64_t b200sr_param_numel(const b200sr_plan* plan);

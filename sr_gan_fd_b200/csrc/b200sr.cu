@@ -1329,6 +1329,20 @@ void b200sr_plan_destroy(b200sr_plan* p) {
 
 size_t b200sr_workspace_bytes(const b200sr_plan* p) { return p ? (size_t)p->ws_bytes : 0; }
 size_t b200sr_packed_bytes(const b200sr_plan* p) { return p ? (size_t)p->packed_bytes : 0; }
+uint64_t b200sr_pack_layout_id(const b200sr_plan* p) {
+  // FNV-1a over the packing tables: two plans with equal ids produce byte-identical packed buffers from the same parameters
+  if (!p) return 0;
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* data, size_t n) {
+    const unsigned char* c = (const unsigned char*)data;
+    for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+  };
+  for (const PackOp& op : p->pack_ops) mix(&op, sizeof(op));
+  for (const BiasOp& op : p->bias_ops) mix(&op, sizeof(op));
+  mix(&p->total_rows, sizeof(p->total_rows));
+  mix(&p->packed_bytes, sizeof(p->packed_bytes));
+  return h ? h : 1;
+}
 int32_t b200sr_num_params(const b200sr_plan* p) { return p ? (int32_t)p->param_off.size() - 1 : 0; }
 int64_t b200sr_param_numel(const b200sr_plan* p) { return p ? p->param_off.back() : 0; }
 

@@ -17,6 +17,7 @@ from . import lib as _lib
 
 _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 _MAX_PLANS = 8
+_MAX_PACKED = 4  # packed-weight buffers kept per module ((training, pack layout) pairs; ~40 MB each for the x4 net)
 
 
 class _Plan:
@@ -33,6 +34,7 @@ class _Plan:
         self.out_channels = desc["out_channels"]
         self.workspace_bytes = int(lib.b200sr_workspace_bytes(handle))
         self.packed_bytes = int(lib.b200sr_packed_bytes(handle))
+        self.pack_layout = int(lib.b200sr_pack_layout_id(handle))
         self.num_params = int(lib.b200sr_num_params(handle))
         self.param_numel = int(lib.b200sr_param_numel(handle))
         self.flops_fwd = float(lib.b200sr_flops(handle, 0))
@@ -56,9 +58,9 @@ class GeneratorRuntime:
 
     def __init__(self) -> None:
         self.plans: "OrderedDict[tuple, _Plan]" = OrderedDict()
-        self.packed = {}        # training flag -> uint8 tensor
-        self.packed_key = {}    # training flag -> (versions, ptrs)
-        self.pack_serial = {False: 0, True: 0}
+        self.packed = OrderedDict()  # (training, pack layout) -> uint8 tensor
+        self.packed_key = {}    # (training, pack layout) -> (versions, ptrs)
+        self.pack_serial = {}
         # optional hook(flat_grads: Tensor, offset: int, count: int) called as gradient buckets are enqueued
         self.grad_bucket_hook: Optional[Callable[[torch.Tensor, int, int], None]] = None
         # optional hook(flat_grads) called once backward has enqueued all of its kernels
@@ -85,19 +87,26 @@ class GeneratorRuntime:
         return p
 
     def packed_weights(self, plan: _Plan, params: List[torch.Tensor], stream: int, key=None) -> torch.Tensor:
-        t = plan.training
+        # one packed buffer per (training, pack layout): the dense-block schedule -- and with it the packing -- depends on
+        # the geometry (windowed re-association for small batches, per-conv for large frames)
+        slot = (plan.training, plan.pack_layout)
         if key is None:
             key = (tuple([p._version for p in params]), tuple([p.data_ptr() for p in params]))
-        buf = self.packed.get(t)
-        if buf is not None and buf.device == params[0].device and self.packed_key.get(t) == key:
+        buf = self.packed.get(slot)
+        if buf is not None and buf.device == params[0].device and self.packed_key.get(slot) == key:
+            self.packed.move_to_end(slot)
             return buf
         if buf is None or buf.device != params[0].device or buf.numel() != plan.packed_bytes:
             buf = torch.empty(plan.packed_bytes, dtype=torch.uint8, device=params[0].device)
-            self.packed[t] = buf
+            self.packed[slot] = buf
+            while len(self.packed) > _MAX_PACKED:
+                old, _ = self.packed.popitem(last=False)
+                self.packed_key.pop(old, None)
+        self.packed.move_to_end(slot)
         ptrs = (C.c_void_p * len(params))(*key[1])
         _lib.check(_lib.load().b200sr_pack_weights(plan.handle, ptrs, C.c_void_p(buf.data_ptr()), C.c_void_p(stream)))
-        self.packed_key[t] = key
-        self.pack_serial[t] += 1
+        self.packed_key[slot] = key
+        self.pack_serial[slot] = self.pack_serial.get(slot, 0) + 1
         return buf
 
 
@@ -125,7 +134,8 @@ class _RRDBNetFn(torch.autograd.Function):
             ctx.rt = rt
             ctx.workspace = workspace
             ctx.packed = packed
-            ctx.pack_serial = rt.pack_serial[True]
+            ctx.pack_slot = (True, plan.pack_layout)
+            ctx.pack_serial = rt.pack_serial[ctx.pack_slot]
             ctx.x_keepalive = x
         return y
 
@@ -136,7 +146,7 @@ class _RRDBNetFn(torch.autograd.Function):
         rt: GeneratorRuntime = ctx.rt
         if ctx.workspace is None:
             raise RuntimeError("the B200 generator supports one backward per forward (activations already released)")
-        if rt.pack_serial[True] != ctx.pack_serial:
+        if rt.pack_serial.get(ctx.pack_slot) != ctx.pack_serial:
             raise RuntimeError("generator weights were re-packed between this forward and its backward")
         dy = dy.contiguous().float()
         with torch.cuda.device(dy.device):

@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200sr_plan_destroy": (None, [C.c_void_p]),
     "b200sr_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "b200sr_packed_bytes": (C.c_size_t, [C.c_void_p]),
+    "b200sr_pack_layout_id": (C.c_uint64, [C.c_void_p]),
     "b200sr_num_params": (C.c_int32, [C.c_void_p]),
     "b200sr_param_numel": (C.c_int64, [C.c_void_p]),
     "b200sr_flops": (C.c_double, [C.c_void_p, C.c_int]),

@@ -251,3 +251,26 @@ def test_data_parallel_two_gpus():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29577", os.path.join(root, "tools", "dp_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_schedule_switch_repacks_weights():
+    """A module used at two geometries whose dense-block schedules differ (windowed re-association for a small batch,
+    per-conv for a frame with more 8x32 items than SMs) must not share a packed-weight buffer between them."""
+    dev = DEV
+    net, _ = _build(num_blocks=2, seed=3)
+    net.eval()
+    small = torch.rand(2, 3, 32, 32, device=dev)
+    big = torch.rand(1, 3, 160, 264, device=dev)      # 33 x 5 = 165 items per layer > 148 SMs -> per-conv schedule
+    with torch.no_grad():
+        y_small_first = net(small)
+        y_big = net(big)                               # same module, other schedule
+        y_small_again = net(small)
+        fresh = copy.deepcopy(net)                     # fresh runtime: packs for the big geometry only
+        y_big_ref = fresh(big)
+        y_small_ref = copy.deepcopy(net)(small)
+    assert torch.equal(y_big, y_big_ref)
+    assert torch.equal(y_small_first, y_small_ref)
+    assert torch.equal(y_small_again, y_small_ref)
+    plans = net._runtime().plans
+    layouts = {p.pack_layout for p in plans.values()}
+    assert len(layouts) == 2, "the two geometries are expected to use different packings"
