@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1079,9 +1080,22 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
   return 0;
 }
 
+// The constant-memory tables are one per device: chain launches issued to DIFFERENT streams of a device are ordered
+// after one another with an event (they fill the whole GPU anyway), so a later upload can never overtake an earlier
+// launch that still reads its own tables.
+struct ChainOrder { cudaEvent_t ev = nullptr; cudaStream_t last = nullptr; bool any = false; };
+static ChainOrder g_chain_order[64];
+static std::mutex g_chain_mutex;
+
 static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_chain_mutex);
   int grid = s.chain_grid < g_num_sms ? s.chain_grid : g_num_sms;
   if (grid < 1) grid = 1;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  ChainOrder& co = g_chain_order[dev & 63];
+  if (!co.ev) CUDA_TRY(cudaEventCreateWithFlags(&co.ev, cudaEventDisableTiming));
+  if (co.any && co.last != st) CUDA_TRY(cudaStreamWaitEvent(st, co.ev, 0));
   if (s.nentries > kMaxChainEntries || s.nlayers > kMaxChainLayers)
     return fail(B200SR_ERR_INVALID, "chain too long (%d entries, %d layers)", s.nentries, s.nlayers);
   // the producer / MMA warps read their parameters from constant memory: load this chain's slice (stream ordered)
@@ -1105,6 +1119,11 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   } else {
     CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   }
+  if (co.last != st || !co.any) {  // (same stream again: stream order already protects the tables)
+    co.last = st;
+    co.any = true;
+  }
+  CUDA_TRY(cudaEventRecord(co.ev, st));
   return 0;
 }
 

@@ -274,3 +274,28 @@ def test_schedule_switch_repacks_weights():
     plans = net._runtime().plans
     layouts = {p.pack_layout for p in plans.values()}
     assert len(layouts) == 2, "the two geometries are expected to use different packings"
+
+
+def test_two_streams_do_not_mix_chain_tables():
+    """Two generators driven from two CUDA streams: the per-device constant tables of the chain kernel must not leak from
+    one launch into the other (launches on different streams are ordered after one another by the library)."""
+    net_a, _ = _build(num_blocks=2, seed=5)
+    net_b, _ = _build(num_blocks=3, seed=6)
+    net_a.eval(); net_b.eval()
+    xa = torch.rand(2, 3, 40, 24, device=DEV)
+    xb = torch.rand(3, 3, 24, 48, device=DEV)
+    with torch.no_grad():
+        ref_a, ref_b = net_a(xa), net_b(xb)
+        torch.cuda.synchronize()
+        sa, sb = torch.cuda.Stream(device=DEV), torch.cuda.Stream(device=DEV)
+        outs = []
+        for _ in range(6):
+            with torch.cuda.stream(sa):
+                ya = net_a(xa)
+            with torch.cuda.stream(sb):
+                yb = net_b(xb)
+            outs.append((ya, yb))
+        torch.cuda.synchronize()
+    for ya, yb in outs:
+        assert torch.equal(ya, ref_a)
+        assert torch.equal(yb, ref_b)
