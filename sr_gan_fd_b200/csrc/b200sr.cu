@@ -1195,8 +1195,11 @@ static int launch_wgrad_cluster(const Step& s, const CUtensorMap& tmXc, const CU
   return 0;
 }
 
+// SMs one wgrad wave may use (B200SR_WGRAD_SMS, experiment: leave room for concurrently running NCCL kernels)
+static const int g_wgrad_sms_cap = [] { const char* e = getenv("B200SR_WGRAD_SMS"); return e ? atoi(e) : 0; }();
 static int launch_wgrad(const Step& s, const CUtensorMap& tmX, const CUtensorMap& tmDY, const Bases& b, cudaStream_t st) {
   WgradBatch wb = s.wb;
+  const int sms = (g_wgrad_sms_cap > 0 && g_wgrad_sms_cap < g_num_sms) ? g_wgrad_sms_cap : g_num_sms;
   // deal the CTAs of one wave out in proportion to each problem's cost (max of tensor cycles and L2->SM bytes / 42 B per clock)
   double work[kWgMaxProblems], total = 0;
   for (int j = 0; j < wb.num_problems; ++j) {
@@ -1212,7 +1215,7 @@ static int launch_wgrad(const Step& s, const CUtensorMap& tmX, const CUtensorMap
   for (int j = 0; j < wb.num_problems; ++j) {
     WgradParams& wp = wb.prob[j];
     const int ntap = wp.bias_mode ? 1 : 3;
-    int splits = (int)(g_num_sms * work[j] / total / ntap + 0.5);
+    int splits = (int)(sms * work[j] / total / ntap + 0.5);
     if (splits < 1) splits = 1;
     if (splits > wb.num_tiles) splits = wb.num_tiles;
     wp.splits = splits;
