@@ -156,7 +156,9 @@ struct b200sr_plan {
   long long o_xin = 0, o_t0 = 0, o_tr = 0, o_c1 = 0, o_c2 = 0, o_splt = 0, o_splc = 0, o_cmask = 0;
   std::vector<long long> o_dense, o_spl;
   long long o_dyp = 0, o_g3 = 0, o_gt = 0, o_gtb = 0, o_gr = 0, o_gc1 = 0, o_gc2 = 0, o_go1 = 0;
-  long long o_dyb[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<long long> o_dyb;      // output-gradient buffers [dY5|dY4|dY3|dY2|dY1] of the dense blocks: one per block when the
+                                      // whole backward is ONE data-gradient chain (default), else a ring of six
+  bool single_bwd_chain = true;       // B200SR_BWDCHAIN=0: one chain per gradient bucket, weight gradients interleaved
   std::vector<long long> o_gu;
   bool reassoc = true;                // dense blocks re-associated by input slice (B200SR_REASSOC=0: per-conv schedule, 1: all five convs resident, 2 = default: windowed)
   int groups = 1;                     // image groups that flow through a chain independently
@@ -389,7 +391,8 @@ static int build_plan(b200sr_plan& P) {
     P.o_gc1 = B.alloc(carrier_bytes);
     P.o_gc2 = B.alloc(carrier_bytes);
     P.o_go1 = B.alloc(Ppix * 64 * 2);
-    for (int i = 0; i < 6; ++i) P.o_dyb[i] = B.alloc(Ppix * 192 * 2);
+    P.o_dyb.assign(P.single_bwd_chain ? R : 6, 0);
+    for (size_t i = 0; i < P.o_dyb.size(); ++i) P.o_dyb[i] = B.alloc(Ppix * 192 * 2);
   }
   P.ws_bytes = B.cursor;
 
@@ -675,7 +678,7 @@ static int build_plan(b200sr_plan& P) {
     std::vector<Step> seg_convs, seg_others;
     auto emit = [&](const Step& st) {
       if (st.type == ST_CONV) seg_convs.push_back(st); else seg_others.push_back(st);
-      if (st.type == ST_UNPACK) {
+      if (st.type == ST_UNPACK && !P.single_bwd_chain) {
         for (const Step& c : seg_convs) P.bwd.push_back(c);
         for (const Step& o : seg_others) P.bwd.push_back(o);
         seg_convs.clear(); seg_others.clear();
@@ -760,7 +763,7 @@ static int build_plan(b200sr_plan& P) {
       ConvParams cp = base_conv_params(N, H, W, 1, 4, 0, 1 << 20, row0, 64, 64);
       Step s = conv_step(B.add_map(P.o_gtb, 64, 64, N, H, W, kABoxRows), cp, 1);
       s.of = ws(P.o_gr);
-      s.ob = ws(P.o_dyb[3 * ((d.num_blocks - 1) & 1)]); s.cp.epi.ob_stride = 192; s.cp.epi.delta = 0.04f;
+      s.ob = ws(P.single_bwd_chain ? P.o_dyb[R - 1] : P.o_dyb[3 * ((d.num_blocks - 1) & 1)]); s.cp.epi.ob_stride = 192; s.cp.epi.delta = 0.04f;
       emit(s);
       // tail bucket: conv2 .. conv4 are contiguous at the end of the flat buffer
       emit(unpack_step(ci_conv2, nconv));
@@ -770,8 +773,9 @@ static int build_plan(b200sr_plan& P) {
       const int j = r % 3;
       const long long D = P.o_dense[r];
       const int blk = r / 3;
-      const long long DYc = P.o_dyb[3 * (blk & 1) + (2 - j)];
-      const long long DYn = (j > 0) ? P.o_dyb[3 * (blk & 1) + (2 - (j - 1))] : P.o_dyb[3 * ((blk + 1) & 1)];
+      const long long DYc = P.single_bwd_chain ? P.o_dyb[r] : P.o_dyb[3 * (blk & 1) + (2 - j)];
+      const long long DYn = P.single_bwd_chain ? P.o_dyb[r > 0 ? r - 1 : 0]
+                                               : ((j > 0) ? P.o_dyb[3 * (blk & 1) + (2 - (j - 1))] : P.o_dyb[3 * ((blk + 1) & 1)]);
       // epilogue of the block-input (x) slice: fp32 gradient carriers and the next block's dY5
       auto xslice_epilogue = [&](Step& s) {
         if (j == 2) { s.r1 = ws(P.o_gr); s.cp.epi.beta1 = 0.2f; s.of = ws(P.o_gc2); s.cp.epi.delta = 0.2f; }
@@ -918,6 +922,13 @@ static int build_plan(b200sr_plan& P) {
       add_bseg(b1, 0, 64, bref(0), 64);
       emit(b1);
       emit(unpack_step(0, 1));
+    }
+    if (P.single_bwd_chain) {
+      // ONE data-gradient chain for the whole backward pass (no pipeline drain / refill at every gradient bucket), then
+      // the weight- and bias-gradient kernels bucket by bucket: every dense block has its own dY buffer for that.
+      for (const Step& c : seg_convs) P.bwd.push_back(c);
+      for (const Step& o : seg_others) P.bwd.push_back(o);
+      seg_convs.clear(); seg_others.clear();
     }
   }
 
@@ -1328,6 +1339,7 @@ int b200sr_plan_create(const b200sr_net_desc* desc, b200sr_plan** out) {
   if (const char* e = getenv("B200SR_REASSOC")) { p->reassoc = atoi(e) != 0; p->window = atoi(e) == 2; }
   if (const char* e = getenv("B200SR_SPLIT")) p->split_passes = atoi(e) != 0;
   if (const char* e = getenv("B200SR_UNIT")) p->unit_all = atoi(e) != 0;
+  if (const char* e = getenv("B200SR_BWDCHAIN")) p->single_bwd_chain = atoi(e) != 0;
   if (const char* e = getenv("B200SR_GROUPS")) p->groups_env = atoi(e);
   int rc = build_plan(*p);
   if (rc) { delete p; return rc; }
