@@ -158,6 +158,8 @@ struct b200sr_plan {
   long long o_dyp = 0, o_g3 = 0, o_gt = 0, o_gtb = 0, o_gr = 0, o_gc1 = 0, o_gc2 = 0, o_go1 = 0;
   std::vector<long long> o_dyb;      // output-gradient buffers [dY5|dY4|dY3|dY2|dY1] of the dense blocks: one per block when the
                                       // whole backward is ONE data-gradient chain (default), else a ring of six
+  cudaStream_t side_stream = nullptr; // second stream for the weight-gradient launches (their tails / heads overlap)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool single_bwd_chain = true;       // B200SR_BWDCHAIN=0: one chain per gradient bucket, weight gradients interleaved
   std::vector<long long> o_gu;
   bool reassoc = true;                // dense blocks re-associated by input slice (B200SR_REASSOC=0: per-conv schedule, 1: all five convs resident, 2 = default: windowed)
@@ -1242,7 +1244,29 @@ static int launch_wgrad(const Step& s, const CUtensorMap& tmX, const CUtensorMap
 static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, const void* x, int x_dtype, const int64_t* xs,
                      b200sr_bucket_cb cb, void* user, cudaStream_t st) {
   const b200sr_net_desc& d = P.d;
+  // Weight-gradient launches of different dense blocks are independent of one another: once the data-gradient chain is
+  // done they alternate between the caller's stream and a side stream, so the flush tail of one launch overlaps the ramp-up
+  // of the next (each launch fills the GPU with one CTA per SM).  Everything that consumes their results joins first.
+  static const bool two_streams = [] { const char* e = getenv("B200SR_WGRAD_STREAMS"); return !(e && atoi(e) == 1); }();
+  const bool alternate = two_streams && P.single_bwd_chain && (&steps == &P.bwd);
+  bool forked = false, side_dirty = false;
+  int wcount = 0;
+  auto join = [&]() -> int {
+    if (side_dirty) {
+      CUDA_TRY(cudaEventRecord(P.ev_join, P.side_stream));
+      CUDA_TRY(cudaStreamWaitEvent(st, P.ev_join, 0));
+      side_dirty = false;
+    }
+    return 0;
+  };
   for (Step& s : steps) {
+    if (alternate) {
+      // the gradient unpack consumes what the weight-gradient launches of BOTH streams produced: join first (without a
+      // bucket callback only the last unpack step launches anything)
+      if (s.type == ST_UNPACK && (cb || s.i0 == 0)) { int rc = join(); if (rc) return rc; }
+      // the carrier add feeds conv1's weight gradient: the side stream has to be forked again after it
+      if (s.type == ST_ADD) forked = false;
+    }
     switch (s.type) {
       case ST_CONV:
         return fail(B200SR_ERR_INVALID, "internal: unchained conv step");
@@ -1252,8 +1276,22 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         break;
       }
       case ST_WGRAD: {
-        int rc = (g_wgrad_cluster && s.xmap_c >= 0) ? launch_wgrad_cluster(s, P.maps[s.xmap_c], P.maps[s.dymap], b, st)
-                                                    : launch_wgrad(s, P.maps[s.xmap], P.maps[s.dymap], b, st);
+        cudaStream_t ws = st;
+        if (alternate) {
+          if (!P.side_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&P.side_stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&P.ev_fork, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&P.ev_join, cudaEventDisableTiming));
+          }
+          if (!forked) {  // the side stream starts after everything enqueued so far (the data-gradient chain)
+            CUDA_TRY(cudaEventRecord(P.ev_fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(P.side_stream, P.ev_fork, 0));
+            forked = true;
+          }
+          if (wcount++ & 1) { ws = P.side_stream; side_dirty = true; }
+        }
+        int rc = (g_wgrad_cluster && s.xmap_c >= 0) ? launch_wgrad_cluster(s, P.maps[s.xmap_c], P.maps[s.dymap], b, ws)
+                                                    : launch_wgrad(s, P.maps[s.xmap], P.maps[s.dymap], b, ws);
         if (rc) return rc;
         break;
       }
@@ -1318,7 +1356,7 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
     }
     if (cb && s.cb_count > 0) cb(user, s.cb_off, s.cb_count);
   }
-  return 0;
+  return join();
 }
 
 // =================================================================================================== C ABI =====
@@ -1355,6 +1393,9 @@ void b200sr_plan_destroy(b200sr_plan* p) {
   if (p->d_unpack_ops) cudaFree(p->d_unpack_ops);
   if (p->d_layers) cudaFree(p->d_layers);
   if (p->d_entries) cudaFree(p->d_entries);
+  if (p->side_stream) cudaStreamDestroy(p->side_stream);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
   if (p->d_layer_rec) cudaFree(p->d_layer_rec);
   if (p->d_entry_rec) cudaFree(p->d_entry_rec);
   if (p->d_counters) cudaFree(p->d_counters);
