@@ -7,6 +7,7 @@
 //   backward: the mirror image; every data-gradient is the SAME implicit-GEMM kernel over transposed/flipped
 //             weights reading a dense gradient buffer [dY5|dY4|dY3|dY2|dY1]; weight gradients are one tcgen05 GEMM
 //             per dense block slice (pixel axis = reduction) with fp32 reductions into the flat gradient buffer.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
@@ -949,7 +950,12 @@ static int build_plan(b200sr_plan& P) {
     for (Step& s : v) {
       if (s.type != ST_CONV) { out.push_back(s); continue; }
       const int work = s.cp.num_tiles * s.cp.col_groups;
-      if (out.empty() || out.back().type != ST_CHAIN) {
+      // A chain is limited by the constant-memory tables (layers, entries = layers x image groups).  Long chains are cut
+      // where a layer starts fresh accumulators (never inside a dense block whose partial sums live in TMEM).
+      const int max_layers = std::min(kMaxChainLayers, kMaxChainEntries / (P.groups > 0 ? P.groups : 1)) - 8;
+      const bool cut = !out.empty() && out.back().type == ST_CHAIN && out.back().nlayers >= max_layers && s.cp.acc_first &&
+                       !(s.cp.acc_hold && s.cp.epi_cols == 0);
+      if (out.empty() || out.back().type != ST_CHAIN || cut) {
         Step c; c.type = ST_CHAIN; c.layer0 = (int)P.layer_steps.size(); c.nlayers = 0; c.chain_grid = 0;
         out.push_back(c);
       }

@@ -299,3 +299,27 @@ def test_two_streams_do_not_mix_chain_tables():
     for ya, yb in outs:
         assert torch.equal(ya, ref_a)
         assert torch.equal(yb, ref_b)
+
+
+def test_large_batch_splits_the_chain():
+    """Batch 64 needs 8 image groups in the windowed schedule: 351 layers x 8 groups exceeds one chain's entry table, so
+    the plan cuts the forward / backward chains at dense-block boundaries.  Results must match the same images run 16 at a time."""
+    net, _ = _build(num_blocks=23, seed=11, in_range=True)
+    net.train()
+    x = torch.rand(64, 3, 64, 64, device=DEV)
+    gt = torch.rand(64, 3, 256, 256, device=DEV)
+    net.zero_grad(set_to_none=True)
+    y = net(x)
+    F.l1_loss(y, gt).backward()
+    g_big = torch.cat([p.grad.flatten() for p in net.parameters()]).clone()
+    plan = net._runtime().last_plan
+    assert plan.launches_fwd >= 3, "expected the forward chain to be split"
+    net.zero_grad(set_to_none=True)
+    ys = []
+    for i in range(4):
+        yi = net(x[16 * i:16 * i + 16])
+        (F.l1_loss(yi, gt[16 * i:16 * i + 16]) / 4).backward()
+        ys.append(yi.detach())
+    g_small = torch.cat([p.grad.flatten() for p in net.parameters()])
+    assert torch.equal(y.detach(), torch.cat(ys))
+    assert orc.rel_l2(g_big, g_small) <= 2e-3
