@@ -166,6 +166,9 @@ struct b200sr_plan {
   bool reassoc = true;                // dense blocks re-associated by input slice (B200SR_REASSOC=0: per-conv schedule, 1: all five convs resident, 2 = default: windowed)
   int groups = 1;                     // image groups that flow through a chain independently
   bool window = true;                 // with reassoc: only convs 1-4 (128 columns per 128-pixel half) stay resident, conv5 is an ordinary N=64 layer
+  bool early_x = false;               // windowed schedule, opt-in (B200SR_EARLYX=1): the block-input slice's share of conv5 / of the x gradient runs early as a
+                                      // layer without epilogue (latency filler).  Parity-green, measured slower (14.1 vs 13.9 ms/step): two more entries per block
+  bool stagger_fillers = true;        // entry order: one group's filler layer per dependency gap (B200SR_STAGGER=0: all groups at once)
   bool unit_all = false;              // experimental: every chain layer works on single 8 x 16 units (B200SR_UNIT=1)
   int groups_env = 0;                 // experimental: force the number of image groups (B200SR_GROUPS)
   bool split_passes = false;          // experimental: split every pass into a critical and a deferred sub-layer
@@ -476,15 +479,30 @@ static int build_plan(b200sr_plan& P) {
         s.cp.epi.act = 1;
         s.ob = ws(D); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * q;
         P.fwd.push_back(s);
+        if (q == 1 && P.early_x) {
+          // conv5's contribution of the block input x (K = 64 of its 192) does not depend on anything this block computes.
+          // It runs here as a layer WITHOUT epilogue into accumulator columns [0, 64) -- free since the epilogues of passes
+          // 0 and 1 took conv1 / conv2 out -- so the MMA warp works it off while pass 2 waits for pass 1's outputs, and
+          // conv5 proper shrinks to K = 128.
+          const int ci = conv_index_rdb(r, 5);
+          PackOp o5; memset(&o5, 0, sizeof(o5));
+          o5.n_total = 64; o5.n_cols = 64; o5.n_valid = 64; o5.num_chunks = 1; o5.mode = kPackFwd; o5.nseg = 1;
+          o5.seg[0] = seg(0, 64, 2 * ci, 64, 192, 0, 0, 0);
+          const int r5 = B.add_pack(o5);
+          ConvParams c5 = base_conv_params(N, H, W, 1, 4, 0, 1 << 20, r5, 64, 64);
+          c5.acc_hold = 1; c5.acc_first = 1; c5.acc_col0 = 0; c5.epi_cols = 0;
+          P.fwd.push_back(conv_step(B.add_map(D, 64, 192, N, H, W, kABoxRows), c5, 1));
+        }
       }
       {
         const int ci = conv_index_rdb(r, 5);
+        const int k0 = P.early_x ? 64 : 0, klen = 192 - k0;  // input channels still to be accumulated
         PackOp op; memset(&op, 0, sizeof(op));
-        op.n_total = 64; op.n_valid = 64; op.num_chunks = 3; op.mode = kPackFwd; op.nseg = 1;
-        op.seg[0] = seg(0, 192, 2 * ci, 64, 192, 0, 0, 0);
+        op.n_total = 64; op.n_valid = 64; op.num_chunks = klen / 64; op.mode = kPackFwd; op.nseg = 1;
+        op.seg[0] = seg(0, klen, 2 * ci, 64, 192, 0, k0, 0);
         const int row0 = B.add_pack(op);
-        ConvParams cp = base_conv_params(N, H, W, 3, 4, 0, 1 << 20, row0, 64, 64);
-        cp.acc_hold = 1; cp.acc_first = 1; cp.acc_col0 = 0; cp.epi_cols = 64;
+        ConvParams cp = base_conv_params(N, H, W, klen / 64, 4, k0, 1 << 20, row0, 64, 64);
+        cp.acc_hold = 1; cp.acc_first = P.early_x ? 0 : 1; cp.acc_col0 = 0; cp.epi_cols = 64;
         Step s = conv_step(B.add_map(D, 192, 192, N, H, W, kABoxRows), cp, 1);
         s.bias = packed_bias(B.add_bias(64, 2 * ci + 1, 64, 0));
         conv5_epilogue(s);
@@ -808,18 +826,30 @@ static int build_plan(b200sr_plan& P) {
           s.mask = ws(D); s.cp.epi.mask_stride = 192; s.cp.epi.mask_coff = 64 + 32 * (sl - 1);
           s.ob = ws(DYc); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * q;
           emit(s);
+          if (q == 1 && P.early_x) {
+            // mirror of the forward: dY5's contribution to the block-input gradient (K = 64 of 192) is available from the
+            // start of the block; it runs here without epilogue into columns [0, 64)
+            PackOp o5; memset(&o5, 0, sizeof(o5));
+            o5.n_total = 64; o5.n_cols = 64; o5.n_valid = 64; o5.num_chunks = 1; o5.mode = kPackDgrad; o5.nseg = 1;
+            o5.seg[0] = seg(0, 64, 2 * conv_index_rdb(r, 5), 64, 192, 0, 0, 0);
+            const int r5 = B.add_pack(o5);
+            ConvParams c5 = base_conv_params(N, H, W, 1, 4, 0, 1 << 20, r5, 64, 64);
+            c5.acc_hold = 1; c5.acc_first = 1; c5.acc_col0 = 0; c5.epi_cols = 0;
+            emit(conv_step(B.add_map(DYc, 64, 192, N, H, W, kABoxRows), c5, 1));
+          }
         }
         {
+          const int kbase = P.early_x ? 64 : 0;  // dY channels still to be accumulated: [kbase, 192)
           PackOp op; memset(&op, 0, sizeof(op));
-          op.n_total = 64; op.n_valid = 64; op.num_chunks = 3; op.mode = kPackDgrad; op.nseg = 0;
-          for (int k = 5; k > 0; --k) {
-            const int k0 = (k == 5) ? 0 : 64 + 32 * (4 - k);
+          op.n_total = 64; op.n_valid = 64; op.num_chunks = (192 - kbase) / 64; op.mode = kPackDgrad; op.nseg = 0;
+          for (int k = P.early_x ? 4 : 5; k > 0; --k) {
+            const int k0 = ((k == 5) ? 0 : 64 + 32 * (4 - k)) - kbase;
             const int klen = (k == 5) ? 64 : 32;
             op.seg[op.nseg++] = seg(k0, klen, 2 * conv_index_rdb(r, k), klen, 64 + 32 * (k - 1), 0, 0, 0);
           }
           const int row0 = B.add_pack(op);
-          ConvParams cp = base_conv_params(N, H, W, 3, 4, 0, 1 << 20, row0, 64, 64);
-          cp.acc_hold = 1; cp.acc_first = 1; cp.acc_col0 = 0; cp.epi_cols = 64;
+          ConvParams cp = base_conv_params(N, H, W, (192 - kbase) / 64, 4, kbase, 1 << 20, row0, 64, 64);
+          cp.acc_hold = 1; cp.acc_first = P.early_x ? 0 : 1; cp.acc_col0 = 0; cp.epi_cols = 64;
           Step s = conv_step(B.add_map(DYc, 192, 192, N, H, W, kABoxRows), cp, 1);
           xslice_epilogue(s);
           emit(s);
@@ -1027,9 +1057,17 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
             while (l1 < s.nlayers && P.layer_steps[s.layer0 + l1].cp.acc_hold &&
                    !(P.layer_steps[s.layer0 + l1].cp.acc_first && P.layer_steps[s.layer0 + l1].cp.epi_cols > 0)) ++l1;
             // two groups are resident in a CTA's TMEM at a time: interleave them pass by pass, pair after pair
-            for (int g0 = 0; g0 < groups; g0 += 2)
-              for (int ll = l; ll < l1; ++ll)
-                for (int g = g0; g < g0 + 2 && g < groups; ++g) order.push_back({ll, g});
+            for (int g0 = 0; g0 < groups; g0 += 2) {
+              std::vector<std::pair<int, int>> late;  // a no-epilogue filler layer runs once per dependency gap: its second group follows the next layer
+              for (int ll = l; ll < l1; ++ll) {
+                const bool filler = P.layer_steps[s.layer0 + ll].cp.epi_cols == 0 && P.stagger_fillers;
+                for (int g = g0; g < g0 + 2 && g < groups; ++g) {
+                  if (filler && g > g0) late.push_back({ll, g}); else order.push_back({ll, g});
+                }
+                if (!filler && !late.empty()) { order.push_back(late.front()); late.erase(late.begin()); }
+              }
+              for (auto& e2 : late) order.push_back(e2);
+            }
             l = l1;
           } else {
             for (int g = 0; g < groups; ++g) order.push_back({l, g});
@@ -1383,6 +1421,8 @@ int b200sr_plan_create(const b200sr_net_desc* desc, b200sr_plan** out) {
   if (const char* e = getenv("B200SR_REASSOC")) { p->reassoc = atoi(e) != 0; p->window = atoi(e) == 2; }
   if (const char* e = getenv("B200SR_SPLIT")) p->split_passes = atoi(e) != 0;
   if (const char* e = getenv("B200SR_UNIT")) p->unit_all = atoi(e) != 0;
+  if (const char* e = getenv("B200SR_EARLYX")) p->early_x = atoi(e) != 0;
+  if (const char* e = getenv("B200SR_STAGGER")) p->stagger_fillers = atoi(e) != 0;
   if (const char* e = getenv("B200SR_BWDCHAIN")) p->single_bwd_chain = atoi(e) != 0;
   if (const char* e = getenv("B200SR_GROUPS")) p->groups_env = atoi(e);
   int rc = build_plan(*p);
