@@ -129,3 +129,35 @@ def test_compat_shims_export_reference_names():
         assert n in bs.__dict__
     re_ = importlib.import_module("sr_gan_fd_b200.compat.real_esrgan_model")
     assert "RRDBNet" in re_.__dict__ and "rrdbnet_x4" in re_.__dict__
+
+
+def test_schedule_dependent_bookkeeping(L):
+    """The dense-block schedule depends on the geometry: small batches use the windowed re-association, a frame with more
+    8x32 items than SMs the per-conv schedule -- different packed layouts; large batches cut the chains; the backward pass
+    is one data-gradient chain plus the weight-gradient launches."""
+    L.b200sr_pack_layout_id.restype = C.c_uint64
+    rc, small = _plan(L, False, batch=16, h=64, w=64)
+    rc2, frame = _plan(L, False, batch=1, h=512, w=512)
+    rc3, small2 = _plan(L, False, batch=8, h=64, w=64)
+    assert rc == 0 and rc2 == 0 and rc3 == 0
+    try:
+        assert L.b200sr_pack_layout_id(small) != 0
+        assert L.b200sr_pack_layout_id(small) == L.b200sr_pack_layout_id(small2)   # same schedule, other batch
+        assert L.b200sr_pack_layout_id(small) != L.b200sr_pack_layout_id(frame)    # windowed vs per-conv
+        assert L.b200sr_packed_bytes(small) != L.b200sr_packed_bytes(frame)
+    finally:
+        for h in (small, frame, small2):
+            L.b200sr_plan_destroy(h)
+    rc, big = _plan(L, True, batch=64)
+    rc2, base = _plan(L, True, batch=16)
+    assert rc == 0 and rc2 == 0
+    try:
+        assert L.b200sr_num_launches(base, 0) == 2
+        assert L.b200sr_num_launches(big, 0) > 2                                    # 351 layers x 8 groups: the chain is cut
+        # backward: ingest + ONE chain + 77 weight-gradient launches + bias grads + add + one merged unpack
+        n1, n2 = L.b200sr_num_launches(base, 1), L.b200sr_num_launches(base, 2)
+        assert 80 <= n1 <= 95
+        assert n2 - n1 == 24                                                         # 25 gradient buckets instead of one unpack
+    finally:
+        L.b200sr_plan_destroy(big)
+        L.b200sr_plan_destroy(base)
