@@ -12,12 +12,14 @@
 // (Measured on B200, tools/probe_desc.cu: the 128B swizzle is applied on absolute shared-memory address bits, so
 // start addresses that are not 1024-byte aligned and strides that are not multiples of 1024 read exactly the rows
 // TMA wrote; the descriptor's base_offset field must stay 0.)  Weights are pre-packed per (chunk, dx, dy) as
-// [cout][64] K-major bf16 rows and stream through their own smem ring, three taps (one dx column) per slot.
+// pre-swizzled [cout][64] K-major bf16 rows and stream through their own smem ring (10 granules of 12 KB), ONE 1-D bulk
+// copy per stage of nine, three (one dx column) or one tap tile.
 //
 // Warp roles (352 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warp 10 = signaller,
 // warps 2..5 / 6..9 = epilogue of the upper / lower 128-pixel half (TMEM -> registers -> fused bias / LeakyReLU /
-// mask / residuals -> global).  Accumulators are double buffered in TMEM so the epilogue of item i overlaps the MMAs
-// of item i+1 (persistent CTAs).
+// mask / residuals -> global).  Ordinary layers double buffer their accumulators in TMEM (epilogue of item i overlaps
+// the MMAs of item i+1); the passes of a re-associated dense block keep their partial sums resident in the image
+// group's accumulator slot from one layer to the next.
 #pragma once
 #include "ptx.cuh"
 
@@ -29,10 +31,7 @@ constexpr int kABoxRows = kTileH + 2;                   // 34 image rows incl. t
 constexpr int kABoxW = kTileW + 2;                      // 10 pixels incl. the horizontal halo
 constexpr int kABytes = kABoxRows * kABoxW * 128;       // 43520 B: one haloed activation tile per 64-channel chunk
 constexpr int kASlot = 44032;                           // A-ring slot (1024-byte multiple)
-constexpr int kMaxAStages = 4;
-constexpr int kMaxWStages = 6;
 constexpr int kConvThreads = 352;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of the upper 128-pixel half, warps 6-9 of the lower half
-constexpr int kMaxStages = 8;
 
 enum StoreMode : int {
   kStorePix = 0,        // same lattice position
@@ -92,7 +91,6 @@ struct ConvParams {
   ConvEpilogue epi;
 };
 
-__host__ __device__ inline int conv_wslot_bytes(int n_cols) { return 3 * n_cols * 128; }  // the three dy taps of one dx column
 __host__ __device__ constexpr int conv_smem_bytes(int ctas_per_sm) { return ctas_per_sm == 1 ? 227 * 1024 : 112 * 1024; }
 __host__ inline int conv_pick_stages(int n_cols) { return n_cols >= 128 ? 2 : 3; }  // A-ring depth (informational)
 
@@ -403,7 +401,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   uint8_t* fixed = smemW + kWGranules * kWGranule;
   uint64_t* bars = reinterpret_cast<uint64_t*>(fixed);
   uint64_t* fullA = bars;        // [4]
-  uint64_t* emptyA = bars + 4;   // [4]
+  // (bars + 4 .. 7: spare; the activation slots are released through the weight-stage barriers)
   uint64_t* fullW = bars + 8;    // [10]
   uint64_t* emptyW = bars + 18;  // [10]
   uint64_t* tfull = bars + 28;   // [2]
@@ -429,7 +427,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages (each: two halves x <= 128 columns)
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < 4; ++s) mbar_init(&fullA[s], 1);
     for (int s = 0; s < kWGranules; ++s) { mbar_init(&fullW[s], 1); mbar_init(&emptyW[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); mbar_init(&sig[a], 8); }
     *dep_flag = 0;
