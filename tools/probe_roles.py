@@ -20,7 +20,7 @@ full = np.array(buf, dtype=np.float64)
 a = full[:148 * 12].reshape(148, 12)
 extra = full[160 * 12 - 320: 160 * 12 - 320 + 296].reshape(148, 2)
 names = ["prod: dependency wait", "prod: wait A slot free", "prod: wait W granules free", "prod: TOTAL",
-         "mma: wait accumulator free", "mma: wait A tile landed", "mma: wait W stage landed", "mma: TOTAL",
+         "mma: wait accumulator free", "mma: wait A tile landed", "mma: (weight-stage waits are inside the issue figure)", "mma: TOTAL",
          "epi: dependency wait + barriers", "epi: wait accumulator ready", "epi: TOTAL", "items per CTA"]
 clk = 1.965e9
 print("per-CTA average over 148 CTAs (ms at 1.965 GHz) | min | max")
@@ -29,4 +29,4 @@ for i, n in enumerate(names):
     if i == 11: print(f"{n:34s} {col.mean():9.1f} {col.min():9.0f} {col.max():9.0f}")
     else: print(f"{n:34s} {col.mean()/clk*1e3:9.3f} {col.min()/clk*1e3:9.3f} {col.max()/clk*1e3:9.3f}")
 print(f"{'mma: entry parameter fetch':34s} {extra[:,0].mean()/clk*1e3:9.3f}")
-print(f"{'mma: issue blocks (elect..commit)':34s} {extra[:,1].mean()/clk*1e3:9.3f}")
+print(f"{'mma: issue incl. weight-stage waits':34s} {extra[:,1].mean()/clk*1e3:9.3f}")
