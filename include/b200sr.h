@@ -123,8 +123,10 @@ int b200sr_fused_adam_ema(const void* tensor_table, const int32_t* block_tensor,
 
 const char* b200sr_last_error(void);
 int b200sr_version(void);
-/* timing probes for profiling only (results become wrong): bit0 no epilogue traffic, bit1 no MMAs, bit2 no activation
- * loads, bit3 no weight loads in the conv kernel.  0 = normal operation (default). */
+/* timing probes for profiling only (results become wrong unless noted): bit 0 (1) no epilogue traffic, bit 1 (2) no MMAs,
+ * bit 2 (4) no activation / weight loads, bit 3 (8) no bf16 output stores, bit 4 (16) no dependency waits, bit 6 (64) role
+ * profiler and bit 7 (128) per-entry timeline (both harmless), bit 8 (256) no signaller fence, bit 9 (512) no proxy fence.
+ * 0 = normal operation (default). */
 void b200sr_debug_set(int flags);
 /* bit 6 (64) of the debug flags makes the chain kernel record, per CTA, the cycles each warp role waited on each barrier
  * kind (12 counters per CTA, see conv_kernel.cuh); this copies the first n counters of the last launch to the host. */

@@ -519,7 +519,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         }
         if (lane == 0) {
           if (!nb_sync && !(debug & 16)) wait_entry_done(counters, dep, dep_need);
-          asm volatile("fence.proxy.async.global;" ::: "memory");  // TMA (async proxy) reads after generic-proxy stores
+          if (!(debug & 512)) asm volatile("fence.proxy.async.global;" ::: "memory");  // TMA (async proxy) reads after generic-proxy stores (bit 512: timing experiment)
           // tell this CTA's epilogue warps (they read residual carriers written by earlier entries): acquire.gpu above,
           // release.cta here, acquire.cta on their side -- causality order is transitive
           asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(dep_flag))), "r"(e + 1) : "memory");
@@ -710,7 +710,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       TL_MARK(11);
       if (lane == 0) {
         if (v < num_work) {  // CTAs without work in this entry have nothing to publish and are not counted
-          __threadfence();
+          if (!(debug & 256)) __threadfence();  // (bit 256: timing experiment only)
           if (item_flags)
             for (unsigned int w = v; w < num_work; w += grid) item_flags[static_cast<long long>(e) * flag_stride + w] = 1u;
           atomicAdd(counters + e, 1u);
