@@ -538,6 +538,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         for (int c = 0; c < num_chunks; ++c) {
           const int ac = a_c0 + (c % a_wrap) * 64;
           { PROF_T0(pf); ensure_stage(a_seq[sa]); PROF_ADD(pf, 1); }  // activation slot free (waits on older stages only)
+          if (c == 0 && w == v) TL_MARK(14);
           const int sa_used = sa;
           if (++sa == kNumASlots) sa = 0;
           auto load_activations = [&]() {
@@ -577,6 +578,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             }
             ensure_stage(need);
             PROF_ADD(pf, 2); }
+            if (c == 0 && d == 0 && w == v) TL_MARK(15);
             if (elect_one_sync()) {
               if (debug & 4) {
                 mbar_arrive(&fullW[gw]);

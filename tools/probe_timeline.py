@@ -23,7 +23,7 @@ print(f"sustained SM clock during the launch: {full[160*12-16] / full[160*12-15]
 t = full[160 * 12:].reshape(NC, NE, 16)
 t0 = t[t > 0].min()
 t = np.where(t > 0, (t - t0) / 1e3, np.nan)  # us
-names = ["prod@", "depOK", "mma0", "Aland", "mmaEnd", "accRdy", "stored", "signal", "epi@", "epiDep", "tmemLd", "sigArr", "preSt", "postSt", "-", "-"]
+names = ["prod@", "depOK", "mma0", "Aland", "mmaEnd", "accRdy", "stored", "signal", "epi@", "epiDep", "tmemLd", "sigArr", "preSt", "postSt", "pAfree", "pW0free"]
 lo = int(os.environ.get("LO", 40)); hi = int(os.environ.get("HI", 64))
 for c in range(0 if os.environ.get('BRIEF') else int(os.environ.get('NCP', NC))):
     print(f"--- CTA {c * 37}: entries {E0 + lo}..{E0 + hi - 1} (us)")
