@@ -410,10 +410,6 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 512);
   volatile uint32_t* dep_flag = reinterpret_cast<volatile uint32_t*>(fixed + 516);  // producer -> epilogue: e + 1 once entry e's dependency is done
   volatile uint32_t* sig_done = reinterpret_cast<volatile uint32_t*>(fixed + 520);  // signaller -> epilogue: entries announced so far
-  // producer-private bookkeeping of the weight-stage FIFO (see the producer role)
-  volatile uint32_t* gran_seq = reinterpret_cast<volatile uint32_t*>(fixed + 576);   // [10] 1 + sequence number of the last stage that used the granule
-  volatile uint32_t* stage_bar = reinterpret_cast<volatile uint32_t*>(fixed + 640);  // [16] first granule (= barrier index) of stage seq & 15
-  volatile uint32_t* a_seq = reinterpret_cast<volatile uint32_t*>(fixed + 704);      // [4]  1 + sequence number of the last stage that read the A slot
   uint8_t* sp_base = fixed + 1024;                                  // 4 x 384 B
   float* sbias_base = reinterpret_cast<float*>(fixed + 3072);       // 4 x 1 KB
   constexpr int kFixedBytes = 3072 + 4096;
@@ -432,8 +428,6 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); mbar_init(&sig[a], 8); }
     *dep_flag = 0;
     *sig_done = 0;
-    for (int i = 0; i < kWGranules; ++i) gran_seq[i] = 0;
-    for (int i = 0; i < 4; ++i) a_seq[i] = 0;
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_imm<kTmemCols>(tmem_slot);
@@ -449,16 +443,26 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     // Weight stages form one FIFO: the MMA warp commits ONCE per stage (to the barrier of the stage's first granule; a
     // tcgen05.commit costs about as much tensor-pipe time as 1.5 MMAs) and stages complete in issue order, so "granule
     // free" and "A slot free" both reduce to "stage number s has completed".  `confirmed` stages have been waited for.
+    // All of the bookkeeping lives in (warp-uniform) registers: a FIFO of the outstanding stages (first granule and length,
+    // 4 bits each, oldest in the low bits), a mask of the granules no unconfirmed stage occupies, and per activation slot
+    // the number of the last stage that reads it.  This warp's own instruction path sits on the critical path whenever the
+    // weight ring is too shallow for it to run ahead, so it must stay short.
     uint32_t cW_bits = 0;               // next phase parity to wait for, per stage barrier
     uint32_t issued = 0, confirmed = 0;
-    auto ensure_stage = [&](uint32_t seq_p1) {
-      while (confirmed < seq_p1) {
-        const uint32_t j = stage_bar[confirmed & 15];
-        mbar_wait(&emptyW[j], (cW_bits >> j) & 1u);
-        cW_bits ^= (1u << j);
-        ++confirmed;
-      }
+    uint64_t fifo_start = 0, fifo_len = 0;
+    uint32_t free_mask = (1u << kWGranules) - 1u;
+    uint32_t a_need[kNumASlots] = {0, 0};
+    static_assert(kNumASlots == 2 && kWGranules <= 15, "producer bookkeeping is sized for 2 A slots and 4-bit granule indices");
+    auto confirm_oldest = [&]() {
+      const uint32_t j = static_cast<uint32_t>(fifo_start) & 15u, n = static_cast<uint32_t>(fifo_len) & 15u;
+      mbar_wait(&emptyW[j], (cW_bits >> j) & 1u);
+      cW_bits ^= (1u << j);
+      free_mask |= ((1u << n) - 1u) << j;
+      fifo_start >>= 4;
+      fifo_len >>= 4;
+      ++confirmed;
     };
+    auto ensure_stage = [&](uint32_t seq_p1) { while (confirmed < seq_p1) confirm_oldest(); };
     int sa = 0, gw = 0;
     const bool pf = (debug & 64) != 0;
     long long prof[4] = {0, 0, 0, 0};
@@ -537,7 +541,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const int y0 = ty * tile_h;
         for (int c = 0; c < num_chunks; ++c) {
           const int ac = a_c0 + (c % a_wrap) * 64;
-          { PROF_T0(pf); ensure_stage(a_seq[sa]); PROF_ADD(pf, 1); }  // activation slot free (waits on older stages only)
+          { PROF_T0(pf); ensure_stage(sa == 0 ? a_need[0] : a_need[1]); PROF_ADD(pf, 1); }  // activation slot free (waits on older stages only)
           if (c == 0 && w == v) TL_MARK(14);
           const int sa_used = sa;
           if (++sa == kNumASlots) sa = 0;
@@ -568,15 +572,14 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             else if (w_taps == 3) tap_row = ((d == 0) ? 1 : (d == 1 ? 0 : 2)) * 3;
             else { const int o1 = d / 3, o2 = d - o1 * 3; tap_row = ((o1 == 0) ? 1 : (o1 == 1 ? 0 : 2)) * 3 + ((o2 == 0) ? 1 : (o2 == 1 ? 0 : 2)); }
             if (gw + g > kWGranules) gw = 0;
+            const uint32_t gmask = ((1u << g) - 1u) << gw;
             { PROF_T0(pf);
-            uint32_t need = 0;
-            for (int j = 0; j < g; ++j) { const uint32_t q = gran_seq[gw + j]; need = q > need ? q : need; }
             if (!a_done && (d > 0)) {  // (measured: polling the dependency to squeeze more weight stages in front of it does not pay)
               if (gated) dependency_wait(w, ty, x0 / kTileW);
               load_activations();
               a_done = true;
             }
-            ensure_stage(need);
+            while ((free_mask & gmask) != gmask) confirm_oldest();  // stages complete in order: confirm the oldest until the granules are free
             PROF_ADD(pf, 2); }
             if (c == 0 && d == 0 && w == v) TL_MARK(15);
             if (elect_one_sync()) {
@@ -589,13 +592,16 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
               }
             }
             __syncwarp();
-            if (lane == 0) {
-              for (int j = 0; j < g; ++j) gran_seq[gw + j] = issued + 1;
-              stage_bar[issued & 15] = gw;
-              if (d == wsteps - 1) a_seq[sa_used] = issued + 1;  // the chunk's last stage also releases its activation tile
+            {
+              const uint32_t slot4 = 4u * (issued - confirmed);  // at most kWGranules stages are outstanding
+              fifo_start |= static_cast<uint64_t>(gw) << slot4;
+              fifo_len |= static_cast<uint64_t>(g) << slot4;
+              free_mask &= ~gmask;
+              ++issued;
+              if (d == wsteps - 1) {  // the chunk's last stage also releases its activation tile
+                if (sa_used == 0) a_need[0] = issued; else a_need[1] = issued;
+              }
             }
-            __syncwarp();
-            ++issued;
             gw += g;
           }
           if (!a_done) {

@@ -11,7 +11,7 @@ net = b200.rrdbnet_x4(num_blocks=23).to(dev).eval()
 lr = torch.rand(16, 3, 64, 64, device=dev)
 with torch.no_grad():
     for _ in range(2): net(lr)
-    L.b200sr_debug_set(64)
+    L.b200sr_debug_set(64 | int(os.environ.get("DBG", 0)))
     net(lr); torch.cuda.synchronize()
     L.b200sr_debug_set(0)
 buf = (C.c_ulonglong * (160 * 12))()
