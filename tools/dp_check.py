@@ -1,11 +1,15 @@
 """torchrun --nproc-per-node 2 tools/dp_check.py : data-parallel equivalence on real GPUs.
-2 ranks x 4 images (bucketed NCCL all-reduce overlapped with backward) must equal 1 rank x 8 images."""
+2 ranks x 4 images (NCCL gradient all-reduce) must equal 1 rank x 8 images."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist, torch.nn.functional as F
 import sr_gan_fd_b200 as b200
 from sr_gan_fd_b200 import dist as b200dist
-from oracle import rrdbnet_oracle as orc
+
+def rel_l2(a, b):  # (tools do not import the oracle: it is test infrastructure)
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
@@ -13,7 +17,7 @@ torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0)
 net = b200.rrdbnet_x4(num_blocks=3)
-net.load_state_dict(orc.in_range_fixture({k: v.clone() for k, v in net.state_dict().items()}))
+# (seeded reference init; the check is DP vs single replica, the weights themselves do not matter)
 net = net.to(dev).train()
 b200dist.broadcast_parameters(net)
 g = torch.Generator().manual_seed(5)
@@ -30,7 +34,7 @@ for it in range(3):
     F.l1_loss(net(lr[sl]), gt[sl]).backward()
 got = torch.cat([p.grad.flatten() for p in net.parameters()])
 torch.cuda.synchronize()
-err = orc.rel_l2(got, ref)
+err = rel_l2(got, ref)
 print(f"rank {rank}: DP vs single-replica flat-grad rel-L2 {err:.3e}; buckets {len(red.buckets_seen)//3} per step", flush=True)
 assert err < 2e-3, err
 dist.barrier()
