@@ -6,7 +6,8 @@
 Workload at every N = BASELINE.json configs[1]/[2]: RRDBNet x4 (23 RRDB, 64 ch, growth 32) L1 pre-training step,
 forward + backward, 16 synthetic 64x64 LR images per GPU -> 256x256 GT, bf16 tensor-core arithmetic with fp32
 accumulation (weak scaling: N=8 is exactly config 3's global batch 128); for N>1 the 16.7 M-parameter gradient is
-all-reduced (NCCL, averaged) bucket by bucket overlapped with backward.  One "step" = one fwd+bwd(+all-reduce) of the
+all-reduced (NCCL, averaged; by default ONE coalesced call issued when backward has enqueued its last kernel -- see
+sr_gan_fd_b200/dist.py).  One "step" = one fwd+bwd(+all-reduce) of the
 generator.  `value` = images/s with inputs resident in HBM, `e2e` = the same step driven through the public module API
 with pinned-host inputs copied in and the loss read back every step.  Rank 0 prints ONE JSON line.
 
@@ -109,38 +110,105 @@ def cpu_reference_step(batch, threads):
     return time.perf_counter() - t0
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def cpu_full_batch(warmup, steps, budget_s=420.0):
+    """THE CPU method of both arms: the oracle restatement (fp32, torch CPU, every host thread) on the FULL workload batch
+    (16 images, 64x64 LR -> 256x256, fwd+bwd L1), `warmup` untimed + `steps` timed steps.  Only if the first step shows the
+    whole run would exceed `budget_s` is the per-step sample cut to 8 / 4 images (and said so in `sample`)."""
     import torch
     from oracle import rrdbnet_oracle as orc
     torch.manual_seed(0)
     threads = os.cpu_count() or 1
     cpu_reference_step.params = orc.init_params(seed=0, num_blocks=NUM_BLOCKS, upscale_factor=SCALE)
-    budget_s = 150.0
-    t1 = cpu_reference_step(1, threads)  # probe (also warms the allocator / oneDNN primitives)
-    batch = 1
-    for b in (16, 8, 4, 2):
-        if b * t1 * 0.8 * (args.steps + args.warmup) <= budget_s:
-            batch = b
-            break
-    for _ in range(args.warmup):
+    cpu_reference_step(1, threads)  # allocator / oneDNN primitive warm-up (1 image, untimed)
+    batch = BATCH_PER_GPU
+    t_first = cpu_reference_step(batch, threads)  # counts as the first warm-up step
+    while batch > 4 and t_first * (batch / BATCH_PER_GPU) * (warmup + steps) > budget_s:
+        batch //= 2
+    for _ in range(max(warmup - 1, 0)):
         cpu_reference_step(batch, threads)
-    times = [cpu_reference_step(batch, threads) for _ in range(args.steps)]
+    times = [cpu_reference_step(batch, threads) for _ in range(steps)]
     sec = sum(times) / len(times)
-    value = batch / sec
-    sample = f"{batch} of {BATCH_PER_GPU} images per step, fp32 fwd+bwd L1, oracle restatement of ESRGAN/model.py, torch CPU"
+    sample = (f"{batch} of {BATCH_PER_GPU} images per step ({'the full batch' if batch == BATCH_PER_GPU else 'bounded sample'}), "
+              f"{steps} timed steps after {max(warmup, 1)} warm-up, fp32 fwd+bwd L1, oracle restatement of ESRGAN/model.py, torch CPU")
+    return {"value": batch / sec, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+            "sec_per_step": sec, "batch": batch}
+
+
+def bench_config(world):
+    return {"workload": WORKLOAD, "global_batch": world * BATCH_PER_GPU, "parallelism": f"dp{world}",
+            "l2_policy": "activation working set per step (3.1 GB) is far larger than the 126 MB L2, no flush needed",
+            "precision": "bf16 operands / fp32 accumulate in the trunk, fp32 residual carrier, hi+lo split bf16 in head/tail"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_full_batch(args.warmup, args.steps)
+    sec, batch = cb.pop("sec_per_step"), cb.pop("batch")
+    value = cb["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3 * (BATCH_PER_GPU / batch), "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": bench_config(max(args.gpus, 1)),
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ library baseline
+def library_baseline(net, lr_dev, gt_dev, iters=5):
+    """The reference generator graph through stock torch / cuDNN on the SAME GPU ("the bar becomes: beat what
+    torch+cuDNN runs"): the drop-in's own nn.Conv2d children driven by plain torch ops (cat / conv2d / leaky_relu /
+    interpolate -- the op sequence of ESRGAN/model.py:49-60,77-86,211-232; /root/reference itself is absent on the GPU box),
+    same batch, same L1 step as ESRGAN/train_rrdbnet.py:256-261, cudnn.benchmark on as in rrdbnet_config.py:25."""
+    import copy
+    import torch
+    import torch.nn.functional as F
+    from sr_gan_fd_b200.function import eager_forward
+    out = {"what": "same generator, stock torch ops on cuDNN/cuBLAS kernels, fwd+bwd L1, 16 x 64x64 LR, img/s (higher is better)"}
+    prev = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    variants = [("fp32_tf32_nchw", None, False, True), ("fp32_tf32_channels_last", None, True, True),
+                ("fp32_strict_nchw", None, False, False),
+                ("fp16_autocast_nchw", torch.float16, False, True), ("fp16_autocast_channels_last", torch.float16, True, True),
+                ("bf16_autocast_nchw", torch.bfloat16, False, True), ("bf16_autocast_channels_last", torch.bfloat16, True, True)]
+    for name, dtype, cl, tf32 in variants:
+        try:
+            torch.backends.cudnn.allow_tf32 = tf32
+            m = copy.deepcopy(net)
+            x = lr_dev
+            if cl:
+                m = m.to(memory_format=torch.channels_last)
+                x = lr_dev.contiguous(memory_format=torch.channels_last)
+
+            def step():
+                m.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=dtype or torch.float16, enabled=dtype is not None):
+                    loss = F.l1_loss(eager_forward(m, x), gt_dev)
+                (loss * (1024.0 if dtype is torch.float16 else 1.0)).backward()
+
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = BATCH_PER_GPU / (e0.elapsed_time(e1) / iters * 1e-3)
+            del m
+            torch.cuda.empty_cache()
+        except Exception as exc:  # a baseline variant that cannot run is reported, not fatal
+            out[name] = f"failed: {type(exc).__name__}: {str(exc)[:80]}"
+    torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = prev
+    nums = [v for v in out.values() if isinstance(v, float)]
+    out["best"] = max(nums) if nums else None
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------ our arm
@@ -165,7 +233,28 @@ def run_b200(args):
     torch.manual_seed(0)  # identical replicas on every rank (same seed, rrdbnet_config.py:20-23)
     net = b200.rrdbnet_x4(in_channels=3, out_channels=3, channels=64, growth_channels=32, num_blocks=NUM_BLOCKS).to(dev)
     net.train()
+    dp_err = None
+    if world > 1:
+        # data-parallel equivalence, checked on every run before anything is timed: `world` ranks x 2 images with the NCCL
+        # gradient averaging must equal ONE replica on the 2*world-image global batch (flat-gradient rel-L2)
+        g = torch.Generator().manual_seed(77)
+        xs = torch.rand(2 * world, 3, 32, 32, generator=g).to(dev)
+        ys = torch.rand(2 * world, 3, 128, 128, generator=g).to(dev)
+        F.l1_loss(net(xs), ys).backward()
+        ref_flat = torch.cat([p.grad.flatten() for p in net.parameters()]).double()
+        net.zero_grad(set_to_none=True)
     reducer = b200dist.make_data_parallel(net) if world > 1 else None
+    if world > 1:
+        sl = slice(2 * rank, 2 * rank + 2)
+        F.l1_loss(net(xs[sl]), ys[sl]).backward()
+        got_flat = torch.cat([p.grad.flatten() for p in net.parameters()]).double()
+        err = ((got_flat - ref_flat).norm() / ref_flat.norm()).reshape(1)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        dp_err = float(err.item())
+        net.zero_grad(set_to_none=True)
+        del xs, ys, ref_flat, got_flat
+        if not dp_err < 2e-3:
+            raise RuntimeError(f"data-parallel gradients differ from the single-replica gradients: rel-L2 {dp_err:.3e}")
 
     torch.manual_seed(1234 + rank)
     lr_host = torch.rand(BATCH_PER_GPU, 3, LR_HW, LR_HW).pin_memory()
@@ -241,6 +330,7 @@ def run_b200(args):
     ms_total = timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
     plan = net._runtime().last_plan
+    bucketed = world > 1 and net._runtime().grad_bucket_hook is not None
     ms_step = ms_total / args.steps
     value = world * BATCH_PER_GPU / (ms_step * 1e-3)
 
@@ -285,9 +375,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": world * BATCH_PER_GPU, "parallelism": f"dp{world}",
-                   "l2_policy": "activation working set per step (3.1 GB) is far larger than the 126 MB L2, no flush needed",
-                   "precision": "bf16 operands / fp32 accumulate in the trunk, fp32 residual carrier, hi+lo split bf16 in head/tail"},
+        "config": bench_config(world),
         "step_tflops": step_tflops, "step_frac_of_peak": step_tflops / burst,
         "infer_out_mpix_per_s": world * BATCH_PER_GPU * (LR_HW * SCALE) ** 2 / (ms_fwd_eval * 1e-3) / 1e6,
         "roofline": {"bound": "tensor", "kernel": "conv3x3_chain_kernel (the whole forward pass = 1 launch, 351 conv layers = 2.3497 TFLOP algorithmic)", "achieved": achieved,
@@ -297,18 +385,21 @@ def run_b200(args):
                 "h2d_bytes_per_step": int(lr_host.numel() * 4 + gt_host.numel() * 4), "d2h_bytes_per_step": 4},
         # kernels of libb200sr.so launched inside the timed region (chain / wgrad / bias-grad / ingest / unpack / add); with the
         # data-parallel bucket hook (N > 1) the gradient unpack runs once per bucket instead of once per step
-        "gpu_launches": int((plan.launches_fwd + (plan.launches_bwd_bucketed if world > 1 else plan.launches_bwd)) * args.steps),
+        "gpu_launches": int((plan.launches_fwd + (plan.launches_bwd_bucketed if bucketed else plan.launches_bwd)) * args.steps),
         "clocks": clocks,
     }
+    if dp_err is not None:
+        line["dp_equiv_rel_l2"] = dp_err
+    if world == 1 and not args.no_library_baseline:
+        line["library_baseline"] = library_baseline(net, lr_dev, gt_dev)
+        if line["library_baseline"].get("best"):
+            line["vs_library_best"] = value / line["library_baseline"]["best"]
     if world == 1 and not args.no_cpu_baseline:
-        import torch as _t
-        from oracle import rrdbnet_oracle as orc
-        threads = os.cpu_count() or 1
-        cpu_reference_step.params = orc.init_params(seed=0, num_blocks=NUM_BLOCKS, upscale_factor=SCALE)
-        cpu_reference_step(1, threads)
-        sec = cpu_reference_step(2, threads)
-        line["cpu_baseline"] = {"value": 2 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "2 of 16 images, one fp32 fwd+bwd L1 step of the oracle restatement (torch CPU, all host threads), after a 1-image warm-up"}
+        del net
+        torch.cuda.empty_cache()
+        cb = cpu_full_batch(1, 2)  # same method as the --impl reference arm: the full 16-image batch, 2 timed steps
+        cb.pop("sec_per_step"); cb.pop("batch")
+        line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -321,6 +412,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: the driver launches N>1 through torch.distributed.run itself; do the same when run by hand

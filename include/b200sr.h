@@ -88,9 +88,11 @@ int b200sr_forward(b200sr_plan* plan, const void* x, int x_dtype, const int64_t*
                    void* workspace, float* y, b200sr_stream stream);
 
 /* dy: gradient w.r.t. y, fp32 contiguous.  workspace/packed must be the ones used by the matching forward.
- * flat_grads: b200sr_param_numel() floats, OVERWRITTEN with the parameter gradients (state_dict order). */
+ * flat_grads: b200sr_param_numel() floats, OVERWRITTEN with the parameter gradients (state_dict order).
+ * dx_or_null: NULL, or [batch, in_channels, height, width] fp32 contiguous, OVERWRITTEN with the gradient w.r.t. x
+ * (what autograd produces in the reference when x.requires_grad). */
 int b200sr_backward(b200sr_plan* plan, const float* dy, const void* packed, void* workspace, float* flat_grads,
-                    b200sr_bucket_cb cb, void* user, b200sr_stream stream);
+                    float* dx_or_null, b200sr_bucket_cb cb, void* user, b200sr_stream stream);
 
 /* ---- single-layer entry points (used by the parity tests) ------------------------------------------------------
  * x: NHWC bf16 [n*h*w][x_stride], the conv reads channels [0, cin).  w: fp32 OIHW [cout][cin][3][3], bias [cout] or

@@ -28,12 +28,17 @@ CASES = [
     ("esrgan_x4_b1_rand", "esrgan", 4, 1, (2, 3, 16, 16), False),
     ("bsrgan_x2_b1", "bsrgan", 2, 1, (1, 3, 19, 13), True),
     ("real_x4_b1", "real", 4, 1, (1, 3, 17, 9), True),
+    # the full 23-RRDB depth of every BASELINE config (round 2)
+    ("esrgan_x4_b23", "esrgan", 4, 23, (2, 3, 32, 32), True),
 ]
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate
     for name, flavour, scale, blocks, shape, in_range in CASES:
+        if only and name not in only:
+            continue
         torch.manual_seed(0)
         net = rl.build_generator(flavour, scale, blocks)
         params = {k: v.detach().clone() for k, v in net.state_dict().items()}

@@ -5,6 +5,29 @@ import os
 import sys
 
 
+def _stub_basicsr() -> None:
+    """A-ESRGAN/model.py:30 imports ``basicsr.utils.registry.ARCH_REGISTRY`` only to decorate classes; when basicsr is not
+    installed a no-op registry with the same ``register()`` surface lets the reference file execute unchanged."""
+    try:
+        import basicsr.utils.registry  # noqa: F401
+        return
+    except Exception:
+        pass
+    import types
+
+    class _Registry:
+        def register(self, *a, **k):
+            return (lambda f: f) if not a or not callable(a[0]) else a[0]
+
+    basicsr = types.ModuleType("basicsr")
+    utils = types.ModuleType("basicsr.utils")
+    registry = types.ModuleType("basicsr.utils.registry")
+    registry.ARCH_REGISTRY = _Registry()
+    basicsr.utils = utils
+    utils.registry = registry
+    sys.modules.update({"basicsr": basicsr, "basicsr.utils": utils, "basicsr.utils.registry": registry})
+
+
 def load_reference_model(folder: str):
     root = os.environ.get("SRGANFD_REFERENCE", "/root/reference")
     path = os.path.join(root, folder, "model.py")
@@ -14,6 +37,8 @@ def load_reference_model(folder: str):
     if name in sys.modules:
         return sys.modules[name]
     sys.dont_write_bytecode = True
+    if folder == "A-ESRGAN":
+        _stub_basicsr()
     here = os.path.join(root, folder)
     added = here not in sys.path
     if added:

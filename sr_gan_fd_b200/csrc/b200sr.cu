@@ -139,6 +139,7 @@ struct Step {
   int i0 = 0, i1 = 0;
   // gradient-bucket announcement after this step
   long long cb_off = 0, cb_count = 0;
+  bool needs_dx = false;  // only launched when the caller asks for the gradient w.r.t. the LR input
 };
 
 struct b200sr_plan {
@@ -963,6 +964,23 @@ static int build_plan(b200sr_plan& P) {
       for (const Step& o : seg_others) P.bwd.push_back(o);
       seg_convs.clear(); seg_others.clear();
     }
+    // Gradient w.r.t. the LR input = conv1's data gradient of GO1 (64 -> in_channels), stored fp32 NCHW to the caller's dx.
+    // The reference produces it whenever x.requires_grad (input-gradient probes); it is launched only when dx != NULL.
+    {
+      const int C = d.in_channels;
+      const int npad = (int)align_up(C, 16);
+      PackOp op; memset(&op, 0, sizeof(op));
+      op.n_total = npad; op.n_cols = 16; op.n_valid = C; op.num_chunks = 1; op.mode = kPackDgrad; op.nseg = 1;
+      op.seg[0] = seg(0, 64, 0, 64, C, 0, 0, 0);
+      const int row0 = B.add_pack(op);
+      ConvParams cp = base_conv_params(N, H, W, 1, 4, 0, 1 << 20, row0, 16, npad);
+      Step s = conv_step(B.add_map(P.o_go1, 64, 64, N, H, W, kABoxRows), cp, 1);
+      s.cp.epi.store_mode = kStoreNCHW;
+      s.cp.epi.n_valid = C;
+      s.of.kind = RK_Y;
+      s.needs_dx = true;
+      P.bwd.push_back(s);
+    }
   }
 
   // packed buffer = bf16 tile rows followed by the fp32 biases
@@ -983,10 +1001,12 @@ static int build_plan(b200sr_plan& P) {
       // A chain is limited by the constant-memory tables (layers, entries = layers x image groups).  Long chains are cut
       // where a layer starts fresh accumulators (never inside a dense block whose partial sums live in TMEM).
       const int max_layers = std::min(kMaxChainLayers, kMaxChainEntries / (P.groups > 0 ? P.groups : 1)) - 8;
-      const bool cut = !out.empty() && out.back().type == ST_CHAIN && out.back().nlayers >= max_layers && s.cp.acc_first &&
-                       !(s.cp.acc_hold && s.cp.epi_cols == 0);
+      const bool cut = !out.empty() && out.back().type == ST_CHAIN &&
+                       ((out.back().nlayers >= max_layers && s.cp.acc_first && !(s.cp.acc_hold && s.cp.epi_cols == 0)) ||
+                        out.back().needs_dx != s.needs_dx);
       if (out.empty() || out.back().type != ST_CHAIN || cut) {
         Step c; c.type = ST_CHAIN; c.layer0 = (int)P.layer_steps.size(); c.nlayers = 0; c.chain_grid = 0;
+        c.needs_dx = s.needs_dx;
         out.push_back(c);
       }
       out.back().nlayers++;
@@ -1315,6 +1335,7 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
       case ST_CONV:
         return fail(B200SR_ERR_INVALID, "internal: unchained conv step");
       case ST_CHAIN: {
+        if (s.needs_dx && !b.y) break;  // nobody asked for the input gradient
         int rc = launch_chain(P, s, b, st);
         if (rc) return rc;
         break;
@@ -1492,7 +1513,7 @@ int32_t b200sr_num_launches(const b200sr_plan* p, int backward) {
   // kernel launches of one pass.  backward = 1: no gradient-bucket callback, the per-bucket unpack steps collapse into one
   // launch; backward = 2: with a callback (data-parallel training), one unpack launch per bucket.
   int n = 0, unpacks = 0;
-  for (const Step& s : v) { n += (s.type != ST_MEMSET); unpacks += (s.type == ST_UNPACK); }
+  for (const Step& s : v) { n += (s.type != ST_MEMSET && !s.needs_dx); unpacks += (s.type == ST_UNPACK); }
   if (backward == 1 && unpacks > 1) n -= unpacks - 1;
   return n;
 }
@@ -1533,8 +1554,8 @@ int b200sr_forward(b200sr_plan* p, const void* x, int x_dtype, const int64_t* x_
   return run_steps(*p, p->fwd, b, x, x_dtype, x_strides, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-int b200sr_backward(b200sr_plan* p, const float* dy, const void* packed, void* workspace, float* flat_grads, b200sr_bucket_cb cb,
-                    void* user, b200sr_stream stream) {
+int b200sr_backward(b200sr_plan* p, const float* dy, const void* packed, void* workspace, float* flat_grads, float* dx_or_null,
+                    b200sr_bucket_cb cb, void* user, b200sr_stream stream) {
   if (!p || !dy || !packed || !workspace || !flat_grads) return fail(B200SR_ERR_INVALID, "null argument");
   if (!p->d.training) return fail(B200SR_ERR_INVALID, "plan was created with training=0");
   int rc = runtime_init();
@@ -1546,7 +1567,7 @@ int b200sr_backward(b200sr_plan* p, const float* dy, const void* packed, void* w
     CUDA_TRY(cudaMemcpyAsync(p->d_unpack_ops, p->unpack_ops.data(), p->unpack_ops.size() * sizeof(UnpackOp), cudaMemcpyHostToDevice,
                              (cudaStream_t)stream));
   }
-  Bases b{workspace, (void*)packed, nullptr, dy, flat_grads};
+  Bases b{workspace, (void*)packed, dx_or_null, dy, flat_grads};
   return run_steps(*p, p->bwd, b, nullptr, 0, nullptr, cb, user, (cudaStream_t)stream);
 }
 

@@ -37,7 +37,8 @@ enum StoreMode : int {
   kStorePix = 0,        // same lattice position
   kStoreShuffle = 1,    // pixel-shuffle: column group (col / 64) = phase (a, b) -> pixel (2y+a, 2x+b), channel col % 64
   kStoreUnshuffle = 2,  // pixel-unshuffle: pixel (y, x) -> (y/2, x/2), channel ((y&1)*2 + (x&1)) * 64 + col
-  kStoreFinal = 3       // clamp to [0,1], NCHW fp32 image + clamp mask bytes (generator output head)
+  kStoreFinal = 3,      // clamp to [0,1], NCHW fp32 image + clamp mask bytes (generator output head)
+  kStoreNCHW = 4        // plain NCHW fp32 store of channels < n_valid to the per-launch output pointer (gradient w.r.t. the LR input)
 };
 
 struct ConvEpilogue {
@@ -181,6 +182,15 @@ __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const 
 __device__ __forceinline__ void conv_epilogue_write(const HW p, const ConvEpilogue& e, float* y_dyn, long long cbase, int n, int y, int x,
                                                     int col0, float (&v)[32], bool ok, int lane) {
   const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
+  if (e.store_mode == kStoreNCHW) {
+    if (!ok) return;
+    const long long plane = static_cast<long long>(p.H) * p.W;
+    const long long base = static_cast<long long>(n) * e.n_valid * plane + static_cast<long long>(y) * p.W + x;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (col0 + i < e.n_valid) st_global_f32(y_dyn + base + (col0 + i) * plane, v[i]);
+    return;
+  }
   if (e.store_mode == kStoreFinal) {
     if (!ok) return;
     const long long plane = static_cast<long long>(p.H) * p.W;

@@ -75,6 +75,15 @@ class GradBucketReducer:
             work = dist.all_reduce(view, op=op, group=self.group, async_op=True)
             self._works.append((work, view if self.average else None))
 
+    def reduce_all(self, flat: torch.Tensor) -> None:
+        """Coalesced mode: ONE all-reduce of the whole flat gradient buffer once backward has enqueued everything.  No
+        bucket callback is installed, so the backward pass keeps its merged gradient unpack and two-stream wgrad overlap."""
+        self.buckets_seen.append((0, flat.numel()))
+        if self.world_size == 1:
+            return
+        self._launch(flat, 0, flat.numel())
+        self.finish(flat)
+
     def finish(self, flat: Optional[torch.Tensor] = None) -> None:
         """Make the compute stream wait for every outstanding bucket (called once backward has enqueued all work)."""
         if self._pending is not None:
@@ -107,12 +116,15 @@ def make_data_parallel(module, process_group=None, min_bucket_numel: Optional[in
     (8 GPUs: 8730 vs 8537 img/s; 2 GPUs: 2193 vs 2146).  Pass a number (elements) to all-reduce buckets of at least
     that size as soon as they are ready instead (0 = every bucket the backward pass announces)."""
     import os
-    if min_bucket_numel is None:
-        min_bucket_numel = 1 << 62
-    if "B200SR_DP_MIN_BUCKET" in os.environ:  # experiment switch: coalesce buckets up to this many elements
+    if "B200SR_DP_MIN_BUCKET" in os.environ:  # experiment switch: all-reduce buckets of at least this many elements early
         min_bucket_numel = int(float(os.environ["B200SR_DP_MIN_BUCKET"]))
-    reducer = GradBucketReducer(process_group, average=True, min_bucket_numel=min_bucket_numel)
     rt: GeneratorRuntime = module._runtime()
+    if min_bucket_numel is None:
+        reducer = GradBucketReducer(process_group, average=True, min_bucket_numel=1 << 62)
+        rt.grad_bucket_hook = None          # backward is not told about buckets: no per-bucket unpack launches / stream joins
+        rt.grad_done_hook = reducer.reduce_all
+        return reducer
+    reducer = GradBucketReducer(process_group, average=True, min_bucket_numel=min_bucket_numel)
     rt.grad_bucket_hook = reducer.bucket_ready
     rt.grad_done_hook = reducer.finish
     return reducer

@@ -137,6 +137,10 @@ class _RRDBNetFn(torch.autograd.Function):
             ctx.pack_slot = (True, plan.pack_layout)
             ctx.pack_serial = rt.pack_serial[ctx.pack_slot]
             ctx.x_keepalive = x
+            ctx.x_meta = (tuple(x.shape), x.dtype)
+        else:
+            ctx.plan = None
+            ctx.mark_non_differentiable(y)
         return y
 
     @staticmethod
@@ -157,27 +161,34 @@ class _RRDBNetFn(torch.autograd.Function):
                 cb = _lib.BUCKET_CB(lambda user, off, cnt: hook(flat, int(off), int(cnt)))
             else:
                 cb = _lib.BUCKET_CB()
+            need = ctx.needs_input_grad
+            dx = None
+            if need[1]:  # gradient w.r.t. the LR input: conv1's data gradient, fp32 NCHW (only when x.requires_grad)
+                dx = torch.empty(ctx.x_meta[0], dtype=torch.float32, device=dy.device)
             _lib.check(lib.b200sr_backward(plan.handle, C.c_void_p(dy.data_ptr()), C.c_void_p(ctx.packed.data_ptr()),
-                                           C.c_void_p(ctx.workspace.data_ptr()), C.c_void_p(flat.data_ptr()), cb, None,
+                                           C.c_void_p(ctx.workspace.data_ptr()), C.c_void_p(flat.data_ptr()),
+                                           C.c_void_p(dx.data_ptr()) if dx is not None else None, cb, None,
                                            C.c_void_p(stream)))
             if rt.grad_done_hook is not None:
                 rt.grad_done_hook(flat)
         ctx.workspace = None
         ctx.x_keepalive = None
-        need = ctx.needs_input_grad
+        if dx is not None and ctx.x_meta[1] != torch.float32:
+            dx = dx.to(ctx.x_meta[1])
         pieces = flat.split(rt.param_numels)  # one call: 702 views of the flat gradient buffer, state_dict order
         grads = [t.view(shp) if need[3 + i] else None for i, (t, shp) in enumerate(zip(pieces, rt.param_shapes))]
-        return (None, None, None, *grads)
+        return (None, dx, None, *grads)
 
 
 def generator_forward(module, x: torch.Tensor) -> torch.Tensor:
     """Entry used by the drop-in modules' ``forward``."""
-    if not x.is_cuda:
-        raise RuntimeError(
-            "sr_gan_fd_b200 generators run only on CUDA (sm_100a) tensors; there is no CPU / eager fallback. "
-            "Move the model and input to a B200 device.")
     if x.dim() != 4:
         raise RuntimeError(f"expected NCHW input, got shape {tuple(x.shape)}")
+    if not x.is_cuda:
+        # CPU tensors (the reference scripts' default ``--device_type cpu``, ESRGAN/inference.py:92-99) take the module's own
+        # nn.Conv2d children through plain torch ops.  This is NOT a fallback for the CUDA path: a CUDA tensor always goes to
+        # libb200sr.so and raises if the library is missing.
+        return eager_forward(module, x)
     if x.dtype not in _DTYPES:
         x = x.float()
     rt = module._runtime()
@@ -200,10 +211,37 @@ def generator_forward(module, x: torch.Tensor) -> torch.Tensor:
     elif params[0].device != x.device:
         raise RuntimeError("generator parameters must be contiguous fp32 tensors on the input's device")
     rt.cur_key = (tuple([p._version for p in params]), ptrs)
-    training = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-    if x.requires_grad and training:
-        raise NotImplementedError("gradient w.r.t. the LR input is not produced by the B200 generator path")
+    training = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
     return _RRDBNetFn.apply(module, x, training, *params)
+
+
+def eager_forward(module, x: torch.Tensor) -> torch.Tensor:
+    """The generator graph on the module's own ``nn.Conv2d`` children with stock torch ops (autograd-capable), for
+    tensors that do not live on a CUDA device.  Same wiring as ESRGAN/model.py:49-60,77-86,211-232 (BSRGAN/model.py:366-381,
+    Real_ESRGAN/model.py:246-263): dense blocks with 0.2 residual scaling, long skip, nearest-x2 + conv stages, clamp."""
+    import torch.nn.functional as F
+
+    def act(t):
+        return F.leaky_relu(t, 0.2)
+
+    def dense_block(rdb, t):
+        feats = [t]
+        for conv in (rdb.conv1, rdb.conv2, rdb.conv3, rdb.conv4):
+            feats.append(act(conv(torch.cat(feats, 1))))
+        return rdb.conv5(torch.cat(feats, 1)) * 0.2 + t
+
+    head = module.conv1(x)
+    t = head
+    for rrdb in module.trunk:
+        inner = t
+        for rdb in (rrdb.rdb1, rrdb.rdb2, rrdb.rdb3):
+            inner = dense_block(rdb, inner)
+        t = inner * 0.2 + t
+    t = head + module.conv2(t)
+    for u in range(1, module._n_up + 1):
+        t = act(getattr(module, f"upsampling{u}")[0](F.interpolate(t, scale_factor=2, mode="nearest")))
+    t = module.conv4(act(module.conv3[0](t)))
+    return torch.clamp(t, 0.0, 1.0)
 
 
 def attach_grad_bucket_hook(module, hook: Optional[Callable[[torch.Tensor, int, int], None]]) -> None:

@@ -36,7 +36,7 @@ SIGNATURES = {
     "b200sr_pack_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "b200sr_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
-    "b200sr_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, BUCKET_CB,
+    "b200sr_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, BUCKET_CB,
                                   C.c_void_p, C.c_void_p]),
     "b200sr_conv3x3_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "b200sr_conv3x3_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -103,10 +103,34 @@ def test_module_protocol_cpu():
     assert copy.deepcopy(net).conv1.weight.data_ptr() != net.conv1.weight.data_ptr()
 
 
-def test_cpu_input_fails_loudly():
-    net = b200.rrdbnet_x4(num_blocks=1)
-    with pytest.raises(RuntimeError, match="no CPU"):
-        net(torch.rand(1, 3, 8, 8))
+@pytest.mark.parametrize("factory,kw,unshuffle", [
+    ("rrdbnet_x4", dict(num_blocks=2), 1), ("rrdbnet_x2", dict(num_blocks=1), 1), ("bsrgan_x2", dict(num_rrdb=1), 1),
+    ("RealRRDBNet", dict(in_channels=3, out_channels=3, channels=64, growth_channels=32, num_rrdb=1, upscale_factor=2), 2),
+])
+def test_cpu_tensors_take_the_eager_torch_path(factory, kw, unshuffle):
+    """CPU input -> the module's own nn.Conv2d children through torch (ESRGAN/inference.py defaults to
+    --device_type cpu).  Bit-equal to the fp32 restatement, differentiable w.r.t. parameters and input."""
+    from oracle import rrdbnet_oracle as orc
+    torch.manual_seed(3)
+    net = getattr(b200, factory)(**kw)
+    params = orc.in_range_fixture({k: v.detach().clone() for k, v in net.state_dict().items()})
+    net.load_state_dict(params)
+    x = torch.rand(2, 3, 12, 8, requires_grad=True)
+    y = net(x)
+    ref = orc.rrdbnet_forward(params, x.detach(), unshuffle)
+    assert torch.equal(y.detach(), ref)
+    y.mean().backward()
+    assert x.grad is not None and float(x.grad.abs().sum()) > 0
+    assert all(p.grad is not None for p in net.parameters())
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """The CUDA path never falls back: without libb200sr.so loading raises (checked without touching a GPU)."""
+    from sr_gan_fd_b200 import lib as _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setenv("B200SR_LIB", str(tmp_path / "missing.so"))
+    with pytest.raises(RuntimeError, match="missing"):
+        _lib.load()
 
 
 def test_factories_and_kwargs():
@@ -129,6 +153,13 @@ def test_compat_shims_export_reference_names():
         assert n in bs.__dict__
     re_ = importlib.import_module("sr_gan_fd_b200.compat.real_esrgan_model")
     assert "RRDBNet" in re_.__dict__ and "rrdbnet_x4" in re_.__dict__
+    ae = importlib.import_module("sr_gan_fd_b200.compat.a_esrgan_model")
+    assert ae.BSRGAN is b200.BSRGAN and ae.bsrgan_x2 is b200.bsrgan_x2
+    import os
+    if os.path.isfile("/root/reference/A-ESRGAN/model.py"):  # the folder's other entry points are the reference's own objects
+        for n in ("uNetDiscriminatorAesrgan", "bsrgantrans_x2", "gen_rrdb2x", "ContentLoss"):
+            assert n in ae.__dict__
+        assert ae.__dict__["uNetDiscriminatorAesrgan"].__module__.startswith("_srganfd_reference")
 
 
 def test_schedule_dependent_bookkeeping(L):

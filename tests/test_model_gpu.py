@@ -323,3 +323,114 @@ def test_large_batch_splits_the_chain():
     g_small = torch.cat([p.grad.flatten() for p in net.parameters()])
     assert torch.equal(y.detach(), torch.cat(ys))
     assert orc.rel_l2(g_big, g_small) <= 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parity AT THE BENCHMARKED SHAPES (BASELINE.json configs): the CPU oracle runs the full problem (seconds on the GPU
+# box's host cores), so the comparison is against the fp32 reference arithmetic, not self-consistency
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("in_range", [True, False], ids=["in_range_fixture", "random_init"])
+def test_full_config2_against_oracle(in_range):
+    """BASELINE configs[1] at FULL size: 16 x 64x64 LR -> 256x256, 23 RRDB, L1 step.  SR rel-L2 <= 5e-3, flat gradient
+    rel-L2 <= 1e-2 versus the fp32 CPU oracle on the same seeded inputs; worst per-tensor gradient error reported.
+    (256 work items per layer = two image groups x 128 CTAs: the regime the bench runs in.)"""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    net, params = _build("rrdbnet_x4", in_range=in_range, num_blocks=23)
+    net.train()
+    g = torch.Generator().manual_seed(2024)
+    lr = torch.rand(16, 3, 64, 64, generator=g)
+    gt = torch.rand(16, 3, 256, 256, generator=g)
+    sr = net(lr.to(DEV))
+    F.l1_loss(sr, gt.to(DEV)).backward()
+    sr_ref, _, grads_ref = orc.rrdbnet_l1_step(params, lr, gt)
+    e_sr = orc.rel_l2(sr, sr_ref)
+    names = list(grads_ref.keys())
+    got = {n: p.grad.detach().cpu() for n, p in net.named_parameters()}
+    flat = torch.cat([got[n].flatten() for n in names])
+    flat_ref = torch.cat([grads_ref[n].flatten() for n in names])
+    e_grad = orc.rel_l2(flat, flat_ref)
+    worst = max((orc.rel_l2(got[n], grads_ref[n]), n) for n in names if float(grads_ref[n].norm()) > 0)
+    print(f"config 2 full size ({'in-range' if in_range else 'random-init'}): SR rel-L2 {e_sr:.3e}, flat grad rel-L2 {e_grad:.3e}, "
+          f"worst tensor {worst[1]} {worst[0]:.3e}")
+    assert e_sr <= TOL_SR, e_sr
+    assert e_grad <= TOL_GRAD, (e_grad, worst)
+    assert worst[0] <= 5e-2, worst
+
+
+def test_config1_against_oracle():
+    """BASELINE configs[0]: 16 x 32x32 LR -> 128x128, eval / no_grad (the reference's CPU-runnable inference case)."""
+    net, params = _build("rrdbnet_x4", in_range=True, num_blocks=23)
+    g = torch.Generator().manual_seed(11)
+    lr = torch.rand(16, 3, 32, 32, generator=g)
+    sr, ref, err = _fwd_check(net, params, lr)
+    gt = torch.rand(16, 3, 128, 128, generator=g)
+    d_psnr = (orc.psnr_y(sr, gt) - orc.psnr_y(ref, gt)).abs().max().item()
+    d_ssim = (orc.ssim_y(sr, gt) - orc.ssim_y(ref, gt)).abs().max().item()
+    print(f"config 1: SR rel-L2 {err:.3e}, dPSNR {d_psnr:.2e} dB, dSSIM {d_ssim:.2e}")
+    assert err <= TOL_SR and d_psnr <= TOL_PSNR and d_ssim <= TOL_SSIM
+
+
+def test_config4_crop_against_oracle():
+    """A 256x256 LR crop of BASELINE configs[3] (1 x 1024x1024 frame): one image with more 8x32 items than SMs, i.e. the
+    large-frame schedule the whole-frame / band inference runs on."""
+    net, params = _build("rrdbnet_x4", in_range=True, num_blocks=23)
+    g = torch.Generator().manual_seed(12)
+    lr = torch.rand(1, 3, 256, 256, generator=g)
+    sr, ref, err = _fwd_check(net, params, lr)
+    print(f"config 4 crop (1x256x256): SR rel-L2 {err:.3e}")
+    assert err <= TOL_SR
+
+
+@pytest.mark.parametrize("scale,shape", [(2, (2, 3, 24, 40)), (1, (1, 3, 32, 48))])
+def test_real_esrgan_pixel_unshuffle_front(scale, shape):
+    """Real_ESRGAN/model.py:190-204,248: x2 / x1 nets pixel-unshuffle the input (12 / 48 channels into conv1's hi/lo
+    packed input buffer).  Forward and gradients vs the oracle."""
+    import sr_gan_fd_b200 as b200
+    torch.manual_seed(4)
+    net = b200.RealRRDBNet(3, 3, 64, 32, 2, scale)
+    params = orc.in_range_fixture({k: v.detach().clone() for k, v in net.state_dict().items()})
+    net.load_state_dict(params)
+    net = net.to(DEV).train()
+    ds = {2: 2, 1: 4}[scale]
+    g = torch.Generator().manual_seed(5)
+    lr = torch.rand(*shape, generator=g)
+    out_hw = (shape[2] // ds * 4, shape[3] // ds * 4)
+    gt = torch.rand(shape[0], 3, *out_hw, generator=g)
+    sr = net(lr.to(DEV))
+    assert tuple(sr.shape[2:]) == out_hw
+    F.l1_loss(sr, gt.to(DEV)).backward()
+    ref = orc.rrdbnet_forward(params, lr, ds)
+    assert orc.rel_l2(sr, ref) <= TOL_SR, orc.rel_l2(sr, ref)
+    # gradients: autograd through the oracle forward
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    F.l1_loss(orc.rrdbnet_forward(p_ref, lr, ds), gt).backward()
+    flat = torch.cat([p.grad.flatten().cpu() for p in net.parameters()])
+    flat_ref = torch.cat([p_ref[n].grad.flatten() for n, _ in net.named_parameters()])
+    assert orc.rel_l2(flat, flat_ref) <= TOL_GRAD, orc.rel_l2(flat, flat_ref)
+
+
+@pytest.mark.parametrize("frozen", [False, True], ids=["trainable", "frozen_generator"])
+def test_gradient_wrt_lr_input(frozen):
+    """differentiable w.r.t. x if x.requires_grad (b200sr_backward's dx_or_null) -- also with a frozen generator."""
+    net, params = _build("rrdbnet_x4", in_range=True, num_blocks=2)
+    net.train()
+    if frozen:
+        for p in net.parameters():
+            p.requires_grad_(False)
+    g = torch.Generator().manual_seed(21)
+    lr = torch.rand(2, 3, 24, 20, generator=g)
+    gt = torch.rand(2, 3, 96, 80, generator=g)
+    x = lr.to(DEV).requires_grad_(True)
+    F.l1_loss(net(x), gt.to(DEV)).backward()
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    x_ref = lr.clone().requires_grad_(True)
+    F.l1_loss(orc.rrdbnet_forward(p_ref, x_ref), gt).backward()
+    err = orc.rel_l2(x.grad.cpu(), x_ref.grad)
+    print(f"dL/dx rel-L2 {err:.3e}")
+    assert x.grad.shape == x.shape and err <= TOL_GRAD, err
+    if frozen:
+        assert all(p.grad is None for p in net.parameters())
+    else:
+        flat = torch.cat([p.grad.flatten().cpu() for p in net.parameters()])
+        flat_ref = torch.cat([p_ref[n].grad.flatten() for n, _ in net.named_parameters()])
+        assert orc.rel_l2(flat, flat_ref) <= TOL_GRAD
