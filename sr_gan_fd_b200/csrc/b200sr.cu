@@ -49,9 +49,6 @@ static int g_num_sms = 0;
 static bool g_attr_set = false;
 static int g_ctas_per_sm = 1;
 static int g_debug = 0;  // timing probes only (b200sr_debug_set)
-// Neighbour-tile dependencies (B200SR_NBSYNC=1) are correct but measured no faster than the per-entry counters on config 2
-// (the chain is bound by per-layer latencies every CTA sees alike, not by skew between CTAs): opt-in.
-static const bool g_no_neighbour_sync = [] { const char* e = getenv("B200SR_NBSYNC"); return !(e && atoi(e) == 1); }();
 
 static int runtime_init() {
   if (!g_encode) {
@@ -69,8 +66,8 @@ static int runtime_init() {
     CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   if (!g_attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
     CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
-    CUDA_TRY(cudaFuncSetAttribute(wgrad3x3_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     g_attr_set = true;
   }
@@ -126,7 +123,7 @@ struct Step {
   int layer0 = 0, nlayers = 0, chain_grid = 0;  // ST_CHAIN: range of the plan's layer list
   int entry0 = 0, nentries = 0;                 // ... and of its entry list (filled when the device tables are built)
   // wgrad
-  int xmap = -1, dymap = -1, xmap_c = -1;  // xmap_c: X map with a 10-pixel-wide haloed box (cluster-multicast wgrad)
+  int xmap = -1, dymap = -1;
   WgradBatch wb;
   Ref seg_out[5];                 // bias-grad kernel outputs
   Ref wseg_out[kWgMaxProblems][5];  // wgrad batch outputs
@@ -158,21 +155,15 @@ struct b200sr_plan {
   long long o_xin = 0, o_t0 = 0, o_tr = 0, o_c1 = 0, o_c2 = 0, o_splt = 0, o_splc = 0, o_cmask = 0;
   std::vector<long long> o_dense, o_spl;
   long long o_dyp = 0, o_g3 = 0, o_gt = 0, o_gtb = 0, o_gr = 0, o_gc1 = 0, o_gc2 = 0, o_go1 = 0;
-  std::vector<long long> o_dyb;      // output-gradient buffers [dY5|dY4|dY3|dY2|dY1] of the dense blocks: one per block when the
-                                      // whole backward is ONE data-gradient chain (default), else a ring of six
+  std::vector<long long> o_dyb;      // output-gradient buffers [dY5|dY4|dY3|dY2|dY1] of the dense blocks, one per block: the whole
+                                      // backward is ONE data-gradient chain, the weight gradients run after it
   cudaStream_t side_stream = nullptr; // second stream for the weight-gradient launches (their tails / heads overlap)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool single_bwd_chain = true;       // B200SR_BWDCHAIN=0: one chain per gradient bucket, weight gradients interleaved
   std::vector<long long> o_gu;
-  bool reassoc = true;                // dense blocks re-associated by input slice (B200SR_REASSOC=0: per-conv schedule, 1: all five convs resident, 2 = default: windowed)
+  bool reassoc = true;                // dense blocks re-associated by input slice ("windowed": convs 1-4 resident in TMEM, 128 columns per
+                                      // 128-pixel half, conv5 spread over filler layers); B200SR_REASSOC=0 or a frame with more 8x32 items
+                                      // per image than SMs: plain per-conv schedule
   int groups = 1;                     // image groups that flow through a chain independently
-  bool window = true;                 // with reassoc: only convs 1-4 (128 columns per 128-pixel half) stay resident, conv5 is an ordinary N=64 layer
-  bool early_x = false;               // windowed schedule, opt-in (B200SR_EARLYX=1): the block-input slice's share of conv5 / of the x gradient runs early as a
-                                      // layer without epilogue (latency filler).  Parity-green, measured slower (14.1 vs 13.9 ms/step): two more entries per block
-  bool stagger_fillers = true;        // entry order: one group's filler layer per dependency gap (B200SR_STAGGER=0: all groups at once)
-  bool unit_all = false;              // experimental: every chain layer works on single 8 x 16 units (B200SR_UNIT=1)
-  int groups_env = 0;                 // experimental: force the number of image groups (B200SR_GROUPS)
-  bool split_passes = false;          // experimental: split every pass into a critical and a deferred sub-layer
   int plan_sms = 148;                 // SM count the schedule was laid out for
   long long gw_bytes = 0;
   long long o_gw = 0;                 // staged weight gradients, per conv [tap][ci][co_pad] fp32
@@ -213,7 +204,6 @@ struct Builder {
     return o;
   }
   int add_map(long long off, int c_valid, int c_pix, int n, int h, int w, int box_rows, int box_w = -1) {
-    if (P.unit_all && box_rows == kABoxRows) { box_rows = 18; box_w = kABoxW; }
     for (size_t i = 0; i < P.map_specs.size(); ++i) {
       const ActMapSpec& s = P.map_specs[i];
       if (s.off == off && s.c_valid == c_valid && s.c_pix == c_pix && s.n == n && s.h == h && s.w == w && s.box_rows == box_rows &&
@@ -272,12 +262,6 @@ PackSeg nseg(int n0, int nlen, int k0, int klen, int w_index, int O, int I, int 
   s.n0 = n0; s.nlen = nlen;
   return s;
 }
-// dense-block pass layers work on single 8 x 16 units (one 128-pixel half per item)
-void make_unit_layer(ConvParams& p) {
-  p.halves = 1;
-  p.tiles_y = (p.H + 15) / 16;
-  p.num_tiles = p.N * p.tiles_x * p.tiles_y;
-}
 }  // namespace
 
 // conv index helpers (state_dict order)
@@ -318,14 +302,13 @@ static int build_plan(b200sr_plan& P) {
       cudaGetLastError();
     }
     if (sms > 0) P.plan_sms = sms;
-    const int tpi = ((d.width + kTileW - 1) / kTileW) * (P.window ? (d.height + 31) / 32 : (d.height + 15) / 16);  // resident items per image (8 x 16 units, window mode: 8 x 32)
+    const int tpi = ((d.width + kTileW - 1) / kTileW) * ((d.height + kTileH - 1) / kTileH);  // resident 8 x 32 items per image
     P.groups = d.batch >= 2 ? 2 : 1;
     if (P.reassoc) {
       int g = P.groups;
       while (g <= d.batch && ((d.batch + g - 1) / g) * tpi > P.plan_sms) ++g;
       if (g <= d.batch) P.groups = g; else P.reassoc = false;  // a single image already exceeds one item per CTA
     }
-    if (P.groups_env > 0 && !P.reassoc) P.groups = P.groups_env < d.batch ? P.groups_env : d.batch;
   }
   const int R = P.R, L = P.L;
   const bool train = d.training != 0;
@@ -398,7 +381,7 @@ static int build_plan(b200sr_plan& P) {
     P.o_gc1 = B.alloc(carrier_bytes);
     P.o_gc2 = B.alloc(carrier_bytes);
     P.o_go1 = B.alloc(Ppix * 64 * 2);
-    P.o_dyb.assign(P.single_bwd_chain ? R : 6, 0);
+    P.o_dyb.assign(R, 0);
     for (size_t i = 0; i < P.o_dyb.size(); ++i) P.o_dyb[i] = B.alloc(Ppix * 192 * 2);
   }
   P.ws_bytes = B.cursor;
@@ -410,7 +393,6 @@ static int build_plan(b200sr_plan& P) {
     s.amap = amap;
     s.wmap = wmap_index(cp.n_cols);
     s.cp = cp;
-    if (P.unit_all && s.cp.halves == 2) make_unit_layer(s.cp);
     s.grid = dim3(1, grid_y, 1);
     s.smem = 0;
     return s;
@@ -458,12 +440,31 @@ static int build_plan(b200sr_plan& P) {
         s.ob = ws(P.o_splt); s.cp.epi.ob_stride = 128; s.cp.epi.ob_coff = 0; s.cp.epi.split_off = 64;
       }
     };
-    if (reassoc && P.window) {
+    if (reassoc) {
       // WINDOWED re-association: passes 0..3 feed slice q (x, o1, o2, o3) to convs q+1..4 at once (N = 128, 96, 64, 32);
       // their partial sums (4 x 32 columns per 128-pixel half, so 8 x 32-pixel items and two resident image groups still
-      // fit the 512 TMEM columns) stay in TMEM between the passes.  conv5 (N = 64, K = 192) runs as an ordinary layer in the
-      // same accumulator slot.  An SS tcgen05.mma costs ~(32 + N/4) cycles (shared-memory operand reads), so a pass with
-      // N = 128 does four convs' worth of work in 1.6x the time of one.
+      // fit the 512 TMEM columns) stay in TMEM between the passes.  An SS tcgen05.mma costs ~(32 + N/4) cycles (shared-memory
+      // operand reads), so a pass with N = 128 does four convs' worth of work in 1.6x the time of one.
+      // conv5 (N = 64, K = 192) is SPREAD over the block: once the epilogues of passes 0 and 1 have taken conv1 / conv2 out,
+      // accumulator columns [0, 64) are free, and conv5's contributions of the slices that already exist run there as
+      // FILLER layers without epilogue -- F1 = x (after pass 1), F2 = o1|o2 (after pass 2), F3 = o3 (after pass 3) -- which
+      // the MMA warp works off while the next pass waits for its cross-CTA dependency.  Only the o4 share (K = 32) and the
+      // epilogue are left for the block's last layer.
+      const int ci5 = conv_index_rdb(r, 5);
+      auto conv5_piece = [&](int k0, int klen, bool first, bool last) {
+        PackOp op; memset(&op, 0, sizeof(op));
+        op.n_total = 64; op.n_cols = 64; op.n_valid = 64; op.num_chunks = 1; op.mode = kPackFwd; op.nseg = 1;
+        op.seg[0] = seg(0, klen, 2 * ci5, 64, 192, 0, k0, 0);
+        const int row0 = B.add_pack(op);
+        ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, k0, 1 << 20, row0, 64, 64);
+        cp.acc_hold = 1; cp.acc_first = first ? 1 : 0; cp.acc_col0 = 0; cp.epi_cols = last ? 64 : 0;
+        Step s = conv_step(B.add_map(D, k0 + klen, 192, N, H, W, kABoxRows), cp, 1);
+        if (last) {
+          s.bias = packed_bias(B.add_bias(64, 2 * ci5 + 1, 64, 0));
+          conv5_epilogue(s);
+        }
+        P.fwd.push_back(s);
+      };
       for (int q = 0; q < 4; ++q) {
         const int c_q = (q == 0) ? 0 : 64 + 32 * (q - 1);
         const int klen = (q == 0) ? 64 : 32;
@@ -480,78 +481,11 @@ static int build_plan(b200sr_plan& P) {
         s.cp.epi.act = 1;
         s.ob = ws(D); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * q;
         P.fwd.push_back(s);
-        if (q == 1 && P.early_x) {
-          // conv5's contribution of the block input x (K = 64 of its 192) does not depend on anything this block computes.
-          // It runs here as a layer WITHOUT epilogue into accumulator columns [0, 64) -- free since the epilogues of passes
-          // 0 and 1 took conv1 / conv2 out -- so the MMA warp works it off while pass 2 waits for pass 1's outputs, and
-          // conv5 proper shrinks to K = 128.
-          const int ci = conv_index_rdb(r, 5);
-          PackOp o5; memset(&o5, 0, sizeof(o5));
-          o5.n_total = 64; o5.n_cols = 64; o5.n_valid = 64; o5.num_chunks = 1; o5.mode = kPackFwd; o5.nseg = 1;
-          o5.seg[0] = seg(0, 64, 2 * ci, 64, 192, 0, 0, 0);
-          const int r5 = B.add_pack(o5);
-          ConvParams c5 = base_conv_params(N, H, W, 1, 4, 0, 1 << 20, r5, 64, 64);
-          c5.acc_hold = 1; c5.acc_first = 1; c5.acc_col0 = 0; c5.epi_cols = 0;
-          P.fwd.push_back(conv_step(B.add_map(D, 64, 192, N, H, W, kABoxRows), c5, 1));
-        }
+        if (q == 1) conv5_piece(0, 64, true, false);     // F1: x
+        if (q == 2) conv5_piece(64, 64, false, false);   // F2: o1 | o2
+        if (q == 3) conv5_piece(128, 32, false, false);  // F3: o3
       }
-      {
-        const int ci = conv_index_rdb(r, 5);
-        const int k0 = P.early_x ? 64 : 0, klen = 192 - k0;  // input channels still to be accumulated
-        PackOp op; memset(&op, 0, sizeof(op));
-        op.n_total = 64; op.n_valid = 64; op.num_chunks = klen / 64; op.mode = kPackFwd; op.nseg = 1;
-        op.seg[0] = seg(0, klen, 2 * ci, 64, 192, 0, k0, 0);
-        const int row0 = B.add_pack(op);
-        ConvParams cp = base_conv_params(N, H, W, klen / 64, 4, k0, 1 << 20, row0, 64, 64);
-        cp.acc_hold = 1; cp.acc_first = P.early_x ? 0 : 1; cp.acc_col0 = 0; cp.epi_cols = 64;
-        Step s = conv_step(B.add_map(D, 192, 192, N, H, W, kABoxRows), cp, 1);
-        s.bias = packed_bias(B.add_bias(64, 2 * ci + 1, 64, 0));
-        conv5_epilogue(s);
-        P.fwd.push_back(s);
-      }
-      continue;
-    }
-    if (reassoc) {
-      // Dense block RE-ASSOCIATED BY INPUT SLICE: pass q feeds slice q (x, o1..o4) to ALL convs that consume it at once
-      // (N = 192, 160, 128, 96, 64 instead of 32,32,32,32,64); the partial sums stay in TMEM between the passes.
-      for (int q = 0; q < 5; ++q) {
-        const int c_q = (q == 0) ? 0 : 64 + 32 * (q - 1);
-        const int klen = (q == 0) ? 64 : 32;
-        // every pass is two sub-layers over the same input slice: CRITICAL = the columns of conv q+1, which this slice
-        // completes (small N, has the epilogue that produces the next slice) and DEFERRED = the partial sums of the later
-        // convs (large N, no epilogue), which the MMA warp works off while the critical epilogue and the cross-CTA
-        // dependency of the next pass are in flight.
-        for (int part = 0; part < (P.split_passes ? 2 : 1); ++part) {
-          const int col_lo = (part == 0) ? 32 * q : 32 * (q + 1);          // accumulator columns [col_lo, col_hi)
-          const int col_hi = !P.split_passes ? 192 : ((part == 0) ? ((q < 4) ? 32 * (q + 1) : 192) : 192);
-          const int ncols = col_hi - col_lo;
-          if (ncols <= 0) continue;
-          PackOp op; memset(&op, 0, sizeof(op));
-          op.n_total = ncols; op.n_cols = ncols; op.n_valid = ncols; op.num_chunks = 1; op.mode = kPackFwd; op.nseg = 0;
-          for (int k = q + 1; k <= 5; ++k) {
-            const int k_lo = (k < 5) ? 32 * (k - 1) : 128, k_hi = (k < 5) ? 32 * k : 192;  // accumulator columns of conv k
-            if (k_lo < col_lo || k_hi > col_hi) continue;
-            const int ci = conv_index_rdb(r, k);
-            op.seg[op.nseg++] = nseg(k_lo - col_lo, k_hi - k_lo, 0, klen, 2 * ci, (k < 5) ? 32 : 64, 64 + 32 * (k - 1), 0, c_q);
-          }
-          const int row0 = B.add_pack(op);
-          ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, c_q, 1 << 20, row0, ncols, ncols);
-          cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = (part == 0) ? ((q < 4) ? 32 : 64) : 0;
-          make_unit_layer(cp);
-          Step s = conv_step(B.add_map(D, c_q + klen, 192, N, H, W, 18, kABoxW), cp, 1);
-          if (part == 0) {
-            const int ci_done = conv_index_rdb(r, q + 1);  // the conv that is complete after this pass
-            s.bias = packed_bias(B.add_bias(cp.epi_cols, 2 * ci_done + 1, cp.epi_cols, 0));
-            if (q < 4) {
-              s.cp.epi.act = 1;
-              s.ob = ws(D); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * q;
-            } else {
-              conv5_epilogue(s);
-            }
-          }
-          P.fwd.push_back(s);
-        }
-      }
+      conv5_piece(160, 32, false, true);                 // o4 + epilogue
       continue;
     }
     for (int k = 1; k <= 5; ++k) {

@@ -323,11 +323,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 #define TL_MARK(ev)                                                                                                   \
   do {                                                                                                                \
-    if (tl && e >= kTlFirst && e < kTlFirst + kTlEntries)                                                              \
+    if (kInstr && tl && e >= kTlFirst && e < kTlFirst + kTlEntries)                                                    \
       g_conv_prof[160 * 12 + ((blockIdx.x / kTlStride) * kTlEntries + (e - kTlFirst)) * 16 + (ev)] = globaltimer_ns();   \
   } while (0)
-#define PROF_T0(flag) const long long _t0 = (flag) ? clock64() : 0
-#define PROF_ADD(flag, slot) do { if (flag) prof[slot] += clock64() - _t0; } while (0)
+#define PROF_T0(flag) const long long _t0 = (kInstr && (flag)) ? clock64() : 0
+#define PROF_ADD(flag, slot) do { if (kInstr && (flag)) prof[slot] += clock64() - _t0; } while (0)
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
@@ -398,11 +398,13 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_lo, uint
   }
 }
 
-template <int kUnused>
+// kInstr = 0: production build (no probes: every `debug` test folds away).  kInstr = 1: the same kernel with the timing
+// switches, role profiler and per-entry timeline compiled in (used only while b200sr_debug_set() is non-zero).
+template <int kInstr>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __restrict__ entries, int num_entries,
-                     const uint8_t* __restrict__ packed_w, unsigned int* counters, float* y_dyn, int debug, int layer0,
-                     unsigned int* item_flags, int flag_stride) {
+                     const uint8_t* __restrict__ packed_w, unsigned int* counters, float* y_dyn, int debug_arg, int layer0) {
+  const int debug = kInstr ? debug_arg : 0;
   // `entries` points at the first entry of THIS chain; c_entry_rec[0..num_entries) / c_layer_rec[2 * (layer - layer0)] mirror it
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, still provably a shared-memory pointer
@@ -480,15 +482,14 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     for (int e = 0; e < num_entries; ++e) {
       const uint4 er = c_entry_rec[e];
       const int li = static_cast<int>(er.x & 0xFFFFF);
-      const bool nb_sync = ((er.x >> 21) & 1) != 0;  // wait per item on the dependency's 3 x 3 tile neighbourhood
       const int tile_lo = static_cast<int>(er.y), tile_hi = static_cast<int>(er.z);
       const int rot = static_cast<int>(er.w & 0xFFFF), dep = static_cast<int>(er.w >> 16) - 1;
       const uint4 la = c_layer_rec[(li - layer0) * 2], lb = c_layer_rec[(li - layer0) * 2 + 1];
       const int n_cols = la.x & 0x3FF, num_chunks = (la.x >> 10) & 0xF, w_taps = (la.x >> 19) & 0xF, col_groups = (la.x >> 23) & 0x1F;
-      const int tile_h = 16 * static_cast<int>((la.x >> 17) & 0x3);
+      constexpr int tile_h = kTileH;
       const int w_row0 = static_cast<int>(la.z), a_c0 = static_cast<int>(la.w), a_wrap = static_cast<int>(lb.y);
       const int tiles_x = static_cast<int>(lb.x & 0xFFFF), tiles_y = static_cast<int>(lb.x >> 16);
-      const int a_bytes = (tile_h + 2) * kABoxW * 128;
+      constexpr int a_bytes = kABytes;
       const CUtensorMap* tmA = &layers[li].tmA;
       const int tiles_per_img = tiles_x * tiles_y;
       const int num_work = (tile_hi - tile_lo) * col_groups;
@@ -507,32 +508,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const unsigned int dwork = (dr.z - dr.y) * dcg;
         dep_need = dwork < grid ? dwork : grid;
       }
-      auto dependency_ready = [&]() -> bool {  // one non-blocking look at the counter
-        unsigned int seen = 0;
-        if (lane == 0) seen = (debug & 16) ? dep_need : ld_acquire_gpu(counters + dep);
-        return __shfl_sync(0xffffffffu, seen, 0) >= dep_need;
-      };
-      // (a) whole-entry form: the dependency's counter shows every CTA that worked on it
-      // (b) neighbour form (same tiling in both layers): the flags of the <= 9 items around item w0 of the dependency
-      auto dependency_wait = [&](int w0, int ty, int tx) {
+      // the dependency's counter shows every CTA that worked on it
+      auto dependency_wait = [&]() {
         PROF_T0(pf);
-        if (nb_sync && !(debug & 16)) {
-          const int dy = lane / 3 - 1, dx = lane % 3 - 1;
-          const bool look = lane < 9 && ty + dy >= 0 && ty + dy < tiles_y && tx + dx >= 0 && tx + dx < tiles_x;
-          const unsigned int* f = item_flags + static_cast<long long>(dep) * flag_stride + (w0 + dy * tiles_x + dx);
-          const long long t0 = clock64();
-          bool ok = !look;
-          while (true) {
-            if (!ok) ok = ld_acquire_gpu(f) != 0;
-            if (__all_sync(0xffffffffu, ok)) break;
-            if (clock64() - t0 > 4000000000LL) {
-              if (lane == 0) printf("b200sr: neighbour dependency timeout (block %d entry %d item %d)\n", blockIdx.x, e, w0);
-              __trap();
-            }
-          }
-        }
         if (lane == 0) {
-          if (!nb_sync && !(debug & 16)) wait_entry_done(counters, dep, dep_need);
+          if (!(debug & 16)) wait_entry_done(counters, dep, dep_need);
           if (!(debug & 512)) asm volatile("fence.proxy.async.global;" ::: "memory");  // TMA (async proxy) reads after generic-proxy stores (bit 512: timing experiment)
           // tell this CTA's epilogue warps (they read residual carriers written by earlier entries): acquire.gpu above,
           // release.cta here, acquire.cta on their side -- causality order is transitive
@@ -571,21 +551,19 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           // this item's own stages (those cannot complete before the activations arrive).
           bool a_done = (c != 0);
           if (c != 0) load_activations();
-          const uint32_t item_first = issued + 1;
           // the entry's first activation load waits for the dependency (neighbour form: every item's first load)
-          const bool gated = (c == 0 && dep >= 0 && (w == v || nb_sync));
+          const bool gated = (c == 0 && dep >= 0 && w == v);
           for (int d = 0; d < wsteps; ++d) {
             // stage d of this chunk holds w_taps consecutive taps of the centre-first order: dx in {1,0,2}, dy in {1,0,2}.
             // Packed rows are [dx][dy][n]; a 9-tap stage is the whole block, a 3-tap stage one dx column, a 1-tap stage one tile.
             int tap_row;
             if (w_taps == 9) tap_row = 0;
-            else if (w_taps == 3) tap_row = ((d == 0) ? 1 : (d == 1 ? 0 : 2)) * 3;
-            else { const int o1 = d / 3, o2 = d - o1 * 3; tap_row = ((o1 == 0) ? 1 : (o1 == 1 ? 0 : 2)) * 3 + ((o2 == 0) ? 1 : (o2 == 1 ? 0 : 2)); }
+            else tap_row = ((d == 0) ? 1 : (d == 1 ? 0 : 2)) * 3;
             if (gw + g > kWGranules) gw = 0;
             const uint32_t gmask = ((1u << g) - 1u) << gw;
             { PROF_T0(pf);
             if (!a_done && (d > 0)) {  // (measured: polling the dependency to squeeze more weight stages in front of it does not pay)
-              if (gated) dependency_wait(w, ty, x0 / kTileW);
+              if (gated) dependency_wait();
               load_activations();
               a_done = true;
             }
@@ -615,7 +593,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             gw += g;
           }
           if (!a_done) {
-            if (gated) dependency_wait(w, ty, x0 / kTileW);
+            if (gated) dependency_wait();
             load_activations();
           }
         }
@@ -629,8 +607,6 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     // ================================================== MMA issuer ==================================================
     // Whole warp runs the loops (uniform address math), one elected lane issues.  Descriptor hi words are loop
     // invariant; a K-step / tap advance is one 32-bit add on the lo word.
-    constexpr uint32_t kHi = smem_desc_hi(1024);            // weights: 8-row groups 1024 B apart
-    constexpr uint32_t kHiA = smem_desc_hi(kABoxW * 128);   // activations: 8 pixels of a patch row, rows 1280 B apart
     uint32_t fA_bits = 0, fW_bits = 0;  // phase parity per A slot / W granule (full barriers)
     uint32_t acc_bits = 0;              // phase parity of the two accumulator stages (tempty barriers)
     int acc_toggle = 0, last_hold = 0;
@@ -645,13 +621,12 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int li = static_cast<int>(er.x & 0xFFFFF), slot = static_cast<int>((er.x >> 20) & 1);
       const int tile_lo = static_cast<int>(er.y), tile_hi = static_cast<int>(er.z), rot = static_cast<int>(er.w & 0xFFFF);
       const uint4 la = c_layer_rec[(li - layer0) * 2];
-      const int n_cols = la.x & 0x3FF, num_chunks = (la.x >> 10) & 0xF, ksteps_last = (la.x >> 14) & 0x7, halves = (la.x >> 17) & 0x3;
+      const int n_cols = la.x & 0x3FF, num_chunks = (la.x >> 10) & 0xF, ksteps_last = (la.x >> 14) & 0x7;
       const int w_taps = (la.x >> 19) & 0xF, col_groups = (la.x >> 23) & 0x1F;
       const int acc_col0 = la.y & 0xFF, acc_first = (la.y >> 8) & 1, acc_hold = (la.y >> 9) & 1;
       const bool has_epi = ((la.y >> 10) & 1) != 0;  // deferred partial-sum layers have no epilogue: nothing to hand over
       const int num_work = (tile_hi - tile_lo) * col_groups;
       const int g = (w_taps * n_cols * 128 + kWGranule - 1) / kWGranule;
-      const int wsteps = 9 / w_taps;
       const uint32_t idesc = make_idesc_bf16(128, n_cols, 0, 0);
       const uint32_t b_dy = static_cast<uint32_t>(n_cols) * 8;  // (n_cols * 128 B) >> 4
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
@@ -686,11 +661,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     case 2: B200SR_CHUNK(T, H, 2); break;                      \
     default: B200SR_CHUNK(T, H, 1); break;                     \
   }
-          if (halves == 2) {
-            if (w_taps == 9) { B200SR_CHUNK_K(9, 2) } else if (w_taps == 3) { B200SR_CHUNK_K(3, 2) } else { B200SR_CHUNK_K(1, 2) }
-          } else {
-            if (w_taps == 9) { B200SR_CHUNK_K(9, 1) } else if (w_taps == 3) { B200SR_CHUNK_K(3, 1) } else { B200SR_CHUNK_K(1, 1) }
-          }
+          if (w_taps == 9) { B200SR_CHUNK_K(9, 2) } else { B200SR_CHUNK_K(3, 2) }
 #undef B200SR_CHUNK_K
 #undef B200SR_CHUNK
           if (pf) prof[9] += clock64() - _ti;  // MMA issue incl. the weight-stage waits of this chunk
@@ -721,16 +692,16 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     const unsigned long long sg0 = globaltimer_ns();
     for (int e = 0; e < num_entries; ++e) {
       const uint4 er = c_entry_rec[e];
-      const uint32_t cg = (c_layer_rec[(static_cast<int>(er.x & 0xFFFFF) - layer0) * 2].x >> 23) & 0x1F;
+      const uint4 la = c_layer_rec[(static_cast<int>(er.x & 0xFFFFF) - layer0) * 2];
+      const uint32_t cg = (la.x >> 23) & 0x1F;
+      const bool has_epi = ((la.y >> 10) & 1) != 0;  // a partial-sum (filler) layer stores nothing: nothing to announce
       const unsigned int num_work = (er.z - er.y) * cg;
       const unsigned int v = (blockIdx.x + grid - (er.w & 0xFFFF)) % grid;
       mbar_wait(&sig[e & 1], (e >> 1) & 1);
       TL_MARK(11);
       if (lane == 0) {
-        if (v < num_work) {  // CTAs without work in this entry have nothing to publish and are not counted
+        if (has_epi && v < num_work) {  // CTAs without work in this entry have nothing to publish and are not counted
           if (!(debug & 256)) __threadfence();  // (bit 256: timing experiment only)
-          if (item_flags)
-            for (unsigned int w = v; w < num_work; w += grid) item_flags[static_cast<long long>(e) * flag_stride + w] = 1u;
           atomicAdd(counters + e, 1u);
         }
         *sig_done = e + 1;
@@ -789,6 +760,14 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       PROF_ADD(pf, 8); }
       if (warp == 2) TL_MARK(8);
       stage_entry(e + 2);        // ring slot (e + 2) & 3 was last read in entry e - 2
+      {
+        const uint4 la0 = c_layer_rec[(static_cast<int>(c_entry_rec[e].x & 0xFFFFF) - layer0) * 2];
+        if (((la0.y >> 10) & 1) == 0) {  // partial-sum (filler) layer: no epilogue, only the hand-over to the signaller
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sig[e & 1]);
+          continue;
+        }
+      }
       const ConvParams& p = *reinterpret_cast<const ConvParams*>(sp_base + (e & 3) * 384);
       const ConvEpilogue& ep = p.epi;
       const HW hw{p.H, p.W, (debug & 8) != 0};
@@ -819,7 +798,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const int x = (t2 - ty * p.tiles_x) * kTileW + (m & 7);
         // two-half items: this warp set owns half `half`; single-unit items: both warp sets see the same 128 pixels and
         // split the columns (set 0: columns 0-31, set 1: columns 32-63 if the epilogue has that many)
-        const int y = (p.halves == 2) ? ty * 32 + half * 16 + (m >> 3) : ty * 16 + (m >> 3);
+        const int y = ty * 32 + half * 16 + (m >> 3);
         const bool valid = (x < p.W) && (y < p.H);
         const int as = p.acc_hold ? ent_slot : (acc_toggle & 1);
         if (!p.acc_hold) ++acc_toggle;
@@ -828,8 +807,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const bool pre = valid && !(debug & 1);
         const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
         // fp32 carriers are tile-blocked over 8 x 32 patches: a 16-row unit is half (ty & 1) of patch (n, ty / 2, tx)
-        const long long cbase = (p.halves == 2) ? carrier_base(tile, half, m)
-                                                : carrier_base((n * ((p.H + 31) / 32) + (ty >> 1)) * p.tiles_x + (t2 - ty * p.tiles_x), ty & 1, m);
+        const long long cbase = carrier_base(tile, half, m);
         float res[32];
         uint32_t maskw[16];
         const bool has_res = (ep.r1 != nullptr);
@@ -861,19 +839,17 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             }
           }
         };
-        const int first_c0 = (p.halves == 2) ? 0 : half * 32;  // single-unit items: warp set `half` owns columns [32 half, 32 half + 32)
-        if (first_c0 < p.epi_cols) prefetch_cols(first_c0);
+        if (0 < p.epi_cols) prefetch_cols(0);
         { PROF_T0(pf); mbar_wait(&tfull[as], (acc_bits >> as) & 1u); PROF_ADD(pf, 9); }
         if (warp == 2) TL_MARK(5);
         acc_bits ^= (1u << as);
         tcgen05_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + ((p.halves == 2) ? half * 128u : 0u) +
-                                p.acc_col0;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * 128u + p.acc_col0;
         bool released = false;
 #pragma unroll
         for (int gq = 0; gq < 2; ++gq) {
           const int c0 = gq * 32;
-          if (c0 < p.epi_cols && (p.halves == 2 || gq == half)) {
+          if (c0 < p.epi_cols) {
             float vv[32];
             const int ncol = (p.epi_cols - c0) >= 32 ? 32 : 16;
             if (ncol == 32) {
@@ -883,7 +859,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
               if (warp == 2 && gq == 0) TL_MARK(10);
 #pragma unroll
               for (int i = 0; i < 32; ++i) vv[i] = __uint_as_float(r[i]);
-              if (c0 + 32 >= p.epi_cols || p.halves == 1) {  // last TMEM read of this warp set: release the accumulator before the global stores
+              if (c0 + 32 >= p.epi_cols) {  // last TMEM read of this warp set: release the accumulator before the global stores
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
@@ -905,7 +881,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             if (warp == 2 && gq == 0) TL_MARK(12);
             conv_epilogue_math(ep, sbias, res, has_res, maskw, has_mask, colbase + c0, ncol, vv);
             // the residual / mask registers are free again: fetch the second 32 columns' while the first are stored
-            if (gq == 0 && p.halves == 2 && 32 < p.epi_cols) prefetch_cols(32);
+            if (gq == 0 && 32 < p.epi_cols) prefetch_cols(32);
             conv_epilogue_write(hw, ep, y_dyn, cbase, n, y, x, colbase + c0, vv, pre, lane);
             if (warp == 2 && gq == 0) TL_MARK(13);
           }

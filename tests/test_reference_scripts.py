@@ -81,7 +81,8 @@ def test_inference_script_cuda(tmp_path):
         _run(extra + ["ESRGAN", "inference.py", "--inputs_path", lr_png, "--output_path", out, "--model_weights_path", ckpt,
                       "--device_type", "cuda"], cwd=str(tmp_path))
         outs.append(cv2.imread(out).astype(np.int32))
-    assert outs[0].shape == (492, 480, 3)
+    h, w = cv2.imread(lr_png).shape[:2]
+    assert outs[0].shape == outs[1].shape == (4 * h, 4 * w, 3)
     diff = np.abs(outs[0] - outs[1])
     print(f"inference.py cuda: B200 path vs stock torch/cuDNN path: max |d| {diff.max()} of 255, mean {diff.mean():.4f}")
     assert diff.max() <= 2 and diff.mean() < 0.1
