@@ -243,8 +243,7 @@ ConvParams base_conv_params(int n, int h, int w, int num_chunks, int ksteps_last
   p.a_c0 = a_c0; p.a_wrap = a_wrap;
   p.w_row0 = row0; p.n_cols = n_cols; p.n_total = n_total;
   p.col_groups = n_total / n_cols;
-  p.w_taps = (9 * n_cols * 128 <= 5 * kWGranule) ? 9 : ((3 * n_cols * 128 <= 5 * kWGranule) ? 3 : 1);  // bytes per weight bulk copy <= 60 KB
-  if (const char* e = getenv("B200SR_WTAPS")) { const int m = atoi(e); if (m == 3 && p.w_taps == 9) p.w_taps = 3; }  // experiment
+  p.w_taps = (9 * n_cols * 128 <= 5 * kWGranule) ? 9 : 3;  // bytes per weight bulk copy <= 60 KB (n_cols <= 128: a dx column always fits)
   p.acc_col0 = 0; p.acc_first = 1; p.acc_hold = 0; p.epi_cols = n_cols; p.halves = 2;
   p.num_stages = conv_pick_stages(n_cols);
   p.epi.alpha = 1.f; p.epi.delta = 1.f; p.epi.beta1 = 1.f; p.epi.beta2 = 1.f;
@@ -447,9 +446,9 @@ static int build_plan(b200sr_plan& P) {
       // operand reads), so a pass with N = 128 does four convs' worth of work in 1.6x the time of one.
       // conv5 (N = 64, K = 192) is SPREAD over the block: once the epilogues of passes 0 and 1 have taken conv1 / conv2 out,
       // accumulator columns [0, 64) are free, and conv5's contributions of the slices that already exist run there as
-      // FILLER layers without epilogue -- F1 = x (after pass 1), F2 = o1|o2 (after pass 2), F3 = o3 (after pass 3) -- which
-      // the MMA warp works off while the next pass waits for its cross-CTA dependency.  Only the o4 share (K = 32) and the
-      // epilogue are left for the block's last layer.
+      // FILLER layers without epilogue -- F1 = x (emitted after pass 2), F2 = o1|o2 (after pass 3) -- which the MMA warp
+      // works off while the other image group's next pass waits for its cross-CTA dependency.  Only the o3|o4 share (K = 64)
+      // and the epilogue are left for the block's last layer.
       const int ci5 = conv_index_rdb(r, 5);
       auto conv5_piece = [&](int k0, int klen, bool first, bool last) {
         PackOp op; memset(&op, 0, sizeof(op));
@@ -481,11 +480,10 @@ static int build_plan(b200sr_plan& P) {
         s.cp.epi.act = 1;
         s.ob = ws(D); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * q;
         P.fwd.push_back(s);
-        if (q == 1) conv5_piece(0, 64, true, false);     // F1: x
-        if (q == 2) conv5_piece(64, 64, false, false);   // F2: o1 | o2
-        if (q == 3) conv5_piece(128, 32, false, false);  // F3: o3
+        if (q == 2) conv5_piece(0, 64, true, false);     // F1: x        (after pass 2; columns [0, 64) are free once pass 1's epilogue ran)
+        if (q == 3) conv5_piece(64, 64, false, false);   // F2: o1 | o2  (after pass 3)
       }
-      conv5_piece(160, 32, false, true);                 // o4 + epilogue
+      conv5_piece(128, 64, false, true);                 // o3 | o4 + epilogue
       continue;
     }
     for (int k = 1; k <= 5; ++k) {
@@ -570,7 +568,6 @@ static int build_plan(b200sr_plan& P) {
     auto wgrad_batch = [&](long long x_off, int x_cvalid, int x_cpix, long long dy_off, int dy_cvalid, int dy_cpix, int n, int h, int w) {
       Step s; s.type = ST_WGRAD;
       s.xmap = B.add_map(x_off, x_cvalid, x_cpix, n, h, w, kWgXRows);
-      s.xmap_c = B.add_map(x_off, x_cvalid, x_cpix, n, h, w, kWgXRows, kABoxW);
       s.dymap = B.add_map(dy_off, dy_cvalid, dy_cpix, n, h, w, kWgTileH);
       WgradBatch& wb = s.wb; memset(&wb, 0, sizeof(wb));
       wb.N = n; wb.H = h; wb.W = w;
@@ -634,11 +631,6 @@ static int build_plan(b200sr_plan& P) {
     std::vector<Step> seg_convs, seg_others;
     auto emit = [&](const Step& st) {
       if (st.type == ST_CONV) seg_convs.push_back(st); else seg_others.push_back(st);
-      if (st.type == ST_UNPACK && !P.single_bwd_chain) {
-        for (const Step& c : seg_convs) P.bwd.push_back(c);
-        for (const Step& o : seg_others) P.bwd.push_back(o);
-        seg_convs.clear(); seg_others.clear();
-      }
     };
     // conv4: wgrad, bias grad, dgrad (-> G3, masked by lrelu'(conv3 out))
     {
@@ -719,7 +711,7 @@ static int build_plan(b200sr_plan& P) {
       ConvParams cp = base_conv_params(N, H, W, 1, 4, 0, 1 << 20, row0, 64, 64);
       Step s = conv_step(B.add_map(P.o_gtb, 64, 64, N, H, W, kABoxRows), cp, 1);
       s.of = ws(P.o_gr);
-      s.ob = ws(P.single_bwd_chain ? P.o_dyb[R - 1] : P.o_dyb[3 * ((d.num_blocks - 1) & 1)]); s.cp.epi.ob_stride = 192; s.cp.epi.delta = 0.04f;
+      s.ob = ws(P.o_dyb[R - 1]); s.cp.epi.ob_stride = 192; s.cp.epi.delta = 0.04f;
       emit(s);
       // tail bucket: conv2 .. conv4 are contiguous at the end of the flat buffer
       emit(unpack_step(ci_conv2, nconv));
@@ -728,10 +720,8 @@ static int build_plan(b200sr_plan& P) {
     for (int r = R - 1; r >= 0; --r) {
       const int j = r % 3;
       const long long D = P.o_dense[r];
-      const int blk = r / 3;
-      const long long DYc = P.single_bwd_chain ? P.o_dyb[r] : P.o_dyb[3 * (blk & 1) + (2 - j)];
-      const long long DYn = P.single_bwd_chain ? P.o_dyb[r > 0 ? r - 1 : 0]
-                                               : ((j > 0) ? P.o_dyb[3 * (blk & 1) + (2 - (j - 1))] : P.o_dyb[3 * ((blk + 1) & 1)]);
+      const long long DYc = P.o_dyb[r];
+      const long long DYn = P.o_dyb[r > 0 ? r - 1 : 0];
       // epilogue of the block-input (x) slice: fp32 gradient carriers and the next block's dY5
       auto xslice_epilogue = [&](Step& s) {
         if (j == 2) { s.r1 = ws(P.o_gr); s.cp.epi.beta1 = 0.2f; s.of = ws(P.o_gc2); s.cp.epi.delta = 0.2f; }
@@ -739,10 +729,28 @@ static int build_plan(b200sr_plan& P) {
         else { s.r1 = ws(P.o_gc1); s.r2 = ws(P.o_gr); s.of = ws(P.o_gr); s.cp.epi.delta = 0.04f; }
         if (r > 0) { s.ob = ws(DYn); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 0; }
       };
-      if (P.reassoc && P.window) {
+      if (P.reassoc) {
         // Mirror image of the windowed forward: passes 0..3 feed dY_{5-q} to the growth slices o_{4-q}..o_1 it reads
-        // (accumulator columns [o4 | o3 | o2 | o1], N = 128, 96, 64, 32); the block-input slice x (N = 64, K = 192) is an
-        // ordinary layer in the same accumulator slot.
+        // (accumulator columns [o4 | o3 | o2 | o1], N = 128, 96, 64, 32).  The block-input gradient (N = 64, K = 192 over
+        // [dY5|dY4|dY3|dY2|dY1]) is spread like conv5 in the forward: filler layers G1 = dY5 (after pass 2), G2 = dY4|dY3
+        // (after pass 3) accumulate into the freed columns [0, 64) while the other group's pass waits for its dependency; the
+        // last layer adds dY2|dY1's share (K = 64) and runs the epilogue.
+        auto xgrad_piece = [&](int k0, int klen, bool first, bool last) {  // dY channels [k0, k0 + klen) -> x-slice gradient
+          PackOp op; memset(&op, 0, sizeof(op));
+          op.n_total = 64; op.n_cols = 64; op.n_valid = 64; op.num_chunks = 1; op.mode = kPackDgrad; op.nseg = 0;
+          for (int k = 5; k > 0; --k) {
+            const int kc0 = (k == 5) ? 0 : 64 + 32 * (4 - k);   // dY_k inside [dY5|dY4|dY3|dY2|dY1]
+            const int kcl = (k == 5) ? 64 : 32;
+            if (kc0 < k0 || kc0 + kcl > k0 + klen) continue;
+            op.seg[op.nseg++] = seg(kc0 - k0, kcl, 2 * conv_index_rdb(r, k), kcl, 64 + 32 * (k - 1), 0, 0, 0);
+          }
+          const int row0 = B.add_pack(op);
+          ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, k0, 1 << 20, row0, 64, 64);
+          cp.acc_hold = 1; cp.acc_first = first ? 1 : 0; cp.acc_col0 = 0; cp.epi_cols = last ? 64 : 0;
+          Step s = conv_step(B.add_map(DYc, k0 + klen, 192, N, H, W, kABoxRows), cp, 1);
+          if (last) xslice_epilogue(s);
+          emit(s);
+        };
         for (int q = 0; q < 4; ++q) {
           const int kk = 5 - q;
           const int klen = (kk == 5) ? 64 : 32;
@@ -761,73 +769,10 @@ static int build_plan(b200sr_plan& P) {
           s.mask = ws(D); s.cp.epi.mask_stride = 192; s.cp.epi.mask_coff = 64 + 32 * (sl - 1);
           s.ob = ws(DYc); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * q;
           emit(s);
-          if (q == 1 && P.early_x) {
-            // mirror of the forward: dY5's contribution to the block-input gradient (K = 64 of 192) is available from the
-            // start of the block; it runs here without epilogue into columns [0, 64)
-            PackOp o5; memset(&o5, 0, sizeof(o5));
-            o5.n_total = 64; o5.n_cols = 64; o5.n_valid = 64; o5.num_chunks = 1; o5.mode = kPackDgrad; o5.nseg = 1;
-            o5.seg[0] = seg(0, 64, 2 * conv_index_rdb(r, 5), 64, 192, 0, 0, 0);
-            const int r5 = B.add_pack(o5);
-            ConvParams c5 = base_conv_params(N, H, W, 1, 4, 0, 1 << 20, r5, 64, 64);
-            c5.acc_hold = 1; c5.acc_first = 1; c5.acc_col0 = 0; c5.epi_cols = 0;
-            emit(conv_step(B.add_map(DYc, 64, 192, N, H, W, kABoxRows), c5, 1));
-          }
+          if (q == 2) xgrad_piece(0, 64, true, false);     // G1: dY5
+          if (q == 3) xgrad_piece(64, 64, false, false);   // G2: dY4 | dY3
         }
-        {
-          const int kbase = P.early_x ? 64 : 0;  // dY channels still to be accumulated: [kbase, 192)
-          PackOp op; memset(&op, 0, sizeof(op));
-          op.n_total = 64; op.n_valid = 64; op.num_chunks = (192 - kbase) / 64; op.mode = kPackDgrad; op.nseg = 0;
-          for (int k = P.early_x ? 4 : 5; k > 0; --k) {
-            const int k0 = ((k == 5) ? 0 : 64 + 32 * (4 - k)) - kbase;
-            const int klen = (k == 5) ? 64 : 32;
-            op.seg[op.nseg++] = seg(k0, klen, 2 * conv_index_rdb(r, k), klen, 64 + 32 * (k - 1), 0, 0, 0);
-          }
-          const int row0 = B.add_pack(op);
-          ConvParams cp = base_conv_params(N, H, W, (192 - kbase) / 64, 4, kbase, 1 << 20, row0, 64, 64);
-          cp.acc_hold = 1; cp.acc_first = P.early_x ? 0 : 1; cp.acc_col0 = 0; cp.epi_cols = 64;
-          Step s = conv_step(B.add_map(DYc, 192, 192, N, H, W, kABoxRows), cp, 1);
-          xslice_epilogue(s);
-          emit(s);
-        }
-      } else if (P.reassoc) {
-        // Mirror image of the forward passes: pass q feeds dY_{5-q} (64 or 32 channels) to ALL input slices its conv
-        // reads; accumulator columns are [o4 | o3 | o2 | o1 | x], so after pass q the leading 32 columns (slice o_{4-q})
-        // are complete and become dY_{4-q} (times the LeakyReLU derivative); the x columns complete last.
-        for (int q = 0; q < 5; ++q) {
-          const int kk = 5 - q;                               // the conv whose output gradient is consumed
-          const int klen = (kk == 5) ? 64 : 32;
-          const int a_c0 = (q == 0) ? 0 : 64 + 32 * (q - 1);   // dY_kk inside [dY5 | dY4 | dY3 | dY2 | dY1]
-          const int ci = conv_index_rdb(r, kk);
-          for (int part = 0; part < (P.split_passes ? 2 : 1); ++part) {  // optional critical / deferred split, as forward
-            const int col_lo = (part == 0) ? 32 * q : 32 * (q + 1);
-            const int col_hi = !P.split_passes ? 192 : ((part == 0) ? ((q < 4) ? 32 * (q + 1) : 192) : 192);
-            const int ncols = col_hi - col_lo;
-            if (ncols <= 0) continue;
-            PackOp op; memset(&op, 0, sizeof(op));
-            op.n_total = ncols; op.n_cols = ncols; op.n_valid = ncols; op.num_chunks = 1; op.mode = kPackDgrad; op.nseg = 0;
-            for (int sidx = 4 - q; sidx >= 0; --sidx) {          // input slices read by conv kk: o_sidx (sidx >= 1) and x (sidx = 0)
-              const int s_lo = (sidx >= 1) ? 32 * (4 - sidx) : 128, s_hi = (sidx >= 1) ? s_lo + 32 : 192;
-              if (s_lo < col_lo || s_hi > col_hi) continue;
-              op.seg[op.nseg++] = nseg(s_lo - col_lo, s_hi - s_lo, 0, klen, 2 * ci, klen, 64 + 32 * (kk - 1), 0,
-                                       (sidx >= 1) ? 64 + 32 * (sidx - 1) : 0);
-            }
-            const int row0 = B.add_pack(op);
-            ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, a_c0, 1 << 20, row0, ncols, ncols);
-            cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = (part == 0) ? ((q < 4) ? 32 : 64) : 0;
-            make_unit_layer(cp);
-            Step s = conv_step(B.add_map(DYc, a_c0 + klen, 192, N, H, W, 18, kABoxW), cp, 1);
-            if (part == 0) {
-              if (q < 4) {
-                const int sl = 4 - q;  // completed slice o_sl
-                s.mask = ws(D); s.cp.epi.mask_stride = 192; s.cp.epi.mask_coff = 64 + 32 * (sl - 1);
-                s.ob = ws(DYc); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 64 + 32 * q;
-              } else {
-                xslice_epilogue(s);
-              }
-            }
-            emit(s);
-          }
-        }
+        xgrad_piece(128, 64, false, true);                 // dY2 | dY1 + epilogue
       } else
       for (int sl = 4; sl >= 0; --sl) {
         // gradient w.r.t. input slice sl (0: the 64-ch block input x, 1..4: growth outputs o_sl) = sum over consumer convs
@@ -891,13 +836,11 @@ static int build_plan(b200sr_plan& P) {
       emit(b1);
       emit(unpack_step(0, 1));
     }
-    if (P.single_bwd_chain) {
-      // ONE data-gradient chain for the whole backward pass (no pipeline drain / refill at every gradient bucket), then
-      // the weight- and bias-gradient kernels bucket by bucket: every dense block has its own dY buffer for that.
-      for (const Step& c : seg_convs) P.bwd.push_back(c);
-      for (const Step& o : seg_others) P.bwd.push_back(o);
-      seg_convs.clear(); seg_others.clear();
-    }
+    // ONE data-gradient chain for the whole backward pass (no pipeline drain / refill at every gradient bucket), then
+    // the weight- and bias-gradient kernels bucket by bucket: every dense block has its own dY buffer for that.
+    for (const Step& c : seg_convs) P.bwd.push_back(c);
+    for (const Step& o : seg_others) P.bwd.push_back(o);
+    seg_convs.clear(); seg_others.clear();
     // Gradient w.r.t. the LR input = conv1's data gradient of GO1 (64 -> in_channels), stored fp32 NCHW to the caller's dx.
     // The reference produces it whenever x.requires_grad (input-gradient probes); it is launched only when dx != NULL.
     {
@@ -1000,27 +943,30 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
         const int grid = s.chain_grid < g_num_sms ? s.chain_grid : g_num_sms;
         const int groups = P.groups;
         s.entry0 = (int)P.h_entries.size();
-        // emission order: ordinary layers go (layer, group A), (layer, group B); the five pass layers of a dense block go
-        // group-major (A: pass 0..4, then B: pass 0..4) because a block's accumulators occupy the CTA's TMEM for all five
+        // emission order: ordinary layers go (layer, group A), (layer, group B), ...  The layers of a dense block (passes +
+        // fillers, whose accumulators occupy the CTA's TMEM throughout) go pair of groups by pair of groups -- two groups are
+        // resident at a time -- interleaved layer by layer; a FILLER (partial sums, no epilogue) directly follows the producing
+        // layer of ITS OWN GROUP it was emitted after: the producer warp first resolves that layer's dependency and then streams
+        // the filler's operands, and the MMA warp works the filler off while the OTHER group's dependency is in flight:
+        //   p0A p0B p1A p1B | p2A F1A p2B F1B | p3A F2A p3B F2B | c5A c5B
         std::vector<std::pair<int, int>> order;  // (layer, group)
+        auto is_filler = [&](int l) { return P.layer_steps[s.layer0 + l].cp.epi_cols == 0; };
         for (int l = 0; l < s.nlayers;) {
           const ConvParams& cp = P.layer_steps[s.layer0 + l].cp;
-          if (cp.acc_hold && cp.acc_first) {
+          if (cp.acc_hold && cp.acc_first && !is_filler(l)) {
             int l1 = l + 1;
-            // a dense block = the run of pass sub-layers up to (not including) the next block's first critical sub-layer
+            // a dense block = the run of resident layers up to (not including) the next block's first pass
             while (l1 < s.nlayers && P.layer_steps[s.layer0 + l1].cp.acc_hold &&
-                   !(P.layer_steps[s.layer0 + l1].cp.acc_first && P.layer_steps[s.layer0 + l1].cp.epi_cols > 0)) ++l1;
-            // two groups are resident in a CTA's TMEM at a time: interleave them pass by pass, pair after pair
+                   !(P.layer_steps[s.layer0 + l1].cp.acc_first && !is_filler(l1))) ++l1;
             for (int g0 = 0; g0 < groups; g0 += 2) {
-              std::vector<std::pair<int, int>> late;  // a no-epilogue filler layer runs once per dependency gap: its second group follows the next layer
               for (int ll = l; ll < l1; ++ll) {
-                const bool filler = P.layer_steps[s.layer0 + ll].cp.epi_cols == 0 && P.stagger_fillers;
-                for (int g = g0; g < g0 + 2 && g < groups; ++g) {
-                  if (filler && g > g0) late.push_back({ll, g}); else order.push_back({ll, g});
+                if (!is_filler(ll) && ll + 1 < l1 && is_filler(ll + 1)) {
+                  for (int g = g0; g < g0 + 2 && g < groups; ++g) { order.push_back({ll, g}); order.push_back({ll + 1, g}); }
+                  ++ll;
+                } else {
+                  for (int g = g0; g < g0 + 2 && g < groups; ++g) order.push_back({ll, g});
                 }
-                if (!filler && !late.empty()) { order.push_back(late.front()); late.erase(late.begin()); }
               }
-              for (auto& e2 : late) order.push_back(e2);
             }
             l = l1;
           } else {
@@ -1038,23 +984,15 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
           EntryDesc e; memset(&e, 0, sizeof(e));
           e.layer = s.layer0 + l;
           e.tile_lo = img_lo * tpi; e.tile_hi = img_hi * tpi;
-          // dependency = the nearest earlier layer that PRODUCES data (has an epilogue).  A deferred partial-sum layer reads the
-          // same slice as the critical sub-layer right before it, so it inherits that layer's dependency.
-          int lp = (cp.epi_cols == 0) ? l - 2 : l - 1;
+          // dependency = the nearest earlier layer that PRODUCES data (has an epilogue).  A filler only reads slices whose
+          // producing layers an EARLIER entry of the same group already waited for (it is emitted after the pass that follows
+          // them), so it carries no dependency of its own.
+          int lp = l - 1;
           while (lp >= 0 && P.layer_steps[s.layer0 + lp].cp.epi_cols == 0) --lp;
-          e.dep = (lp >= 0) ? index_of[(size_t)lp * groups + g] : -1;
+          e.dep = (lp >= 0 && cp.epi_cols > 0) ? index_of[(size_t)lp * groups + g] : -1;
           e.rot = (int)(((long long)img_lo * tpi * cp.col_groups) % grid);
           e.slot = g & 1;  // each group starts where the previous one's last round ended
-          // Neighbour-tile dependency: when this layer and the one it depends on tile the same lattice the same way (one
-          // item per tile), an item only needs the 3 x 3 neighbourhood of its tile to be finished in the dependency --
-          // not all of it -- and waits on per-item flags instead of the entry's counter.
           e.pad[0] = 0;
-          if (lp >= 0 && !g_no_neighbour_sync) {
-            const ConvParams& dp = P.layer_steps[s.layer0 + lp].cp;
-            if (dp.N == cp.N && dp.H == cp.H && dp.W == cp.W && dp.halves == cp.halves && dp.tiles_x == cp.tiles_x &&
-                dp.tiles_y == cp.tiles_y && dp.col_groups == 1 && cp.col_groups == 1 && dp.epi.store_mode == kStorePix)
-              e.pad[0] = 1;
-          }
           P.h_entries.push_back(e);
         }
         s.nentries = (int)P.h_entries.size() - s.entry0;
@@ -1066,14 +1004,7 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
   if (!P.d_layers) {
     CUDA_TRY(cudaMalloc(&P.d_layers, P.h_layers.size() * sizeof(LayerDesc)));
     CUDA_TRY(cudaMalloc(&P.d_entries, P.h_entries.size() * sizeof(EntryDesc)));
-    // completion counters (16 KB) followed by the per-item "done" flags of the largest chain (entries x items, one word each)
-    size_t flag_words = 0;
-    auto scan = [&](const std::vector<Step>& steps) {
-      for (const Step& s : steps)
-        if (s.type == ST_CHAIN) { const size_t wds = (size_t)s.nentries * (size_t)s.chain_grid; if (wds > flag_words) flag_words = wds; }
-    };
-    scan(P.fwd); scan(P.bwd);
-    P.counters_bytes = 16384 + flag_words * sizeof(unsigned int);
+    P.counters_bytes = 16384;  // per-entry completion counters of the chain being launched
     CUDA_TRY(cudaMalloc(&P.d_counters, P.counters_bytes));
     CUDA_TRY(cudaMemcpyAsync(P.d_entries, P.h_entries.data(), P.h_entries.size() * sizeof(EntryDesc), cudaMemcpyHostToDevice, st));
     std::vector<uint4> lrec(P.h_layers.size() * 2), erec(P.h_entries.size());
@@ -1119,12 +1050,10 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   float* y = (float*)b.y;
   int dbg = g_debug;
   unsigned int* ctr = P.d_counters;
-  unsigned int* flags = P.d_counters + 4096;
-  int flag_stride = s.chain_grid;  // items of the chain's largest entry
-  CUDA_TRY(cudaMemsetAsync(ctr, 0, 16384 + (size_t)ne * (size_t)flag_stride * sizeof(unsigned int), st));
+  CUDA_TRY(cudaMemsetAsync(ctr, 0, 16384, st));
   const uint8_t* pw = (const uint8_t*)b.packed;
-  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&y, (void*)&dbg, (void*)&layer0, (void*)&flags, (void*)&flag_stride};
-  const void* fn = (const void*)conv3x3_chain_kernel<1>;
+  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&y, (void*)&dbg, (void*)&layer0};
+  const void* fn = dbg ? (const void*)conv3x3_chain_kernel<1> : (const void*)conv3x3_chain_kernel<0>;  // <1>: probes compiled in
   if (ne > 1) {
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   } else {
@@ -1135,74 +1064,6 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
     co.any = true;
   }
   CUDA_TRY(cudaEventRecord(co.ev, st));
-  return 0;
-}
-
-// Cluster-multicast launch: clusters of 3 CTAs (the three horizontal taps of one pixel split) share every load.
-// Opt-in (B200SR_WGRAD_CLUSTER=1): parity-green, cuts the L2 reads 3x, but measured slower (15.65 vs 14.9 ms/step): only
-// 45 clusters of 3 are co-resident (135 of 148 SMs) and the main loop is bound by shared-memory bandwidth (MMA operand
-// reads 125 B/clk + TMA fills 49 B/clk against 128 B/clk), which multicast does not change.
-static const bool g_wgrad_cluster = [] { const char* e = getenv("B200SR_WGRAD_CLUSTER"); return e && atoi(e) == 1; }();
-static int launch_wgrad_cluster(const Step& s, const CUtensorMap& tmXc, const CUtensorMap& tmDY, const Bases& b, cudaStream_t st) {
-  WgradBatch wb = s.wb;
-  double work[kWgMaxProblems], total = 0;
-  for (int j = 0; j < wb.num_problems; ++j) {
-    WgradParams& wp = wb.prob[j];
-    for (int i = 0; i < wp.num_seg; ++i) wp.seg[i].out = (float*)resolve(s.wseg_out[j][i], b);
-    const int nacc = wp.bias_mode ? 1 : 3;
-    const double mma = nacc * 8.0 * (32.0 + wp.n_cols / 4.0 > wp.n_cols / 2.0 ? 32.0 + wp.n_cols / 4.0 : wp.n_cols / 2.0);
-    const double ld = wgrad_cluster_tx_bytes(wp) / 64.0;  // shared-memory fill rate of one SM
-    work[j] = (mma > ld ? mma : ld) * nacc;
-    total += work[j];
-  }
-  // one wave of 3-CTA clusters: how many are co-resident depends on the GPC layout, ask the runtime once
-  static int max_clusters = 0;
-  if (max_clusters == 0) {
-    cudaLaunchConfig_t qc; memset(&qc, 0, sizeof(qc));
-    qc.gridDim = dim3(3 * 64); qc.blockDim = dim3(kWgThreads); qc.dynamicSmemBytes = kWgSmemBytes;
-    cudaLaunchAttribute qa[1];
-    qa[0].id = cudaLaunchAttributeClusterDimension;
-    qa[0].val.clusterDim.x = 3; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-    qc.attrs = qa; qc.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, wgrad3x3_cluster_kernel, &qc) != cudaSuccess || n < 1) { cudaGetLastError(); n = g_num_sms / 3 - 4; }
-    max_clusters = n;
-    if (getenv("B200SR_VERBOSE")) fprintf(stderr, "b200sr: wgrad clusters of 3 co-resident: %d\n", n);
-  }
-  const int clusters = max_clusters;
-  int cl_of[kWgMaxProblems], cl_sum = 0, largest = 0;
-  for (int j = 0; j < wb.num_problems; ++j) {
-    cl_of[j] = (int)(clusters * work[j] / total);  // round down, then hand the remainder to the largest problem
-    if (cl_of[j] < 1) cl_of[j] = 1;
-    cl_sum += cl_of[j];
-    if (work[j] > work[largest]) largest = j;
-  }
-  if (cl_sum < clusters) cl_of[largest] += clusters - cl_sum;
-  int ctas = 0;
-  for (int j = 0; j < wb.num_problems; ++j) {
-    WgradParams& wp = wb.prob[j];
-    int cl = cl_of[j];  // clusters of this problem
-    if (wp.bias_mode) {                   // three independent CTAs per cluster, each its own split
-      int splits = cl * 3;
-      while (splits > wb.num_tiles && splits > 3) splits -= 3;
-      wp.splits = splits;
-      wb.cta_begin[j] = ctas;
-      ctas += splits;
-    } else {
-      if (cl > wb.num_tiles) cl = wb.num_tiles;
-      wp.splits = cl;
-      wb.cta_begin[j] = ctas;
-      ctas += cl * 3;
-    }
-  }
-  wb.cta_begin[wb.num_problems] = ctas;
-  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(kWgThreads); cfg.dynamicSmemBytes = kWgSmemBytes; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 3; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, wgrad3x3_cluster_kernel, tmXc, tmDY, wb));
   return 0;
 }
 
@@ -1246,7 +1107,7 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
   // done they alternate between the caller's stream and a side stream, so the flush tail of one launch overlaps the ramp-up
   // of the next (each launch fills the GPU with one CTA per SM).  Everything that consumes their results joins first.
   static const bool two_streams = [] { const char* e = getenv("B200SR_WGRAD_STREAMS"); return !(e && atoi(e) == 1); }();
-  const bool alternate = two_streams && P.single_bwd_chain && (&steps == &P.bwd);
+  const bool alternate = two_streams && (&steps == &P.bwd);
   bool forked = false, side_dirty = false;
   int wcount = 0;
   auto join = [&]() -> int {
@@ -1289,8 +1150,7 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
           }
           if (wcount++ & 1) { ws = P.side_stream; side_dirty = true; }
         }
-        int rc = (g_wgrad_cluster && s.xmap_c >= 0) ? launch_wgrad_cluster(s, P.maps[s.xmap_c], P.maps[s.dymap], b, ws)
-                                                    : launch_wgrad(s, P.maps[s.xmap], P.maps[s.dymap], b, ws);
+        int rc = launch_wgrad(s, P.maps[s.xmap], P.maps[s.dymap], b, ws);
         if (rc) return rc;
         break;
       }
@@ -1373,13 +1233,7 @@ int b200sr_plan_create(const b200sr_net_desc* desc, b200sr_plan** out) {
   if (!desc || !out) return fail(B200SR_ERR_INVALID, "null argument");
   b200sr_plan* p = new b200sr_plan();
   p->d = *desc;
-  if (const char* e = getenv("B200SR_REASSOC")) { p->reassoc = atoi(e) != 0; p->window = atoi(e) == 2; }
-  if (const char* e = getenv("B200SR_SPLIT")) p->split_passes = atoi(e) != 0;
-  if (const char* e = getenv("B200SR_UNIT")) p->unit_all = atoi(e) != 0;
-  if (const char* e = getenv("B200SR_EARLYX")) p->early_x = atoi(e) != 0;
-  if (const char* e = getenv("B200SR_STAGGER")) p->stagger_fillers = atoi(e) != 0;
-  if (const char* e = getenv("B200SR_BWDCHAIN")) p->single_bwd_chain = atoi(e) != 0;
-  if (const char* e = getenv("B200SR_GROUPS")) p->groups_env = atoi(e);
+  if (const char* e = getenv("B200SR_REASSOC")) p->reassoc = atoi(e) != 0;  // 0: per-conv schedule everywhere
   int rc = build_plan(*p);
   if (rc) { delete p; return rc; }
   *out = p;
@@ -1575,10 +1429,9 @@ static int single_conv(int mode, const void* x, int n, int h, int w, int cin, in
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_layer_rec, lrec, sizeof(lrec), 0, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_entry_rec, &erec, sizeof(erec), 0, cudaMemcpyHostToDevice, st));
   int layer0 = 0;
-  unsigned int* flags = nullptr;  // a single layer has no dependencies
-  int flag_stride = 0;
-  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&ydyn, (void*)&dbg, (void*)&layer0, (void*)&flags, (void*)&flag_stride};
-  CUDA_TRY(cudaLaunchKernel((const void*)conv3x3_chain_kernel<1>, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
+  void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&ydyn, (void*)&dbg, (void*)&layer0};
+  const void* fn = dbg ? (const void*)conv3x3_chain_kernel<1> : (const void*)conv3x3_chain_kernel<0>;
+  CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   (void)grid_y;
   return 0;
 }
