@@ -405,6 +405,115 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------- config 4: large-frame inference
+def run_c4(args):
+    """BASELINE.json configs[3]: ONE 3x1024x1024 LR frame -> 4096x4096 SR, halo-tiled across the ranks (row bands, no
+    collective on the data path; ESRGAN/inference.py:68-69 runs the whole frame in one call).  Every rank super-resolves its
+    band(s) with `--halo` extra LR rows on interior edges; the HR rows are then gathered on rank 0.  Reports output Mpix/s
+    (compute only, max over ranks, and including the gather) and the rel-L2 of the stitched frame against the whole frame."""
+    import torch
+    import torch.distributed as dist
+    import sr_gan_fd_b200 as b200
+    from sr_gan_fd_b200 import tile
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    net = b200.rrdbnet_x4(num_blocks=NUM_BLOCKS)
+    # in-range weights (same transformation as the test fixture, restated here: bench does not import oracle/ on this path)
+    sd = net.state_dict()
+    with torch.no_grad():
+        for k in ("conv1.weight", "conv2.weight", "upsampling1.0.weight", "upsampling2.0.weight", "conv3.0.weight", "conv4.weight"):
+            sd[k].mul_(3.7)
+        sd["conv4.bias"].fill_(0.5)
+    net = net.to(dev).eval()
+    H = W = args.frame
+    g = torch.Generator().manual_seed(4)
+    lr = torch.rand(1, 3, H, W, generator=g).to(dev)
+    bands = world * args.bands_per_rank
+    out_rows = H * SCALE
+
+    out_buf = torch.zeros((1, 3, out_rows, W * SCALE), dtype=torch.float32, device=dev) if bands > 1 else None
+
+    def compute():
+        with torch.no_grad():
+            if bands == 1:
+                return net(lr), (0, out_rows)
+            return tile.tiled_forward(net, lr, SCALE, bands, args.halo, rank, world, out=out_buf)
+
+    def gather(out, rows):
+        if world == 1:
+            return out
+        mine = out[:, :, rows[0]:rows[1]].contiguous()
+        parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None  # equal bands: H divisible by bands
+        dist.gather(mine, parts, dst=0)
+        return torch.cat(parts, 2) if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        o, rows = compute()
+        full = gather(o, rows)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    times = {}
+    for name, with_gather in (("compute", False), ("with_gather", True)):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            o, rows = compute()
+            if with_gather:
+                full = gather(o, rows)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        times[name] = ms
+    clocks = sampler.stop() if sampler else None
+    err = None
+    if rank == 0:
+        with torch.no_grad():
+            whole = net(lr)
+        if full is not None and bands > 1:
+            err = float(((full.double() - whole.double()).norm() / whole.double().norm()).item())
+        del whole
+    if rank == 0:
+        mpix = out_rows * W * SCALE / 1e6
+        plan = net._runtime().last_plan
+        burst, sustained, how = measured_peaks()
+        flops_frame = 35.853696e6 * H * W  # algorithmic: 35.854 MFLOP per LR pixel (SURVEY 8d), no credit for the halo rows
+        line = {
+            "metric": "RRDBNet x4 output Mpix/s (BASELINE configs[3]: 1x3x%dx%d LR -> %dx%d SR, halo-tiled inference)" % (H, W, out_rows, W * SCALE),
+            "value": mpix / (times["compute"] * 1e-3), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": times["compute"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "config 4 large-frame inference", "bands": bands, "halo_lr_rows": args.halo,
+                       "redundant_rows_fraction": tile.redundant_fraction(H, bands, args.halo) if bands > 1 else 0.0,
+                       "l2_policy": "one frame's activations (>10 GB workspace traffic) are far larger than L2"},
+            "with_gather": {"value": mpix / (times["with_gather"] * 1e-3), "unit": "Mpix/s", "ms_per_step": times["with_gather"]},
+            "tiled_vs_whole_rel_l2": err,
+            "frac_of_peak": flops_frame / (times["compute"] * 1e-3) / 1e12 / (burst * world),
+            "gpu_launches": int(plan.launches_fwd * args.bands_per_rank * args.steps * 2), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -413,6 +522,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "c4"],
+                    help="train: the contract's workload (configs[1]/[2]); c4: large-frame halo-tiled inference (configs[3])")
+    ap.add_argument("--frame", type=int, default=1024)
+    ap.add_argument("--halo", type=int, default=16)
+    ap.add_argument("--bands-per-rank", type=int, default=1)
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: the driver launches N>1 through torch.distributed.run itself; do the same when run by hand
@@ -420,6 +534,8 @@ def main():
                                    "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:])
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4":
+        run_c4(args)
     else:
         run_b200(args)
 

@@ -508,11 +508,15 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const unsigned int dwork = (dr.z - dr.y) * dcg;
         dep_need = dwork < grid ? dwork : grid;
       }
+      // One look at the dependency's counter is issued NOW and consumed only when the first activation load is due: its L2
+      // round trip overlaps the waits for a free activation slot / weight granules below.
+      unsigned int early_seen = 0;
+      if (dep >= 0 && v < num_work && lane == 0 && !(debug & 16)) early_seen = ld_acquire_gpu(counters + dep);
       // the dependency's counter shows every CTA that worked on it
       auto dependency_wait = [&]() {
         PROF_T0(pf);
         if (lane == 0) {
-          if (!(debug & 16)) wait_entry_done(counters, dep, dep_need);
+          if (!(debug & 16) && early_seen < dep_need) wait_entry_done(counters, dep, dep_need);
           if (!(debug & 512)) asm volatile("fence.proxy.async.global;" ::: "memory");  // TMA (async proxy) reads after generic-proxy stores (bit 512: timing experiment)
           // tell this CTA's epilogue warps (they read residual carriers written by earlier entries): acquire.gpu above,
           // release.cta here, acquire.cta on their side -- causality order is transitive
