@@ -1,0 +1,187 @@
+"""BASELINE.json configs[4]: the BSRGAN full GAN step with the B200 generator and the reference's critics UNCHANGED.
+
+One iteration restates ``BSRGAN/train_bsrgan.py:412-470`` around objects the reference itself defines:
+
+  * ``d_model``          = the reference ``DiscriminatorUNet(3, 1, 64)``            (BSRGAN/model.py:91-167, through the compat shim)
+  * ``content_criterion``= the reference ``ContentLoss`` on torchvision VGG19        (BSRGAN/model.py:501-554).  The ImageNet
+                           weights are not cached in this image and there is no network, so ``torchvision.models.vgg19`` is
+                           patched to return a SEEDED RANDOM-INIT VGG19 (same FLOPs, says so in the output);
+  * ``g_model``          = ``bsrgan_x4`` -- the B200 drop-in (``--generator b200``) or the reference's own torch module
+                           (``--generator stock``) for the A/B number;
+  * autocast + GradScaler(65536), Adam (lr 8e-5, betas (0.9, 0.999), eps 1e-4), D step BETWEEN the generator's forward and its
+    backward, generator backward under the summed (pixel 20 + content 1 + adversarial 0.5) x 65536 upstream gradient.
+
+Needs the reference tree (``$SRGANFD_REFERENCE`` or /root/reference) for the critics.  Under torchrun every rank runs 16 images;
+the generator's gradients are averaged by ``sr_gan_fd_b200.dist`` (NCCL), the discriminator is wrapped in stock DDP.
+
+    python tools/gan_step.py --steps 10                      # 1 GPU, prints one JSON line
+    torchrun --nproc-per-node 8 tools/gan_step.py --steps 10
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+from torch import nn, optim
+
+PIXEL_W, CONTENT_W, ADV_W = [20.0], [1.0], [0.5]                                   # BSRGAN/bsrgan_config.py:137-143
+NODES = ["features.2", "features.7", "features.16", "features.25", "features.34"]  # :130
+MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]                            # :131-132
+LR, BETAS, EPS = 8e-5, (0.9, 0.999), 1e-4                                           # :147-150
+
+
+def patch_vgg19(seed=1234):
+    """torchvision.models.vgg19(weights=IMAGENET1K_V1) would download: return a seeded random-init VGG19 instead."""
+    import torchvision.models as models
+    real = models.vgg19
+
+    def seeded(*a, **k):
+        state = torch.random.get_rng_state()
+        torch.manual_seed(seed)
+        m = real(weights=None)
+        torch.random.set_rng_state(state)
+        return m
+
+    models.vgg19 = seeded
+
+
+def build(generator, device, seed=0):
+    patch_vgg19()
+    from sr_gan_fd_b200.compat import bsrgan_model as model  # reference critics + B200 generator
+    if "discriminator_unet" not in model.__dict__:
+        raise SystemExit("the reference tree is needed for the critics (set SRGANFD_REFERENCE)")
+    torch.manual_seed(seed)
+    d_model = model.discriminator_unet(in_channels=3, out_channels=1, channels=64).to(device)
+    torch.manual_seed(seed)
+    if generator == "b200":
+        g_model = model.bsrgan_x4(in_channels=3, out_channels=3, channels=64, growth_channels=32, num_rrdb=23)
+    else:
+        from sr_gan_fd_b200.compat._passthrough import load_reference_model
+        g_model = load_reference_model("BSRGAN").bsrgan_x4(in_channels=3, out_channels=3, channels=64, growth_channels=32, num_rrdb=23)
+    g_model = g_model.to(device)
+    content = model.ContentLoss(NODES, MEAN, STD).to(device)
+    return d_model, g_model, content
+
+
+class GanStep:
+    def __init__(self, d_model, g_model, content, device, world=1):
+        self.d, self.g, self.content, self.dev = d_model, g_model, content, device
+        self.d_core = d_model.module if hasattr(d_model, "module") else d_model
+        self.pixel = nn.L1Loss().to(device)
+        self.adv = nn.BCEWithLogitsLoss().to(device)
+        self.d_opt = optim.Adam(self.d_core.parameters(), LR, BETAS, EPS, 0.0)
+        self.g_opt = optim.Adam(self.g.parameters(), LR, BETAS, EPS, 0.0)
+        self.scaler = torch.amp.GradScaler("cuda")
+        self.pw = torch.Tensor(PIXEL_W).to(device)
+        self.cw = torch.Tensor(CONTENT_W).to(device)
+        self.aw = torch.Tensor(ADV_W).to(device)
+        self.sr_grad = None
+
+    def __call__(self, lr, gt, step_d=True, step_g=True, keep_sr_grad=False):
+        d_model, g_model, scaler = self.d, self.g, self.scaler
+        b, _, h, w = gt.shape
+        real_label = torch.full([b, 1, h, w], 1.0, dtype=gt.dtype, device=self.dev)
+        fake_label = torch.full([b, 1, h, w], 0.0, dtype=gt.dtype, device=self.dev)
+        for p in self.d_core.parameters():
+            p.requires_grad = True
+        d_model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda"):
+            gt_output = d_model(gt)
+            d_loss_hr = self.adv(gt_output, real_label)
+        scaler.scale(d_loss_hr).backward(retain_graph=True)
+        with torch.autocast("cuda"):
+            sr = g_model(lr)                       # generator forward ONCE; its activations wait for the backward below
+            sr_output = d_model(sr.detach().clone())
+            d_loss_sr = self.adv(sr_output, fake_label)
+        scaler.scale(d_loss_sr).backward()
+        if step_d:
+            scaler.step(self.d_opt)                # the discriminator changes BETWEEN the generator's forward and backward
+            scaler.update()
+        for p in self.d_core.parameters():
+            p.requires_grad = False
+        g_model.zero_grad(set_to_none=True)
+        if keep_sr_grad:
+            sr.register_hook(lambda gr: setattr(self, "sr_grad", gr.detach().clone()))
+        with torch.autocast("cuda"):
+            pixel_loss = self.pixel(sr, gt)
+            content_loss = self.content(sr, gt)
+            adversarial_loss = self.adv(self.d_core(sr), real_label)
+            pixel_loss = torch.sum(torch.mul(self.pw, pixel_loss))
+            content_loss = torch.sum(torch.mul(self.cw, content_loss))
+            adversarial_loss = torch.sum(torch.mul(self.aw, adversarial_loss))
+            g_loss = pixel_loss + content_loss + adversarial_loss
+        scaler.scale(g_loss).backward()
+        if step_g:
+            scaler.step(self.g_opt)
+            scaler.update()
+        return sr, g_loss.detach(), (d_loss_hr + d_loss_sr).detach()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--generator", default="b200", choices=["b200", "stock"])
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--lr-size", type=int, default=64)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    d_model, g_model, content = build(args.generator, dev)
+    d_model.train(); g_model.train()
+    if world > 1:
+        d_model = nn.parallel.DistributedDataParallel(d_model, device_ids=[local], broadcast_buffers=True)
+        if args.generator == "b200":
+            from sr_gan_fd_b200 import dist as b200dist
+            b200dist.make_data_parallel(g_model)
+        else:
+            g_model = nn.parallel.DistributedDataParallel(g_model, device_ids=[local])
+    step = GanStep(d_model, g_model, content, dev, world)
+    torch.manual_seed(100 + rank)
+    lr = torch.rand(args.batch, 3, args.lr_size, args.lr_size, device=dev)
+    gt = torch.rand(args.batch, 3, 4 * args.lr_size, 4 * args.lr_size, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(lr, gt)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        _, g_loss, d_loss = step(lr, gt)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "BSRGAN full GAN step imgs/s (BASELINE configs[4]: generator fwd+bwd + reference U-Net discriminator x3 + VGG19 content loss)",
+            "generator": args.generator, "value": world * args.batch / (ms * 1e-3), "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "data": "synthetic",
+            "config": {"batch_per_gpu": args.batch, "lr": args.lr_size, "scale": 4, "num_rrdb": 23, "critics": "reference DiscriminatorUNet(3,1,64) "
+                       "+ ContentLoss on a SEEDED RANDOM-INIT VGG19 (ImageNet weights unavailable offline), autocast fp16 + GradScaler",
+                       "discriminator_parallelism": "stock DDP" if world > 1 else "single", "g_loss": float(g_loss), "d_loss": float(d_loss)}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
