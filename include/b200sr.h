@@ -53,6 +53,9 @@ typedef struct b200sr_net_desc {
   int32_t n_up;         /* nearest-x2 + conv stages: 0 (x1) .. 3 (x8) */
   int32_t batch, height, width; /* LR input geometry */
   int32_t training;     /* 1: keep activations for backward, build the backward schedule */
+  int32_t grad_bucket_rrdbs; /* gradient buckets announced through b200sr_bucket_cb: RRDBs per bucket (0 = 1; the tail convs and
+                              * conv1 are buckets of their own, the last trunk bucket holds at most two RRDBs so that little
+                              * communication is left exposed after the last kernel) */
 } b200sr_net_desc;
 
 /* Called from inside b200sr_backward (on the calling host thread) each time every kernel that contributes to a

@@ -717,6 +717,7 @@ static int build_plan(b200sr_plan& P) {
       emit(unpack_step(ci_conv2, nconv));
     }
     // trunk, last dense block first
+    int bucket_hi = ci_conv2;  // conv index (exclusive) up to which trunk gradients have been announced
     for (int r = R - 1; r >= 0; --r) {
       const int j = r % 3;
       const long long D = P.o_dense[r];
@@ -820,8 +821,16 @@ static int build_plan(b200sr_plan& P) {
         add_seg(wg, 128, 160, bref(conv_index_rdb(r, 2)), 1, 0, 32);
         add_seg(wg, 160, 192, bref(conv_index_rdb(r, 1)), 1, 0, 32);
         emit(wg);
-        if (j == 0)  // one bucket per RRDB (its 15 convs are contiguous in the flat buffer)
-          emit(unpack_step(conv_index_rdb(r, 1), conv_index_rdb(r + 2, 5) + 1));
+        if (j == 0) {
+          // gradient buckets: G RRDBs each (their convs are contiguous in the flat buffer); the LAST trunk bucket is at most two
+          // RRDBs so that little communication is left after the final kernels
+          const int blk = r / 3;
+          const int G = d.grad_bucket_rrdbs > 0 ? d.grad_bucket_rrdbs : 1;
+          if (blk % G == 0 || (G > 2 && blk == 2)) {
+            emit(unpack_step(conv_index_rdb(r, 1), bucket_hi));
+            bucket_hi = conv_index_rdb(r, 1);
+          }
+        }
       }
     }
     // conv1: gradient of its output = trunk path (GR) + long skip (GT)

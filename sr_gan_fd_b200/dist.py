@@ -1,7 +1,7 @@
 """Data-parallel training of the generator: one process per GPU, one logical all-reduce of the flat gradient buffer.
-The backward pass announces gradient buckets as they become ready; the reducer either all-reduces them right away on a
-side stream (overlapped with the remaining kernels) or -- the default, faster on B200 -- coalesces them into a single
-all-reduce at the end of backward.
+Default: ONE all-reduce of the whole buffer when backward has enqueued its last kernel (no bucket callback is installed, so
+backward keeps its merged gradient unpack).  Optional (``overlap=True``): the backward pass announces gradient buckets as they
+become ready and the reducer all-reduces them right away on a few-CTA, high-priority NCCL communicator.
 
 The reference has no distributed code; this is the new capability BASELINE.json config 3 asks for.
 The generator has no BatchNorm / dropout / buffers, so averaging gradients over ranks is mathematically identical to
@@ -107,24 +107,50 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, process_group=No
         dist.broadcast(p.data, src=src, group=process_group)
 
 
-def make_data_parallel(module, process_group=None, min_bucket_numel: Optional[int] = None) -> GradBucketReducer:
+def _overlap_group(process_group=None, max_ctas: int = 4):
+    """A dedicated NCCL communicator for the gradient buckets: few CTAs (the buckets only need ~30 GB/s to hide behind the
+    weight-gradient kernels, and every SM NCCL holds is one the backward pass loses) on a HIGH-PRIORITY stream, so that its
+    blocks are scheduled as soon as running weight-gradient CTAs retire instead of queueing behind the next launch."""
+    try:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        opts.config.max_ctas = max_ctas
+        opts.config.min_ctas = 1
+        ranks = dist.get_process_group_ranks(process_group) if process_group is not None else list(range(dist.get_world_size()))
+        return dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+    except Exception:
+        return process_group
+
+
+def make_data_parallel(module, process_group=None, min_bucket_numel: Optional[int] = None,
+                       overlap: Optional[bool] = None) -> GradBucketReducer:
     """Attach gradient averaging to a drop-in generator.  Returns the reducer (for inspection).
 
-    ``min_bucket_numel=None`` (default): adjacent buckets are coalesced into ONE all-reduce issued when backward has
-    enqueued everything.  Measured on B200 this beats overlapping: the backward pass fills every SM with one-CTA-per-SM
-    kernels, so NCCL kernels launched in the middle of it only take SMs away from the weight-gradient launches
-    (8 GPUs: 8730 vs 8537 img/s; 2 GPUs: 2193 vs 2146).  Pass a number (elements) to all-reduce buckets of at least
-    that size as soon as they are ready instead (0 = every bucket the backward pass announces)."""
+    ``overlap=False``: ONE all-reduce of the whole flat gradient buffer, issued when backward has enqueued everything (no
+    bucket callback: backward keeps its merged gradient unpack).  ``overlap=True``: backward announces buckets of
+    ``B200SR_DP_BUCKET_RRDBS`` (default 6) RRDBs as their weight-gradient kernels are enqueued; each is all-reduced right away
+    on a few-CTA, high-priority NCCL communicator while the remaining weight-gradient kernels run, and only the last small
+    bucket (two RRDBs + conv1) is left exposed.  Default: ``B200SR_DP_OVERLAP`` (0: coalesced -- measured on 2 x B200 the single
+    all-reduce costs 0.12 ms per step over one GPU, the overlapped buckets 0.21 ms: their NCCL kernels take SMs from the
+    weight-gradient launches and backward needs one unpack launch + stream join per bucket).  ``min_bucket_numel``
+    (elements) additionally coalesces adjacent announced buckets below that size."""
     import os
-    if "B200SR_DP_MIN_BUCKET" in os.environ:  # experiment switch: all-reduce buckets of at least this many elements early
+    if overlap is None:
+        overlap = os.environ.get("B200SR_DP_OVERLAP", "0") == "1"
+    if "B200SR_DP_MIN_BUCKET" in os.environ:  # experiment switch
         min_bucket_numel = int(float(os.environ["B200SR_DP_MIN_BUCKET"]))
     rt: GeneratorRuntime = module._runtime()
-    if min_bucket_numel is None:
+    cuda = next(module.parameters()).is_cuda
+    if not overlap:
         reducer = GradBucketReducer(process_group, average=True, min_bucket_numel=1 << 62)
         rt.grad_bucket_hook = None          # backward is not told about buckets: no per-bucket unpack launches / stream joins
+        rt.grad_bucket_rrdbs = 0
         rt.grad_done_hook = reducer.reduce_all
         return reducer
-    reducer = GradBucketReducer(process_group, average=True, min_bucket_numel=min_bucket_numel)
+    group = process_group
+    if cuda and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        group = _overlap_group(process_group, int(os.environ.get("B200SR_DP_MAX_CTAS", "4")))
+    reducer = GradBucketReducer(group, average=True, min_bucket_numel=min_bucket_numel or 0)
+    rt.grad_bucket_rrdbs = int(os.environ.get("B200SR_DP_BUCKET_RRDBS", "6"))
     rt.grad_bucket_hook = reducer.bucket_ready
     rt.grad_done_hook = reducer.finish
     return reducer

@@ -21,10 +21,10 @@ _MAX_PACKED = 4  # packed-weight buffers kept per module ((training, pack layout
 
 
 class _Plan:
-    def __init__(self, desc: dict, batch: int, height: int, width: int, training: bool) -> None:
+    def __init__(self, desc: dict, batch: int, height: int, width: int, training: bool, grad_bucket_rrdbs: int = 0) -> None:
         lib = _lib.load()
         nd = _lib.NetDesc(desc["in_channels"], desc["out_channels"], desc["channels"], desc["growth"],
-                          desc["num_blocks"], desc["n_up"], batch, height, width, 1 if training else 0)
+                          desc["num_blocks"], desc["n_up"], batch, height, width, 1 if training else 0, grad_bucket_rrdbs)
         handle = C.c_void_p()
         _lib.check(lib.b200sr_plan_create(C.byref(nd), C.byref(handle)))
         self.handle = handle
@@ -65,6 +65,7 @@ class GeneratorRuntime:
         self.grad_bucket_hook: Optional[Callable[[torch.Tensor, int, int], None]] = None
         # optional hook(flat_grads) called once backward has enqueued all of its kernels
         self.grad_done_hook: Optional[Callable[[torch.Tensor], None]] = None
+        self.grad_bucket_rrdbs = 0  # RRDBs per announced gradient bucket (0: one)
         self.last_plan: Optional[_Plan] = None
         # host fast path: the conv modules in state_dict order, and what was already validated about their parameters
         self.convs = None
@@ -74,10 +75,10 @@ class GeneratorRuntime:
         self.cur_key = None
 
     def plan(self, desc: dict, device: torch.device, batch: int, height: int, width: int, training: bool) -> _Plan:
-        key = (device.index, batch, height, width, training)
+        key = (device.index, batch, height, width, training, self.grad_bucket_rrdbs)
         p = self.plans.get(key)
         if p is None:
-            p = _Plan(desc, batch, height, width, training)
+            p = _Plan(desc, batch, height, width, training, self.grad_bucket_rrdbs)
             self.plans[key] = p
             while len(self.plans) > _MAX_PLANS:
                 self.plans.popitem(last=False)

@@ -16,7 +16,7 @@ BUCKET_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64)
 class NetDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "in_channels", "out_channels", "channels", "growth", "num_blocks", "n_up",
-        "batch", "height", "width", "training")]
+        "batch", "height", "width", "training", "grad_bucket_rrdbs")]
 
 
 _lock = threading.Lock()
