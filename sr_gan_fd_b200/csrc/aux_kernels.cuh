@@ -150,15 +150,19 @@ __global__ void ingest_grad_kernel(const float* __restrict__ dy, const unsigned 
   if (pix >= total) return;
   const long long n = pix / plane;
   const long long r = pix - n * plane;
-  __nv_bfloat16* o = out + pix * out_stride;
+  float v[16];
+#pragma unroll
   for (int c = 0; c < 16; ++c) {
-    float v = 0.f;
+    v[c] = 0.f;
     if (c < C) {
       const long long i = (n * C + c) * plane + r;
-      v = mask[i] ? dy[i] : 0.f;
+      v[c] = mask[i] ? dy[i] : 0.f;
     }
-    o[c] = __float2bfloat16_rn(v);
   }
+  // 16 channels = 32 bytes per pixel: two 16-byte stores (out_stride is a multiple of 8 channels)
+  uint4* o = reinterpret_cast<uint4*>(out + pix * out_stride);
+  o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
 }
 
 // ------------------------------------------------------------------------------------------------ bias gradients
@@ -179,10 +183,22 @@ __global__ void __launch_bounds__(kBiasGradThreads) bias_grad_kernel(const BiasG
   if (pl < PL) {
     const __nv_bfloat162* base = reinterpret_cast<const __nv_bfloat162*>(p.g + p.c0) + cp;
     const long long step = static_cast<long long>(gridDim.x) * PL;
-    for (long long px = static_cast<long long>(blockIdx.x) * PL + pl; px < p.P; px += step) {
-      const float2 v = __bfloat1622float2(base[px * (p.stride >> 1)]);
+    const long long sp = p.stride >> 1;
+    long long px = static_cast<long long>(blockIdx.x) * PL + pl;
+    // four independent loads in flight per thread (the loop is latency-bound otherwise)
+    float2 a1 = make_float2(0.f, 0.f), a2 = a1, a3 = a1;
+    for (; px + 3 * step < p.P; px += 4 * step) {
+      const float2 v0 = __bfloat1622float2(base[px * sp]);
+      const float2 v1 = __bfloat1622float2(base[(px + step) * sp]);
+      const float2 v2 = __bfloat1622float2(base[(px + 2 * step) * sp]);
+      const float2 v3 = __bfloat1622float2(base[(px + 3 * step) * sp]);
+      acc.x += v0.x; acc.y += v0.y; a1.x += v1.x; a1.y += v1.y; a2.x += v2.x; a2.y += v2.y; a3.x += v3.x; a3.y += v3.y;
+    }
+    for (; px < p.P; px += step) {
+      const float2 v = __bfloat1622float2(base[px * sp]);
       acc.x += v.x; acc.y += v.y;
     }
+    acc.x += a1.x + a2.x + a3.x; acc.y += a1.y + a2.y + a3.y;
   }
   red[threadIdx.x] = acc;
   __syncthreads();

@@ -1169,7 +1169,7 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         for (int i = 0; i < bp.nseg; ++i) bp.seg[i].out = (float*)resolve(s.seg_out[i], b);
         const int pl = kBiasGradThreads / (bp.ncols / 2);
         long long blocks = (bp.P + pl * 16 - 1) / (pl * 16);
-        if (blocks > 2 * g_num_sms) blocks = 2 * g_num_sms;
+        if (blocks > 8 * g_num_sms) blocks = 8 * g_num_sms;
         bias_grad_kernel<<<(int)blocks, kBiasGradThreads, 0, st>>>(bp);
         CUDA_TRY(cudaGetLastError());
         break;
