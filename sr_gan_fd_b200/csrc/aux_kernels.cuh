@@ -31,6 +31,7 @@ struct PackOp {
   int num_chunks;  // 64-channel K chunks
   int mode;
   int nseg;
+  int k32;         // 1: a single K chunk of 32 channels, packed as 64-byte rows under the 64B swizzle (half the bytes of a padded 128-byte row)
   PackSeg seg[5];
 };
 
@@ -92,6 +93,17 @@ __global__ void pack_weights_kernel(const PackOp* __restrict__ ops, int num_ops,
     if (ops[mid].row0 <= row) lo = mid; else hi = mid - 1;
   }
   const PackOp& op = ops[lo];
+  if (op.k32) {
+    // two 64-byte rows per 128-byte unit; 16-byte chunk j of row n lands at position j ^ ((n >> 1) & 3) (64B swizzle on address bits 7-8)
+    const int r2 = static_cast<int>(row - op.row0) * 2 + (kk >> 5);
+    const int kc = kk & 31;
+    const int ng2 = r2 % op.n_cols, t2 = r2 / op.n_cols;
+    const int cgs2 = op.n_total / op.n_cols;
+    const int dy2 = t2 % 3, dx2 = (t2 / 3) % 3, cg2 = (t2 / 9) % cgs2, c2 = t2 / (9 * cgs2);
+    const float v2 = (c2 < op.num_chunks) ? pack_fetch(op, params, cg2 * op.n_cols + ng2, c2 * 64 + kc, dy2, dx2) : 0.f;
+    packed[op.row0 * 64LL + static_cast<long long>(r2) * 32 + (((kc >> 3) ^ ((ng2 >> 1) & 3)) * 8) + (kc & 7)] = __float2bfloat16_rn(v2);
+    return;
+  }
   const int r = static_cast<int>(row - op.row0);
   const int ng = r % op.n_cols;          // row inside the tap tile
   const int t = r / op.n_cols;           // ((chunk*CG + cg)*3 + dx)*3 + dy
@@ -238,14 +250,22 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const UnpackOp* __res
   const int co0 = (tb % tiles_co) * 32, ci0 = (tb / tiles_co) * 32;
   const float* src = staging + op.src_off;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  if (!op.fold) {
+    // staging layout [tap][co/4][ci][4]: one 16-byte load per thread and tap, consecutive threads -> consecutive ci (coalesced)
+    const int ci = ci0 + tx, cq = (co0 >> 2) + ty;  // ty = 0..7: the tile's eight co quads
+    for (int tap = 0; tap < 9; ++tap) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ci < op.ci && 4 * cq < op.co_pad)
+        v = *reinterpret_cast<const float4*>(src + ((static_cast<long long>(tap) * (op.co_pad >> 2) + cq) * op.ci + ci) * 4);
+      tile[tap][tx][4 * ty] = v.x; tile[tap][tx][4 * ty + 1] = v.y; tile[tap][tx][4 * ty + 2] = v.z; tile[tap][tx][4 * ty + 3] = v.w;
+    }
+  } else
   for (int tap = 0; tap < 9; ++tap) {
     for (int r = ty; r < 32; r += 8) {
       const int ci = ci0 + tx, co = co0 + r;  // consecutive threads -> consecutive ci (16-byte stride in the staging layout)
       float v = 0.f;
       if (ci < op.ci && co < op.co) {
-        if (!op.fold) {
-          v = src[((static_cast<long long>(tap) * (op.co_pad >> 2) + (co >> 2)) * op.ci + ci) * 4 + (co & 3)];
-        } else {
+        {
           const int dy = tap / 3, dx = tap % 3;
           for (int ph = 0; ph < 4; ++ph) {
             int ry = -1, rx = -1;

@@ -188,6 +188,8 @@ struct b200sr_plan {
   size_t counters_bytes = 0;          // 16 KB of counters + the largest chain's (entries x items) flag matrix
 };
 
+// K = 32 pass layers carry 64-byte weight rows (B200SR_K32=0: padded 128-byte rows as for every other layer)
+static const bool g_k32 = [] { const char* e = getenv("B200SR_K32"); return !(e && atoi(e) == 0); }();
 static int wmap_index(int n_cols) { return n_cols == 16 ? 0 : n_cols == 32 ? 1 : n_cols == 64 ? 2 : 3; }
 static const int kWmapCols[4] = {16, 32, 64, 128};
 
@@ -217,7 +219,7 @@ struct Builder {
   int add_pack(PackOp op) {
     if (op.n_cols == 0) op.n_cols = op.n_total > 64 ? 64 : op.n_total;  // column groups of 64 (the upsample convs' four phases)
     op.row0 = (int)P.total_rows;
-    P.total_rows += (long long)op.num_chunks * 9 * op.n_total;
+    P.total_rows += (long long)op.num_chunks * 9 * op.n_total / (op.k32 ? 2 : 1);  // 128-byte units
     P.pack_ops.push_back(op);
     return op.row0;
   }
@@ -232,7 +234,7 @@ struct Builder {
 };
 
 ConvParams base_conv_params(int n, int h, int w, int num_chunks, int ksteps_last, int a_c0, int a_wrap, int row0,
-                            int n_cols, int n_total) {
+                            int n_cols, int n_total, int k32 = 0) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.N = n; p.H = h; p.W = w;
@@ -243,7 +245,8 @@ ConvParams base_conv_params(int n, int h, int w, int num_chunks, int ksteps_last
   p.a_c0 = a_c0; p.a_wrap = a_wrap;
   p.w_row0 = row0; p.n_cols = n_cols; p.n_total = n_total;
   p.col_groups = n_total / n_cols;
-  p.w_taps = (9 * n_cols * 128 <= 5 * kWGranule) ? 9 : 3;  // bytes per weight bulk copy <= 60 KB (n_cols <= 128: a dx column always fits)
+  p.k32 = k32;
+  p.w_taps = (9 * n_cols * (k32 ? 64 : 128) <= 5 * kWGranule) ? 9 : 3;  // bytes per weight bulk copy <= 60 KB (n_cols <= 128: a dx column always fits)
   p.acc_col0 = 0; p.acc_first = 1; p.acc_hold = 0; p.epi_cols = n_cols; p.halves = 2;
   p.num_stages = conv_pick_stages(n_cols);
   p.epi.alpha = 1.f; p.epi.delta = 1.f; p.epi.beta1 = 1.f; p.epi.beta2 = 1.f;
@@ -470,10 +473,11 @@ static int build_plan(b200sr_plan& P) {
         const int col_lo = 32 * q, ncols = 128 - col_lo;
         PackOp op; memset(&op, 0, sizeof(op));
         op.n_total = ncols; op.n_cols = ncols; op.n_valid = ncols; op.num_chunks = 1; op.mode = kPackFwd; op.nseg = 0;
+        op.k32 = (klen == 32 && g_k32) ? 1 : 0;
         for (int k = q + 1; k <= 4; ++k)
           op.seg[op.nseg++] = nseg(32 * (k - 1) - col_lo, 32, 0, klen, 2 * conv_index_rdb(r, k), 32, 64 + 32 * (k - 1), 0, c_q);
         const int row0 = B.add_pack(op);
-        ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, c_q, 1 << 20, row0, ncols, ncols);
+        ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, c_q, 1 << 20, row0, ncols, ncols, op.k32);
         cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = 32;
         Step s = conv_step(B.add_map(D, c_q + klen, 192, N, H, W, kABoxRows), cp, 1);
         s.bias = packed_bias(B.add_bias(32, 2 * conv_index_rdb(r, q + 1) + 1, 32, 0));
@@ -760,10 +764,11 @@ static int build_plan(b200sr_plan& P) {
           const int col_lo = 32 * q, ncols = 128 - col_lo;
           PackOp op; memset(&op, 0, sizeof(op));
           op.n_total = ncols; op.n_cols = ncols; op.n_valid = ncols; op.num_chunks = 1; op.mode = kPackDgrad; op.nseg = 0;
+          op.k32 = (klen == 32 && g_k32) ? 1 : 0;
           for (int sidx = 4 - q; sidx >= 1; --sidx)
             op.seg[op.nseg++] = nseg(32 * (4 - sidx) - col_lo, 32, 0, klen, 2 * ci, klen, 64 + 32 * (kk - 1), 0, 64 + 32 * (sidx - 1));
           const int row0 = B.add_pack(op);
-          ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, a_c0, 1 << 20, row0, ncols, ncols);
+          ConvParams cp = base_conv_params(N, H, W, 1, klen / 16, a_c0, 1 << 20, row0, ncols, ncols, op.k32);
           cp.acc_col0 = col_lo; cp.acc_first = (q == 0); cp.acc_hold = 1; cp.epi_cols = 32;
           Step s = conv_step(B.add_map(DYc, a_c0 + klen, 192, N, H, W, kABoxRows), cp, 1);
           const int sl = 4 - q;  // completed slice o_sl

@@ -89,6 +89,8 @@ struct ConvParams {
   int acc_hold;
   int epi_cols;
   int num_stages;
+  int k32;         // weights of this (single-chunk, 32-channel) layer are packed as 64-byte rows (64B swizzle)
+  int pad_[3];
   ConvEpilogue epi;
 };
 
@@ -283,7 +285,8 @@ __constant__ uint4 c_layer_rec[kMaxChainLayers * 2];
 __constant__ uint4 c_entry_rec[kMaxChainEntries];
 inline void make_layer_rec(const ConvParams& p, uint4 out[2], const void* packed_base) {
   out[0].x = static_cast<uint32_t>(p.n_cols) | (p.num_chunks << 10) | (p.ksteps_last << 14) | (p.halves << 17) | (p.w_taps << 19) | (p.col_groups << 23);
-  out[0].y = static_cast<uint32_t>(p.acc_col0) | ((p.acc_first ? 1u : 0u) << 8) | ((p.acc_hold ? 1u : 0u) << 9) | ((p.epi_cols > 0 ? 1u : 0u) << 10);
+  out[0].y = static_cast<uint32_t>(p.acc_col0) | ((p.acc_first ? 1u : 0u) << 8) | ((p.acc_hold ? 1u : 0u) << 9) | ((p.epi_cols > 0 ? 1u : 0u) << 10) |
+             ((p.k32 ? 1u : 0u) << 11);
   out[0].z = static_cast<uint32_t>(p.w_row0);
   out[0].w = static_cast<uint32_t>(p.a_c0);
   out[1].x = static_cast<uint32_t>(p.tiles_x) | (static_cast<uint32_t>(p.tiles_y) << 16);
@@ -351,8 +354,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;"
 // dy of one dx column -- a_lo / b_base already point at that column; 1: a single tap), HALVES = 128-pixel halves of
 // the work item (the second half reuses the weight tile), KSTEPS = 16-channel K steps of this chunk.
 template <int TAPS, int HALVES, int KSTEPS>
-__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a_lo, uint32_t b_base, uint32_t b_dy, uint32_t idesc, uint32_t first) {
-  constexpr uint32_t kHi = smem_desc_hi(1024);            // weights: 8-row groups 1024 B apart
+__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a_lo, uint32_t b_base, uint32_t b_dy, uint32_t idesc, uint32_t first,
+                                            uint32_t kHi /* weight descriptor hi word: 128-byte rows (SBO 1024) or 64-byte rows (SBO 512, 64B swizzle) */) {
   constexpr uint32_t kHiA = smem_desc_hi(kABoxW * 128);   // activations: 8 pixels of a patch row, rows 1280 B apart
   constexpr int ord[3] = {1, 0, 2};
 #pragma unroll
@@ -375,7 +378,7 @@ __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a_lo, uint
 // barrier wait, the unrolled MMAs, one commit and the ring bookkeeping.  Executed by the whole MMA warp (uniform).
 template <int TAPS, int HALVES, int KSTEPS>
 __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_lo, uint32_t smemW_addr, uint32_t b_dy, uint32_t idesc, bool fresh,
-                                            int g, int& gw, uint32_t& fW_bits, uint64_t* fullW, uint64_t* emptyW, bool no_mma) {
+                                            int g, int& gw, uint32_t& fW_bits, uint64_t* fullW, uint64_t* emptyW, bool no_mma, uint32_t b_hi) {
   constexpr int kStages = 9 / TAPS;
   constexpr int ord[3] = {1, 0, 2};
 #pragma unroll
@@ -389,7 +392,7 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_lo, uint
     mbar_wait(&fullW[gw], (fW_bits >> gw) & 1u);
     // (no tcgen05 fence here: the mbarrier wait orders the TMA writes before the MMAs that read them)
     if (elect_one_sync()) {
-      if (!no_mma) issue_stage<TAPS, HALVES, KSTEPS>(d_tmem, a1, b_base, b_dy, idesc, (fresh && d == 0) ? 0u : 1u);
+      if (!no_mma) issue_stage<TAPS, HALVES, KSTEPS>(d_tmem, a1, b_base, b_dy, idesc, (fresh && d == 0) ? 0u : 1u, b_hi);
       umma_commit(&emptyW[gw]);  // one commit per stage: frees its weight granules and (last stage of a chunk) the activation tile
     }
     __syncwarp();
@@ -493,7 +496,9 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const CUtensorMap* tmA = &layers[li].tmA;
       const int tiles_per_img = tiles_x * tiles_y;
       const int num_work = (tile_hi - tile_lo) * col_groups;
-      const int wbytes = w_taps * n_cols * 128;              // one weight stage = w_taps tap tiles, fetched by ONE bulk copy
+      const int k32 = static_cast<int>((la.y >> 11) & 1);    // 64-byte weight rows (32 channels)
+      const int tap_rows = k32 ? (n_cols >> 1) : n_cols;     // 128-byte units of one tap tile
+      const int wbytes = w_taps * tap_rows * 128;            // one weight stage = w_taps tap tiles, fetched by ONE bulk copy
       const int g = (wbytes + kWGranule - 1) / kWGranule;    // W granules per stage
       const int wsteps = 9 / w_taps;                         // stages per K chunk (1 or 3)
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
@@ -579,7 +584,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
                 mbar_arrive(&fullW[gw]);
               } else {
                 mbar_arrive_expect_tx(&fullW[gw], wbytes);
-                const long long row = w_row0 + (static_cast<long long>(c * col_groups + (w % col_groups)) * 9 + tap_row) * n_cols;
+                const long long row = w_row0 + (static_cast<long long>(c * col_groups + (w % col_groups)) * 9 + tap_row) * tap_rows;
                 bulk_load_1d(smemW + gw * kWGranule, packed_w + row * 128, wbytes, &fullW[gw]);
               }
             }
@@ -630,9 +635,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int acc_col0 = la.y & 0xFF, acc_first = (la.y >> 8) & 1, acc_hold = (la.y >> 9) & 1;
       const bool has_epi = ((la.y >> 10) & 1) != 0;  // deferred partial-sum layers have no epilogue: nothing to hand over
       const int num_work = (tile_hi - tile_lo) * col_groups;
-      const int g = (w_taps * n_cols * 128 + kWGranule - 1) / kWGranule;
+      const int k32 = static_cast<int>((la.y >> 11) & 1);
+      const int g = (w_taps * n_cols * (k32 ? 64 : 128) + kWGranule - 1) / kWGranule;
       const uint32_t idesc = make_idesc_bf16(128, n_cols, 0, 0);
-      const uint32_t b_dy = static_cast<uint32_t>(n_cols) * 8;  // (n_cols * 128 B) >> 4
+      const uint32_t b_dy = static_cast<uint32_t>(n_cols) * (k32 ? 4u : 8u);  // bytes of one tap tile >> 4
+      const uint32_t b_hi = k32 ? smem_desc_hi_sw64(512) : smem_desc_hi(1024);
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
       if (pf) prof[8] += clock64() - _tp + (v == 0x7fffffff ? n_cols + idesc : 0);  // entry parameter fetch (forces the loads to be complete)
       for (int w = v; w < num_work; w += static_cast<int>(grid), ++it) {
@@ -657,7 +664,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           const uint32_t a_lo = smem_desc_lo(smem_u32(smem + sa * kASlot), 16);
           const bool fresh = acc_first && c == 0;  // the very first MMA of a fresh item overwrites the accumulators
           const long long _ti = pf ? clock64() : 0;
-#define B200SR_CHUNK(T, H, K) issue_chunk<T, H, K>(d_tmem, a_lo, smemW_addr, b_dy, idesc, fresh, g, gw, fW_bits, fullW, emptyW, no_mma)
+#define B200SR_CHUNK(T, H, K) issue_chunk<T, H, K>(d_tmem, a_lo, smemW_addr, b_dy, idesc, fresh, g, gw, fW_bits, fullW, emptyW, no_mma, b_hi)
 #define B200SR_CHUNK_K(T, H)                                   \
   switch (ksteps) {                                            \
     case 4: B200SR_CHUNK(T, H, 4); break;                      \

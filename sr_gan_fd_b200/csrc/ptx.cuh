@@ -187,6 +187,8 @@ __device__ __forceinline__ void st_global_f32(void* p, float a) { asm volatile("
 __device__ __forceinline__ void st_global_u8(void* p, uint32_t a) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(a)); }
 // hi / lo words of a 128B-swizzle descriptor
 __host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+// ... the same for 64-byte rows under the 64B swizzle (layout type 4): K-major tiles of 32 bf16 channels
+__host__ __device__ constexpr uint32_t smem_desc_hi_sw64(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (4u << 29); }
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
   return ((smem_addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
 }
