@@ -24,26 +24,53 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
+STAMP_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash() -> str:
+    """SHA-256 over the sources, headers and compiler flags the library is built from."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     for f in SOURCES + HEADERS:
         p = os.path.join(CSRC, f)
-        if os.path.exists(p) and os.path.getmtime(p) > t:
-            return True
-    return False
+        h.update(f.encode())
+        with open(p, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def is_stale() -> bool:
+    """The library is current iff it exists and was built from exactly these sources (hash stamp next to it; file times are
+    meaningless after a checkout or a copy to the GPU box)."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP_PATH):
+        return True
+    with open(STAMP_PATH) as fh:
+        return fh.read().strip() != source_hash()
+
+
+LAST_BUILD = {"ran_nvcc": False, "reason": "not called"}
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu -> sr_gan_fd_b200/libb200sr.so.  Returns the library path."""
+    """Compile csrc/*.cu -> sr_gan_fd_b200/libb200sr.so.  Returns the library path; LAST_BUILD says whether nvcc ran."""
     if not force and not is_stale():
+        LAST_BUILD.update(ran_nvcc=False, reason="library matches the source hash " + source_hash()[:12])
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    try:
+        nvcc = _nvcc()
+    except RuntimeError:
+        if os.path.exists(LIB_PATH) and not force:  # GPU box without a toolchain: the shipped library is what there is
+            LAST_BUILD.update(ran_nvcc=False, reason="nvcc not found; using the shipped library (source hash NOT verified)")
+            return LIB_PATH
+        raise
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    with open(STAMP_PATH, "w") as fh:
+        fh.write(source_hash())
+    LAST_BUILD.update(ran_nvcc=True, reason="forced" if force else "sources changed (hash stamp missing or different)")
     if verbose:
         print(res.stderr)
     return LIB_PATH

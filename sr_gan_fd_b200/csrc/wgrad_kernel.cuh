@@ -211,178 +211,4 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Cluster variant: the three horizontal-tap CTAs of one pixel split form a thread-block cluster of 3.  They need the
-// same dY tile and the same X rows shifted by one pixel, so every box is fetched ONCE per cluster and multicast into
-// all three CTAs' shared memory (the X box carries a one-pixel halo on both sides, 10 instead of 8 pixels wide; tap dx
-// reads it through a descriptor that starts dx pixels in, rows 1280 B apart).  L2->SM traffic per tile drops from
-// 3 x (X + dY) to (1.25 X + dY): the non-cluster kernel moves 5.8 TB/s through the L2 and is bound by it.
-// Pipeline: CTA r issues boxes r, r+3, ... of the stage; each CTA arms its own full barrier with the stage's total
-// bytes; a stage is free again when the MMA warps of ALL three CTAs have committed it (multicast commit, count 3).
-// The bias-gradient problem (one "tap") runs in the same grid without multicast: its clusters are three independent CTAs.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kWgXcBytes = kWgXRows * kABoxW * 128;   // 23040 B: haloed X tile, 10 pixels wide
-constexpr int kWgXcSlot = 23552;                      // ... in a 1024-byte-multiple slot
-
-__host__ __device__ inline int wgrad_cluster_stage_bytes(const WgradParams& p) {
-  return (p.bias_mode ? 0 : p.a_blocks * kWgXcSlot) + p.n_blocks * kWgBBytes;
-}
-__host__ __device__ inline int wgrad_cluster_tx_bytes(const WgradParams& p) {
-  return (p.bias_mode ? 0 : p.a_blocks * kWgXcBytes) + p.n_blocks * kWgBBytes;
-}
-
-__global__ void __launch_bounds__(kWgThreads, 1)
-wgrad3x3_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
-                        const __grid_constant__ WgradBatch batch) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int kRing = kWgSmemBytes - 1024 - kWgOnesBytes - 1024;
-  uint8_t* ones = smem + kRing;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRing + kWgOnesBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + 4;
-  uint64_t* done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int rank = static_cast<int>(cluster_ctarank());  // 0..2
-  int pj = 0;
-  while (pj + 1 < batch.num_problems && static_cast<int>(blockIdx.x) >= batch.cta_begin[pj + 1]) ++pj;
-  const WgradParams& p = batch.prob[pj];
-  const int local = blockIdx.x - batch.cta_begin[pj];
-  const bool shared_loads = !p.bias_mode;             // the cluster's three CTAs are the three dx taps of one split
-  const int dxi = p.bias_mode ? 1 : rank;
-  const int split = p.bias_mode ? local : local / 3;
-  const int nacc = p.bias_mode ? 1 : 3;
-  const int stage_bytes = wgrad_cluster_stage_bytes(p);
-  const int tx_bytes = wgrad_cluster_tx_bytes(p);
-  int S = kRing / stage_bytes;
-  if (S > 4) S = 4;
-  const int b_off = p.bias_mode ? 0 : p.a_blocks * kWgXcSlot;
-  const uint16_t mask = shared_loads ? uint16_t(7) : uint16_t(1u << rank);
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tmX);
-    prefetch_tensormap(&tmDY);
-    for (int s = 0; s < 4; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], shared_loads ? 3 : 1);
-    }
-    mbar_init(done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc_imm<512>(tmem_slot);
-  if (p.bias_mode) {
-    for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += kWgThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;  // bf16 1.0 x2
-    fence_proxy_async_smem();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // nobody multicasts into, or arrives on, a peer whose barriers are not initialised yet
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int tiles_per_img = batch.tiles_x * batch.tiles_y;
-  const bool has_work = split < batch.num_tiles;
-
-  if (warp == 0) {
-    int s = 0;
-    uint32_t ph = 0;
-    const int nbox = (p.bias_mode ? 0 : p.a_blocks) + p.n_blocks;
-    for (int tile = split; tile < batch.num_tiles; tile += p.splits) {
-      const int n = tile / tiles_per_img;
-      const int t2 = tile - n * tiles_per_img;
-      const int ty = t2 / batch.tiles_x;
-      const int x0 = (t2 - ty * batch.tiles_x) * kTileW;
-      const int y0 = ty * kWgTileH;
-      mbar_wait(&empty[s], ph ^ 1);  // all consumers of this stage (in every CTA of the cluster) are done with it
-      if (elect_one_sync()) {
-        uint8_t* st = smem + s * stage_bytes;
-        mbar_arrive_expect_tx(&full[s], tx_bytes);
-        for (int i = 0; i < nbox; ++i) {
-          if (shared_loads && (i % 3) != rank) continue;  // box i of the stage is fetched by CTA i mod 3 for the whole cluster
-          if (!p.bias_mode && i < p.a_blocks)
-            tma_load_4d_mc(st + i * kWgXcSlot, &tmX, &full[s], p.a_c0 + 64 * i, x0 - 1, y0 - 1, n, mask);
-          else {
-            const int j = i - (p.bias_mode ? 0 : p.a_blocks);
-            tma_load_4d_mc(st + b_off + j * kWgBBytes, &tmDY, &full[s], p.b_c0 + 64 * j, x0, y0, n, mask);
-          }
-        }
-      }
-      __syncwarp();
-      if (++s == S) { s = 0; ph ^= 1; }
-    }
-  } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, p.n_cols, 1, 1);  // both operands MN-major
-    constexpr uint32_t kHiB = smem_desc_hi(1024);                  // dY: 8-pixel groups 1024 B apart
-    constexpr uint32_t kHiX = smem_desc_hi(kABoxW * 128);          // X: 8-pixel groups one 10-pixel row (1280 B) apart
-    int s = 0;
-    uint32_t ph = 0;
-    uint32_t acc = 0;
-    for (int tile = split; tile < batch.num_tiles; tile += p.splits) {
-      mbar_wait(&full[s], ph);
-      tcgen05_fence_after();
-      if (elect_one_sync()) {
-        const uint32_t a0 = smem_u32(smem + s * stage_bytes);
-        const uint32_t b_lo = smem_desc_lo(a0 + b_off, kWgBBytes);  // LBO = stride between 64-ch N blocks
-        if (p.bias_mode) {
-          const uint32_t o_lo = smem_desc_lo(smem_u32(ones), 2048);  // every K step reads the same all-ones tile
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) umma_bf16_ss_lohi2(tmem_base, o_lo, kHiB, b_lo + ks * 128, kHiB, idesc, (ks == 0) ? acc : 1u);
-        } else {
-          const uint32_t a_lo = smem_desc_lo(a0 + dxi * 128, kWgXcSlot);  // LBO = stride between the two 64-ch M blocks
-#pragma unroll
-          for (int dyi = 0; dyi < 3; ++dyi) {
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)  // 16 pixels (two 8-pixel runs of consecutive tile rows) per UMMA
-              umma_bf16_ss_lohi2(tmem_base + dyi * p.n_cols, a_lo + (dyi + 2 * ks) * (kABoxW * 8), kHiX, b_lo + ks * 128, kHiB, idesc,
-                                 (ks == 0) ? acc : 1u);
-          }
-        }
-        umma_commit_mc(&empty[s], mask);
-      }
-      __syncwarp();
-      acc = 1;
-      if (++s == S) { s = 0; ph ^= 1; }
-    }
-    if (elect_one_sync()) umma_commit(done);
-    __syncwarp();
-  } else if (has_work) {
-    // epilogue: flush the accumulators with 16-byte fp32 vector reductions into [tap][ci][co] staging tensors
-    const int q = warp & 3;
-    const int m = q * 32 + lane;  // accumulator row = input channel a_c0 + m
-    mbar_wait(done, 0);
-    tcgen05_fence_after();
-    for (int dyi = 0; dyi < nacc; ++dyi) {
-      const int tap = p.bias_mode ? 0 : dyi * 3 + dxi;
-      for (int c0 = 0; c0 < p.n_cols; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + dyi * p.n_cols + c0, r);
-        tmem_ld_wait();
-        int sgi = 0;
-        while (sgi < p.num_seg - 1 && c0 >= p.seg[sgi].col_end) ++sgi;
-        const WgradSegment& sg = p.seg[sgi];
-        const int co = c0 - sg.col_begin;
-        const int ci = sg.ci0 + m;
-        if (c0 >= sg.col_begin && c0 < sg.col_end && ci < sg.ci_total) {
-          float* dst = sg.out + ((static_cast<long long>(tap) * (sg.co_pad >> 2) + (co >> 2)) * sg.ci_total + ci) * 4;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (co + 4 * j < sg.co_pad)
-              red_add_v4_f32(dst + static_cast<long long>(j) * sg.ci_total * 4, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        }
-      }
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // no CTA may exit while a peer can still multicast into it or arrive on its barriers
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc_imm<512>(tmem_base);
-  }
-}
-
 }  // namespace b200sr
