@@ -126,6 +126,18 @@ int b200sr_fused_adam_ema(const void* tensor_table, const int32_t* block_tensor,
                           float beta1, float beta2, float eps, float weight_decay, float* step, float ema_decay, int ema_copy,
                           const float* grad_scale, const float* found_inf, b200sr_stream stream);
 
+/* ---- next to the path: the evaluation epilogue of validate() / test_*.py / inference.py -------
+ * PSNR / SSIM on the Y channel as ESRGAN/image_quality_assessment.py:361-541 computes them (crop_border, rgb_to_ycbcr_torch with
+ * only_use_y_channel, fp64, 11x11 gaussian window = outer product of window11, valid convolution), one pass per metric.
+ * raw, dst: [n, 3, h, w] fp32 RGB in [0, 1].  Outputs are per-image SUMS (device doubles, either may be NULL):
+ * psnr_sqerr_sum[i] = sum over the cropped frame of (255 Y_raw - 255 Y_dst)^2   -> PSNR = 10 log10(255^2 / (sum / count + 1e-8))
+ * ssim_map_sum[i]   = sum of the SSIM map over its (h - 2 crop - 10) x (w - 2 crop - 10) positions -> SSIM = sum / count */
+int b200sr_iqa_psnr_ssim_y(const float* raw, const float* dst, int n, int h, int w, int crop_border, const double* window11,
+                           double* psnr_sqerr_sum, double* ssim_map_sum, b200sr_stream stream);
+/* ESRGAN/imgproc.py:160-183 tensor_to_image: x [c, h, w] fp32 -> out_hwc [h, w, c] uint8 = trunc(clamp(255 x, 0, 255));
+ * range_norm: x <- (x + 1) / 2 first; half: round to fp16 and multiply in fp16 as the reference does with half=True */
+int b200sr_tensor_to_image_u8(const float* x, int c, int h, int w, int range_norm, int half, uint8_t* out_hwc, b200sr_stream stream);
+
 const char* b200sr_last_error(void);
 int b200sr_version(void);
 /* timing probes for profiling only (results become wrong unless noted): bit 0 (1) no epilogue traffic, bit 1 (2) no MMAs,

@@ -28,12 +28,12 @@ def _stub_basicsr() -> None:
     sys.modules.update({"basicsr": basicsr, "basicsr.utils": utils, "basicsr.utils.registry": registry})
 
 
-def load_reference_model(folder: str):
+def load_reference_model(folder: str, module: str = "model"):
     root = os.environ.get("SRGANFD_REFERENCE", "/root/reference")
-    path = os.path.join(root, folder, "model.py")
+    path = os.path.join(root, folder, module + ".py")
     if not os.path.isfile(path):
         return None
-    name = f"_srganfd_reference_{folder.replace('-', '_').lower()}_model"
+    name = f"_srganfd_reference_{folder.replace('-', '_').lower()}_{module}"
     if name in sys.modules:
         return sys.modules[name]
     sys.dont_write_bytecode = True
@@ -54,8 +54,8 @@ def load_reference_model(folder: str):
     return mod
 
 
-def export(namespace: dict, folder: str, overrides: dict) -> None:
-    ref = load_reference_model(folder)
+def export(namespace: dict, folder: str, overrides: dict, module: str = "model") -> None:
+    ref = load_reference_model(folder, module)
     if ref is not None:
         for k, v in ref.__dict__.items():
             if not k.startswith("__"):

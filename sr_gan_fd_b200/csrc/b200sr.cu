@@ -21,6 +21,7 @@
 #include "aux_kernels.cuh"
 #include "conv_kernel.cuh"
 #include "optim_kernels.cuh"
+#include "iqa_kernels.cuh"
 #include "wgrad_kernel.cuh"
 
 using namespace b200sr;
@@ -1517,6 +1518,41 @@ int b200sr_fused_adam_ema(const void* tensor_table, const int32_t* block_tensor,
   fused_adam_ema_kernel<<<(unsigned)total_blocks, kOptBlock, 0, (cudaStream_t)stream>>>((const OptTensor*)tensor_table, n_tensors, h);
   CUDA_TRY(cudaGetLastError());
   adam_step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step, found_inf);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ evaluation epilogue
+int b200sr_iqa_psnr_ssim_y(const float* raw, const float* dst, int n, int h, int w, int crop_border, const double* window11,
+                           double* psnr_sqerr_sum, double* ssim_map_sum, b200sr_stream stream) {
+  if (!raw || !dst || !window11 || (!psnr_sqerr_sum && !ssim_map_sum)) return fail(B200SR_ERR_INVALID, "null argument");
+  if (n < 1 || crop_border < 0 || h - 2 * crop_border < 11 || w - 2 * crop_border < 11)
+    return fail(B200SR_ERR_INVALID, "frame %dx%d with crop %d is smaller than the 11x11 SSIM window", h, w, crop_border);
+  cudaStream_t st = (cudaStream_t)stream;
+  IqaParams p;
+  p.raw = raw; p.dst = dst; p.N = n; p.H = h; p.W = w; p.crop = crop_border;
+  for (int i = 0; i < 11; ++i) p.win[i] = window11[i];
+  p.psnr_sum = psnr_sqerr_sum; p.ssim_sum = ssim_map_sum;
+  const int hc = h - 2 * crop_border, wc = w - 2 * crop_border;
+  if (psnr_sqerr_sum) {
+    CUDA_TRY(cudaMemsetAsync(psnr_sqerr_sum, 0, sizeof(double) * n, st));
+    long long blocks = ((long long)hc * wc + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    iqa_psnr_y_kernel<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (ssim_map_sum) {
+    CUDA_TRY(cudaMemsetAsync(ssim_map_sum, 0, sizeof(double) * n, st));
+    iqa_ssim_y_kernel<<<dim3((unsigned)((wc - 10 + 15) / 16), (unsigned)((hc - 10 + 15) / 16), (unsigned)n), dim3(16, 16), 0, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+int b200sr_tensor_to_image_u8(const float* x, int c, int h, int w, int range_norm, int half, uint8_t* out_hwc, b200sr_stream stream) {
+  if (!x || !out_hwc || c < 1 || c > 4 || h < 1 || w < 1) return fail(B200SR_ERR_INVALID, "bad argument");
+  const long long plane = (long long)h * w;
+  tensor_to_image_u8_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, c, h, w, range_norm, half, out_hwc);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -111,38 +111,51 @@ class GeneratorRuntime:
         return buf
 
 
+class _Launched:
+    """What one enqueued native forward leaves behind (handed to the autograd Function as a non-tensor argument)."""
+    __slots__ = ("y", "plan", "rt", "workspace", "packed", "pack_slot", "pack_serial")
+
+
+def _launch_forward(module, rt: "GeneratorRuntime", x: torch.Tensor, training: bool, params) -> _Launched:
+    """Enqueue the whole native forward NOW.  It runs before the autograd bookkeeping of the 702-input Function, so the GPU
+    is already working while the host builds the graph (the host path in front of the first kernel is what an end-to-end
+    step with a per-step ``loss.item()`` pays in full)."""
+    lib = _lib.load()
+    desc = module.net_desc()
+    n, c, h, w = x.shape
+    if c != desc["in_channels"]:
+        raise RuntimeError(f"expected {desc['in_channels']} input channels, got {c}")
+    st = _Launched()
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        plan = rt.plan(desc, x.device, n, h, w, training)
+        packed = rt.packed_weights(plan, params, stream, rt.cur_key)
+        workspace = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=x.device)
+        y = torch.empty((n, plan.out_channels, h * plan.scale, w * plan.scale), dtype=torch.float32, device=x.device)
+        strides = (C.c_int64 * 4)(*x.stride())
+        _lib.check(lib.b200sr_forward(plan.handle, C.c_void_p(x.data_ptr()), _DTYPES[x.dtype], strides,
+                                      C.c_void_p(packed.data_ptr()), C.c_void_p(workspace.data_ptr()),
+                                      C.c_void_p(y.data_ptr()), C.c_void_p(stream)))
+    st.y, st.plan, st.rt, st.workspace, st.packed = y, plan, rt, workspace, packed
+    st.pack_slot = (training, plan.pack_layout)
+    st.pack_serial = rt.pack_serial[st.pack_slot]
+    return st
+
+
 class _RRDBNetFn(torch.autograd.Function):
+    """Autograd node of one (already enqueued) training forward: keeps the workspace alive and runs the native backward."""
+
     @staticmethod
-    def forward(ctx, module, x, training, *params):
-        lib = _lib.load()
-        rt: GeneratorRuntime = module._runtime()
-        desc = module.net_desc()
-        n, c, h, w = x.shape
-        if c != desc["in_channels"]:
-            raise RuntimeError(f"expected {desc['in_channels']} input channels, got {c}")
-        with torch.cuda.device(x.device):
-            stream = torch.cuda.current_stream().cuda_stream
-            plan = rt.plan(desc, x.device, n, h, w, training)
-            packed = rt.packed_weights(plan, params, stream, rt.cur_key)
-            workspace = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=x.device)
-            y = torch.empty((n, plan.out_channels, h * plan.scale, w * plan.scale), dtype=torch.float32, device=x.device)
-            strides = (C.c_int64 * 4)(*x.stride())
-            _lib.check(lib.b200sr_forward(plan.handle, C.c_void_p(x.data_ptr()), _DTYPES[x.dtype], strides,
-                                          C.c_void_p(packed.data_ptr()), C.c_void_p(workspace.data_ptr()),
-                                          C.c_void_p(y.data_ptr()), C.c_void_p(stream)))
-        if training:
-            ctx.plan = plan
-            ctx.rt = rt
-            ctx.workspace = workspace
-            ctx.packed = packed
-            ctx.pack_slot = (True, plan.pack_layout)
-            ctx.pack_serial = rt.pack_serial[ctx.pack_slot]
-            ctx.x_keepalive = x
-            ctx.x_meta = (tuple(x.shape), x.dtype)
-        else:
-            ctx.plan = None
-            ctx.mark_non_differentiable(y)
-        return y
+    def forward(ctx, launched: _Launched, x, *params):
+        ctx.plan = launched.plan
+        ctx.rt = launched.rt
+        ctx.workspace = launched.workspace
+        ctx.packed = launched.packed
+        ctx.pack_slot = launched.pack_slot
+        ctx.pack_serial = launched.pack_serial
+        ctx.x_keepalive = x
+        ctx.x_meta = (tuple(x.shape), x.dtype)
+        return launched.y
 
     @staticmethod
     def backward(ctx, dy):
@@ -177,8 +190,8 @@ class _RRDBNetFn(torch.autograd.Function):
         if dx is not None and ctx.x_meta[1] != torch.float32:
             dx = dx.to(ctx.x_meta[1])
         pieces = flat.split(rt.param_numels)  # one call: 702 views of the flat gradient buffer, state_dict order
-        grads = [t.view(shp) if need[3 + i] else None for i, (t, shp) in enumerate(zip(pieces, rt.param_shapes))]
-        return (None, dx, None, *grads)
+        grads = [t.view(shp) if need[2 + i] else None for i, (t, shp) in enumerate(zip(pieces, rt.param_shapes))]
+        return (None, dx, *grads)
 
 
 def generator_forward(module, x: torch.Tensor) -> torch.Tensor:
@@ -213,7 +226,10 @@ def generator_forward(module, x: torch.Tensor) -> torch.Tensor:
         raise RuntimeError("generator parameters must be contiguous fp32 tensors on the input's device")
     rt.cur_key = (tuple([p._version for p in params]), ptrs)
     training = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
-    return _RRDBNetFn.apply(module, x, training, *params)
+    launched = _launch_forward(module, rt, x, training, params)
+    if not training:
+        return launched.y  # nothing to differentiate: no autograd node at all
+    return _RRDBNetFn.apply(launched, x, *params)
 
 
 def eager_forward(module, x: torch.Tensor) -> torch.Tensor:

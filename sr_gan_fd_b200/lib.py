@@ -48,6 +48,9 @@ SIGNATURES = {
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200sr_fused_adam_ema": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                         C.c_float, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200sr_iqa_psnr_ssim_y": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
+    "b200sr_tensor_to_image_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b200sr_last_error": (C.c_char_p, []),
     "b200sr_version": (C.c_int, []),
     "b200sr_debug_set": (None, [C.c_int]),

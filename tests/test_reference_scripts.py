@@ -106,7 +106,7 @@ def test_train_rrdbnet_script_cuda(tmp_path):
     args = []
     for k, v in sets.items():
         args += ["--set", f"rrdbnet_config.{k}={v!r}"]
-    log = _run(args + ["ESRGAN", "train_rrdbnet.py"], cwd=str(tmp_path))
+    log = _run(["--iqa"] + args + ["ESRGAN", "train_rrdbnet.py"], cwd=str(tmp_path))  # validate() also uses the fused PSNR / SSIM
     assert "Build `rrdbnet_x4` model successfully." in log
     assert "Epoch: [1][3/3]" in log or "[3/3]" in log, log[-1500:]
     ck = torch.load(str(tmp_path / "results" / "RRDBNet_x4" / "g_last.pth.tar"), map_location="cpu")
