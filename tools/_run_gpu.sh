@@ -1,11 +1,4 @@
-mkdir -p gpurun_out/r2
-export SRGANFD_REFERENCE=$GRAFT_REPO_ROOT/baseline/_ref
-TR() { n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 "$@"; }
-TR 8 bench.py --gpus 8 --steps 20 --warmup 5 2> gpurun_out/r2/train_n8.err | tail -1 > gpurun_out/r2/train_n8.json; head -c 200 gpurun_out/r2/train_n8.json; echo
-B200SR_DP_OVERLAP=1 TR 8 bench.py --gpus 8 --steps 20 --warmup 5 2> /dev/null | tail -1 > gpurun_out/r2/train_n8_overlap.json; head -c 200 gpurun_out/r2/train_n8_overlap.json; echo
-for n in 2 4 8; do
-  TR $n bench.py --workload c4 --gpus $n --steps 5 --warmup 3 2> gpurun_out/r2/c4_n$n.err | tail -1 > gpurun_out/r2/c4_n$n.json; head -c 260 gpurun_out/r2/c4_n$n.json; echo
+for sw in "10 3" "20 5" "40 5"; do set -- $sw
+python bench.py --steps $1 --warmup $2 --no-cpu-baseline --no-library-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('steps $1', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['ms_per_step'],3))"
 done
-TR 8 tools/gan_step.py --generator b200 --steps 10 2> gpurun_out/r2/gan_b200_n8.err | tail -1 > gpurun_out/r2/gan_b200_n8.json; head -c 330 gpurun_out/r2/gan_b200_n8.json; echo
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-library-baseline 2>/dev/null > gpurun_out/r2/train_n1_samebox.json; head -c 200 gpurun_out/r2/train_n1_samebox.json; echo
-python -m pytest tests/test_kernels_gpu.py -x -q -m gpu 2>&1 | tail -2
+python tools/probe_host_e2e.py 2>&1 | tail -15
