@@ -158,8 +158,8 @@ struct b200sr_plan {
   long long o_dyp = 0, o_g3 = 0, o_gt = 0, o_gtb = 0, o_gr = 0, o_gc1 = 0, o_gc2 = 0, o_go1 = 0;
   std::vector<long long> o_dyb;      // output-gradient buffers [dY5|dY4|dY3|dY2|dY1] of the dense blocks, one per block: the whole
                                       // backward is ONE data-gradient chain, the weight gradients run after it
-  cudaStream_t side_stream = nullptr; // second stream for the weight-gradient launches (their tails / heads overlap)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side_stream[3] = {nullptr, nullptr, nullptr};  // extra streams for the weight-gradient launches (tails / heads overlap)
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   std::vector<long long> o_gu;
   bool reassoc = true;                // dense blocks re-associated by input slice ("windowed": convs 1-4 resident in TMEM, 128 columns per
                                       // 128-pixel half, conv5 spread over filler layers); B200SR_REASSOC=0 or a frame with more 8x32 items
@@ -1121,14 +1121,16 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
   // Weight-gradient launches of different dense blocks are independent of one another: once the data-gradient chain is
   // done they alternate between the caller's stream and a side stream, so the flush tail of one launch overlaps the ramp-up
   // of the next (each launch fills the GPU with one CTA per SM).  Everything that consumes their results joins first.
-  static const bool two_streams = [] { const char* e = getenv("B200SR_WGRAD_STREAMS"); return !(e && atoi(e) == 1); }();
-  const bool alternate = two_streams && (&steps == &P.bwd);
+  static const int nstreams = [] { const char* e = getenv("B200SR_WGRAD_STREAMS"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+  const bool alternate = nstreams > 1 && (&steps == &P.bwd);
   bool forked = false, side_dirty = false;
   int wcount = 0;
   auto join = [&]() -> int {
     if (side_dirty) {
-      CUDA_TRY(cudaEventRecord(P.ev_join, P.side_stream));
-      CUDA_TRY(cudaStreamWaitEvent(st, P.ev_join, 0));
+      for (int k = 0; k < nstreams - 1; ++k) {
+        CUDA_TRY(cudaEventRecord(P.ev_join[k], P.side_stream[k]));
+        CUDA_TRY(cudaStreamWaitEvent(st, P.ev_join[k], 0));
+      }
       side_dirty = false;
     }
     return 0;
@@ -1153,17 +1155,20 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
       case ST_WGRAD: {
         cudaStream_t ws = st;
         if (alternate) {
-          if (!P.side_stream) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&P.side_stream, cudaStreamNonBlocking));
+          if (!P.ev_fork) {
+            for (int k = 0; k < 3; ++k) {
+              CUDA_TRY(cudaStreamCreateWithFlags(&P.side_stream[k], cudaStreamNonBlocking));
+              CUDA_TRY(cudaEventCreateWithFlags(&P.ev_join[k], cudaEventDisableTiming));
+            }
             CUDA_TRY(cudaEventCreateWithFlags(&P.ev_fork, cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&P.ev_join, cudaEventDisableTiming));
           }
           if (!forked) {  // the side stream starts after everything enqueued so far (the data-gradient chain)
             CUDA_TRY(cudaEventRecord(P.ev_fork, st));
-            CUDA_TRY(cudaStreamWaitEvent(P.side_stream, P.ev_fork, 0));
+            for (int k = 0; k < nstreams - 1; ++k) CUDA_TRY(cudaStreamWaitEvent(P.side_stream[k], P.ev_fork, 0));
             forked = true;
           }
-          if (wcount++ & 1) { ws = P.side_stream; side_dirty = true; }
+          const int lane_ = wcount++ % nstreams;
+          if (lane_ > 0) { ws = P.side_stream[lane_ - 1]; side_dirty = true; }
         }
         int rc = launch_wgrad(s, P.maps[s.xmap], P.maps[s.dymap], b, ws);
         if (rc) return rc;
@@ -1263,9 +1268,11 @@ void b200sr_plan_destroy(b200sr_plan* p) {
   if (p->d_unpack_ops) cudaFree(p->d_unpack_ops);
   if (p->d_layers) cudaFree(p->d_layers);
   if (p->d_entries) cudaFree(p->d_entries);
-  if (p->side_stream) cudaStreamDestroy(p->side_stream);
+  for (int k = 0; k < 3; ++k) {
+    if (p->side_stream[k]) cudaStreamDestroy(p->side_stream[k]);
+    if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]);
+  }
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-  if (p->ev_join) cudaEventDestroy(p->ev_join);
   if (p->d_layer_rec) cudaFree(p->d_layer_rec);
   if (p->d_entry_rec) cudaFree(p->d_entry_rec);
   if (p->d_counters) cudaFree(p->d_counters);
