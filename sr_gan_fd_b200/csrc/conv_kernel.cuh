@@ -23,6 +23,7 @@
 #pragma once
 #include "ptx.cuh"
 
+
 namespace b200sr {
 
 constexpr int kTileW = 8;
@@ -712,8 +713,11 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       TL_MARK(11);
       if (lane == 0) {
         if (has_epi && v < num_work) {  // CTAs without work in this entry have nothing to publish and are not counted
-          if (!(debug & 256)) __threadfence();  // (bit 256: timing experiment only)
-          atomicAdd(counters + e, 1u);
+          // release: the epilogue warps' stores (ordered before this thread by the mbarrier hand-over) become visible at gpu
+          // scope before the counter update -- one red.release instead of __threadfence() (fence.sc) + atomicAdd
+          // (same-box A/B: 12.14 -> 12.08 ms/step; bit 256 of the timing probes: plain relaxed add)
+          if (debug & 256) atomicAdd(counters + e, 1u);
+          else asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counters + e), "r"(1u) : "memory");
         }
         *sig_done = e + 1;
       }
