@@ -138,6 +138,32 @@ int b200sr_iqa_psnr_ssim_y(const float* raw, const float* dst, int n, int h, int
  * range_norm: x <- (x + 1) / 2 first; half: round to fp16 and multiply in fp16 as the reference does with half=True */
 int b200sr_tensor_to_image_u8(const float* x, int c, int h, int w, int range_norm, int half, uint8_t* out_hwc, b200sr_stream stream);
 
+/* ---- next to the path: VGG19 perceptual features / content loss -----------------------------------
+ * The sixteen 3x3 convs of torchvision vgg19().features (up to conv5_4, index `last_conv` 0..15) on the chain kernel, input
+ * normalisation, ReLU, 2x2 max-pools, the L1 feature loss of ESRGAN/model.py:246-292 / BSRGAN/model.py:501-554 and (optionally) its
+ * gradient w.r.t. the first `grad_images` images.  The batch holds the sr images followed by the gt images (batch = 2 x pairs).
+ * Plans share b200sr_workspace_bytes / b200sr_packed_bytes / b200sr_pack_weights (params: conv l weight at 2l, bias at 2l+1, fp32
+ * OIHW) / b200sr_plan_destroy with the generator plans. */
+typedef struct b200sr_vgg_desc {
+  int32_t batch, height, width; /* images (sr then gt), input geometry */
+  int32_t last_conv;            /* last conv to evaluate (0..15; 15 = conv5_4 = torchvision features.34) */
+  int32_t feat_mask;            /* bit l set: keep conv l's output as fp32 (a feature node): BEFORE the ReLU for l == last_conv, AFTER it
+                                 * for l < last_conv -- what torchvision's create_feature_extractor hands the reference, whose
+                                 * in-place ReLUs overwrite every extracted conv output except the one that ends the graph */
+  int32_t grad_conv;            /* -1, or the conv whose L1 feature loss is differentiated w.r.t. the input images */
+  int32_t grad_images;          /* images (from 0) that receive a gradient: the sr half */
+  float mean[3], std[3];        /* transforms.Normalize of the input */
+} b200sr_vgg_desc;
+int b200sr_vgg_plan_create(const b200sr_vgg_desc* desc, b200sr_plan** out);
+/* x: [batch, 3, height, width] fp32 in [0, 1] with element strides x_strides[4] */
+int b200sr_vgg_forward(b200sr_plan* plan, const float* x, const int64_t* x_strides, const void* packed, void* workspace,
+                       b200sr_stream stream);
+/* *out_sum (device double) = sum |f_sr - f_gt| over conv_index's feature map (mean = sum / (pairs * H_l * W_l * C_l)) */
+int b200sr_vgg_feature_l1(b200sr_plan* plan, const void* workspace, int conv_index, int pairs, double* out_sum, b200sr_stream stream);
+/* dx: [grad_images, 3, height, width] fp32, gradient of upstream[0] * mean|f_sr - f_gt| (grad_conv's features) w.r.t. the NORMALISED
+ * input images (divide by std for the raw images); upstream: device float */
+int b200sr_vgg_backward(b200sr_plan* plan, const float* upstream, const void* packed, void* workspace, float* dx, b200sr_stream stream);
+
 const char* b200sr_last_error(void);
 int b200sr_version(void);
 /* timing probes for profiling only (results become wrong unless noted): bit 0 (1) no epilogue traffic, bit 1 (2) no MMAs,

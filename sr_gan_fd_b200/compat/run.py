@@ -9,6 +9,7 @@ What it does (nothing in the reference tree is edited or copied):
   * puts the reference folder on ``sys.path`` for the script's sibling imports (``imgproc``, ``dataset``, ``utils``, ``*_config``);
   * optional ``--set module.attr=value`` edits a config module IN MEMORY before the script imports it (the reference keeps its
     run configuration in ``*_config.py`` files users edit by hand: dataset paths, epochs, batch size);
+  * optional ``--vgg`` swaps the folder's ``ContentLoss`` for the B200 VGG19 feature path (``sr_gan_fd_b200.vgg``);
   * optional ``--iqa`` also registers a shim for ``image_quality_assessment`` whose ``PSNR`` / ``SSIM`` are the fused B200 kernels;
   * optional ``--stub name`` installs an empty stand-in for a logging dependency that is not installed (mlflow, lpips, ...);
   * the script then runs under ``runpy`` with ``__name__ == "__main__"`` from the current working directory.
@@ -56,6 +57,7 @@ def main(argv=None) -> None:
     ap.add_argument("--stub", action="append", default=[], metavar="module")
     ap.add_argument("--stock", action="store_true", help="do NOT install the shim: run the reference's own model.py (A/B runs)")
     ap.add_argument("--iqa", action="store_true", help="also replace image_quality_assessment.PSNR / SSIM by the fused B200 versions")
+    ap.add_argument("--vgg", action="store_true", help="also replace model.ContentLoss / content_loss by the B200 VGG19 feature path")
     ap.add_argument("folder", choices=sorted(SHIMS))
     ap.add_argument("script")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
@@ -75,6 +77,14 @@ def main(argv=None) -> None:
         sys.path.insert(0, folder)
     if not args.stock:
         shim = importlib.import_module(f"sr_gan_fd_b200.compat.{SHIMS[args.folder]}")
+        if args.vgg:
+            from sr_gan_fd_b200 import vgg as _vgg
+            cls = _vgg.ContentLoss if args.folder == "ESRGAN" else _vgg.ContentLossMulti
+            ns = dict(shim.__dict__)
+            ns["ContentLoss"] = cls
+            ns["content_loss"] = lambda **kwargs: cls(**kwargs)
+            shim = types.ModuleType("model")
+            shim.__dict__.update(ns)
         sys.modules["model"] = shim
         if args.iqa:
             from sr_gan_fd_b200.compat import iqa_module

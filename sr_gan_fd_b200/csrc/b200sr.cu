@@ -22,6 +22,7 @@
 #include "conv_kernel.cuh"
 #include "optim_kernels.cuh"
 #include "iqa_kernels.cuh"
+#include "vgg_kernels.cuh"
 #include "wgrad_kernel.cuh"
 
 using namespace b200sr;
@@ -111,14 +112,16 @@ static Ref ws(long long off) { Ref r; r.kind = RK_WS; r.off = off; return r; }
 struct ActMapSpec { long long off; int c_valid, c_pix, n, h, w, box_rows, box_w; };
 struct Bases { void* ws; void* packed; void* y; const void* dy; void* grads; };
 
-enum StepType { ST_CONV, ST_CHAIN, ST_WGRAD, ST_BIASGRAD, ST_UNPACK, ST_ADD, ST_MEMSET, ST_INGEST_X, ST_INGEST_DY };
+enum StepType { ST_CONV, ST_CHAIN, ST_WGRAD, ST_BIASGRAD, ST_UNPACK, ST_ADD, ST_MEMSET, ST_INGEST_X, ST_INGEST_DY,
+                ST_VGG_INGEST, ST_VGG_POOL, ST_VGG_POOL_BWD };
 
 struct Step {
   int type = ST_CONV;
   // conv
   int amap = -1, wmap = -1;  // wmap: index into {16,32,64,128}
   ConvParams cp;
-  Ref bias, mask, r1, r2, of, ofb, ob, cm;
+  Ref bias, mask, r1, r2, of, ofb, ob, cm, feat;
+  int pn = 0, ph = 0, pw = 0, pc = 0;  // VGG pool steps: geometry of the pooled layer's input
   dim3 grid;
   int smem = 0;
   int layer0 = 0, nlayers = 0, chain_grid = 0;  // ST_CHAIN: range of the plan's layer list
@@ -166,6 +169,11 @@ struct b200sr_plan {
                                       // per image than SMs: plain per-conv schedule
   int groups = 1;                     // image groups that flow through a chain independently
   int plan_sms = 148;                 // SM count the schedule was laid out for
+  // VGG19 feature plans (b200sr_vgg_plan_create): the same step / chain machinery over another layer list
+  bool is_vgg = false;
+  b200sr_vgg_desc vd;
+  long long o_vgg_feat[16] = {0}, o_vgg_g[16] = {0};  // fp32 pre-activation features / bf16 output gradients per conv (0: absent)
+  int vgg_h[16] = {0}, vgg_w[16] = {0};
   long long gw_bytes = 0;
   long long o_gw = 0;                 // staged weight gradients, per conv [tap][ci][co_pad] fp32
   std::vector<long long> gw_off;      // float offsets per conv into the staging buffer
@@ -949,6 +957,7 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
     L.p.epi.out_f32_b = (float*)resolve(s.ofb, b);
     L.p.epi.out_bf16 = (__nv_bfloat16*)resolve(s.ob, b);
     L.p.epi.clamp_mask = (unsigned char*)resolve(s.cm, b);
+    L.p.epi.feat_out = (float*)resolve(s.feat, b);
   }
   // entry lists: every layer of a chain is split into (up to) two image groups that flow through the chain independently
   if (P.h_entries.empty()) {
@@ -995,7 +1004,7 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
           const int l = order[i].first, g = order[i].second;
           const ConvParams& cp = P.layer_steps[s.layer0 + l].cp;
           const int tpi = cp.tiles_x * cp.tiles_y;
-          const int img_lo = (int)((long long)P.d.batch * g / groups), img_hi = (int)((long long)P.d.batch * (g + 1) / groups);
+          const int img_lo = (int)((long long)cp.N * g / groups), img_hi = (int)((long long)cp.N * (g + 1) / groups);
           EntryDesc e; memset(&e, 0, sizeof(e));
           e.layer = s.layer0 + l;
           e.tile_lo = img_lo * tpi; e.tile_hi = img_hi * tpi;
@@ -1224,6 +1233,29 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         CUDA_TRY(cudaGetLastError());
         break;
       }
+      case ST_VGG_INGEST: {
+        const long long npix = (long long)P.vd.batch * P.vd.height * P.vd.width;
+        VggNorm nm;
+        for (int c = 0; c < 3; ++c) { nm.mean[c] = P.vd.mean[c]; nm.std[c] = P.vd.std[c]; }
+        nm.mean[3] = 0.f; nm.std[3] = 1.f;
+        vgg_ingest_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>((const float*)x, xs[0], xs[1], xs[2], xs[3], P.vd.batch, P.vd.height, P.vd.width, nm,
+                                                                          (__nv_bfloat16*)((char*)b.ws + P.o_xin));
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_VGG_POOL: {
+        const long long n = (long long)s.pn * (s.ph >> 1) * (s.pw >> 1) * (s.pc >> 3);
+        vgg_maxpool_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (__nv_bfloat16*)resolve(s.c, b), s.pn, s.ph, s.pw, s.pc);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_VGG_POOL_BWD: {
+        const long long n = (long long)s.pn * ((s.ph + 1) >> 1) * ((s.pw + 1) >> 1) * (s.pc >> 1);
+        vgg_maxpool_relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
+                                                                                (__nv_bfloat16*)resolve(s.c, b), s.pn, s.ph, s.pw, s.pc);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
       case ST_INGEST_DY: {
         const int hH = d.height << P.L, hW = d.width << P.L;
         const long long npix = (long long)d.batch * hH * hW;
@@ -1236,6 +1268,153 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
     if (cb && s.cb_count > 0) cb(user, s.cb_off, s.cb_count);
   }
   return join();
+}
+
+// ------------------------------------------------------------------------------------------------ VGG19 feature plan
+// torchvision vgg19().features up to conv5_4: sixteen 3x3 convs (+ReLU), 2x2 max-pools after convs 1, 3, 7, 11.
+static const int kVggCin[16] = {3, 64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512, 512, 512};
+static const int kVggCout[16] = {64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512, 512, 512, 512};
+static const bool kVggPoolAfter[16] = {false, true, false, true, false, false, false, true, false, false, false, true, false, false, false, false};
+
+static int build_vgg_plan(b200sr_plan& P) {
+  const b200sr_vgg_desc& v = P.vd;
+  if (v.batch < 1 || v.height < 1 || v.width < 1) return fail(B200SR_ERR_INVALID, "bad geometry");
+  if (v.last_conv < 0 || v.last_conv > 15) return fail(B200SR_ERR_INVALID, "last_conv must be in [0, 15]");
+  if (v.grad_conv > v.last_conv || v.grad_images > v.batch) return fail(B200SR_ERR_INVALID, "bad gradient request");
+  const bool bwd = v.grad_conv >= 0 && v.grad_images > 0;
+  P.is_vgg = true;
+  P.reassoc = false;
+  P.groups = v.batch >= 2 ? 2 : 1;
+  memset(&P.d, 0, sizeof(P.d));
+  P.d.batch = v.batch; P.d.height = v.height; P.d.width = v.width; P.d.training = bwd ? 1 : 0;
+  const int NL = v.last_conv + 1;
+  const int N = v.batch, NB = v.grad_images;
+  Builder B(P);
+  P.param_off.assign(2 * NL + 1, 0);
+  {
+    long long off = 0;
+    for (int l = 0; l < NL; ++l) {
+      P.param_off[2 * l] = off; off += 9LL * kVggCin[l] * kVggCout[l];
+      P.param_off[2 * l + 1] = off; off += kVggCout[l];
+    }
+    P.param_off[2 * NL] = off;
+  }
+  int h = v.height, w = v.width;
+  P.xin_stride = 64;
+  P.o_xin = B.alloc((long long)N * h * w * 64 * 2);
+  std::vector<long long> o_act(NL, 0), o_pool(NL, 0);
+  for (int l = 0; l < NL; ++l) {
+    if (h < 1 || w < 1) return fail(B200SR_ERR_INVALID, "input too small for conv %d", l);
+    P.vgg_h[l] = h; P.vgg_w[l] = w;
+    o_act[l] = B.alloc((long long)N * h * w * kVggCout[l] * 2);
+    if ((v.feat_mask >> l) & 1) P.o_vgg_feat[l] = B.alloc((long long)N * h * w * kVggCout[l] * 4) + 1;  // +1: 0 means absent
+    if (kVggPoolAfter[l] && l + 1 < NL) {
+      o_pool[l] = B.alloc((long long)N * (h >> 1) * (w >> 1) * kVggCout[l] * 2);
+      h >>= 1; w >>= 1;
+    }
+  }
+  std::vector<long long> o_gpool(NL, 0);
+  if (bwd) {
+    for (int l = 0; l <= v.grad_conv; ++l) {
+      P.o_vgg_g[l] = B.alloc((long long)NB * P.vgg_h[l] * P.vgg_w[l] * kVggCout[l] * 2) + 1;
+      if (kVggPoolAfter[l] && l + 1 <= v.grad_conv) o_gpool[l] = B.alloc((long long)NB * (P.vgg_h[l] >> 1) * (P.vgg_w[l] >> 1) * kVggCout[l] * 2);
+    }
+  }
+  P.ws_bytes = B.cursor;
+  auto packed_bias = [&](long long off_floats) { Ref r; r.kind = RK_PACKED; r.off = -1 - off_floats; return r; };
+  auto conv_step = [&](int amap, const ConvParams& cp) {
+    Step s; s.type = ST_CONV; s.amap = amap; s.wmap = 0; s.cp = cp; s.grid = dim3(1, 1, 1); s.smem = 0;
+    return s;
+  };
+  // ---- forward
+  { Step s; s.type = ST_VGG_INGEST; P.fwd.push_back(s); }
+  for (int l = 0; l < NL; ++l) {
+    const int cin = kVggCin[l], cout = kVggCout[l], hh = P.vgg_h[l], ww = P.vgg_w[l];
+    const int n_cols = 64;  // column groups of 64 (the epilogue handles up to 64 accumulator columns per work item)
+    PackOp op; memset(&op, 0, sizeof(op));
+    op.n_total = cout; op.n_cols = n_cols; op.n_valid = cout; op.mode = kPackFwd;
+    int amap, chunks, ksl;
+    if (l == 0) {  // [hi | lo | hi] input x [w_hi | w_hi | w_lo] weights: fp32-accurate products from bf16 MMAs
+      op.num_chunks = 1; op.nseg = 3;
+      op.seg[0] = seg(0, 3, 0, cout, 3, 0, 0, 0); op.seg[1] = seg(3, 3, 0, cout, 3, 0, 0, 0); op.seg[2] = seg(6, 3, 0, cout, 3, 0, 0, 1);
+      amap = B.add_map(P.o_xin, 64, 64, N, hh, ww, kABoxRows); chunks = 1; ksl = 1;
+    } else {
+      const long long in_off = (kVggPoolAfter[l - 1]) ? o_pool[l - 1] : o_act[l - 1];
+      op.num_chunks = cin / 64; op.nseg = 1;
+      op.seg[0] = seg(0, cin, 2 * l, cout, cin, 0, 0, 0);
+      amap = B.add_map(in_off, cin, cin, N, hh, ww, kABoxRows); chunks = cin / 64; ksl = 4;
+    }
+    const int row0 = B.add_pack(op);
+    ConvParams cp = base_conv_params(N, hh, ww, chunks, ksl, 0, 1 << 20, row0, n_cols, cout);
+    Step s = conv_step(amap, cp);
+    s.bias = packed_bias(B.add_bias(cout, 2 * l + 1, cout, 0));
+    s.cp.epi.act = 2;  // ReLU
+    s.ob = ws(o_act[l]); s.cp.epi.ob_stride = cout; s.cp.epi.ob_coff = 0;
+    if (P.o_vgg_feat[l]) {
+      s.feat = ws(P.o_vgg_feat[l] - 1); s.cp.epi.feat_stride = cout;
+      // torchvision's feature extractor returns the conv's output tensor, which the NEXT module -- ReLU(inplace=True) -- then
+      // overwrites: every node but the one that ends the extracted graph is effectively read AFTER the ReLU
+      if (l < v.last_conv) s.cp.epi.mask_relu |= 2;
+    }
+    P.fwd.push_back(s);
+    if (kVggPoolAfter[l] && l + 1 < NL) {
+      Step pl; pl.type = ST_VGG_POOL; pl.a = ws(o_act[l]); pl.c = ws(o_pool[l]); pl.pn = N; pl.ph = hh; pl.pw = ww; pl.pc = cout;
+      P.fwd.push_back(pl);
+    }
+  }
+  // ---- backward (data gradients only: the VGG weights are frozen): G[l] = gradient w.r.t. conv l's pre-activation output
+  if (bwd) {
+    for (int l = v.grad_conv; l >= 0; --l) {
+      const int cin = kVggCin[l], cout = kVggCout[l], hh = P.vgg_h[l], ww = P.vgg_w[l];
+      const int nin = (l == 0) ? 16 : cin;  // dgrad output channels (conv 0: 3 padded to 16, stored NCHW fp32 to dx)
+      const int n_cols = (l == 0) ? 16 : 64;
+      PackOp op; memset(&op, 0, sizeof(op));
+      op.n_total = nin; op.n_cols = n_cols; op.n_valid = (l == 0) ? 3 : cin; op.num_chunks = cout / 64; op.mode = kPackDgrad; op.nseg = 1;
+      op.seg[0] = seg(0, cout, 2 * l, cout, cin, 0, 0, 0);
+      const int row0 = B.add_pack(op);
+      ConvParams cp = base_conv_params(NB, hh, ww, cout / 64, 4, 0, 1 << 20, row0, n_cols, nin);
+      Step s = conv_step(B.add_map(P.o_vgg_g[l] - 1, cout, cout, NB, hh, ww, kABoxRows), cp);
+      if (l == 0) {
+        s.cp.epi.store_mode = kStoreNCHW; s.cp.epi.n_valid = 3; s.of.kind = RK_Y;
+        P.bwd.push_back(s);
+      } else if (kVggPoolAfter[l - 1]) {
+        // conv l reads the POOLED activation of conv l-1: its data gradient lives on the pooled lattice, then pool + ReLU backward
+        s.ob = ws(o_gpool[l - 1]); s.cp.epi.ob_stride = cin; s.cp.epi.ob_coff = 0;
+        P.bwd.push_back(s);
+        Step pb; pb.type = ST_VGG_POOL_BWD; pb.a = ws(o_act[l - 1]); pb.b = ws(o_gpool[l - 1]); pb.c = ws(P.o_vgg_g[l - 1] - 1);
+        pb.pn = NB; pb.ph = P.vgg_h[l - 1]; pb.pw = P.vgg_w[l - 1]; pb.pc = cin;
+        P.bwd.push_back(pb);
+      } else {
+        s.mask = ws(o_act[l - 1]); s.cp.epi.mask_stride = cin; s.cp.epi.mask_coff = 0; s.cp.epi.mask_relu = 1;
+        s.ob = ws(P.o_vgg_g[l - 1] - 1); s.cp.epi.ob_stride = cin; s.cp.epi.ob_coff = 0;
+        P.bwd.push_back(s);
+      }
+    }
+  }
+  const long long bias_base = align_up(P.total_rows * 128, 1024);
+  P.packed_bytes = bias_base + P.bias_floats * 4;
+  auto fix = [&](std::vector<Step>& vv) {
+    for (Step& s : vv)
+      if (s.bias.kind == RK_PACKED) s.bias.off = bias_base + (-1 - s.bias.off) * 4;
+  };
+  fix(P.fwd); fix(P.bwd);
+  auto chainify = [&](std::vector<Step>& vv) {
+    std::vector<Step> out;
+    for (Step& s : vv) {
+      if (s.type != ST_CONV) { out.push_back(s); continue; }
+      if (out.empty() || out.back().type != ST_CHAIN) {
+        Step c; c.type = ST_CHAIN; c.layer0 = (int)P.layer_steps.size(); c.nlayers = 0; c.chain_grid = 0;
+        out.push_back(c);
+      }
+      out.back().nlayers++;
+      const int work = s.cp.num_tiles * s.cp.col_groups;
+      if (work > out.back().chain_grid) out.back().chain_grid = work;
+      P.layer_steps.push_back(s);
+    }
+    vv.swap(out);
+  };
+  chainify(P.fwd); chainify(P.bwd);
+  return 0;
 }
 
 // =================================================================================================== C ABI =====
@@ -1562,6 +1741,58 @@ int b200sr_tensor_to_image_u8(const float* x, int c, int h, int w, int range_nor
   tensor_to_image_u8_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, c, h, w, range_norm, half, out_hwc);
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ VGG19 features
+int b200sr_vgg_plan_create(const b200sr_vgg_desc* desc, b200sr_plan** out) {
+  if (!desc || !out) return fail(B200SR_ERR_INVALID, "null argument");
+  b200sr_plan* p = new b200sr_plan();
+  p->vd = *desc;
+  int rc = build_vgg_plan(*p);
+  if (rc) { delete p; return rc; }
+  *out = p;
+  return 0;
+}
+
+int b200sr_vgg_forward(b200sr_plan* p, const float* x, const int64_t* x_strides, const void* packed, void* workspace, b200sr_stream stream) {
+  if (!p || !p->is_vgg || !x || !x_strides || !packed || !workspace) return fail(B200SR_ERR_INVALID, "bad argument");
+  int rc = runtime_init();
+  if (rc) return rc;
+  rc = ensure_maps(*p, workspace, (void*)packed, (cudaStream_t)stream);
+  if (rc) return rc;
+  Bases b{workspace, (void*)packed, nullptr, nullptr, nullptr};
+  return run_steps(*p, p->fwd, b, x, B200SR_F32, x_strides, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int b200sr_vgg_feature_l1(b200sr_plan* p, const void* workspace, int conv_index, int pairs, double* out_sum, b200sr_stream stream) {
+  if (!p || !p->is_vgg || !workspace || !out_sum) return fail(B200SR_ERR_INVALID, "bad argument");
+  if (conv_index < 0 || conv_index > p->vd.last_conv || !p->o_vgg_feat[conv_index]) return fail(B200SR_ERR_INVALID, "conv %d has no feature buffer in this plan", conv_index);
+  if (2 * pairs != p->vd.batch) return fail(B200SR_ERR_INVALID, "pairs must be half of the plan's batch");
+  const long long half = (long long)pairs * p->vgg_h[conv_index] * p->vgg_w[conv_index] * kVggCout[conv_index];
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
+  long long blocks = (half / 4 + 255) / 256;
+  if (blocks > 8 * 148) blocks = 8 * 148;
+  vgg_l1_pair_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)((const char*)workspace + p->o_vgg_feat[conv_index] - 1), half, out_sum);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200sr_vgg_backward(b200sr_plan* p, const float* upstream, const void* packed, void* workspace, float* dx, b200sr_stream stream) {
+  if (!p || !p->is_vgg || !upstream || !packed || !workspace || !dx) return fail(B200SR_ERR_INVALID, "bad argument");
+  const int gc = p->vd.grad_conv, nb = p->vd.grad_images;
+  if (gc < 0 || nb < 1 || 2 * nb != p->vd.batch || !p->o_vgg_feat[gc]) return fail(B200SR_ERR_INVALID, "plan was created without a gradient request");
+  int rc = runtime_init();
+  if (rc) return rc;
+  rc = ensure_maps(*p, workspace, (void*)packed, (cudaStream_t)stream);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long half = (long long)nb * p->vgg_h[gc] * p->vgg_w[gc] * kVggCout[gc];
+  vgg_l1_grad_kernel<<<(unsigned)((half / 4 + 255) / 256), 256, 0, st>>>((const float*)((char*)workspace + p->o_vgg_feat[gc] - 1), half, upstream,
+                                                                         (__nv_bfloat16*)((char*)workspace + p->o_vgg_g[gc] - 1));
+  CUDA_TRY(cudaGetLastError());
+  Bases b{workspace, (void*)packed, dx, nullptr, nullptr};
+  return run_steps(*p, p->bwd, b, nullptr, 0, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -66,6 +66,12 @@ struct ConvEpilogue {
   int store_mode;
   unsigned char* clamp_mask;  // kStoreFinal, may be nullptr
   int n_valid;                // kStoreFinal: real output channels (<= 16)
+  // VGG feature layers (sr_gan_fd_b200/vgg.py): act == 2 is ReLU, mask_relu makes the dgrad mask the ReLU derivative, and
+  // feat_out receives alpha * (acc + bias) as plain fp32 NHWC rows ([pixel][feat_stride], column col) -- before the activation,
+  // or after it when bit 1 of mask_relu is set
+  int mask_relu;  // bit 0: dgrad mask is the ReLU derivative; bit 1: feat_out is stored after the activation
+  int feat_stride;
+  float* feat_out;
 };
 
 struct ConvParams {
@@ -150,7 +156,8 @@ __device__ __forceinline__ void store_rows_quad(uint32_t (&h)[16], void* row, bo
 struct HW { int H, W; bool nostore; };
 // Part 1 (registers only): bias + scale, LeakyReLU, LeakyReLU-derivative mask, fp32 residuals.
 __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const float* sbias, const float (&res)[32], bool has_res,
-                                                   const uint32_t (&maskw)[16], bool has_mask, int col0, int ncol, float (&v)[32]) {
+                                                   const uint32_t (&maskw)[16], bool has_mask, int col0, int ncol, float (&v)[32],
+                                                   float* feat_row = nullptr) {
   if (ncol == 32) {
     const float4* b4 = reinterpret_cast<const float4*>(sbias + col0);
 #pragma unroll
@@ -163,15 +170,27 @@ __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const 
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = e.alpha * (v[i] + sbias[col0 + i]);
   }
-  if (e.act) {
+  if (feat_row && !(e.mask_relu & 2)) {  // pre-activation feature map (VGG node that ends the graph), fp32
+#pragma unroll
+    for (int q = 0; q < 8; ++q) st_global_v4f(feat_row + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  if (e.act == 1) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);  // LeakyReLU(0.2)
+  } else if (e.act == 2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);          // ReLU
   }
-  if (has_mask) {  // LeakyReLU derivative from the saved forward activation
+  if (feat_row && (e.mask_relu & 2)) {  // feature node followed by torchvision's IN-PLACE ReLU: what the reference reads is post-ReLU
+#pragma unroll
+    for (int q = 0; q < 8; ++q) st_global_v4f(feat_row + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  if (has_mask) {  // activation derivative from the saved forward activation (LeakyReLU 0.2, or ReLU)
+    const float neg = (e.mask_relu & 1) ? 0.f : 0.2f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      v[2 * j] *= (bf16_lo_to_f32(maskw[j]) > 0.f) ? 1.f : 0.2f;
-      v[2 * j + 1] *= (bf16_hi_to_f32(maskw[j]) > 0.f) ? 1.f : 0.2f;
+      v[2 * j] *= (bf16_lo_to_f32(maskw[j]) > 0.f) ? 1.f : neg;
+      v[2 * j + 1] *= (bf16_hi_to_f32(maskw[j]) > 0.f) ? 1.f : neg;
     }
   }
   if (has_res) {  // fp32 residuals (already combined)
@@ -427,8 +446,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   volatile uint32_t* dep_flag = reinterpret_cast<volatile uint32_t*>(fixed + 516);  // producer -> epilogue: e + 1 once entry e's dependency is done
   volatile uint32_t* sig_done = reinterpret_cast<volatile uint32_t*>(fixed + 520);  // signaller -> epilogue: entries announced so far
   uint8_t* sp_base = fixed + 1024;                                  // 4 x 384 B
-  float* sbias_base = reinterpret_cast<float*>(fixed + 3072);       // 4 x 1 KB
-  constexpr int kFixedBytes = 3072 + 4096;
+  float* sbias_base = reinterpret_cast<float*>(fixed + 3072);       // 4 x 2 KB (up to 512 bias floats per layer)
+  constexpr int kFixedBytes = 3072 + 8192;
   static_assert(sizeof(ConvParams) <= 384 && sizeof(ConvParams) % 16 == 0, "ConvParams must fit the 384-byte smem slot in 16-byte pieces");
   static_assert(kNumASlots * kASlot + kWGranules * kWGranule + kFixedBytes + 1024 <= conv_smem_bytes(1), "smem budget");
 
@@ -748,10 +767,10 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const uint32_t boff = lb.z;                 // bias byte offset from the packed buffer + 1 (0: no bias)
         if (et < static_cast<int>(sizeof(ConvParams) / 16)) {
           cp_async_16(sp_base + (e & 3) * 384 + et * 16, reinterpret_cast<const uint8_t*>(&layers[li].p) + et * 16);
-        } else if (et >= 64 && et < 128) {
+        } else if (et >= 64 && et < 192) {
           const int i = et - 64;
           if (4 * i < nt) {
-            uint8_t* dst = reinterpret_cast<uint8_t*>(sbias_base + (e & 3) * 256) + i * 16;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(sbias_base + (e & 3) * 512) + i * 16;
             if (boff) cp_async_16(dst, packed_w + (boff - 1) + i * 16);
             else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -789,7 +808,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const uint4 er = c_entry_rec[e];
       const int ent_tile_lo = static_cast<int>(er.y), ent_tile_hi = static_cast<int>(er.z);
       const int ent_rot = static_cast<int>(er.w & 0xFFFF), ent_dep = static_cast<int>(er.w >> 16) - 1, ent_slot = static_cast<int>((er.x >> 20) & 1);
-      const float* sbias = sbias_base + (e & 3) * 256;
+      const float* sbias = sbias_base + (e & 3) * 512;
       const int tiles_per_img = p.tiles_x * p.tiles_y;
       const int num_work = (ent_tile_hi - ent_tile_lo) * p.col_groups;
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(ent_rot)) % grid);
@@ -894,7 +913,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
               released = true;
             }
             if (warp == 2 && gq == 0) TL_MARK(12);
-            conv_epilogue_math(ep, sbias, res, has_res, maskw, has_mask, colbase + c0, ncol, vv);
+            float* feat_row = (ep.feat_out && pre && ncol == 32) ? ep.feat_out + pix * ep.feat_stride + (colbase + c0) : nullptr;
+            conv_epilogue_math(ep, sbias, res, has_res, maskw, has_mask, colbase + c0, ncol, vv, feat_row);
             // the residual / mask registers are free again: fetch the second 32 columns' while the first are stored
             if (gq == 0 && 32 < p.epi_cols) prefetch_cols(32);
             conv_epilogue_write(hw, ep, y_dyn, cbase, n, y, x, colbase + c0, vv, pre, lane);

@@ -19,6 +19,11 @@ class NetDesc(C.Structure):
         "batch", "height", "width", "training", "grad_bucket_rrdbs")]
 
 
+class VggDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("batch", "height", "width", "last_conv", "feat_mask", "grad_conv", "grad_images")] + \
+               [("mean", C.c_float * 3), ("std", C.c_float * 3)]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -51,6 +56,10 @@ SIGNATURES = {
     "b200sr_iqa_psnr_ssim_y": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "b200sr_tensor_to_image_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "b200sr_vgg_plan_create": (C.c_int, [C.POINTER(VggDesc), C.POINTER(C.c_void_p)]),
+    "b200sr_vgg_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200sr_vgg_feature_l1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "b200sr_vgg_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200sr_last_error": (C.c_char_p, []),
     "b200sr_version": (C.c_int, []),
     "b200sr_debug_set": (None, [C.c_int]),

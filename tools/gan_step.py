@@ -50,7 +50,7 @@ def patch_vgg19(seed=1234):
     models.vgg19 = seeded
 
 
-def build(generator, device, seed=0):
+def build(generator, device, seed=0, content="reference"):
     patch_vgg19()
     from sr_gan_fd_b200.compat import bsrgan_model as model  # reference critics + B200 generator
     if "discriminator_unet" not in model.__dict__:
@@ -64,7 +64,11 @@ def build(generator, device, seed=0):
         from sr_gan_fd_b200.compat._passthrough import load_reference_model
         g_model = load_reference_model("BSRGAN").bsrgan_x4(in_channels=3, out_channels=3, channels=64, growth_channels=32, num_rrdb=23)
     g_model = g_model.to(device)
-    content = model.ContentLoss(NODES, MEAN, STD).to(device)
+    if content == "b200":  # the same loss on the tcgen05 chain kernel (sr_gan_fd_b200.vgg)
+        from sr_gan_fd_b200.vgg import ContentLossMulti
+        content = ContentLossMulti(NODES, MEAN, STD).to(device)
+    else:
+        content = model.ContentLoss(NODES, MEAN, STD).to(device)
     return d_model, g_model, content
 
 
@@ -125,6 +129,7 @@ class GanStep:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--generator", default="b200", choices=["b200", "stock"])
+    ap.add_argument("--content", default="reference", choices=["reference", "b200"], help="VGG19 content loss: the reference's torch module or sr_gan_fd_b200.vgg")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16)
@@ -138,7 +143,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    d_model, g_model, content = build(args.generator, dev)
+    d_model, g_model, content = build(args.generator, dev, content=args.content)
     d_model.train(); g_model.train()
     if world > 1:
         d_model = nn.parallel.DistributedDataParallel(d_model, device_ids=[local], broadcast_buffers=True)
@@ -174,7 +179,7 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": "BSRGAN full GAN step imgs/s (BASELINE configs[4]: generator fwd+bwd + reference U-Net discriminator x3 + VGG19 content loss)",
-            "generator": args.generator, "value": world * args.batch / (ms * 1e-3), "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "generator": args.generator, "content_loss": args.content, "value": world * args.batch / (ms * 1e-3), "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "data": "synthetic",
             "config": {"batch_per_gpu": args.batch, "lr": args.lr_size, "scale": 4, "num_rrdb": 23, "critics": "reference DiscriminatorUNet(3,1,64) "
                        "+ ContentLoss on a SEEDED RANDOM-INIT VGG19 (ImageNet weights unavailable offline), autocast fp16 + GradScaler",
