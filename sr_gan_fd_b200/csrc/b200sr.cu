@@ -68,8 +68,9 @@ static int runtime_init() {
     CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   if (!g_attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
-    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
     CUDA_TRY(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     g_attr_set = true;
   }
@@ -1077,7 +1078,10 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   CUDA_TRY(cudaMemsetAsync(ctr, 0, 16384, st));
   const uint8_t* pw = (const uint8_t*)b.packed;
   void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&y, (void*)&dbg, (void*)&layer0};
-  const void* fn = dbg ? (const void*)conv3x3_chain_kernel<1> : (const void*)conv3x3_chain_kernel<0>;  // <1>: probes compiled in
+  // <1, 0>: probes compiled in; <0, 1>: the VGG feature build (ReLU, feature store, 512-column bias vectors)
+  const void* fn = P.is_vgg ? (const void*)conv3x3_chain_kernel<0, 1>
+                            : (dbg ? (const void*)conv3x3_chain_kernel<1, 0> : (const void*)conv3x3_chain_kernel<0, 0>);
+  if (P.is_vgg) dbg = 0;
   if (ne > 1) {
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   } else {
@@ -1631,7 +1635,7 @@ static int single_conv(int mode, const void* x, int n, int h, int w, int cin, in
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_entry_rec, &erec, sizeof(erec), 0, cudaMemcpyHostToDevice, st));
   int layer0 = 0;
   void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&ydyn, (void*)&dbg, (void*)&layer0};
-  const void* fn = dbg ? (const void*)conv3x3_chain_kernel<1> : (const void*)conv3x3_chain_kernel<0>;
+  const void* fn = dbg ? (const void*)conv3x3_chain_kernel<1, 0> : (const void*)conv3x3_chain_kernel<0, 0>;
   CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   (void)grid_y;
   return 0;

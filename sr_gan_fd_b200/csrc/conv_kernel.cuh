@@ -155,6 +155,7 @@ __device__ __forceinline__ void store_rows_quad(uint32_t (&h)[16], void* row, bo
 // ---------------------------------------------------------------------------------------------------------------
 struct HW { int H, W; bool nostore; };
 // Part 1 (registers only): bias + scale, LeakyReLU, LeakyReLU-derivative mask, fp32 residuals.
+template <int kVgg>
 __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const float* sbias, const float (&res)[32], bool has_res,
                                                    const uint32_t (&maskw)[16], bool has_mask, int col0, int ncol, float (&v)[32],
                                                    float* feat_row = nullptr) {
@@ -170,23 +171,23 @@ __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const 
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = e.alpha * (v[i] + sbias[col0 + i]);
   }
-  if (feat_row && !(e.mask_relu & 2)) {  // pre-activation feature map (VGG node that ends the graph), fp32
+  if (kVgg && feat_row && !(e.mask_relu & 2)) {  // pre-activation feature map (VGG node that ends the graph), fp32
 #pragma unroll
     for (int q = 0; q < 8; ++q) st_global_v4f(feat_row + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
   if (e.act == 1) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);  // LeakyReLU(0.2)
-  } else if (e.act == 2) {
+  } else if (kVgg && e.act == 2) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);          // ReLU
   }
-  if (feat_row && (e.mask_relu & 2)) {  // feature node followed by torchvision's IN-PLACE ReLU: what the reference reads is post-ReLU
+  if (kVgg && feat_row && (e.mask_relu & 2)) {  // feature node followed by torchvision's IN-PLACE ReLU: what the reference reads is post-ReLU
 #pragma unroll
     for (int q = 0; q < 8; ++q) st_global_v4f(feat_row + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
   if (has_mask) {  // activation derivative from the saved forward activation (LeakyReLU 0.2, or ReLU)
-    const float neg = (e.mask_relu & 1) ? 0.f : 0.2f;
+    const float neg = (kVgg && (e.mask_relu & 1)) ? 0.f : 0.2f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       v[2 * j] *= (bf16_lo_to_f32(maskw[j]) > 0.f) ? 1.f : neg;
@@ -423,7 +424,9 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_lo, uint
 
 // kInstr = 0: production build (no probes: every `debug` test folds away).  kInstr = 1: the same kernel with the timing
 // switches, role profiler and per-entry timeline compiled in (used only while b200sr_debug_set() is non-zero).
-template <int kInstr>
+// kVgg = 1: the build used by the VGG19 feature plans (ReLU, ReLU-derivative mask, fp32 feature store, bias vectors of up to 512
+// columns); the generator's build (kVgg = 0) compiles none of it -- its epilogue sits on the dependency chain of every layer.
+template <int kInstr, int kVgg>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __restrict__ entries, int num_entries,
                      const uint8_t* __restrict__ packed_w, unsigned int* counters, float* y_dyn, int debug_arg, int layer0) {
@@ -446,8 +449,9 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
   volatile uint32_t* dep_flag = reinterpret_cast<volatile uint32_t*>(fixed + 516);  // producer -> epilogue: e + 1 once entry e's dependency is done
   volatile uint32_t* sig_done = reinterpret_cast<volatile uint32_t*>(fixed + 520);  // signaller -> epilogue: entries announced so far
   uint8_t* sp_base = fixed + 1024;                                  // 4 x 384 B
-  float* sbias_base = reinterpret_cast<float*>(fixed + 3072);       // 4 x 2 KB (up to 512 bias floats per layer)
-  constexpr int kFixedBytes = 3072 + 8192;
+  float* sbias_base = reinterpret_cast<float*>(fixed + 3072);       // 4 x 1 KB (kVgg: 4 x 2 KB, up to 512 bias floats per layer)
+  constexpr int kBiasSlot = kVgg ? 512 : 256;                       // floats
+  constexpr int kFixedBytes = 3072 + 4 * kBiasSlot * 4;
   static_assert(sizeof(ConvParams) <= 384 && sizeof(ConvParams) % 16 == 0, "ConvParams must fit the 384-byte smem slot in 16-byte pieces");
   static_assert(kNumASlots * kASlot + kWGranules * kWGranule + kFixedBytes + 1024 <= conv_smem_bytes(1), "smem budget");
 
@@ -767,10 +771,10 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const uint32_t boff = lb.z;                 // bias byte offset from the packed buffer + 1 (0: no bias)
         if (et < static_cast<int>(sizeof(ConvParams) / 16)) {
           cp_async_16(sp_base + (e & 3) * 384 + et * 16, reinterpret_cast<const uint8_t*>(&layers[li].p) + et * 16);
-        } else if (et >= 64 && et < 192) {
+        } else if (et >= 64 && et < 64 + kBiasSlot / 4) {
           const int i = et - 64;
           if (4 * i < nt) {
-            uint8_t* dst = reinterpret_cast<uint8_t*>(sbias_base + (e & 3) * 512) + i * 16;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(sbias_base + (e & 3) * kBiasSlot) + i * 16;
             if (boff) cp_async_16(dst, packed_w + (boff - 1) + i * 16);
             else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -808,7 +812,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const uint4 er = c_entry_rec[e];
       const int ent_tile_lo = static_cast<int>(er.y), ent_tile_hi = static_cast<int>(er.z);
       const int ent_rot = static_cast<int>(er.w & 0xFFFF), ent_dep = static_cast<int>(er.w >> 16) - 1, ent_slot = static_cast<int>((er.x >> 20) & 1);
-      const float* sbias = sbias_base + (e & 3) * 512;
+      const float* sbias = sbias_base + (e & 3) * kBiasSlot;
       const int tiles_per_img = p.tiles_x * p.tiles_y;
       const int num_work = (ent_tile_hi - ent_tile_lo) * p.col_groups;
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(ent_rot)) % grid);
@@ -913,8 +917,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
               released = true;
             }
             if (warp == 2 && gq == 0) TL_MARK(12);
-            float* feat_row = (ep.feat_out && pre && ncol == 32) ? ep.feat_out + pix * ep.feat_stride + (colbase + c0) : nullptr;
-            conv_epilogue_math(ep, sbias, res, has_res, maskw, has_mask, colbase + c0, ncol, vv, feat_row);
+            float* feat_row = (kVgg && ep.feat_out && pre && ncol == 32) ? ep.feat_out + pix * ep.feat_stride + (colbase + c0) : nullptr;
+            conv_epilogue_math<kVgg>(ep, sbias, res, has_res, maskw, has_mask, colbase + c0, ncol, vv, feat_row);
             // the residual / mask registers are free again: fetch the second 32 columns' while the first are stored
             if (gq == 0 && 32 < p.epi_cols) prefetch_cols(32);
             conv_epilogue_write(hw, ep, y_dyn, cbase, n, y, x, colbase + c0, vv, pre, lane);

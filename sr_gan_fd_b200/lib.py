@@ -80,6 +80,8 @@ def load() -> C.CDLL:
                 "The B200 generator path has no PyTorch fallback.")
         lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
+            if "B200SR_LIB" in os.environ and not hasattr(lib, name):
+                continue  # an older build loaded for a same-box A/B run may predate newer entry points; the in-tree library must have all
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args

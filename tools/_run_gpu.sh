@@ -1,6 +1,6 @@
-mkdir -p gpurun_out/r2
-export SRGANFD_REFERENCE=$GRAFT_REPO_ROOT/baseline/_ref
-python tools/bench_vgg.py > gpurun_out/r2/bench_vgg.json 2> gpurun_out/r2/bench_vgg.err; cat gpurun_out/r2/bench_vgg.json; tail -3 gpurun_out/r2/bench_vgg.err
-timeout 600 python tools/gan_step.py --generator b200 --content b200 --steps 10 2> gpurun_out/r2/gan_b200_vgg.err | tail -1 > gpurun_out/r2/gan_b200_vgg_n1.json; head -c 350 gpurun_out/r2/gan_b200_vgg_n1.json; echo
-timeout 600 python tools/gan_step.py --generator b200 --content reference --steps 10 2>/dev/null | tail -1 | head -c 350; echo
-timeout 600 python -m pytest tests/test_vgg.py -q -m gpu 2>&1 | tail -2
+run() { python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-library-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1', round(d['ms_per_step'],3), round(d['roofline']['ms_forward'],3), 'e2e', round(d['e2e']['ms_per_step'],3))"; }
+for i in 1 2; do
+  export B200SR_LIB=$GRAFT_REPO_ROOT/sr_gan_fd_b200/libb200sr_base.so; run base
+  unset B200SR_LIB; run cur
+done
+timeout 600 python -m pytest tests/test_vgg.py tests/test_model_gpu.py -q -m gpu -k "vgg or gpu_ or full_config2 or golden" 2>&1 | tail -2
