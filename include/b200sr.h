@@ -164,6 +164,34 @@ int b200sr_vgg_feature_l1(b200sr_plan* plan, const void* workspace, int conv_ind
  * input images (divide by std for the raw images); upstream: device float */
 int b200sr_vgg_backward(b200sr_plan* plan, const float* upstream, const void* packed, void* workspace, float* dx, b200sr_stream stream);
 
+/* ---- next to the path: the U-Net discriminator with spectral-norm convs --------------------------------
+ * Replaces DiscriminatorUNet._forward_impl (BSRGAN/model.py:143-167 = Real_ESRGAN/model.py:81-105) and its autograd backward
+ * (triggered at BSRGAN/train_bsrgan.py:420,430,463): conv1 3x3 -> three 4x4 stride-2 convs + LeakyReLU(0.2) -> three times
+ * [bilinear x2, 3x3 conv + LeakyReLU, + skip] -> two 3x3 convs + LeakyReLU -> 3x3 conv to the logit map.  The spectral
+ * normalisation itself (power iteration, W / sigma) stays with the caller: `params` holds the EFFECTIVE weights, and the returned
+ * gradients are w.r.t. those.  Plans share b200sr_workspace_bytes / b200sr_packed_bytes / b200sr_pack_weights / b200sr_num_params /
+ * b200sr_param_numel / b200sr_flops / b200sr_plan_destroy with the generator plans.
+ * params (b200sr_pack_weights): 20 device pointers, weight then bias of conv1, down1, down2, down3, up1, up2, up3, conv2, conv3,
+ * conv4 in that order; the bias entries of the eight bias-free convs are ignored (pass NULL).  Weights fp32 OIHW. */
+typedef struct b200sr_disc_desc {
+  int32_t in_channels;  /* 1..16 (3) */
+  int32_t out_channels; /* 1..16 (1) */
+  int32_t channels;     /* 64 */
+  int32_t batch, height, width; /* height and width multiples of 8 (the reference's skip additions need that, too) */
+  int32_t training;     /* 1: build the backward schedule */
+} b200sr_disc_desc;
+int b200sr_disc_plan_create(const b200sr_disc_desc* desc, b200sr_plan** out);
+/* x: [batch, in_channels, height, width], element strides x_strides[4], dtype per b200sr_dtype;
+ * y: [batch, out_channels, height, width] fp32 contiguous (the logit map) */
+int b200sr_disc_forward(b200sr_plan* plan, const void* x, int x_dtype, const int64_t* x_strides, const void* packed, void* workspace,
+                        float* y, b200sr_stream stream);
+/* dy: gradient w.r.t. y, fp32 contiguous.  flat_grads_or_null: b200sr_param_numel() floats, OVERWRITTEN with the gradients of the
+ * effective weights in `params` order (absent biases take no room) -- NULL skips every weight-gradient kernel (the generator
+ * update, where the discriminator is frozen).  dx_or_null: [batch, in_channels, height, width] fp32, OVERWRITTEN with the gradient
+ * w.r.t. x -- NULL skips it (the discriminator update, where the input carries no gradient). */
+int b200sr_disc_backward(b200sr_plan* plan, const float* dy, const void* packed, void* workspace, float* flat_grads_or_null,
+                         float* dx_or_null, b200sr_stream stream);
+
 const char* b200sr_last_error(void);
 int b200sr_version(void);
 /* timing probes for profiling only (results become wrong unless noted): bit 0 (1) no epilogue traffic, bit 1 (2) no MMAs,

@@ -66,5 +66,41 @@ def main():
         print(name, "sr mean", float(sr.detach().mean()), "loss", float(loss.detach()), os.path.getsize(os.path.join(OUT, name + ".pt")) // 1024, "KiB")
 
 
+DISC_KEEP = ["conv1.weight", "conv1.bias", "conv3.0.weight_orig", "conv4.weight", "conv4.bias"]
+
+
+def main_disc():
+    """tests/golden/disc/*.pt: the reference DiscriminatorUNet (BSRGAN/model.py:91-167) executed on a seeded input."""
+    out = os.path.join(OUT, "disc")
+    os.makedirs(out, exist_ok=True)
+    m = rl.load_module("bsrgan")
+    for name, seed, shape in [("disc_unet_s0", 0, (2, 3, 32, 40))]:
+        torch.manual_seed(seed)
+        net = m.DiscriminatorUNet(3, 1, 64)
+        params = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        g = torch.Generator().manual_seed(42)
+        x = torch.rand(*shape, generator=g)
+        dy = torch.randn(shape[0], 1, shape[2], shape[3], generator=g)
+        net.train()
+        xr = x.clone().requires_grad_(True)
+        y = net(xr)
+        y.backward(dy)
+        grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+        after = net.state_dict()
+        fix = {
+            "seed": seed, "x": x, "dy": dy, "y": y.detach().clone(), "dx": xr.grad.detach().clone(),
+            "grads": {k: grads[k] for k in DISC_KEEP},
+            "grad_norms": {k: float(v.double().norm()) for k, v in grads.items()},
+            "buffers": {k: after[k].detach().clone() for k in after if k.endswith(("weight_u", "weight_v"))},
+            "param_checksum": float(sum(v.double().sum() for v in params.values())),
+            "torch_version": str(torch.__version__),
+        }
+        torch.save(fix, os.path.join(out, name + ".pt"))
+        print(name, "logit mean", float(y.detach().mean()), os.path.getsize(os.path.join(out, name + ".pt")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if "disc" in sys.argv[1:]:
+        main_disc()
+    else:
+        main()

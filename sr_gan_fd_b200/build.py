@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb200sr.so")
 SOURCES = ["b200sr.cu"]
-HEADERS = ["ptx.cuh", "conv_kernel.cuh", "wgrad_kernel.cuh", "aux_kernels.cuh", "optim_kernels.cuh", os.path.join("..", "..", "include", "b200sr.h")]
+HEADERS = ["ptx.cuh", "conv_kernel.cuh", "wgrad_kernel.cuh", "aux_kernels.cuh", "optim_kernels.cuh", "iqa_kernels.cuh", "vgg_kernels.cuh",
+           "disc_kernels.cuh", os.path.join("..", "..", "include", "b200sr.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

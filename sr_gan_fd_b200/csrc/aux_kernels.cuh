@@ -11,7 +11,11 @@ enum PackMode : int {
   kPackFwd = 0,      // elem(n, k, ty, tx) = W[o_off + n][i_off + k][ty][tx]
   kPackDgrad = 1,    // elem(n, k, ty, tx) = W[o_off + k][i_off + n][2-ty][2-tx]
   kPackUpFwd = 2,    // n = phase*64 + co: sum of the taps of W[co][k] that fold onto LR tap (ty,tx) for that phase
-  kPackUpDgrad = 3   // k = phase*64 + co, n = ci: transposed + flipped version of kPackUpFwd
+  kPackUpDgrad = 3,  // k = phase*64 + co, n = ci: transposed + flipped version of kPackUpFwd
+  // 4x4 stride-2 pad-1 conv (U-Net discriminator, BSRGAN/model.py:103-114) as a 3x3 conv over the pixel-unshuffled input
+  // (channel (py*2+px)*I + c of the half-resolution lattice): kernel position (ky, kx) = (2 ty + py - 1, 2 tx + px - 1)
+  kPackDownFwd = 4,   // elem(n, k = phase*I + c, ty, tx) = W[n][c][ky][kx] (0 where ky / kx fall outside 0..3); W is [O][I][4][4]
+  kPackDownDgrad = 5  // elem(n = phase*I + c, k = co, ty, tx) = kPackDownFwd elem(co, n, 2-ty, 2-tx)
 };
 
 struct PackSeg {
@@ -60,6 +64,14 @@ __device__ __forceinline__ float pack_fetch(const PackOp& op, const float* const
       v = w[((static_cast<long long>(sg.o_off + n) * sg.I + sg.i_off + kl) * 3 + ty) * 3 + tx];
     } else if (op.mode == kPackDgrad) {
       v = w[((static_cast<long long>(sg.o_off + kl) * sg.I + sg.i_off + n) * 3 + (2 - ty)) * 3 + (2 - tx)];
+    } else if (op.mode == kPackDownFwd || op.mode == kPackDownDgrad) {
+      int co, cu, ry, rx;
+      if (op.mode == kPackDownFwd) { co = n; cu = kl; ry = ty; rx = tx; }
+      else                         { co = kl; cu = n; ry = 2 - ty; rx = 2 - tx; }
+      const int phase = cu / sg.I, c = cu - phase * sg.I;
+      const int ky = 2 * ry + (phase >> 1) - 1, kx = 2 * rx + (phase & 1) - 1;
+      if (phase < 4 && ky >= 0 && ky < 4 && kx >= 0 && kx < 4)
+        v = w[((static_cast<long long>(sg.o_off + co) * sg.I + sg.i_off + c) * 4 + ky) * 4 + kx];
     } else {
       int phase, co, ci, ry, rx;
       if (op.mode == kPackUpFwd) { phase = n >> 6; co = n & 63; ci = kl; ry = ty; rx = tx; }

@@ -23,6 +23,7 @@
 #include "optim_kernels.cuh"
 #include "iqa_kernels.cuh"
 #include "vgg_kernels.cuh"
+#include "disc_kernels.cuh"
 #include "wgrad_kernel.cuh"
 
 using namespace b200sr;
@@ -114,14 +115,15 @@ struct ActMapSpec { long long off; int c_valid, c_pix, n, h, w, box_rows, box_w;
 struct Bases { void* ws; void* packed; void* y; const void* dy; void* grads; };
 
 enum StepType { ST_CONV, ST_CHAIN, ST_WGRAD, ST_BIASGRAD, ST_UNPACK, ST_ADD, ST_MEMSET, ST_INGEST_X, ST_INGEST_DY,
-                ST_VGG_INGEST, ST_VGG_POOL, ST_VGG_POOL_BWD };
+                ST_VGG_INGEST, ST_VGG_POOL, ST_VGG_POOL_BWD,
+                ST_DISC_UP, ST_DISC_UP_BWD, ST_DISC_ADD, ST_DISC_MASK, ST_DISC_INGEST_DY, ST_DISC_UNPACK };
 
 struct Step {
   int type = ST_CONV;
   // conv
   int amap = -1, wmap = -1;  // wmap: index into {16,32,64,128}
   ConvParams cp;
-  Ref bias, mask, r1, r2, of, ofb, ob, cm, feat;
+  Ref bias, mask, r1, r2, of, ofb, ob, cm, feat, resb;
   int pn = 0, ph = 0, pw = 0, pc = 0;  // VGG pool steps: geometry of the pooled layer's input
   dim3 grid;
   int smem = 0;
@@ -136,12 +138,13 @@ struct Step {
   BiasGradParams bp;
   Ref bg_g;
   // fold / add / memset / ingest
-  Ref a, b, c;
+  Ref a, b, c, d2;
   long long count = 0;
   int i0 = 0, i1 = 0;
   // gradient-bucket announcement after this step
   long long cb_off = 0, cb_count = 0;
   bool needs_dx = false;  // only launched when the caller asks for the gradient w.r.t. the LR input
+  bool needs_wgrad = false;  // discriminator plans: only launched when the caller asks for the parameter gradients
 };
 
 struct b200sr_plan {
@@ -175,6 +178,9 @@ struct b200sr_plan {
   b200sr_vgg_desc vd;
   long long o_vgg_feat[16] = {0}, o_vgg_g[16] = {0};  // fp32 pre-activation features / bf16 output gradients per conv (0: absent)
   int vgg_h[16] = {0}, vgg_w[16] = {0};
+  // U-Net discriminator plans (b200sr_disc_plan_create)
+  bool is_disc = false;
+  b200sr_disc_desc dd;
   long long gw_bytes = 0;
   long long o_gw = 0;                 // staged weight gradients, per conv [tap][ci][co_pad] fp32
   std::vector<long long> gw_off;      // float offsets per conv into the staging buffer
@@ -959,6 +965,7 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
     L.p.epi.out_bf16 = (__nv_bfloat16*)resolve(s.ob, b);
     L.p.epi.clamp_mask = (unsigned char*)resolve(s.cm, b);
     L.p.epi.feat_out = (float*)resolve(s.feat, b);
+    L.p.epi.res_bf16 = (const __nv_bfloat16*)resolve(s.resb, b);
   }
   // entry lists: every layer of a chain is split into (up to) two image groups that flow through the chain independently
   if (P.h_entries.empty()) {
@@ -1079,9 +1086,9 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   const uint8_t* pw = (const uint8_t*)b.packed;
   void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&y, (void*)&dbg, (void*)&layer0};
   // <1, 0>: probes compiled in; <0, 1>: the VGG feature build (ReLU, feature store, 512-column bias vectors)
-  const void* fn = P.is_vgg ? (const void*)conv3x3_chain_kernel<0, 1>
+  const void* fn = (P.is_vgg || P.is_disc) ? (const void*)conv3x3_chain_kernel<0, 1>
                             : (dbg ? (const void*)conv3x3_chain_kernel<1, 0> : (const void*)conv3x3_chain_kernel<0, 0>);
-  if (P.is_vgg) dbg = 0;
+  if (P.is_vgg || P.is_disc) dbg = 0;
   if (ne > 1) {
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kConvThreads), args, (size_t)conv_smem_bytes(1), st));
   } else {
@@ -1149,6 +1156,8 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
     return 0;
   };
   for (Step& s : steps) {
+    if (s.needs_wgrad && !b.grads) continue;  // discriminator backward for the generator update: data gradients only
+    if (s.type == ST_DISC_UNPACK) { int rc = join(); if (rc) return rc; }
     if (alternate) {
       // the gradient unpack consumes what the weight-gradient launches of BOTH streams produced: join first (without a
       // bucket callback only the last unpack step launches anything)
@@ -1258,6 +1267,53 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         vgg_maxpool_relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
                                                                                 (__nv_bfloat16*)resolve(s.c, b), s.pn, s.ph, s.pw, s.pc);
         CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_DISC_UP: {
+        const long long n = (long long)s.pn * (2 * s.ph) * (2 * s.pw) * (s.pc >> 3);
+        disc_bilinear_up_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
+                                                                            (__nv_bfloat16*)resolve(s.c, b), s.pn, s.ph, s.pw, s.pc);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_DISC_UP_BWD: {
+        const long long n = (long long)s.pn * s.ph * s.pw * (s.pc >> 3);
+        disc_bilinear_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
+                                                                             (__nv_bfloat16*)resolve(s.c, b), (__nv_bfloat16*)resolve(s.d2, b), s.pn, s.ph, s.pw, s.pc);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_DISC_ADD: {
+        const long long n = (long long)s.pn * s.ph * s.pw * (s.pc >> 3);
+        disc_add_u_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
+                                                                      (__nv_bfloat16*)resolve(s.c, b), s.pn, s.ph, s.pw, s.pc);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_DISC_MASK: {
+        const long long n8 = (long long)s.pn * s.ph * s.pw * (s.pc >> 3);
+        disc_lrelu_mask_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
+                                                                           (__nv_bfloat16*)resolve(s.c, b), n8);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_DISC_INGEST_DY: {
+        const long long npix = (long long)s.pn * s.ph * s.pw;
+        disc_ingest_grad_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>((const float*)b.dy, s.pn, s.pc, s.ph, s.pw, (__nv_bfloat16*)resolve(s.c, b), 64);
+        CUDA_TRY(cudaGetLastError());
+        break;
+      }
+      case ST_DISC_UNPACK: {
+        int blocks = 0;
+        for (const UnpackOp& u : P.unpack_ops) blocks += u.nblocks;
+        unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(P.d_unpack_ops, 0, (int)P.unpack_ops.size(), (const float*)((char*)b.ws + P.o_gw), (float*)b.grads);
+        CUDA_TRY(cudaGetLastError());
+        for (const UnpackOp& u : P.unpack_ops) {
+          if (u.fold != 2) continue;
+          const long long n = 16LL * u.co * u.ci;
+          unpack_wgrad_down_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)((char*)b.ws + P.o_gw) + u.src_off, (float*)b.grads + u.dst_off, u.co, u.ci, u.co_pad);
+          CUDA_TRY(cudaGetLastError());
+        }
         break;
       }
       case ST_INGEST_DY: {
@@ -1421,6 +1477,285 @@ static int build_vgg_plan(b200sr_plan& P) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------ U-Net discriminator plan
+// DiscriminatorUNet (BSRGAN/model.py:91-167).  Conv order = parameter order: 0 conv1, 1..3 down1..3, 4..6 up1..3, 7 conv2, 8 conv3, 9 conv4.
+// Tensors that feed a stride-2 conv (out1, down1, down2) live in U layout ([N, h/2, w/2, 4C], channel (py*2+px)*C + c): the 4x4
+// stride-2 conv is then an ordinary 3x3 conv over 4C channels (weights packed with structural zeros, kPackDownFwd), its data
+// gradient an ordinary 3x3 dgrad whose 4C output columns are pixel-shuffled back to the plain layout on store, and its weight
+// gradient the ordinary 3x3 wgrad over the U-layout input, gathered to [co][c][4][4] by unpack_wgrad_down_kernel.
+static int build_disc_plan(b200sr_plan& P) {
+  const b200sr_disc_desc& v = P.dd;
+  if (v.channels != 64) return fail(B200SR_ERR_INVALID, "only channels=64 is supported (got %d)", v.channels);
+  if (v.in_channels < 1 || v.in_channels > 16 || v.out_channels < 1 || v.out_channels > 16) return fail(B200SR_ERR_INVALID, "in/out channels must be in [1,16]");
+  if (v.batch < 1 || v.height < 8 || v.width < 8 || (v.height & 7) || (v.width & 7)) return fail(B200SR_ERR_INVALID, "height and width must be multiples of 8");
+  P.is_disc = true;
+  P.reassoc = false;
+  P.groups = v.batch >= 2 ? 2 : 1;
+  memset(&P.d, 0, sizeof(P.d));
+  P.d.in_channels = v.in_channels; P.d.out_channels = v.out_channels; P.d.channels = 64; P.d.growth = 32;
+  P.d.batch = v.batch; P.d.height = v.height; P.d.width = v.width; P.d.training = v.training;
+  const bool train = v.training != 0;
+  const int N = v.batch, H = v.height, W = v.width, CI = v.in_channels, CO = v.out_channels;
+  const int nconv = 10;
+  // conv geometry: output channels, input channels (of the reference tensor), kernel size, lattice the conv RUNS on (level: H >> lvl)
+  const int cO[10] = {64, 128, 256, 512, 256, 128, 64, 64, 64, CO};
+  const int cI[10] = {CI, 64, 128, 256, 512, 256, 128, 64, 64, 64};
+  const int cK[10] = {3, 4, 4, 4, 3, 3, 3, 3, 3, 3};
+  const int cLvl[10] = {0, 1, 2, 3, 2, 1, 0, 0, 0, 0};
+  const bool cBias[10] = {true, false, false, false, false, false, false, false, false, true};
+  P.param_off.assign(2 * nconv + 1, 0);
+  {
+    long long off = 0;
+    for (int c = 0; c < nconv; ++c) {
+      P.param_off[2 * c] = off; off += (long long)cO[c] * cI[c] * cK[c] * cK[c];
+      P.param_off[2 * c + 1] = off; off += cBias[c] ? cO[c] : 0;
+    }
+    P.param_off[2 * nconv] = off;
+  }
+  auto lh = [&](int lvl) { return H >> lvl; };
+  auto lw = [&](int lvl) { return W >> lvl; };
+  auto npx = [&](int lvl) { return (long long)N * lh(lvl) * lw(lvl); };
+  Builder B(P);
+  P.xin_stride = 64;
+  P.o_xin = B.alloc(npx(0) * 64 * 2);
+  // forward activations (all kept: the backward pass reads every one of them)
+  const long long T0u = B.alloc(npx(0) * 64 * 2), T1u = B.alloc(npx(1) * 128 * 2), T2u = B.alloc(npx(2) * 256 * 2), T3 = B.alloc(npx(3) * 512 * 2);
+  const long long B1 = B.alloc(npx(2) * 512 * 2), A1 = B.alloc(npx(2) * 256 * 2), B2 = B.alloc(npx(1) * 256 * 2), A2 = B.alloc(npx(1) * 128 * 2);
+  const long long B3 = B.alloc(npx(0) * 128 * 2), A3 = B.alloc(npx(0) * 64 * 2), S3 = B.alloc(npx(0) * 64 * 2), A4 = B.alloc(npx(0) * 64 * 2), A5 = B.alloc(npx(0) * 64 * 2);
+  long long DYP = 0, G5 = 0, G4 = 0, GS3 = 0, G3 = 0, GB3 = 0, GS2 = 0, GA2 = 0, GB2 = 0, GS1 = 0, GA1 = 0, GB1 = 0, GT3 = 0, GT2 = 0, GT1 = 0, G0 = 0;
+  // effective (as computed) input channels / staged output channels of every conv's weight gradient
+  int eI[10], coPad[10];
+  for (int c = 0; c < nconv; ++c) { eI[c] = (cK[c] == 4) ? 4 * cI[c] : cI[c]; coPad[c] = (int)align_up(cO[c], 4); }
+  if (train) {
+    DYP = B.alloc(npx(0) * 64 * 2); G5 = B.alloc(npx(0) * 64 * 2); G4 = B.alloc(npx(0) * 64 * 2); GS3 = B.alloc(npx(0) * 64 * 2); G3 = B.alloc(npx(0) * 64 * 2);
+    GB3 = B.alloc(npx(0) * 128 * 2); GS2 = B.alloc(npx(1) * 128 * 2); GA2 = B.alloc(npx(1) * 128 * 2); GB2 = B.alloc(npx(1) * 256 * 2);
+    GS1 = B.alloc(npx(2) * 256 * 2); GA1 = B.alloc(npx(2) * 256 * 2); GB1 = B.alloc(npx(2) * 512 * 2); GT3 = B.alloc(npx(3) * 512 * 2);
+    GT2 = B.alloc(npx(2) * 256 * 2); GT1 = B.alloc(npx(1) * 128 * 2); G0 = B.alloc(npx(0) * 64 * 2);
+    long long off = 0;
+    int blocks = 0;
+    P.gw_off.assign(nconv, 0);
+    for (int c = 0; c < nconv; ++c) {
+      P.gw_off[c] = off;
+      UnpackOp u;
+      u.src_off = off; u.dst_off = P.param_off[2 * c]; u.co = cO[c]; u.ci = cI[c]; u.co_pad = coPad[c]; u.fold = (cK[c] == 4) ? 2 : 0;
+      u.block0 = blocks; u.nblocks = (cK[c] == 4) ? 0 : ((cO[c] + 31) / 32) * ((cI[c] + 31) / 32);  // fold 2: unpack_wgrad_down_kernel
+      blocks += u.nblocks;
+      P.unpack_ops.push_back(u);
+      off += align_up(9LL * eI[c] * coPad[c], 4);
+    }
+    P.o_gw = B.alloc(off * 4);
+    P.gw_bytes = off * 4;
+  }
+  P.ws_bytes = B.cursor;
+
+  auto packed_bias = [&](long long off_floats) { Ref r; r.kind = RK_PACKED; r.off = -1 - off_floats; return r; };
+  auto conv_step = [&](int amap, const ConvParams& cp) {
+    Step s; s.type = ST_CONV; s.amap = amap; s.wmap = 0; s.cp = cp; s.grid = dim3(1, 1, 1); s.smem = 0;
+    return s;
+  };
+  // generic layer: input buffer [.., c_in] (plain or U layout: the conv does not care), K = c_in channels in chunks of 64
+  auto fwd_conv = [&](int c, long long in_off, int c_in, int mode, long long out_off, int out_stride, int act) {
+    const int lvl = cLvl[c], cout = cO[c];
+    const int n_total = (c == 9) ? 16 : cout, n_cols = (c == 9) ? 16 : 64;
+    PackOp op; memset(&op, 0, sizeof(op));
+    op.n_total = n_total; op.n_cols = n_cols; op.n_valid = cout; op.mode = mode; op.num_chunks = c_in / 64; op.nseg = 1;
+    op.seg[0] = seg(0, c_in, 2 * c, cout, cI[c], 0, 0, 0);
+    const int row0 = B.add_pack(op);
+    ConvParams cp = base_conv_params(N, lh(lvl), lw(lvl), op.num_chunks, 4, 0, 1 << 20, row0, n_cols, n_total);
+    Step s = conv_step(B.add_map(in_off, c_in, c_in, N, lh(lvl), lw(lvl), kABoxRows), cp);
+    if (cBias[c]) s.bias = packed_bias(B.add_bias(n_total, 2 * c + 1, cout, 0));
+    s.cp.epi.act = act;
+    if (out_off >= 0) { s.ob = ws(out_off); s.cp.epi.ob_stride = out_stride; s.cp.epi.ob_coff = 0; }
+    return s;
+  };
+  auto up_step = [&](long long in_off, long long skip_u, long long out_off, int lvl_in, int C) {
+    Step s; s.type = ST_DISC_UP; s.a = ws(in_off); if (skip_u >= 0) s.b = ws(skip_u); s.c = ws(out_off);
+    s.pn = N; s.ph = lh(lvl_in); s.pw = lw(lvl_in); s.pc = C;
+    return s;
+  };
+  // ================================================================ forward ================================================================
+  { Step s; s.type = ST_INGEST_X; P.fwd.push_back(s); }
+  {  // conv1: [hi | lo | hi] input x [w_hi | w_hi | w_lo] weights, no activation, stored in U layout for down1
+    PackOp op; memset(&op, 0, sizeof(op));
+    op.n_total = 64; op.n_cols = 64; op.n_valid = 64; op.mode = kPackFwd; op.num_chunks = 1; op.nseg = 3;
+    op.seg[0] = seg(0, CI, 0, 64, CI, 0, 0, 0); op.seg[1] = seg(CI, CI, 0, 64, CI, 0, 0, 0); op.seg[2] = seg(2 * CI, CI, 0, 64, CI, 0, 0, 1);
+    const int row0 = B.add_pack(op);
+    ConvParams cp = base_conv_params(N, H, W, 1, (3 * CI + 15) / 16, 0, 1 << 20, row0, 64, 64);
+    Step s = conv_step(B.add_map(P.o_xin, 64, 64, N, H, W, kABoxRows), cp);
+    s.bias = packed_bias(B.add_bias(64, 1, 64, 0));
+    s.ob = ws(T0u); s.cp.epi.ob_stride = 256; s.cp.epi.store_mode = kStoreUnshuffle; s.cp.epi.shuf_c = 64;
+    P.fwd.push_back(s);
+  }
+  {
+    Step d1 = fwd_conv(1, T0u, 256, kPackDownFwd, T1u, 512, 1);
+    d1.cp.epi.store_mode = kStoreUnshuffle; d1.cp.epi.shuf_c = 128;
+    P.fwd.push_back(d1);
+    Step d2 = fwd_conv(2, T1u, 512, kPackDownFwd, T2u, 1024, 1);
+    d2.cp.epi.store_mode = kStoreUnshuffle; d2.cp.epi.shuf_c = 256;
+    P.fwd.push_back(d2);
+    P.fwd.push_back(fwd_conv(3, T2u, 1024, kPackDownFwd, T3, 512, 1));
+  }
+  P.fwd.push_back(up_step(T3, -1, B1, 3, 512));
+  P.fwd.push_back(fwd_conv(4, B1, 512, kPackFwd, A1, 256, 1));
+  P.fwd.push_back(up_step(A1, T2u, B2, 2, 256));        // (up1 + down2) upsampled
+  P.fwd.push_back(fwd_conv(5, B2, 256, kPackFwd, A2, 128, 1));
+  P.fwd.push_back(up_step(A2, T1u, B3, 1, 128));        // (up2 + down1) upsampled
+  P.fwd.push_back(fwd_conv(6, B3, 128, kPackFwd, A3, 64, 1));
+  { Step s; s.type = ST_DISC_ADD; s.a = ws(A3); s.b = ws(T0u); s.c = ws(S3); s.pn = N; s.ph = H; s.pw = W; s.pc = 64; P.fwd.push_back(s); }  // up3 + out1
+  P.fwd.push_back(fwd_conv(7, S3, 64, kPackFwd, A4, 64, 1));
+  P.fwd.push_back(fwd_conv(8, A4, 64, kPackFwd, A5, 64, 1));
+  {
+    Step s = fwd_conv(9, A5, 64, kPackFwd, -1, 0, 0);
+    s.cp.epi.store_mode = kStoreNCHW; s.cp.epi.n_valid = CO; s.of.kind = RK_Y;
+    P.fwd.push_back(s);
+  }
+  // ================================================================ backward ===============================================================
+  if (train) {
+    // data gradient of conv c: reads the gradient w.r.t. its pre-activation output (K = k_in valid channels of a buffer with
+    // `in_stride` channels), produces n_total input-gradient columns
+    auto dgrad_conv = [&](int c, long long in_off, int k_in, int in_stride, int mode, int n_total, int n_cols, int n_valid) {
+      const int lvl = cLvl[c];
+      PackOp op; memset(&op, 0, sizeof(op));
+      op.n_total = n_total; op.n_cols = n_cols; op.n_valid = n_valid; op.mode = mode; op.num_chunks = (k_in + 63) / 64; op.nseg = 1;
+      op.seg[0] = seg(0, cO[c], 2 * c, cO[c], cI[c], 0, 0, 0);
+      const int row0 = B.add_pack(op);
+      const int kl = k_in - 64 * (op.num_chunks - 1);
+      ConvParams cp = base_conv_params(N, lh(lvl), lw(lvl), op.num_chunks, (kl + 15) / 16, 0, 1 << 20, row0, n_cols, n_total);
+      return conv_step(B.add_map(in_off, k_in, in_stride, N, lh(lvl), lw(lvl), kABoxRows), cp);
+    };
+    auto out_to = [&](Step& s, long long off, int stride) { s.ob = ws(off); s.cp.epi.ob_stride = stride; s.cp.epi.ob_coff = 0; };
+    auto mask_by = [&](Step& s, long long off, int stride) { s.mask = ws(off); s.cp.epi.mask_stride = stride; s.cp.epi.mask_coff = 0; };
+    auto up_bwd = [&](long long gout, long long act, long long gs, long long ga, int lvl_in, int C) {
+      Step s; s.type = ST_DISC_UP_BWD; s.a = ws(gout); s.b = ws(act); if (gs >= 0) s.c = ws(gs); s.d2 = ws(ga);
+      s.pn = N; s.ph = lh(lvl_in); s.pw = lw(lvl_in); s.pc = C;
+      return s;
+    };
+    {
+      Step m; m.type = ST_MEMSET; m.a.kind = RK_GRADS; m.a.off = 0; m.count = P.param_off[2 * nconv] * 4; m.needs_wgrad = true;
+      P.bwd.push_back(m);
+      Step m2; m2.type = ST_MEMSET; m2.a = ws(P.o_gw); m2.count = P.gw_bytes; m2.needs_wgrad = true;
+      P.bwd.push_back(m2);
+      Step g; g.type = ST_DISC_INGEST_DY; g.c = ws(DYP); g.pn = N; g.ph = H; g.pw = W; g.pc = CO;
+      P.bwd.push_back(g);
+    }
+    { Step s = dgrad_conv(9, DYP, 16, 64, kPackDgrad, 64, 64, 64); s.cp.ksteps_last = 1; mask_by(s, A5, 64); out_to(s, G5, 64); P.bwd.push_back(s); }
+    { Step s = dgrad_conv(8, G5, 64, 64, kPackDgrad, 64, 64, 64); mask_by(s, A4, 64); out_to(s, G4, 64); P.bwd.push_back(s); }
+    { Step s = dgrad_conv(7, G4, 64, 64, kPackDgrad, 64, 64, 64); out_to(s, GS3, 64); P.bwd.push_back(s); }   // gradient of (up3 + out1)
+    { Step s; s.type = ST_DISC_MASK; s.a = ws(GS3); s.b = ws(A3); s.c = ws(G3); s.pn = N; s.ph = H; s.pw = W; s.pc = 64; P.bwd.push_back(s); }
+    { Step s = dgrad_conv(6, G3, 64, 64, kPackDgrad, 128, 64, 128); out_to(s, GB3, 128); P.bwd.push_back(s); }
+    P.bwd.push_back(up_bwd(GB3, A2, GS2, GA2, 1, 128));
+    { Step s = dgrad_conv(5, GA2, 128, 128, kPackDgrad, 256, 64, 256); out_to(s, GB2, 256); P.bwd.push_back(s); }
+    P.bwd.push_back(up_bwd(GB2, A1, GS1, GA1, 2, 256));
+    { Step s = dgrad_conv(4, GA1, 256, 256, kPackDgrad, 512, 64, 512); out_to(s, GB1, 512); P.bwd.push_back(s); }
+    P.bwd.push_back(up_bwd(GB1, T3, -1, GT3, 3, 512));
+    // stride-2 convs: 4C output columns on the conv's own lattice, pixel-shuffled to the plain layout of the finer lattice; the
+    // skip connection's gradient (plain layout, finer lattice) joins before the LeakyReLU derivative of the U-layout activation
+    {
+      Step s = dgrad_conv(3, GT3, 512, 512, kPackDownDgrad, 1024, 64, 1024);
+      s.cp.epi.store_mode = kStoreShuffle; s.cp.epi.shuf_c = 256; out_to(s, GT2, 256);
+      s.resb = ws(GS1); s.cp.epi.res_bf16_stride = 256; mask_by(s, T2u, 1024);
+      P.bwd.push_back(s);
+    }
+    {
+      Step s = dgrad_conv(2, GT2, 256, 256, kPackDownDgrad, 512, 64, 512);
+      s.cp.epi.store_mode = kStoreShuffle; s.cp.epi.shuf_c = 128; out_to(s, GT1, 128);
+      s.resb = ws(GS2); s.cp.epi.res_bf16_stride = 128; mask_by(s, T1u, 512);
+      P.bwd.push_back(s);
+    }
+    {
+      Step s = dgrad_conv(1, GT1, 128, 128, kPackDownDgrad, 256, 64, 256);   // out1 has no activation: no mask
+      s.cp.epi.store_mode = kStoreShuffle; s.cp.epi.shuf_c = 64; out_to(s, G0, 64);
+      s.resb = ws(GS3); s.cp.epi.res_bf16_stride = 64;
+      P.bwd.push_back(s);
+    }
+    {  // gradient w.r.t. the input image (the generator update): conv1's data gradient, fp32 NCHW
+      Step s = dgrad_conv(0, G0, 64, 64, kPackDgrad, 16, 16, CI);
+      s.cp.epi.store_mode = kStoreNCHW; s.cp.epi.n_valid = CI; s.of.kind = RK_Y; s.needs_dx = true;
+      P.bwd.push_back(s);
+    }
+    // ---- weight gradients: blocks of (<= 128 input channels) x (<= 128 output channels), four problems per launch
+    auto wref = [&](int c, long long extra_floats) { return ws(P.o_gw + (P.gw_off[c] + extra_floats) * 4); };
+    auto wgrad_conv = [&](int c, long long x_off, int x_cvalid, int x_cpix, long long dy_off, int dy_cvalid, int dy_cpix, int ci_total) {
+      const int lvl = cLvl[c];
+      const int n = N, h = lh(lvl), w = lw(lvl);
+      const int ncols_all = (c == 9) ? 16 : cO[c];
+      Step cur; bool open = false;
+      for (int cib = 0; cib < x_cvalid; cib += 128) {
+        for (int cob = 0; cob < ncols_all; cob += 128) {
+          if (!open) {
+            cur = Step(); cur.type = ST_WGRAD; cur.needs_wgrad = true;
+            cur.xmap = B.add_map(x_off, x_cvalid, x_cpix, n, h, w, kWgXRows);
+            cur.dymap = B.add_map(dy_off, dy_cvalid, dy_cpix, n, h, w, kWgTileH);
+            WgradBatch& wb = cur.wb; memset(&wb, 0, sizeof(wb));
+            wb.N = n; wb.H = h; wb.W = w;
+            wb.tiles_x = (w + kTileW - 1) / kTileW; wb.tiles_y = (h + kWgTileH - 1) / kWgTileH; wb.num_tiles = n * wb.tiles_x * wb.tiles_y;
+            open = true;
+          }
+          const int ncols = std::min(128, ncols_all - cob);
+          const int pj = cur.wb.num_problems++;
+          WgradParams& wp = cur.wb.prob[pj];
+          wp.a_c0 = cib; wp.b_c0 = cob; wp.n_cols = ncols; wp.n_blocks = (ncols + 63) / 64; wp.bias_mode = 0;
+          wp.a_blocks = (x_cvalid - cib > 64) ? 2 : 1;
+          WgradSegment& g = wp.seg[0];
+          g.col_begin = 0; g.col_end = ncols; g.out = nullptr; g.ci_total = ci_total; g.ci0 = cib; g.co_pad = coPad[c];
+          cur.wseg_out[pj][0] = wref(c, (long long)(cob / 4) * ci_total * 4);
+          wp.num_seg = 1;
+          if (cur.wb.num_problems == kWgMaxProblems) { P.bwd.push_back(cur); open = false; }
+        }
+      }
+      if (open) P.bwd.push_back(cur);
+    };
+    auto bias_grad = [&](int c, long long g_off, int ncols, int n_valid) {
+      Step s; s.type = ST_BIASGRAD; s.needs_wgrad = true;
+      memset(&s.bp, 0, sizeof(s.bp));
+      s.bg_g = ws(g_off); s.bp.P = npx(0); s.bp.stride = 64; s.bp.c0 = 0; s.bp.ncols = ncols;
+      BiasGradSeg& g = s.bp.seg[0];
+      g.col_begin = 0; g.col_end = ncols; g.out = nullptr; g.n_valid = n_valid;
+      s.seg_out[0].kind = RK_GRADS; s.seg_out[0].off = P.param_off[2 * c + 1] * 4;
+      s.bp.nseg = 1;
+      P.bwd.push_back(s);
+    };
+    bias_grad(9, DYP, 16, CO);
+    bias_grad(0, G0, 64, 64);
+    wgrad_conv(9, A5, 64, 64, DYP, 16, 64, 64);
+    wgrad_conv(8, A4, 64, 64, G5, 64, 64, 64);
+    wgrad_conv(7, S3, 64, 64, G4, 64, 64, 64);
+    wgrad_conv(6, B3, 128, 128, G3, 64, 64, 128);
+    wgrad_conv(5, B2, 256, 256, GA2, 128, 128, 256);
+    wgrad_conv(4, B1, 512, 512, GA1, 256, 256, 512);
+    wgrad_conv(3, T2u, 1024, 1024, GT3, 512, 512, 1024);
+    wgrad_conv(2, T1u, 512, 512, GT2, 256, 256, 512);
+    wgrad_conv(1, T0u, 256, 256, GT1, 128, 128, 256);
+    wgrad_conv(0, P.o_xin, 64, 64, G0, 64, 64, CI);   // rows >= CI of the [hi | lo | hi] input are not flushed
+    { Step s; s.type = ST_DISC_UNPACK; s.needs_wgrad = true; P.bwd.push_back(s); }
+  }
+  const long long bias_base = align_up(P.total_rows * 128, 1024);
+  P.packed_bytes = bias_base + P.bias_floats * 4;
+  auto fix = [&](std::vector<Step>& vv) {
+    for (Step& s : vv)
+      if (s.bias.kind == RK_PACKED) s.bias.off = bias_base + (-1 - s.bias.off) * 4;
+  };
+  fix(P.fwd); fix(P.bwd);
+  auto chainify = [&](std::vector<Step>& vv) {
+    std::vector<Step> out;
+    for (Step& s : vv) {
+      if (s.type != ST_CONV) { out.push_back(s); continue; }
+      if (out.empty() || out.back().type != ST_CHAIN || out.back().needs_dx != s.needs_dx) {
+        Step c; c.type = ST_CHAIN; c.layer0 = (int)P.layer_steps.size(); c.nlayers = 0; c.chain_grid = 0; c.needs_dx = s.needs_dx;
+        out.push_back(c);
+      }
+      out.back().nlayers++;
+      const int work = s.cp.num_tiles * s.cp.col_groups;
+      if (work > out.back().chain_grid) out.back().chain_grid = work;
+      P.layer_steps.push_back(s);
+    }
+    vv.swap(out);
+  };
+  chainify(P.fwd); chainify(P.bwd);
+  return 0;
+}
+
 // =================================================================================================== C ABI =====
 extern "C" {
 
@@ -1483,6 +1818,22 @@ int64_t b200sr_param_numel(const b200sr_plan* p) { return p ? p->param_off.back(
 
 double b200sr_flops(const b200sr_plan* p, int backward) {
   if (!p) return 0;
+  if (p->is_disc) {
+    // 2 x MACs of the reference graph (BSRGAN/model.py:143-167).  backward = 1: the discriminator update (every weight gradient, every
+    // data gradient but conv1's); backward = 2: the generator update (data gradients only, down to the input image)
+    const b200sr_disc_desc& v = p->dd;
+    const double cO[10] = {64, 128, 256, 512, 256, 128, 64, 64, 64, (double)v.out_channels};
+    const double cI[10] = {(double)v.in_channels, 64, 128, 256, 512, 256, 128, 64, 64, 64};
+    const int cK[10] = {3, 4, 4, 4, 3, 3, 3, 3, 3, 3}, lvl[10] = {0, 1, 2, 3, 2, 1, 0, 0, 0, 0};
+    double total = 0;
+    for (int c = 0; c < 10; ++c) {
+      const double fl = 2.0 * cK[c] * cK[c] * cO[c] * cI[c] * v.batch * (v.height >> lvl[c]) * (v.width >> lvl[c]);
+      if (!backward) total += fl;
+      else if (backward == 1) total += fl * (c == 0 ? 1 : 2);
+      else total += fl;
+    }
+    return total;
+  }
   const int nconv = ((int)p->param_off.size() - 1) / 2;
   const int ntrunk = p->R * 5;
   double px = (double)p->d.batch * p->d.height * p->d.width, total = 0;
@@ -1745,6 +2096,46 @@ int b200sr_tensor_to_image_u8(const float* x, int c, int h, int w, int range_nor
   tensor_to_image_u8_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, c, h, w, range_norm, half, out_hwc);
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------ U-Net discriminator
+int b200sr_disc_plan_create(const b200sr_disc_desc* desc, b200sr_plan** out) {
+  if (!desc || !out) return fail(B200SR_ERR_INVALID, "null argument");
+  b200sr_plan* p = new b200sr_plan();
+  p->dd = *desc;
+  int rc = build_disc_plan(*p);
+  if (rc) { delete p; return rc; }
+  *out = p;
+  return 0;
+}
+
+int b200sr_disc_forward(b200sr_plan* p, const void* x, int x_dtype, const int64_t* x_strides, const void* packed, void* workspace,
+                        float* y, b200sr_stream stream) {
+  if (!p || !p->is_disc || !x || !x_strides || !packed || !workspace || !y) return fail(B200SR_ERR_INVALID, "bad argument");
+  int rc = runtime_init();
+  if (rc) return rc;
+  rc = ensure_maps(*p, workspace, (void*)packed, (cudaStream_t)stream);
+  if (rc) return rc;
+  Bases b{workspace, (void*)packed, y, nullptr, nullptr};
+  return run_steps(*p, p->fwd, b, x, x_dtype, x_strides, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int b200sr_disc_backward(b200sr_plan* p, const float* dy, const void* packed, void* workspace, float* flat_grads_or_null,
+                         float* dx_or_null, b200sr_stream stream) {
+  if (!p || !p->is_disc || !dy || !packed || !workspace) return fail(B200SR_ERR_INVALID, "bad argument");
+  if (!p->dd.training) return fail(B200SR_ERR_INVALID, "plan was created with training=0");
+  int rc = runtime_init();
+  if (rc) return rc;
+  rc = ensure_maps(*p, workspace, (void*)packed, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!p->d_unpack_ops) {
+    CUDA_TRY(cudaMalloc(&p->d_unpack_ops, p->unpack_ops.size() * sizeof(UnpackOp)));
+    CUDA_TRY(cudaMemcpyAsync(p->d_unpack_ops, p->unpack_ops.data(), p->unpack_ops.size() * sizeof(UnpackOp), cudaMemcpyHostToDevice,
+                             (cudaStream_t)stream));
+  }
+  Bases b{workspace, (void*)packed, dx_or_null, dy, flat_grads_or_null};
+  return run_steps(*p, p->bwd, b, nullptr, 0, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ VGG19 features

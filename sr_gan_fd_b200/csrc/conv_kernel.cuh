@@ -72,6 +72,12 @@ struct ConvEpilogue {
   int mask_relu;  // bit 0: dgrad mask is the ReLU derivative; bit 1: feat_out is stored after the activation
   int feat_stride;
   float* feat_out;
+  // U-Net discriminator layers (sr_gan_fd_b200/discriminator.py; extended build only): a bf16 residual read at the DESTINATION
+  // address of the bf16 store (after the pixel shuffle) and added BEFORE the activation-derivative mask -- the skip-connection
+  // gradient joining the data gradient of a stride-2 conv -- and the channel count of one pixel-(un)shuffle phase (0 = 64)
+  const __nv_bfloat16* res_bf16;
+  int res_bf16_stride;
+  int shuf_c;
 };
 
 struct ConvParams {
@@ -159,7 +165,10 @@ template <int kVgg>
 __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const float* sbias, const float (&res)[32], bool has_res,
                                                    const uint32_t (&maskw)[16], bool has_mask, int col0, int ncol, float (&v)[32],
                                                    float* feat_row = nullptr) {
-  if (ncol == 32) {
+  if (kVgg && !e.bias) {  // bias-free layer (its columns may exceed the staged bias slot): scale only
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= e.alpha;
+  } else if (ncol == 32) {
     const float4* b4 = reinterpret_cast<const float4*>(sbias + col0);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -186,6 +195,11 @@ __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const 
 #pragma unroll
     for (int q = 0; q < 8; ++q) st_global_v4f(feat_row + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
+  const bool res_first = kVgg && e.res_bf16 != nullptr;  // skip-connection gradient: joins BEFORE the activation derivative
+  if (res_first && has_res) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += res[i];
+  }
   if (has_mask) {  // activation derivative from the saved forward activation (LeakyReLU 0.2, or ReLU)
     const float neg = (kVgg && (e.mask_relu & 1)) ? 0.f : 0.2f;
 #pragma unroll
@@ -194,17 +208,35 @@ __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const 
       v[2 * j + 1] *= (bf16_hi_to_f32(maskw[j]) > 0.f) ? 1.f : neg;
     }
   }
-  if (has_res) {  // fp32 residuals (already combined)
+  if (has_res && !res_first) {  // fp32 residuals (already combined)
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] += res[i];
   }
 }
 
+// Destination of the bf16 store of global column col0 at lattice position (n, y, x): pixel index and channel, with the pixel
+// (un)shuffle folded in.  kExt = 0 (generator build): a phase is always 64 channels wide.
+template <int kExt>
+__device__ __forceinline__ void conv_store_dest(const HW p, const ConvEpilogue& e, int n, int y, int x, int col0, long long& opix, int& ch) {
+  const int sc = (kExt && e.shuf_c > 0) ? e.shuf_c : 64;
+  if (e.store_mode == kStoreShuffle) {
+    const int phase = kExt ? col0 / sc : (col0 >> 6);
+    opix = (static_cast<long long>(n) * (2 * p.H) + (2 * y + (phase >> 1))) * (2 * p.W) + (2 * x + (phase & 1));
+    ch = kExt ? col0 - phase * sc : (col0 & 63);
+  } else if (e.store_mode == kStoreUnshuffle) {
+    opix = (static_cast<long long>(n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+    ch = (((y & 1) << 1) | (x & 1)) * sc + col0;
+  } else {
+    opix = (static_cast<long long>(n) * p.H + y) * p.W + x;
+    ch = col0;
+  }
+}
+
 // Part 2: stores.  Called by all 32 lanes of the warp (the bf16 store shuffles); `ok` = this lane's pixel exists and
 // stores are enabled.
+template <int kExt>
 __device__ __forceinline__ void conv_epilogue_write(const HW p, const ConvEpilogue& e, float* y_dyn, long long cbase, int n, int y, int x,
                                                     int col0, float (&v)[32], bool ok, int lane) {
-  const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
   if (e.store_mode == kStoreNCHW) {
     if (!ok) return;
     const long long plane = static_cast<long long>(p.H) * p.W;
@@ -244,17 +276,7 @@ __device__ __forceinline__ void conv_epilogue_write(const HW p, const ConvEpilog
   if (e.out_bf16) {
     long long opix;
     int ch;
-    if (e.store_mode == kStoreShuffle) {
-      const int phase = col0 >> 6;
-      opix = (static_cast<long long>(n) * (2 * p.H) + (2 * y + (phase >> 1))) * (2 * p.W) + (2 * x + (phase & 1));
-      ch = col0 & 63;
-    } else if (e.store_mode == kStoreUnshuffle) {
-      opix = (static_cast<long long>(n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
-      ch = (((y & 1) << 1) | (x & 1)) * 64 + col0;
-    } else {
-      opix = pix;
-      ch = col0;
-    }
+    conv_store_dest<kExt>(p, e, n, y, x, col0, opix, ch);
     __nv_bfloat16* ob = e.out_bf16 + opix * e.ob_stride + e.ob_coff + ch;
     uint32_t hi[16];
 #pragma unroll
@@ -298,14 +320,14 @@ struct alignas(32) EntryDesc {
 // The host copies the slice of the chain being launched into these tables right before the launch (stream ordered).
 constexpr int kMaxChainLayers = 768;
 constexpr int kMaxChainEntries = 2048;
-// layer record A: x = n_cols | chunks<<10 | ksteps_last<<14 | halves<<17 | w_taps<<19 | col_groups<<23
+// layer record A: x = n_cols (9 bits) | chunks<<9 (5 bits) | ksteps_last<<14 | halves<<17 | w_taps<<19 | col_groups<<23
 //                 y = acc_col0 | acc_first<<8 | acc_hold<<9 | has_epi<<10      z = w_row0      w = a_c0
 // layer record B: x = tiles_x | tiles_y<<16      y = a_wrap      z = bias byte offset in the packed buffer + 1 (0: none)      w = bias floats
 // entry record  : x = layer (absolute) | slot<<20 | neighbour_sync<<21      y = tile_lo      z = tile_hi      w = rot | (dep+1)<<16
 __constant__ uint4 c_layer_rec[kMaxChainLayers * 2];
 __constant__ uint4 c_entry_rec[kMaxChainEntries];
 inline void make_layer_rec(const ConvParams& p, uint4 out[2], const void* packed_base) {
-  out[0].x = static_cast<uint32_t>(p.n_cols) | (p.num_chunks << 10) | (p.ksteps_last << 14) | (p.halves << 17) | (p.w_taps << 19) | (p.col_groups << 23);
+  out[0].x = static_cast<uint32_t>(p.n_cols) | (p.num_chunks << 9) | (p.ksteps_last << 14) | (p.halves << 17) | (p.w_taps << 19) | (p.col_groups << 23);
   out[0].y = static_cast<uint32_t>(p.acc_col0) | ((p.acc_first ? 1u : 0u) << 8) | ((p.acc_hold ? 1u : 0u) << 9) | ((p.epi_cols > 0 ? 1u : 0u) << 10) |
              ((p.k32 ? 1u : 0u) << 11);
   out[0].z = static_cast<uint32_t>(p.w_row0);
@@ -512,7 +534,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int tile_lo = static_cast<int>(er.y), tile_hi = static_cast<int>(er.z);
       const int rot = static_cast<int>(er.w & 0xFFFF), dep = static_cast<int>(er.w >> 16) - 1;
       const uint4 la = c_layer_rec[(li - layer0) * 2], lb = c_layer_rec[(li - layer0) * 2 + 1];
-      const int n_cols = la.x & 0x3FF, num_chunks = (la.x >> 10) & 0xF, w_taps = (la.x >> 19) & 0xF, col_groups = (la.x >> 23) & 0x1F;
+      const int n_cols = la.x & 0x1FF, num_chunks = (la.x >> 9) & 0x1F, w_taps = (la.x >> 19) & 0xF, col_groups = (la.x >> 23) & 0x1F;
       constexpr int tile_h = kTileH;
       const int w_row0 = static_cast<int>(la.z), a_c0 = static_cast<int>(la.w), a_wrap = static_cast<int>(lb.y);
       const int tiles_x = static_cast<int>(lb.x & 0xFFFF), tiles_y = static_cast<int>(lb.x >> 16);
@@ -654,7 +676,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int li = static_cast<int>(er.x & 0xFFFFF), slot = static_cast<int>((er.x >> 20) & 1);
       const int tile_lo = static_cast<int>(er.y), tile_hi = static_cast<int>(er.z), rot = static_cast<int>(er.w & 0xFFFF);
       const uint4 la = c_layer_rec[(li - layer0) * 2];
-      const int n_cols = la.x & 0x3FF, num_chunks = (la.x >> 10) & 0xF, ksteps_last = (la.x >> 14) & 0x7;
+      const int n_cols = la.x & 0x1FF, num_chunks = (la.x >> 9) & 0x1F, ksteps_last = (la.x >> 14) & 0x7;
       const int w_taps = (la.x >> 19) & 0xF, col_groups = (la.x >> 23) & 0x1F;
       const int acc_col0 = la.y & 0xFF, acc_first = (la.y >> 8) & 1, acc_hold = (la.y >> 9) & 1;
       const bool has_epi = ((la.y >> 10) & 1) != 0;  // deferred partial-sum layers have no epilogue: nothing to hand over
@@ -848,11 +870,26 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const long long cbase = carrier_base(tile, half, m);
         float res[32];
         uint32_t maskw[16];
-        const bool has_res = (ep.r1 != nullptr);
+        const bool has_res = (ep.r1 != nullptr) || (kVgg && ep.res_bf16 != nullptr);
         const bool has_mask = (ep.mask != nullptr);
         // residuals + mask words of 32 columns (only that many are held in registers at a time)
         auto prefetch_cols = [&](int c0) {
-          if (pre && has_res) {
+          if (kVgg && ep.res_bf16 != nullptr) {
+            if (pre) {
+              long long rpix; int rch;
+              conv_store_dest<kVgg>(hw, ep, n, y, x, colbase + c0, rpix, rch);
+              const uint4* rp = reinterpret_cast<const uint4*>(ep.res_bf16 + rpix * ep.res_bf16_stride + rch);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint4 r4 = __ldcg(rp + k);
+                res[8 * k] = bf16_lo_to_f32(r4.x); res[8 * k + 1] = bf16_hi_to_f32(r4.x); res[8 * k + 2] = bf16_lo_to_f32(r4.y); res[8 * k + 3] = bf16_hi_to_f32(r4.y);
+                res[8 * k + 4] = bf16_lo_to_f32(r4.z); res[8 * k + 5] = bf16_hi_to_f32(r4.z); res[8 * k + 6] = bf16_lo_to_f32(r4.w); res[8 * k + 7] = bf16_hi_to_f32(r4.w);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) res[k] = 0.f;
+            }
+          } else if (pre && has_res) {
             const float* r1p = ep.r1 + cbase + ((colbase + c0) >> 2) * kCarrierChunkStride;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -921,7 +958,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             conv_epilogue_math<kVgg>(ep, sbias, res, has_res, maskw, has_mask, colbase + c0, ncol, vv, feat_row);
             // the residual / mask registers are free again: fetch the second 32 columns' while the first are stored
             if (gq == 0 && 32 < p.epi_cols) prefetch_cols(32);
-            conv_epilogue_write(hw, ep, y_dyn, cbase, n, y, x, colbase + c0, vv, pre, lane);
+            conv_epilogue_write<kVgg>(hw, ep, y_dyn, cbase, n, y, x, colbase + c0, vv, pre, lane);
             if (warp == 2 && gq == 0) TL_MARK(13);
           }
         }

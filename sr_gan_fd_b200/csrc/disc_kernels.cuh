@@ -1,0 +1,170 @@
+// Helpers of the U-Net discriminator path (BSRGAN/model.py:91-167 = Real_ESRGAN/model.py:29-105).
+// Its ten convs run on conv3x3_chain_kernel / wgrad3x3_kernel (the 4x4 stride-2 convs as 3x3 convs over the pixel-UNSHUFFLED
+// input: "U layout", [N, H/2, W/2, 4C] with channel (py*2+px)*C + c); these HBM-bound kernels do the rest: the bilinear x2
+// upsampling (align_corners=False) with the U-Net skip addition folded in, its transpose for the backward pass with the
+// LeakyReLU derivative folded in, and the two element-wise joins around conv2.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200sr {
+
+// element offset of (n, y, x, channel 0) of a C-channel tensor over an (H, W) lattice kept in U layout
+__device__ __forceinline__ long long u_layout_off(int n, int y, int x, int H, int W, int C) {
+  return ((static_cast<long long>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * (4LL * C) + (((y & 1) << 1) | (x & 1)) * C;
+}
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 v, float (&f)[8]) {
+  f[0] = bf16_lo_to_f32(v.x); f[1] = bf16_hi_to_f32(v.x); f[2] = bf16_lo_to_f32(v.y); f[3] = bf16_hi_to_f32(v.y);
+  f[4] = bf16_lo_to_f32(v.z); f[5] = bf16_hi_to_f32(v.z); f[6] = bf16_lo_to_f32(v.w); f[7] = bf16_hi_to_f32(v.w);
+}
+__device__ __forceinline__ uint4 f32x8_to_bf16(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) of s = in (+ skip), BSRGAN/model.py:150-159.
+// Output row 2Y reads rows (Y-1, Y) with weights (0.25, 0.75), row 2Y+1 rows (Y, Y+1) with (0.75, 0.25); indices clamp at the
+// border (so the first / last output row copies the first / last input row).  in: [N, h, w, C] bf16; skip_u: nullptr or the
+// tensor added to `in` first, in U layout; out: [N, 2h, 2w, C].  One thread per output pixel and 8 channels.
+__global__ void disc_bilinear_up_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ skip_u,
+                                        __nv_bfloat16* __restrict__ out, int N, int h, int w, int C) {
+  const int c8 = C >> 3;
+  const int Ho = 2 * h, Wo = 2 * w;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(N) * Ho * Wo * c8) return;
+  const int cc = static_cast<int>(i % c8);
+  const long long op = i / c8;
+  const int xo = static_cast<int>(op % Wo), yo = static_cast<int>((op / Wo) % Ho), n = static_cast<int>(op / (static_cast<long long>(Wo) * Ho));
+  // source rows / columns and the weight of the SECOND one (torch: lambda = src - floor(src), src = max(o/2 - 0.25, 0))
+  const int y0 = (yo & 1) ? (yo >> 1) : max((yo >> 1) - 1, 0);
+  const int y1 = (yo & 1) ? min((yo >> 1) + 1, h - 1) : (yo >> 1);
+  const float ly = (yo & 1) ? 0.25f : ((yo == 0) ? 0.f : 0.75f);
+  const int x0 = (xo & 1) ? (xo >> 1) : max((xo >> 1) - 1, 0);
+  const int x1 = (xo & 1) ? min((xo >> 1) + 1, w - 1) : (xo >> 1);
+  const float lx = (xo & 1) ? 0.25f : ((xo == 0) ? 0.f : 0.75f);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int sy = a ? y1 : y0, sx = b ? x1 : x0;
+      const float wgt = (a ? ly : 1.f - ly) * (b ? lx : 1.f - lx);
+      float f[8];
+      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + sy) * w + sx) * C) + cc), f);
+      if (skip_u) {
+        float g[8];
+        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(skip_u + u_layout_off(n, sy, sx, h, w, C)) + cc), g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] += g[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += wgt * f[k];
+    }
+  }
+  reinterpret_cast<uint4*>(out + op * C)[cc] = f32x8_to_bf16(acc);
+}
+
+// Transpose of the above: gin[Y, X] = sum over the (up to) 4 x 4 output positions that read input (Y, X).  Per axis the output
+// indices 2Y-1, 2Y, 2Y+1, 2Y+2 contribute with weights 0.25 (Y >= 1), 0.75 (1.0 when Y == 0), 0.75 (1.0 when Y == h-1),
+// 0.25 (Y <= h-2).  gout: [N, 2h, 2w, C] bf16.  gs_out (or nullptr): the sum itself = gradient w.r.t. the upsampled tensor
+// (in + skip), which is also the skip connection's gradient; ga_out (or nullptr): the sum times the LeakyReLU(0.2) derivative
+// taken from the saved activation `act` ([N, h, w, C], same lattice) = gradient w.r.t. the producing conv's pre-activation.
+__global__ void disc_bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16* __restrict__ act,
+                                         __nv_bfloat16* __restrict__ gs_out, __nv_bfloat16* __restrict__ ga_out, int N, int h, int w, int C) {
+  const int c8 = C >> 3;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(N) * h * w * c8) return;
+  const int cc = static_cast<int>(i % c8);
+  const long long ip = i / c8;
+  const int X = static_cast<int>(ip % w), Y = static_cast<int>((ip / w) % h), n = static_cast<int>(ip / (static_cast<long long>(w) * h));
+  const int Ho = 2 * h, Wo = 2 * w;
+  float wy[4], wx[4];
+  wy[0] = (Y >= 1) ? 0.25f : 0.f; wy[1] = (Y == 0) ? 1.f : 0.75f; wy[2] = (Y == h - 1) ? 1.f : 0.75f; wy[3] = (Y <= h - 2) ? 0.25f : 0.f;
+  wx[0] = (X >= 1) ? 0.25f : 0.f; wx[1] = (X == 0) ? 1.f : 0.75f; wx[2] = (X == w - 1) ? 1.f : 0.75f; wx[3] = (X <= w - 2) ? 0.25f : 0.f;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int oy = 2 * Y - 1 + a;
+    if (wy[a] == 0.f) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int ox = 2 * X - 1 + b;
+      if (wx[b] == 0.f) continue;
+      float f[8];
+      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(gout + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * C) + cc), f);
+      const float wgt = wy[a] * wx[b];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += wgt * f[k];
+    }
+  }
+  if (gs_out) reinterpret_cast<uint4*>(gs_out + ip * C)[cc] = f32x8_to_bf16(acc);
+  if (ga_out) {
+    float m[8];
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(act + ip * C) + cc), m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] *= (m[k] > 0.f) ? 1.f : 0.2f;
+    reinterpret_cast<uint4*>(ga_out + ip * C)[cc] = f32x8_to_bf16(acc);
+  }
+}
+
+// out[N, H, W, C] = a (plain layout) + b_u (U layout): up3 + out1 in front of conv2 (BSRGAN/model.py:161)
+__global__ void disc_add_u_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b_u, __nv_bfloat16* __restrict__ out,
+                                  int N, int H, int W, int C) {
+  const int c8 = C >> 3;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(N) * H * W * c8) return;
+  const int cc = static_cast<int>(i % c8);
+  const long long p = i / c8;
+  const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H), n = static_cast<int>(p / (static_cast<long long>(W) * H));
+  float f[8], g[8];
+  bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(a + p * C) + cc), f);
+  bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(b_u + u_layout_off(n, y, x, H, W, C)) + cc), g);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] += g[k];
+  reinterpret_cast<uint4*>(out + p * C)[cc] = f32x8_to_bf16(f);
+}
+
+// out = g * LeakyReLU'(act): the gradient of (up3 + out1) taken through up3's activation
+__global__ void disc_lrelu_mask_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ out,
+                                       long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float f[8], m[8];
+  bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(g) + i), f);
+  bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(act) + i), m);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] *= (m[k] > 0.f) ? 1.f : 0.2f;
+  reinterpret_cast<uint4*>(out)[i] = f32x8_to_bf16(f);
+}
+
+// dy: [N, C, H, W] fp32 contiguous -> [N*H*W, out_stride] bf16, channels [C, 16) zero (upstream gradient of the logit map)
+__global__ void disc_ingest_grad_kernel(const float* __restrict__ dy, int N, int C, int H, int W, __nv_bfloat16* __restrict__ out, int out_stride) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long plane = static_cast<long long>(H) * W;
+  if (pix >= static_cast<long long>(N) * plane) return;
+  const long long n = pix / plane, r = pix - n * plane;
+  float v[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) v[c] = (c < C) ? dy[(n * C + c) * plane + r] : 0.f;
+  uint4* o = reinterpret_cast<uint4*>(out + pix * out_stride);
+  o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+}
+
+// Staged weight gradient of a 4x4 stride-2 conv computed as a 3x3 conv over the U-layout input -> [co][c][4][4].
+// src: [tap = dy*3+dx][co_pad/4][4C][4] fp32; kernel position (ky, kx) lives at tap (dy, dx) and phase (py, px) with
+// ky = 2 dy + py - 1: ky 0,1,2,3 -> (dy, py) = (0,1), (1,0), (1,1), (2,0).  One thread per destination element.
+__global__ void unpack_wgrad_down_kernel(const float* __restrict__ src, float* __restrict__ dst, int co, int C, int co_pad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(co) * C * 16) return;
+  const int kx = static_cast<int>(i & 3), ky = static_cast<int>((i >> 2) & 3);
+  const int c = static_cast<int>((i >> 4) % C), o = static_cast<int>((i >> 4) / C);
+  const int dy = (ky + 1) >> 1, py = (ky + 1) & 1, dx = (kx + 1) >> 1, px = (kx + 1) & 1;
+  const int cu = (py * 2 + px) * C + c;
+  dst[i] = src[((static_cast<long long>(dy * 3 + dx) * (co_pad >> 2) + (o >> 2)) * (4LL * C) + cu) * 4 + (o & 3)];
+}
+
+}  // namespace b200sr

@@ -24,6 +24,10 @@ class VggDesc(C.Structure):
                [("mean", C.c_float * 3), ("std", C.c_float * 3)]
 
 
+class DiscDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("in_channels", "out_channels", "channels", "batch", "height", "width", "training")]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -60,6 +64,9 @@ SIGNATURES = {
     "b200sr_vgg_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200sr_vgg_feature_l1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b200sr_vgg_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200sr_disc_plan_create": (C.c_int, [C.POINTER(DiscDesc), C.POINTER(C.c_void_p)]),
+    "b200sr_disc_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200sr_disc_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200sr_last_error": (C.c_char_p, []),
     "b200sr_version": (C.c_int, []),
     "b200sr_debug_set": (None, [C.c_int]),
