@@ -10,6 +10,8 @@ What it does (nothing in the reference tree is edited or copied):
   * optional ``--set module.attr=value`` edits a config module IN MEMORY before the script imports it (the reference keeps its
     run configuration in ``*_config.py`` files users edit by hand: dataset paths, epochs, batch size);
   * optional ``--vgg`` swaps the folder's ``ContentLoss`` for the B200 VGG19 feature path (``sr_gan_fd_b200.vgg``);
+  * optional ``--disc`` swaps ``DiscriminatorUNet`` / ``discriminator_unet`` (BSRGAN, Real_ESRGAN) for the B200 U-Net discriminator
+    (``sr_gan_fd_b200.discriminator``);
   * optional ``--iqa`` also registers a shim for ``image_quality_assessment`` whose ``PSNR`` / ``SSIM`` are the fused B200 kernels;
   * optional ``--stub name`` installs an empty stand-in for a logging dependency that is not installed (mlflow, lpips, ...);
   * the script then runs under ``runpy`` with ``__name__ == "__main__"`` from the current working directory.
@@ -58,6 +60,7 @@ def main(argv=None) -> None:
     ap.add_argument("--stock", action="store_true", help="do NOT install the shim: run the reference's own model.py (A/B runs)")
     ap.add_argument("--iqa", action="store_true", help="also replace image_quality_assessment.PSNR / SSIM by the fused B200 versions")
     ap.add_argument("--vgg", action="store_true", help="also replace model.ContentLoss / content_loss by the B200 VGG19 feature path")
+    ap.add_argument("--disc", action="store_true", help="also replace model.DiscriminatorUNet / discriminator_unet by the B200 U-Net discriminator")
     ap.add_argument("folder", choices=sorted(SHIMS))
     ap.add_argument("script")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
@@ -83,6 +86,13 @@ def main(argv=None) -> None:
             ns = dict(shim.__dict__)
             ns["ContentLoss"] = cls
             ns["content_loss"] = lambda **kwargs: cls(**kwargs)
+            shim = types.ModuleType("model")
+            shim.__dict__.update(ns)
+        if args.disc and args.folder in ("BSRGAN", "Real_ESRGAN"):
+            from sr_gan_fd_b200 import discriminator as _disc
+            ns = dict(shim.__dict__)
+            ns["DiscriminatorUNet"] = _disc.DiscriminatorUNet
+            ns["discriminator_unet"] = _disc.discriminator_unet
             shim = types.ModuleType("model")
             shim.__dict__.update(ns)
         sys.modules["model"] = shim

@@ -1235,6 +1235,18 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         const long long npix = (long long)d.batch * d.height * d.width;
         __nv_bfloat16* out = (__nv_bfloat16*)((char*)b.ws + P.o_xin);
         const int blocks = (int)((npix + 127) / 128);
+        if (P.is_disc && d.in_channels == 3) {  // HR-sized RGB inputs: vectorised row stores
+          if (x_dtype == B200SR_F32)
+            disc_ingest_input_kernel<float, 3><<<blocks, 128, 0, st>>>((const float*)x, xs[0], xs[1], xs[2], xs[3], d.batch, d.height, d.width, out);
+          else if (x_dtype == B200SR_F16)
+            disc_ingest_input_kernel<__half, 3><<<blocks, 128, 0, st>>>((const __half*)x, xs[0], xs[1], xs[2], xs[3], d.batch, d.height, d.width, out);
+          else if (x_dtype == B200SR_BF16)
+            disc_ingest_input_kernel<__nv_bfloat16, 3><<<blocks, 128, 0, st>>>((const __nv_bfloat16*)x, xs[0], xs[1], xs[2], xs[3], d.batch, d.height, d.width, out);
+          else
+            return fail(B200SR_ERR_INVALID, "unknown x dtype %d", x_dtype);
+          CUDA_TRY(cudaGetLastError());
+          break;
+        }
         if (x_dtype == B200SR_F32)
           ingest_input_kernel<float><<<blocks, 128, 0, st>>>((const float*)x, xs[0], xs[1], xs[2], xs[3], d.batch, d.in_channels, d.height, d.width, out, P.xin_stride);
         else if (x_dtype == B200SR_F16)
@@ -1270,7 +1282,7 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         break;
       }
       case ST_DISC_UP: {
-        const long long n = (long long)s.pn * (2 * s.ph) * (2 * s.pw) * (s.pc >> 3);
+        const long long n = (long long)s.pn * s.ph * s.pw * (s.pc >> 3);
         disc_bilinear_up_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
                                                                             (__nv_bfloat16*)resolve(s.c, b), s.pn, s.ph, s.pw, s.pc);
         CUDA_TRY(cudaGetLastError());

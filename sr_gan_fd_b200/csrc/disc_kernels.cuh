@@ -21,48 +21,83 @@ __device__ __forceinline__ uint4 f32x8_to_bf16(const float (&f)[8]) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
+// x: [N, C, H, W] (any strides; fp32 / fp16 / bf16; C = 3, other widths take the generator's ingest kernel) -> [N*H*W, 64] bf16 = [hi(C) | lo(C) | hi(C) | 0...] (conv1's weights are
+// packed [w_hi | w_hi | w_lo]).  One thread per pixel: the row is assembled in registers and leaves as eight 16-byte stores (the
+// generator's ingest kernel stores element by element, fine for its 64 x 64 inputs, 0.55 ms for sixteen 256 x 256 images).
+template <typename T, int C>
+__global__ void disc_ingest_input_kernel(const T* __restrict__ x, long long sn, long long sc, long long sh, long long sw, int N, int H, int W,
+                                         __nv_bfloat16* __restrict__ out) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= static_cast<long long>(N) * H * W) return;
+  const int xw = static_cast<int>(pix % W);
+  const int yh = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  __nv_bfloat16 row[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) row[c] = __float2bfloat16_rn(0.f);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float v = static_cast<float>(x[n * sn + c * sc + yh * sh + xw * sw]);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    row[c] = h; row[C + c] = l; row[2 * C + c] = h;
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + pix * 64);
+  const uint4* r = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = r[k];
+}
+
 // F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) of s = in (+ skip), BSRGAN/model.py:150-159.
 // Output row 2Y reads rows (Y-1, Y) with weights (0.25, 0.75), row 2Y+1 rows (Y, Y+1) with (0.75, 0.25); indices clamp at the
 // border (so the first / last output row copies the first / last input row).  in: [N, h, w, C] bf16; skip_u: nullptr or the
-// tensor added to `in` first, in U layout; out: [N, 2h, 2w, C].  One thread per output pixel and 8 channels.
+// tensor added to `in` first, in U layout; out: [N, 2h, 2w, C].  One thread per INPUT pixel and 8 channels: it reads the 3 x 3
+// source neighbourhood once (18 loads with the skip) and writes the 2 x 2 output pixels that sit on top of its pixel.
 __global__ void disc_bilinear_up_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ skip_u,
                                         __nv_bfloat16* __restrict__ out, int N, int h, int w, int C) {
   const int c8 = C >> 3;
-  const int Ho = 2 * h, Wo = 2 * w;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<long long>(N) * Ho * Wo * c8) return;
+  if (i >= static_cast<long long>(N) * h * w * c8) return;
   const int cc = static_cast<int>(i % c8);
-  const long long op = i / c8;
-  const int xo = static_cast<int>(op % Wo), yo = static_cast<int>((op / Wo) % Ho), n = static_cast<int>(op / (static_cast<long long>(Wo) * Ho));
-  // source rows / columns and the weight of the SECOND one (torch: lambda = src - floor(src), src = max(o/2 - 0.25, 0))
-  const int y0 = (yo & 1) ? (yo >> 1) : max((yo >> 1) - 1, 0);
-  const int y1 = (yo & 1) ? min((yo >> 1) + 1, h - 1) : (yo >> 1);
-  const float ly = (yo & 1) ? 0.25f : ((yo == 0) ? 0.f : 0.75f);
-  const int x0 = (xo & 1) ? (xo >> 1) : max((xo >> 1) - 1, 0);
-  const int x1 = (xo & 1) ? min((xo >> 1) + 1, w - 1) : (xo >> 1);
-  const float lx = (xo & 1) ? 0.25f : ((xo == 0) ? 0.f : 0.75f);
-  float acc[8];
+  const long long ip = i / c8;
+  const int X = static_cast<int>(ip % w), Y = static_cast<int>((ip / w) % h), n = static_cast<int>(ip / (static_cast<long long>(w) * h));
+  const int ys[3] = {max(Y - 1, 0), Y, min(Y + 1, h - 1)};
+  const int xs[3] = {max(X - 1, 0), X, min(X + 1, w - 1)};
+  float s[3][3][8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int a = 0; a < 3; ++a) {
 #pragma unroll
-  for (int a = 0; a < 2; ++a) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int sy = a ? y1 : y0, sx = b ? x1 : x0;
-      const float wgt = (a ? ly : 1.f - ly) * (b ? lx : 1.f - lx);
-      float f[8];
-      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + sy) * w + sx) * C) + cc), f);
+    for (int b = 0; b < 3; ++b) {
+      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + ys[a]) * w + xs[b]) * C) + cc), s[a][b]);
       if (skip_u) {
         float g[8];
-        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(skip_u + u_layout_off(n, sy, sx, h, w, C)) + cc), g);
+        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(skip_u + u_layout_off(n, ys[a], xs[b], h, w, C)) + cc), g);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] += g[k];
+        for (int k = 0; k < 8; ++k) s[a][b][k] += g[k];
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += wgt * f[k];
     }
   }
-  reinterpret_cast<uint4*>(out + op * C)[cc] = f32x8_to_bf16(acc);
+  // horizontal pass: column 2X = 0.25 s[X-1] + 0.75 s[X], column 2X+1 = 0.75 s[X] + 0.25 s[X+1] (clamped neighbours repeat the edge)
+  float hz[3][2][8];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      hz[a][0][k] = 0.25f * s[a][0][k] + 0.75f * s[a][1][k];
+      hz[a][1][k] = 0.75f * s[a][1][k] + 0.25f * s[a][2][k];
+    }
+  }
+  const int Wo = 2 * w;
+#pragma unroll
+  for (int py = 0; py < 2; ++py) {
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = py ? 0.75f * hz[1][px][k] + 0.25f * hz[2][px][k] : 0.25f * hz[0][px][k] + 0.75f * hz[1][px][k];
+      reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * (2 * h) + 2 * Y + py) * Wo + 2 * X + px) * C)[cc] = f32x8_to_bf16(o);
+    }
+  }
 }
 
 // Transpose of the above: gin[Y, X] = sum over the (up to) 4 x 4 output positions that read input (Y, X).  Per axis the output

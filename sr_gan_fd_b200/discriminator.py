@@ -145,6 +145,8 @@ class _DiscFn(torch.autograd.Function):
 class DiscriminatorUNet(nn.Module):
     """``BSRGAN/model.py:91-167``.  Same constructor arguments, children and ``state_dict`` as the reference class."""
 
+    use_native = True  # A/B switch (benchmarks): False sends CUDA tensors through the stock torch ops as well
+
     def __init__(
             self,
             in_channels: int,
@@ -201,7 +203,7 @@ class DiscriminatorUNet(nn.Module):
                 self.up_block3[0], self.conv2[0], self.conv3[0]]
 
     def _native_ok(self, x: Tensor) -> bool:
-        return (x.is_cuda and x.dim() == 4 and self._channels == 64 and self.upsample_method == "bilinear"
+        return (self.use_native and x.is_cuda and x.dim() == 4 and self._channels == 64 and self.upsample_method == "bilinear"
                 and 1 <= self._in_channels <= 16 and 1 <= self._out_channels <= 16 and x.shape[1] == self._in_channels
                 and x.shape[2] >= 8 and x.shape[3] >= 8 and x.shape[2] % 8 == 0 and x.shape[3] % 8 == 0
                 and self.conv1.weight.is_cuda)

@@ -117,6 +117,8 @@ class _VggL1Fn(torch.autograd.Function):
 
 
 class _ContentLossBase(nn.Module):
+    use_native = True  # A/B switch (benchmarks): False sends CUDA tensors through the stock torch ops as well
+
     def _setup(self, nodes: Sequence[str], mean, std) -> None:
         # exactly the reference's construction (ESRGAN/model.py:266-281): torchvision VGG19, frozen, eval
         model = models.vgg19(weights=models.VGG19_Weights.IMAGENET1K_V1)
@@ -138,7 +140,7 @@ class _ContentLossBase(nn.Module):
         return out
 
     def _native_ok(self, sr: torch.Tensor, gt: torch.Tensor) -> bool:
-        return (all(c is not None for c in self._convs) and sr.is_cuda and gt.is_cuda and sr.dtype == torch.float32 and gt.dtype == torch.float32
+        return (self.use_native and all(c is not None for c in self._convs) and sr.is_cuda and gt.is_cuda and sr.dtype == torch.float32 and gt.dtype == torch.float32
                 and sr.dim() == 4 and sr.shape[1] == 3 and sr.shape == gt.shape and len(self._mean) == 3)
 
     def _native_losses(self, sr, gt, convs, grad_conv=-1):

@@ -50,13 +50,19 @@ def patch_vgg19(seed=1234):
     models.vgg19 = seeded
 
 
-def build(generator, device, seed=0, content="reference"):
+def build(generator, device, seed=0, content="reference", disc="reference"):
     patch_vgg19()
     from sr_gan_fd_b200.compat import bsrgan_model as model  # reference critics + B200 generator
-    if "discriminator_unet" not in model.__dict__:
-        raise SystemExit("the reference tree is needed for the critics (set SRGANFD_REFERENCE)")
+    if "discriminator_unet" not in model.__dict__ and (disc == "reference" or content == "reference" or generator == "stock"):
+        raise SystemExit("the reference tree is needed for the reference critics / generator (set SRGANFD_REFERENCE), "
+                         "or run with --disc b200|torch --content b200|torch")
     torch.manual_seed(seed)
-    d_model = model.discriminator_unet(in_channels=3, out_channels=1, channels=64).to(device)
+    if disc == "reference":
+        d_model = model.discriminator_unet(in_channels=3, out_channels=1, channels=64).to(device)
+    else:  # the drop-in class -- natively (b200) or through its stock torch ops (torch = the reference's op sequence)
+        from sr_gan_fd_b200.discriminator import discriminator_unet
+        d_model = discriminator_unet(in_channels=3, out_channels=1, channels=64).to(device)
+        d_model.use_native = disc == "b200"
     torch.manual_seed(seed)
     if generator == "b200":
         g_model = model.bsrgan_x4(in_channels=3, out_channels=3, channels=64, growth_channels=32, num_rrdb=23)
@@ -64,9 +70,11 @@ def build(generator, device, seed=0, content="reference"):
         from sr_gan_fd_b200.compat._passthrough import load_reference_model
         g_model = load_reference_model("BSRGAN").bsrgan_x4(in_channels=3, out_channels=3, channels=64, growth_channels=32, num_rrdb=23)
     g_model = g_model.to(device)
-    if content == "b200":  # the same loss on the tcgen05 chain kernel (sr_gan_fd_b200.vgg)
+    if content in ("b200", "torch"):  # the same loss on the tcgen05 chain kernel (sr_gan_fd_b200.vgg)
         from sr_gan_fd_b200.vgg import ContentLossMulti
+        native = content == "b200"
         content = ContentLossMulti(NODES, MEAN, STD).to(device)
+        content.use_native = native
     else:
         content = model.ContentLoss(NODES, MEAN, STD).to(device)
     return d_model, g_model, content
@@ -129,7 +137,11 @@ class GanStep:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--generator", default="b200", choices=["b200", "stock"])
-    ap.add_argument("--content", default="reference", choices=["reference", "b200"], help="VGG19 content loss: the reference's torch module or sr_gan_fd_b200.vgg")
+    ap.add_argument("--content", default="reference", choices=["reference", "b200", "torch"],
+                    help="VGG19 content loss: the reference's torch module, sr_gan_fd_b200.vgg natively, or the drop-in's stock torch path")
+    ap.add_argument("--disc", default="reference", choices=["reference", "b200", "torch"],
+                    help="U-Net discriminator: the reference's torch module, sr_gan_fd_b200.discriminator natively, or the drop-in's stock torch path")
+    ap.add_argument("--profile", default="", help="write a per-kernel GPU-time table of ONE extra step (torch.profiler) to this file")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16)
@@ -143,7 +155,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    d_model, g_model, content = build(args.generator, dev, content=args.content)
+    d_model, g_model, content = build(args.generator, dev, content=args.content, disc=args.disc)
     d_model.train(); g_model.train()
     if world > 1:
         d_model = nn.parallel.DistributedDataParallel(d_model, device_ids=[local], broadcast_buffers=True)
@@ -179,11 +191,27 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": "BSRGAN full GAN step imgs/s (BASELINE configs[4]: generator fwd+bwd + reference U-Net discriminator x3 + VGG19 content loss)",
-            "generator": args.generator, "content_loss": args.content, "value": world * args.batch / (ms * 1e-3), "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "generator": args.generator, "content_loss": args.content, "discriminator": args.disc, "value": world * args.batch / (ms * 1e-3), "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "data": "synthetic",
             "config": {"batch_per_gpu": args.batch, "lr": args.lr_size, "scale": 4, "num_rrdb": 23, "critics": "reference DiscriminatorUNet(3,1,64) "
                        "+ ContentLoss on a SEEDED RANDOM-INIT VGG19 (ImageNet weights unavailable offline), autocast fp16 + GradScaler",
                        "discriminator_parallelism": "stock DDP" if world > 1 else "single", "g_loss": float(g_loss), "d_loss": float(d_loss)}}), flush=True)
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step(lr, gt)
+            torch.cuda.synchronize()
+        rows = {}
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                r = rows.setdefault(ev.name[:70], [0.0, 0])
+                r[0] += ev.device_time
+                r[1] += 1
+        total = sum(r[0] for r in rows.values())
+        with open(args.profile, "w") as fh:
+            fh.write(f"GPU kernel time of one step: {total / 1e3:.2f} ms in {sum(r[1] for r in rows.values())} launches (step wall {ms:.2f} ms)\n")
+            for name, (t, c) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:45]:
+                fh.write(f"{t / 1e3:9.3f} ms {c:5d} x  {name}\n")
     if world > 1:
         dist.destroy_process_group()
 
