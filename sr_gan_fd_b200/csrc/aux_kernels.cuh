@@ -36,6 +36,8 @@ struct PackOp {
   int mode;
   int nseg;
   int k32;         // 1: a single K chunk of 32 channels, packed as 64-byte rows under the 64B swizzle (half the bytes of a padded 128-byte row)
+  int down_c;      // > 0 (modes kPackDownFwd / kPackDownDgrad): channels of one unshuffle phase; only the FOUR non-zero tap tiles of every
+                   // (chunk, column group) are packed, rows [chunk][column group][tap 0..3][n] (see ConvParams::down_mode)
   PackSeg seg[5];
 };
 
@@ -120,7 +122,19 @@ __global__ void pack_weights_kernel(const PackOp* __restrict__ ops, int num_ops,
   const int ng = r % op.n_cols;          // row inside the tap tile
   const int t = r / op.n_cols;           // ((chunk*CG + cg)*3 + dx)*3 + dy
   const int cgs = op.n_total / op.n_cols;
-  const int dy = t % 3, dx = (t / 3) % 3, cg = (t / 9) % cgs, c = t / (9 * cgs);
+  int dy, dx, cg, c;
+  if (op.down_c > 0) {
+    // four tap tiles per (chunk, column group): tile i = (row i >> 1, column i & 1) of the 2 x 2 non-zero block, which starts at
+    // row / column 1 (selector 0) or 0 (selector 1); selector = phase bits (forward) or their complement (data gradient)
+    const int i = t % 4;
+    cg = (t / 4) % cgs; c = t / (4 * cgs);
+    const int phase = (op.mode == kPackDownFwd) ? (c * 64) / op.down_c : (cg * op.n_cols) / op.down_c;
+    const int sel = (op.mode == kPackDownFwd) ? phase : (phase ^ 3);
+    dy = ((sel >> 1) ? 0 : 1) + (i >> 1);
+    dx = ((sel & 1) ? 0 : 1) + (i & 1);
+  } else {
+    dy = t % 3; dx = (t / 3) % 3; cg = (t / 9) % cgs; c = t / (9 * cgs);
+  }
   const int n = cg * op.n_cols + ng;
   float v = (c < op.num_chunks) ? pack_fetch(op, params, n, c * 64 + kk, dy, dx) : 0.f;
   const int chunk16 = (kk >> 3) ^ (ng & 7);

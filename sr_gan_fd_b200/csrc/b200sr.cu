@@ -190,12 +190,20 @@ struct b200sr_plan {
   PackOp* d_pack_ops = nullptr;
   BiasOp* d_bias_ops = nullptr;
   const float** d_params = nullptr;
-  void* cached_ws = nullptr;
-  void* cached_packed = nullptr;
-  std::vector<CUtensorMap> maps;
+  // TMA descriptors and the device layer list hold absolute addresses: one cached set per (workspace, packed) address pair, a few
+  // of them (least recently used is replaced) -- callers whose allocator hands out alternating blocks (several forwards in flight,
+  // the three discriminator passes of a GAN step) do not re-encode on every call
+  struct MapSlot { void* ws = nullptr; void* packed = nullptr; std::vector<CUtensorMap> maps; LayerDesc* d_layers = nullptr; unsigned long long stamp = 0; };
+  static constexpr int kMapSlots = 4;
+  MapSlot slots[kMapSlots];
+  int cur_slot = 0;
+  unsigned long long slot_clock = 0;
+  long long map_encodes = 0;  // cache misses so far (b200sr_debug: B200SR_TRACE=1 prints them)
+  const std::vector<CUtensorMap>& maps() const { return slots[cur_slot].maps; }
   std::vector<Step> layer_steps;      // every conv launch of fwd then bwd, in execution order (= layer list)
   std::vector<LayerDesc> h_layers;
-  LayerDesc* d_layers = nullptr;
+  LayerDesc* d_layers() const { return slots[cur_slot].d_layers; }
+  bool tables_ready = false;
   std::vector<EntryDesc> h_entries;   // (layer, image group) entries of every chain, chain after chain
   EntryDesc* d_entries = nullptr;
   uint4* d_layer_rec = nullptr;       // constant-memory images of the two tables (copied device -> constant per launch)
@@ -235,7 +243,7 @@ struct Builder {
   int add_pack(PackOp op) {
     if (op.n_cols == 0) op.n_cols = op.n_total > 64 ? 64 : op.n_total;  // column groups of 64 (the upsample convs' four phases)
     op.row0 = (int)P.total_rows;
-    P.total_rows += (long long)op.num_chunks * 9 * op.n_total / (op.k32 ? 2 : 1);  // 128-byte units
+    P.total_rows += (long long)op.num_chunks * (op.down_c > 0 ? 4 : 9) * op.n_total / (op.k32 ? 2 : 1);  // 128-byte units
     P.pack_ops.push_back(op);
     return op.row0;
   }
@@ -941,11 +949,27 @@ static void* resolve(const Ref& r, const Bases& b) {
 
 static void* resolve(const Ref& r, const Bases& b);
 static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st) {
-  if (P.cached_ws == wsp && P.cached_packed == packed && P.maps.size() == P.map_specs.size()) return 0;
-  P.maps.resize(P.map_specs.size());
+  ++P.slot_clock;
+  int victim = 0;
+  for (int i = 0; i < b200sr_plan::kMapSlots; ++i) {
+    b200sr_plan::MapSlot& sl = P.slots[i];
+    if (sl.ws == wsp && sl.packed == packed && sl.maps.size() == P.map_specs.size() && sl.d_layers) {
+      sl.stamp = P.slot_clock;
+      P.cur_slot = i;
+      return 0;
+    }
+    if (sl.stamp < P.slots[victim].stamp) victim = i;
+  }
+  static const bool trace = [] { const char* e = getenv("B200SR_TRACE"); return e && atoi(e) != 0; }();
+  ++P.map_encodes;
+  if (trace) fprintf(stderr, "b200sr: plan %p encodes descriptors for workspace %p / packed %p (miss %lld, slot %d)\n", (void*)&P, wsp, packed, P.map_encodes, victim);
+  b200sr_plan::MapSlot& slot = P.slots[victim];
+  slot.ws = nullptr;  // invalid until fully rebuilt
+  P.cur_slot = victim;
+  slot.maps.resize(P.map_specs.size());
   for (size_t i = 0; i < P.map_specs.size(); ++i) {
     const ActMapSpec& s = P.map_specs[i];
-    int rc = encode_act_map(&P.maps[i], (char*)wsp + s.off, s.c_valid, s.c_pix, s.n, s.h, s.w, s.box_rows, s.box_w);
+    int rc = encode_act_map(&slot.maps[i], (char*)wsp + s.off, s.c_valid, s.c_pix, s.n, s.h, s.w, s.box_rows, s.box_w);
     if (rc) return rc;
   }
   // device-resident layer list (pointers resolved against this workspace / packed buffer)
@@ -954,7 +978,7 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
   for (size_t i = 0; i < P.layer_steps.size(); ++i) {
     const Step& s = P.layer_steps[i];
     LayerDesc& L = P.h_layers[i];
-    L.tmA = P.maps[s.amap];
+    L.tmA = slot.maps[s.amap];
     L.p = s.cp;
     L.p.epi.bias = (const float*)resolve(s.bias, b);
     L.p.epi.mask = (const __nv_bfloat16*)resolve(s.mask, b);
@@ -1033,8 +1057,9 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
     build_entries(P.fwd);
     build_entries(P.bwd);
   }
-  if (!P.d_layers) {
-    CUDA_TRY(cudaMalloc(&P.d_layers, P.h_layers.size() * sizeof(LayerDesc)));
+  if (!slot.d_layers) CUDA_TRY(cudaMalloc(&slot.d_layers, P.h_layers.size() * sizeof(LayerDesc)));
+  if (!P.tables_ready) {
+    P.tables_ready = true;
     CUDA_TRY(cudaMalloc(&P.d_entries, P.h_entries.size() * sizeof(EntryDesc)));
     P.counters_bytes = 16384;  // per-entry completion counters of the chain being launched
     CUDA_TRY(cudaMalloc(&P.d_counters, P.counters_bytes));
@@ -1048,9 +1073,10 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
     CUDA_TRY(cudaMemcpyAsync(P.d_entry_rec, erec.data(), erec.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));  // lrec / erec are pageable host vectors that die at scope exit
   }
-  CUDA_TRY(cudaMemcpyAsync(P.d_layers, P.h_layers.data(), P.h_layers.size() * sizeof(LayerDesc), cudaMemcpyHostToDevice, st));
-  P.cached_ws = wsp;
-  P.cached_packed = packed;
+  CUDA_TRY(cudaMemcpyAsync(slot.d_layers, P.h_layers.data(), P.h_layers.size() * sizeof(LayerDesc), cudaMemcpyHostToDevice, st));
+  slot.ws = wsp;
+  slot.packed = packed;
+  slot.stamp = P.slot_clock;
   return 0;
 }
 
@@ -1076,7 +1102,7 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_layer_rec, P.d_layer_rec + 2 * (size_t)s.layer0, (size_t)s.nlayers * 2 * sizeof(uint4), 0, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_entry_rec, P.d_entry_rec + s.entry0, (size_t)s.nentries * sizeof(uint4), 0, cudaMemcpyDeviceToDevice, st));
   int layer0 = s.layer0;
-  const LayerDesc* layers = P.d_layers;
+  const LayerDesc* layers = P.d_layers();
   const EntryDesc* entries = P.d_entries + s.entry0;
   int ne = s.nentries;
   float* y = (float*)b.y;
@@ -1112,16 +1138,17 @@ static int launch_wgrad(const Step& s, const CUtensorMap& tmX, const CUtensorMap
   for (int j = 0; j < wb.num_problems; ++j) {
     WgradParams& wp = wb.prob[j];
     for (int i = 0; i < wp.num_seg; ++i) wp.seg[i].out = (float*)resolve(s.wseg_out[j][i], b);
-    const int nacc = wp.bias_mode ? 1 : 3;
+    const int nacc = wp.bias_mode ? 1 : (wp.dy_mask ? __builtin_popcount(wp.dy_mask) : 3);
     const double mma = nacc * 8.0 * (wp.n_cols / 2.0);
     const double ld = wgrad_stage_bytes(wp) / 42.0;
-    work[j] = (mma > ld ? mma : ld) * nacc;
+    const int ntx = wp.bias_mode ? 1 : (wp.dx_mask ? __builtin_popcount(wp.dx_mask) : 3);
+    work[j] = (mma > ld ? mma : ld) * ntx;
     total += work[j];
   }
   int ctas = 0;
   for (int j = 0; j < wb.num_problems; ++j) {
     WgradParams& wp = wb.prob[j];
-    const int ntap = wp.bias_mode ? 1 : 3;
+    const int ntap = wp.bias_mode ? 1 : (wp.dx_mask ? __builtin_popcount(wp.dx_mask) : 3);
     int splits = (int)(sms * work[j] / total / ntap + 0.5);
     if (splits < 1) splits = 1;
     if (splits > wb.num_tiles) splits = wb.num_tiles;
@@ -1192,7 +1219,7 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
           const int lane_ = wcount++ % nstreams;
           if (lane_ > 0) { ws = P.side_stream[lane_ - 1]; side_dirty = true; }
         }
-        int rc = launch_wgrad(s, P.maps[s.xmap], P.maps[s.dymap], b, ws);
+        int rc = launch_wgrad(s, P.maps()[s.xmap], P.maps()[s.dymap], b, ws);
         if (rc) return rc;
         break;
       }
@@ -1282,15 +1309,15 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         break;
       }
       case ST_DISC_UP: {
-        const long long n = (long long)s.pn * s.ph * s.pw * (s.pc >> 3);
-        disc_bilinear_up_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
+        const dim3 g((unsigned)((s.pw * (s.pc >> 3) + 255) / 256), (unsigned)s.ph, (unsigned)s.pn);
+        disc_bilinear_up_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
                                                                             (__nv_bfloat16*)resolve(s.c, b), s.pn, s.ph, s.pw, s.pc);
         CUDA_TRY(cudaGetLastError());
         break;
       }
       case ST_DISC_UP_BWD: {
-        const long long n = (long long)s.pn * s.ph * s.pw * (s.pc >> 3);
-        disc_bilinear_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
+        const dim3 g((unsigned)((s.pw * (s.pc >> 3) + 255) / 256), (unsigned)s.ph, (unsigned)s.pn);
+        disc_bilinear_bwd_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
                                                                              (__nv_bfloat16*)resolve(s.c, b), (__nv_bfloat16*)resolve(s.d2, b), s.pn, s.ph, s.pw, s.pc);
         CUDA_TRY(cudaGetLastError());
         break;
@@ -1496,6 +1523,8 @@ static int build_vgg_plan(b200sr_plan& P) {
 // stride-2 conv is then an ordinary 3x3 conv over 4C channels (weights packed with structural zeros, kPackDownFwd), its data
 // gradient an ordinary 3x3 dgrad whose 4C output columns are pixel-shuffled back to the plain layout on store, and its weight
 // gradient the ordinary 3x3 wgrad over the U-layout input, gathered to [co][c][4][4] by unpack_wgrad_down_kernel.
+// B200SR_DOWN4=0: the stride-2 convs run all nine taps of the unshuffled 3x3 form (structural zeros included) -- A/B switch
+static const bool g_down4 = [] { const char* e = getenv("B200SR_DOWN4"); return !(e && atoi(e) == 0); }();
 static int build_disc_plan(b200sr_plan& P) {
   const b200sr_disc_desc& v = P.dd;
   if (v.channels != 64) return fail(B200SR_ERR_INVALID, "only channels=64 is supported (got %d)", v.channels);
@@ -1573,8 +1602,10 @@ static int build_disc_plan(b200sr_plan& P) {
     PackOp op; memset(&op, 0, sizeof(op));
     op.n_total = n_total; op.n_cols = n_cols; op.n_valid = cout; op.mode = mode; op.num_chunks = c_in / 64; op.nseg = 1;
     op.seg[0] = seg(0, c_in, 2 * c, cout, cI[c], 0, 0, 0);
+    if (mode == kPackDownFwd && g_down4) op.down_c = cI[c];
     const int row0 = B.add_pack(op);
     ConvParams cp = base_conv_params(N, lh(lvl), lw(lvl), op.num_chunks, 4, 0, 1 << 20, row0, n_cols, n_total);
+    if (op.down_c > 0) { cp.w_taps = 4; cp.down_mode = 1; cp.down_c64 = cI[c] / 64; }
     Step s = conv_step(B.add_map(in_off, c_in, c_in, N, lh(lvl), lw(lvl), kABoxRows), cp);
     if (cBias[c]) s.bias = packed_bias(B.add_bias(n_total, 2 * c + 1, cout, 0));
     s.cp.epi.act = act;
@@ -1631,9 +1662,11 @@ static int build_disc_plan(b200sr_plan& P) {
       PackOp op; memset(&op, 0, sizeof(op));
       op.n_total = n_total; op.n_cols = n_cols; op.n_valid = n_valid; op.mode = mode; op.num_chunks = (k_in + 63) / 64; op.nseg = 1;
       op.seg[0] = seg(0, cO[c], 2 * c, cO[c], cI[c], 0, 0, 0);
+      if (mode == kPackDownDgrad && g_down4) op.down_c = cI[c];
       const int row0 = B.add_pack(op);
       const int kl = k_in - 64 * (op.num_chunks - 1);
       ConvParams cp = base_conv_params(N, lh(lvl), lw(lvl), op.num_chunks, (kl + 15) / 16, 0, 1 << 20, row0, n_cols, n_total);
+      if (op.down_c > 0) { cp.w_taps = 4; cp.down_mode = 2; cp.down_c64 = cI[c] / 64; }
       return conv_step(B.add_map(in_off, k_in, in_stride, N, lh(lvl), lw(lvl), kABoxRows), cp);
     };
     auto out_to = [&](Step& s, long long off, int stride) { s.ob = ws(off); s.cp.epi.ob_stride = stride; s.cp.epi.ob_coff = 0; };
@@ -1711,6 +1744,15 @@ static int build_disc_plan(b200sr_plan& P) {
           wp.a_blocks = (x_cvalid - cib > 64) ? 2 : 1;
           WgradSegment& g = wp.seg[0];
           g.col_begin = 0; g.col_end = ncols; g.out = nullptr; g.ci_total = ci_total; g.ci0 = cib; g.co_pad = coPad[c];
+          if (cK[c] == 4 && g_down4) {
+            // U-layout input channels [cib, cib + 128): phases of the first and the last channel of the block (equal when a phase
+            // is >= 128 channels wide); a phase (py, px) keeps tap rows {1,2} / {0,1} for py = 0 / 1, columns alike
+            const int hi = std::min(cib + 128, x_cvalid) - 1;
+            const int p0 = cib / cI[c], p1 = hi / cI[c];
+            int dym = 0, dxm = 0;
+            for (int ph = p0; ph <= p1; ++ph) { dym |= (ph >> 1) ? 3 : 6; dxm |= (ph & 1) ? 3 : 6; }
+            wp.dy_mask = dym; wp.dx_mask = dxm;
+          }
           cur.wseg_out[pj][0] = wref(c, (long long)(cob / 4) * ci_total * 4);
           wp.num_seg = 1;
           if (cur.wb.num_problems == kWgMaxProblems) { P.bwd.push_back(cur); open = false; }
@@ -1796,7 +1838,7 @@ void b200sr_plan_destroy(b200sr_plan* p) {
   if (p->d_bias_ops) cudaFree(p->d_bias_ops);
   if (p->d_params) cudaFree((void*)p->d_params);
   if (p->d_unpack_ops) cudaFree(p->d_unpack_ops);
-  if (p->d_layers) cudaFree(p->d_layers);
+  for (int i = 0; i < b200sr_plan::kMapSlots; ++i) if (p->slots[i].d_layers) cudaFree(p->slots[i].d_layers);
   if (p->d_entries) cudaFree(p->d_entries);
   for (int k = 0; k < 3; ++k) {
     if (p->side_stream[k]) cudaStreamDestroy(p->side_stream[k]);

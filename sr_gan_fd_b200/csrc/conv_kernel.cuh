@@ -103,7 +103,13 @@ struct ConvParams {
   int epi_cols;
   int num_stages;
   int k32;         // weights of this (single-chunk, 32-channel) layer are packed as 64-byte rows (64B swizzle)
-  int pad_[3];
+  // 4x4 stride-2 convs over the pixel-unshuffled input (U-Net discriminator; extended build only): of the nine taps only a 2 x 2
+  // subset is non-zero for the channels of one unshuffle phase.  w_taps == 4: ONE weight stage per K chunk holding those four tap
+  // tiles.  The phase is that of the K chunk (down_mode 1, forward: chunk / down_c64) or of the item's column group (down_mode 2,
+  // data gradient: column group / down_c64); down_c64 = channels of one phase / 64.
+  int down_mode;
+  int down_c64;
+  int pad_[1];
   ConvEpilogue epi;
 };
 
@@ -321,7 +327,7 @@ struct alignas(32) EntryDesc {
 constexpr int kMaxChainLayers = 768;
 constexpr int kMaxChainEntries = 2048;
 // layer record A: x = n_cols (9 bits) | chunks<<9 (5 bits) | ksteps_last<<14 | halves<<17 | w_taps<<19 | col_groups<<23
-//                 y = acc_col0 | acc_first<<8 | acc_hold<<9 | has_epi<<10      z = w_row0      w = a_c0
+//                 y = acc_col0 | acc_first<<8 | acc_hold<<9 | has_epi<<10 | k32<<11 | down_mode<<12 | down_c64<<14      z = w_row0      w = a_c0
 // layer record B: x = tiles_x | tiles_y<<16      y = a_wrap      z = bias byte offset in the packed buffer + 1 (0: none)      w = bias floats
 // entry record  : x = layer (absolute) | slot<<20 | neighbour_sync<<21      y = tile_lo      z = tile_hi      w = rot | (dep+1)<<16
 __constant__ uint4 c_layer_rec[kMaxChainLayers * 2];
@@ -329,7 +335,7 @@ __constant__ uint4 c_entry_rec[kMaxChainEntries];
 inline void make_layer_rec(const ConvParams& p, uint4 out[2], const void* packed_base) {
   out[0].x = static_cast<uint32_t>(p.n_cols) | (p.num_chunks << 9) | (p.ksteps_last << 14) | (p.halves << 17) | (p.w_taps << 19) | (p.col_groups << 23);
   out[0].y = static_cast<uint32_t>(p.acc_col0) | ((p.acc_first ? 1u : 0u) << 8) | ((p.acc_hold ? 1u : 0u) << 9) | ((p.epi_cols > 0 ? 1u : 0u) << 10) |
-             ((p.k32 ? 1u : 0u) << 11);
+             ((p.k32 ? 1u : 0u) << 11) | (static_cast<uint32_t>(p.down_mode & 3) << 12) | (static_cast<uint32_t>(p.down_c64 & 7) << 14);
   out[0].z = static_cast<uint32_t>(p.w_row0);
   out[0].w = static_cast<uint32_t>(p.a_c0);
   out[1].x = static_cast<uint32_t>(p.tiles_x) | (static_cast<uint32_t>(p.tiles_y) << 16);
@@ -444,6 +450,44 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_lo, uint
   }
 }
 
+// The four non-zero taps of a stride-2 conv's K chunk / column group (see ConvParams::down_mode): rows {1,2} (SY = 0) or {0,1}
+// (SY = 1) times columns {1,2} / {0,1} (SX) of the 3 x 3 neighbourhood; the stage holds the four tap tiles in that order.
+template <int SY, int SX>
+__device__ __forceinline__ void issue_stage_down(uint32_t d_tmem, uint32_t a_lo, uint32_t b_base, uint32_t b_dy, uint32_t idesc, uint32_t first, uint32_t kHi) {
+  constexpr uint32_t kHiA = smem_desc_hi(kABoxW * 128);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int dyi = (SY ? 0 : 1) + (i >> 1), dxi = (SX ? 0 : 1) + (i & 1);
+    const uint32_t b_lo = b_base + i * b_dy;
+    const uint32_t a_tap = a_lo + (dyi * kABoxW + dxi) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t acc = (i == 0 && ks == 0) ? first : 1u;
+      umma_bf16_ss_lohi2(d_tmem, a_tap + ks * 2, kHiA, b_lo + ks * 2, kHi, idesc, acc);
+      umma_bf16_ss_lohi2(d_tmem + 128, a_tap + 16 * kABoxW * 8 + ks * 2, kHiA, b_lo + ks * 2, kHi, idesc, acc);
+    }
+  }
+}
+__device__ __forceinline__ void issue_chunk_down(int sel, uint32_t d_tmem, uint32_t a_lo, uint32_t smemW_addr, uint32_t b_dy, uint32_t idesc, bool fresh,
+                                                 int g, int& gw, uint32_t& fW_bits, uint64_t* fullW, uint64_t* emptyW, uint32_t b_hi) {
+  if (gw + g > kWGranules) gw = 0;
+  const uint32_t b_base = ((smemW_addr + gw * kWGranule) >> 4 & 0x3FFFu) | (1u << 16);
+  mbar_wait(&fullW[gw], (fW_bits >> gw) & 1u);
+  if (elect_one_sync()) {
+    const uint32_t first = fresh ? 0u : 1u;
+    switch (sel) {
+      case 0: issue_stage_down<0, 0>(d_tmem, a_lo, b_base, b_dy, idesc, first, b_hi); break;
+      case 1: issue_stage_down<0, 1>(d_tmem, a_lo, b_base, b_dy, idesc, first, b_hi); break;
+      case 2: issue_stage_down<1, 0>(d_tmem, a_lo, b_base, b_dy, idesc, first, b_hi); break;
+      default: issue_stage_down<1, 1>(d_tmem, a_lo, b_base, b_dy, idesc, first, b_hi); break;
+    }
+    umma_commit(&emptyW[gw]);
+  }
+  __syncwarp();
+  fW_bits ^= (1u << gw);
+  gw += g;
+}
+
 // kInstr = 0: production build (no probes: every `debug` test folds away).  kInstr = 1: the same kernel with the timing
 // switches, role profiler and per-entry timeline compiled in (used only while b200sr_debug_set() is non-zero).
 // kVgg = 1: the build used by the VGG19 feature plans (ReLU, ReLU-derivative mask, fp32 feature store, bias vectors of up to 512
@@ -546,7 +590,8 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int tap_rows = k32 ? (n_cols >> 1) : n_cols;     // 128-byte units of one tap tile
       const int wbytes = w_taps * tap_rows * 128;            // one weight stage = w_taps tap tiles, fetched by ONE bulk copy
       const int g = (wbytes + kWGranule - 1) / kWGranule;    // W granules per stage
-      const int wsteps = 9 / w_taps;                         // stages per K chunk (1 or 3)
+      const int wsteps = (w_taps == 4) ? 1 : 9 / w_taps;     // stages per K chunk (1 or 3; stride-2 layers: one stage of four taps)
+      const int taps_per_chunk = (w_taps == 4) ? 4 : 9;      // tap tiles packed per (chunk, column group)
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
       TL_MARK(0);
       // The entry's inputs may only be read once the entry it depends on is complete on every CTA that worked on it.  The
@@ -612,7 +657,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             // stage d of this chunk holds w_taps consecutive taps of the centre-first order: dx in {1,0,2}, dy in {1,0,2}.
             // Packed rows are [dx][dy][n]; a 9-tap stage is the whole block, a 3-tap stage one dx column, a 1-tap stage one tile.
             int tap_row;
-            if (w_taps == 9) tap_row = 0;
+            if (w_taps == 9 || w_taps == 4) tap_row = 0;
             else tap_row = ((d == 0) ? 1 : (d == 1 ? 0 : 2)) * 3;
             if (gw + g > kWGranules) gw = 0;
             const uint32_t gmask = ((1u << g) - 1u) << gw;
@@ -630,7 +675,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
                 mbar_arrive(&fullW[gw]);
               } else {
                 mbar_arrive_expect_tx(&fullW[gw], wbytes);
-                const long long row = w_row0 + (static_cast<long long>(c * col_groups + (w % col_groups)) * 9 + tap_row) * tap_rows;
+                const long long row = w_row0 + (static_cast<long long>(c * col_groups + (w % col_groups)) * taps_per_chunk + tap_row) * tap_rows;
                 bulk_load_1d(smemW + gw * kWGranule, packed_w + row * 128, wbytes, &fullW[gw]);
               }
             }
@@ -682,6 +727,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const bool has_epi = ((la.y >> 10) & 1) != 0;  // deferred partial-sum layers have no epilogue: nothing to hand over
       const int num_work = (tile_hi - tile_lo) * col_groups;
       const int k32 = static_cast<int>((la.y >> 11) & 1);
+      const int down_mode = kVgg ? static_cast<int>((la.y >> 12) & 3) : 0, down_c64 = kVgg ? static_cast<int>((la.y >> 14) & 7) : 1;
       const int g = (w_taps * n_cols * (k32 ? 64 : 128) + kWGranule - 1) / kWGranule;
       const uint32_t idesc = make_idesc_bf16(128, n_cols, 0, 0);
       const uint32_t b_dy = static_cast<uint32_t>(n_cols) * (k32 ? 4u : 8u);  // bytes of one tap tile >> 4
@@ -718,7 +764,12 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
     case 2: B200SR_CHUNK(T, H, 2); break;                      \
     default: B200SR_CHUNK(T, H, 1); break;                     \
   }
-          if (w_taps == 9) { B200SR_CHUNK_K(9, 2) } else { B200SR_CHUNK_K(3, 2) }
+          if (kVgg && w_taps == 4) {
+            // forward: the chunk's unshuffle phase (py, px) keeps rows {1,2} / {0,1} for py = 0 / 1; data gradient (flipped taps): the
+            // column group's phase keeps rows {0,1} / {1,2} -- i.e. selector = phase (forward) or phase ^ 3 (data gradient)
+            const int phase = (down_mode == 1) ? c / down_c64 : (w % col_groups) / down_c64;
+            issue_chunk_down((down_mode == 1) ? phase : (phase ^ 3), d_tmem, a_lo, smemW_addr, b_dy, idesc, fresh, g, gw, fW_bits, fullW, emptyW, b_hi);
+          } else if (w_taps == 9) { B200SR_CHUNK_K(9, 2) } else { B200SR_CHUNK_K(3, 2) }
 #undef B200SR_CHUNK_K
 #undef B200SR_CHUNK
           if (pf) prof[9] += clock64() - _ti;  // MMA issue incl. the weight-stage waits of this chunk

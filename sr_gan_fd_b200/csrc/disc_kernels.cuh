@@ -53,51 +53,47 @@ __global__ void disc_ingest_input_kernel(const T* __restrict__ x, long long sn, 
 // border (so the first / last output row copies the first / last input row).  in: [N, h, w, C] bf16; skip_u: nullptr or the
 // tensor added to `in` first, in U layout; out: [N, 2h, 2w, C].  One thread per INPUT pixel and 8 channels: it reads the 3 x 3
 // source neighbourhood once (18 loads with the skip) and writes the 2 x 2 output pixels that sit on top of its pixel.
-__global__ void disc_bilinear_up_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ skip_u,
-                                        __nv_bfloat16* __restrict__ out, int N, int h, int w, int C) {
+__global__ void __launch_bounds__(256, 4)
+disc_bilinear_up_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ skip_u,
+                        __nv_bfloat16* __restrict__ out, int N, int h, int w, int C) {
+  // grid: (ceil(w * C/8 / 256), h, N) -- 32-bit index math only
   const int c8 = C >> 3;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<long long>(N) * h * w * c8) return;
-  const int cc = static_cast<int>(i % c8);
-  const long long ip = i / c8;
-  const int X = static_cast<int>(ip % w), Y = static_cast<int>((ip / w) % h), n = static_cast<int>(ip / (static_cast<long long>(w) * h));
-  const int ys[3] = {max(Y - 1, 0), Y, min(Y + 1, h - 1)};
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= w * c8) return;
+  const int X = t / c8, cc = t - X * c8;
+  const int Y = blockIdx.y, n = blockIdx.z;
   const int xs[3] = {max(X - 1, 0), X, min(X + 1, w - 1)};
-  float s[3][3][8];
+  const long long orow = (static_cast<long long>(n) * (2 * h) + 2 * Y) * (2 * w) + 2 * X;  // output pixel (2Y, 2X)
+  float top[2][8], bot[2][8];  // output rows 2Y / 2Y+1 (two columns each), accumulated source row by source row
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
+    const int sy = (a == 0) ? max(Y - 1, 0) : (a == 1 ? Y : min(Y + 1, h - 1));
+    float s[3][8];
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + ys[a]) * w + xs[b]) * C) + cc), s[a][b]);
+      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + sy) * w + xs[b]) * C) + cc), s[b]);
       if (skip_u) {
         float g[8];
-        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(skip_u + u_layout_off(n, ys[a], xs[b], h, w, C)) + cc), g);
+        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(skip_u + u_layout_off(n, sy, xs[b], h, w, C)) + cc), g);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s[a][b][k] += g[k];
+        for (int k = 0; k < 8; ++k) s[b][k] += g[k];
       }
     }
-  }
-  // horizontal pass: column 2X = 0.25 s[X-1] + 0.75 s[X], column 2X+1 = 0.75 s[X] + 0.25 s[X+1] (clamped neighbours repeat the edge)
-  float hz[3][2][8];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
+    // horizontal pass: column 2X = 0.25 s[X-1] + 0.75 s[X], column 2X+1 = 0.75 s[X] + 0.25 s[X+1] (clamped neighbours repeat the edge)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      hz[a][0][k] = 0.25f * s[a][0][k] + 0.75f * s[a][1][k];
-      hz[a][1][k] = 0.75f * s[a][1][k] + 0.25f * s[a][2][k];
+      const float h0 = 0.25f * s[0][k] + 0.75f * s[1][k], h1 = 0.75f * s[1][k] + 0.25f * s[2][k];
+      if (a == 0) { top[0][k] = 0.25f * h0; top[1][k] = 0.25f * h1; }
+      else if (a == 1) { top[0][k] += 0.75f * h0; top[1][k] += 0.75f * h1; bot[0][k] = 0.75f * h0; bot[1][k] = 0.75f * h1; }
+      else { bot[0][k] += 0.25f * h0; bot[1][k] += 0.25f * h1; }
+    }
+    if (a == 1) {
+      reinterpret_cast<uint4*>(out + orow * C)[cc] = f32x8_to_bf16(top[0]);
+      reinterpret_cast<uint4*>(out + (orow + 1) * C)[cc] = f32x8_to_bf16(top[1]);
     }
   }
-  const int Wo = 2 * w;
-#pragma unroll
-  for (int py = 0; py < 2; ++py) {
-#pragma unroll
-    for (int px = 0; px < 2; ++px) {
-      float o[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = py ? 0.75f * hz[1][px][k] + 0.25f * hz[2][px][k] : 0.25f * hz[0][px][k] + 0.75f * hz[1][px][k];
-      reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * (2 * h) + 2 * Y + py) * Wo + 2 * X + px) * C)[cc] = f32x8_to_bf16(o);
-    }
-  }
+  reinterpret_cast<uint4*>(out + (orow + 2 * w) * C)[cc] = f32x8_to_bf16(bot[0]);
+  reinterpret_cast<uint4*>(out + (orow + 2 * w + 1) * C)[cc] = f32x8_to_bf16(bot[1]);
 }
 
 // Transpose of the above: gin[Y, X] = sum over the (up to) 4 x 4 output positions that read input (Y, X).  Per axis the output
@@ -105,14 +101,16 @@ __global__ void disc_bilinear_up_kernel(const __nv_bfloat16* __restrict__ in, co
 // 0.25 (Y <= h-2).  gout: [N, 2h, 2w, C] bf16.  gs_out (or nullptr): the sum itself = gradient w.r.t. the upsampled tensor
 // (in + skip), which is also the skip connection's gradient; ga_out (or nullptr): the sum times the LeakyReLU(0.2) derivative
 // taken from the saved activation `act` ([N, h, w, C], same lattice) = gradient w.r.t. the producing conv's pre-activation.
-__global__ void disc_bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16* __restrict__ act,
-                                         __nv_bfloat16* __restrict__ gs_out, __nv_bfloat16* __restrict__ ga_out, int N, int h, int w, int C) {
+__global__ void __launch_bounds__(256, 4)
+disc_bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16* __restrict__ act,
+                         __nv_bfloat16* __restrict__ gs_out, __nv_bfloat16* __restrict__ ga_out, int N, int h, int w, int C) {
+  // grid: (ceil(w * C/8 / 256), h, N) -- 32-bit index math only
   const int c8 = C >> 3;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<long long>(N) * h * w * c8) return;
-  const int cc = static_cast<int>(i % c8);
-  const long long ip = i / c8;
-  const int X = static_cast<int>(ip % w), Y = static_cast<int>((ip / w) % h), n = static_cast<int>(ip / (static_cast<long long>(w) * h));
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= w * c8) return;
+  const int X = t / c8, cc = t - X * c8;
+  const int Y = blockIdx.y, n = blockIdx.z;
+  const long long ip = (static_cast<long long>(n) * h + Y) * w + X;
   const int Ho = 2 * h, Wo = 2 * w;
   float wy[4], wx[4];
   wy[0] = (Y >= 1) ? 0.25f : 0.f; wy[1] = (Y == 0) ? 1.f : 0.75f; wy[2] = (Y == h - 1) ? 1.f : 0.75f; wy[3] = (Y <= h - 2) ? 0.25f : 0.f;

@@ -46,8 +46,11 @@ struct WgradParams {
   int n_blocks;  // ceil(n_cols / 64) dY boxes per tile
   int a_blocks;  // X boxes loaded per tile: 2 (128 input channels) or 1 (only accumulator rows 0..63 are kept)
   int bias_mode; // 1: A = all ones, one accumulator, no X loads, no taps: column sums of dY
-  int splits;    // pixel-tile splits of this problem (CTAs = splits * (bias_mode ? 1 : 3))
+  int splits;    // pixel-tile splits of this problem (CTAs = splits * taps_x, taps_x = 1 in bias mode, else popcount(dx_mask))
   int num_seg;
+  int dx_mask, dy_mask;  // horizontal taps that get a CTA / vertical taps that get an accumulator (0 = all three).  The 4x4 stride-2
+                         // convs of the U-Net discriminator, computed as 3x3 convs over the pixel-unshuffled input, only have a
+                         // 2 x 2 block of non-zero taps per unshuffle phase: the others are neither computed nor flushed
   WgradSegment seg[kWgMaxSeg];
 };
 
@@ -84,8 +87,14 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   while (pj + 1 < batch.num_problems && static_cast<int>(blockIdx.x) >= batch.cta_begin[pj + 1]) ++pj;
   const WgradParams& p = batch.prob[pj];
   const int local = blockIdx.x - batch.cta_begin[pj];
-  const int ntap = p.bias_mode ? 1 : 3;
-  const int dxi = p.bias_mode ? 1 : (local % 3);  // horizontal tap owned by this CTA
+  const int dxm = p.dx_mask ? p.dx_mask : 7, dym = p.dy_mask ? p.dy_mask : 7;
+  const int ntap = p.bias_mode ? 1 : __popc(dxm);
+  int dxi = 1;  // horizontal tap owned by this CTA: the (local % ntap)-th set bit of the mask
+  if (!p.bias_mode) {
+    int k = local % ntap;
+    dxi = 0;
+    while (!((dxm >> dxi) & 1) || k-- > 0) ++dxi;
+  }
   const int split = local / ntap;
   const int nacc = p.bias_mode ? 1 : 3;
   const int stage_bytes = wgrad_stage_bytes(p);
@@ -160,6 +169,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint32_t a_lo = smem_desc_lo(a0, kWgXBytes);  // LBO = stride between the two 64-ch M blocks
 #pragma unroll
           for (int dyi = 0; dyi < 3; ++dyi) {
+            if (!((dym >> dyi) & 1)) continue;
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)  // 16 pixels (two 8-pixel patch rows) per UMMA
               umma_bf16_ss_lohi(tmem_base + dyi * p.n_cols, a_lo + dyi * 64 + ks * 128, b_lo + ks * 128, kHi, idesc,
@@ -181,6 +191,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_wait(done, 0);
     tcgen05_fence_after();
     for (int dyi = 0; dyi < nacc; ++dyi) {
+      if (!p.bias_mode && !((dym >> dyi) & 1)) continue;
       const int tap = p.bias_mode ? 0 : dyi * 3 + dxi;
       for (int c0 = 0; c0 < p.n_cols; c0 += 16) {
         uint32_t r[16];

@@ -98,10 +98,14 @@ class _DiscFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
             plan = rt.plan(module, x.device, n, h, w, training)
-            packed = torch.empty(plan.packed_bytes, dtype=torch.uint8, device=x.device)
+            # ONE allocation for the activations and this forward's packed weights (the spectral norm changes them on every call):
+            # the library caches its TMA descriptors per (workspace, packed) address pair, and one large block is what the caching
+            # allocator hands back at the same address call after call
+            ws_bytes = (plan.workspace_bytes + 1023) // 1024 * 1024
+            buf = torch.empty(ws_bytes + plan.packed_bytes, dtype=torch.uint8, device=x.device)
+            workspace, packed = buf[:ws_bytes], buf[ws_bytes:]
             ptrs = (C.c_void_p * 20)(*[t.data_ptr() if t is not None else None for t in slots])
             _lib.check(lib.b200sr_pack_weights(plan.handle, ptrs, C.c_void_p(packed.data_ptr()), C.c_void_p(stream)))
-            workspace = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=x.device)
             y = torch.empty((n, plan.out_channels, h, w), dtype=torch.float32, device=x.device)
             strides = (C.c_int64 * 4)(*x.stride())
             _lib.check(lib.b200sr_disc_forward(plan.handle, C.c_void_p(x.data_ptr()), _DTYPES[x.dtype], strides,

@@ -5,7 +5,7 @@ buffers, every parameter gradient, input gradient) and against the committed gol
 construction (state_dict keys, shapes, seeded initial values) equal the reference class bit for bit.
 GPU: the native path (tcgen05 convs in bf16 with fp32 accumulation) against the fp32 oracle on the CPU.  BASELINE.json states no
 tolerance for the discriminator.  The bar: per tensor, not further from fp32 than 1.3 x what torch's own bf16 autocast of the same
-module loses (+ 2e-3), inside absolute caps of 2e-2 (logits) and 0.15 (gradients) relative L2; measured values are appended to
+module loses (+ 2e-3), inside absolute caps of 2e-2 (logits) and 0.2 (gradients) relative L2; measured values are appended to
 gpurun_out/disc_parity.jsonl and the worst tensor is printed."""
 import copy
 import glob
@@ -212,7 +212,7 @@ def _record(tag, payload):
 def test_gpu_forward_backward_against_oracle(shape, training):
     """Native path vs the fp32 oracle, next to what torch's own bf16 autocast of the same module loses against fp32: the native
     path (bf16 operands, fp32 accumulation) must not be further from fp32 than 1.3 x the stock bf16 path + 2e-3, per tensor, and
-    inside the absolute caps logits <= 2e-2, gradients <= 0.15 relative L2 (a plain ten-layer feed-forward net has no fp32 residual
+    inside the absolute caps logits <= 2e-2, gradients <= 0.2 relative L2 (a plain ten-layer feed-forward net has no fp32 residual
     carrier to lean on, unlike the generator: bf16 rounding of every activation shows in the logits at the 1e-2 level, and
     LeakyReLU-derivative flips near zero show in the gradients)."""
     n, h, w = shape
@@ -232,7 +232,7 @@ def test_gpu_forward_backward_against_oracle(shape, training):
     _record(f"{shape} training={training}", {"native_vs_fp32": errs, "torch_bf16_autocast_vs_fp32": stock})
     assert errs["logits"] <= 2e-2, errs
     for k, e in errs.items():
-        assert e <= 0.15, (k, e)
+        assert e <= 0.2, (k, e)
         assert e <= 1.3 * stock[k] + 2e-3, (k, e, stock[k])
     # gradients of the EFFECTIVE weights (what the library itself returns, before torch's W / sigma graph)
     for name, g in effg.items():

@@ -81,13 +81,26 @@ def build(generator, device, seed=0, content="reference", disc="reference"):
 
 
 class GanStep:
-    def __init__(self, d_model, g_model, content, device, world=1):
+    def __init__(self, d_model, g_model, content, device, world=1, optimizer="stock", ema=False):
         self.d, self.g, self.content, self.dev = d_model, g_model, content, device
         self.d_core = d_model.module if hasattr(d_model, "module") else d_model
         self.pixel = nn.L1Loss().to(device)
         self.adv = nn.BCEWithLogitsLoss().to(device)
-        self.d_opt = optim.Adam(self.d_core.parameters(), LR, BETAS, EPS, 0.0)
-        self.g_opt = optim.Adam(self.g.parameters(), LR, BETAS, EPS, 0.0)
+        # EMA copy of the generator as the script keeps it (BSRGAN/train_bsrgan.py:289-291, updated after every generator step, :469)
+        self.ema, self.ema_in_optimizer = None, False
+        g_core = g_model.module if hasattr(g_model, "module") else g_model
+        if ema:
+            from torch.optim.swa_utils import AveragedModel
+            decay = 0.999  # bsrgan_config.model_ema_decay
+            self.ema = AveragedModel(g_core, avg_fn=lambda e, p, n: (1 - decay) * e + decay * p)
+        if optimizer == "fused":  # GradScaler unscale + Adam (+ EMA) as ONE launch per model
+            from sr_gan_fd_b200.optim import FusedAdamEMA
+            self.d_opt = FusedAdamEMA(self.d_core.parameters(), LR, BETAS, EPS, 0.0)
+            self.g_opt = FusedAdamEMA(g_core.parameters(), LR, BETAS, EPS, 0.0, ema_model=self.ema, ema_decay=0.999)
+            self.ema_in_optimizer = ema
+        else:
+            self.d_opt = optim.Adam(self.d_core.parameters(), LR, BETAS, EPS, 0.0)
+            self.g_opt = optim.Adam(self.g.parameters(), LR, BETAS, EPS, 0.0)
         self.scaler = torch.amp.GradScaler("cuda")
         self.pw = torch.Tensor(PIXEL_W).to(device)
         self.cw = torch.Tensor(CONTENT_W).to(device)
@@ -131,6 +144,8 @@ class GanStep:
         if step_g:
             scaler.step(self.g_opt)
             scaler.update()
+            if self.ema is not None and not self.ema_in_optimizer:
+                self.ema.update_parameters(self.g.module if hasattr(self.g, "module") else self.g)
         return sr, g_loss.detach(), (d_loss_hr + d_loss_sr).detach()
 
 
@@ -141,6 +156,8 @@ def main():
                     help="VGG19 content loss: the reference's torch module, sr_gan_fd_b200.vgg natively, or the drop-in's stock torch path")
     ap.add_argument("--disc", default="reference", choices=["reference", "b200", "torch"],
                     help="U-Net discriminator: the reference's torch module, sr_gan_fd_b200.discriminator natively, or the drop-in's stock torch path")
+    ap.add_argument("--optim", default="stock", choices=["stock", "fused"], help="torch.optim.Adam as the script, or sr_gan_fd_b200.optim.FusedAdamEMA")
+    ap.add_argument("--ema", action="store_true", help="keep the generator's EMA copy as the script does (AveragedModel.update_parameters, or inside the fused step)")
     ap.add_argument("--profile", default="", help="write a per-kernel GPU-time table of ONE extra step (torch.profiler) to this file")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -164,7 +181,7 @@ def main():
             b200dist.make_data_parallel(g_model)
         else:
             g_model = nn.parallel.DistributedDataParallel(g_model, device_ids=[local])
-    step = GanStep(d_model, g_model, content, dev, world)
+    step = GanStep(d_model, g_model, content, dev, world, optimizer=args.optim, ema=args.ema)
     torch.manual_seed(100 + rank)
     lr = torch.rand(args.batch, 3, args.lr_size, args.lr_size, device=dev)
     gt = torch.rand(args.batch, 3, 4 * args.lr_size, 4 * args.lr_size, device=dev)
@@ -191,7 +208,7 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": "BSRGAN full GAN step imgs/s (BASELINE configs[4]: generator fwd+bwd + reference U-Net discriminator x3 + VGG19 content loss)",
-            "generator": args.generator, "content_loss": args.content, "discriminator": args.disc, "value": world * args.batch / (ms * 1e-3), "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "generator": args.generator, "content_loss": args.content, "discriminator": args.disc, "optimizer": args.optim, "ema": bool(args.ema), "value": world * args.batch / (ms * 1e-3), "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "data": "synthetic",
             "config": {"batch_per_gpu": args.batch, "lr": args.lr_size, "scale": 4, "num_rrdb": 23, "critics": "reference DiscriminatorUNet(3,1,64) "
                        "+ ContentLoss on a SEEDED RANDOM-INIT VGG19 (ImageNet weights unavailable offline), autocast fp16 + GradScaler",
