@@ -213,6 +213,90 @@ def library_baseline(net, lr_dev, gt_dev, iters=5):
 
 
 # ------------------------------------------------------------------------------------------------------ our arm
+def widened_components(dev, steps=5):
+    """SURVEY.md section 8(f) components next to the path, timed in the same run (N = 1 only; short): the U-Net discriminator's three
+    passes (native vs the same module through stock torch ops: fp16 autocast as the reference scripts run it, and channels_last on
+    top -- the fastest library arm) and the BSRGAN GAN step (BASELINE configs[4]) with every component native."""
+    import importlib.util
+    out = {}
+    try:
+        from sr_gan_fd_b200.discriminator import discriminator_unet
+        torch.manual_seed(0)
+        d = discriminator_unet(in_channels=3, out_channels=1, channels=64).to(dev).train()
+        x = torch.rand(BATCH_PER_GPU, 3, LR_HW * SCALE, LR_HW * SCALE, device=dev)
+        dy = torch.randn(BATCH_PER_GPU, 1, LR_HW * SCALE, LR_HW * SCALE, device=dev) / x[:, :1].numel()
+
+        def t(fn, n=steps):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        def passes(xin, autocast):
+            def d_update():
+                for p in d.parameters():
+                    p.requires_grad = True
+                d.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+                    y = d(xin)
+                y.float().backward(dy)
+
+            def g_update():
+                for p in d.parameters():
+                    p.requires_grad = False
+                xr = xin.detach().requires_grad_(True)
+                with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+                    y = d(xr)
+                y.float().backward(dy)
+            return {"d_update_ms": t(d_update), "g_update_ms": t(g_update)}
+
+        rec = {"shape": [BATCH_PER_GPU, 3, LR_HW * SCALE, LR_HW * SCALE], "b200": passes(x, False)}
+        plan = d._runtime().last_plan
+        rec["b200_d_update_tflops"] = (plan.flops_fwd + plan.flops_bwd_d) / (rec["b200"]["d_update_ms"] * 1e-3) / 1e12
+        d.use_native = False
+        rec["torch_fp16_autocast"] = passes(x, True)
+        d = d.to(memory_format=torch.channels_last)
+        rec["torch_fp16_autocast_channels_last"] = passes(x.contiguous(memory_format=torch.channels_last), True)
+        out["discriminator_unet"] = rec
+        del d, x, dy
+        torch.cuda.empty_cache()
+    except Exception as exc:  # a widened component must never take the headline line down
+        out["discriminator_unet"] = {"error": repr(exc)[:200]}
+    try:
+        spec = importlib.util.spec_from_file_location("_gan_step", os.path.join(ROOT, "tools", "gan_step.py"))
+        gs = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(gs)
+        d_model, g_model, content = gs.build("b200", dev, content="b200", disc="b200")
+        d_model.train(); g_model.train()
+        step = gs.GanStep(d_model, g_model, content, dev, 1, optimizer="fused", ema=True)
+        lr = torch.rand(BATCH_PER_GPU, 3, LR_HW, LR_HW, device=dev)
+        gt = torch.rand(BATCH_PER_GPU, 3, LR_HW * SCALE, LR_HW * SCALE, device=dev)
+        for _ in range(3):
+            step(lr, gt)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(lr, gt)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out["bsrgan_gan_step"] = {"ms_per_step": ms, "img_per_s": BATCH_PER_GPU / (ms * 1e-3),
+                                  "config": "BASELINE configs[4]: generator + U-Net discriminator x3 + VGG19 content loss (seeded random-init VGG19) + fused Adam/EMA, "
+                                            "autocast + GradScaler, all components from sr_gan_fd_b200"}
+        del step, d_model, g_model, content
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out["bsrgan_gan_step"] = {"error": repr(exc)[:200]}
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -402,6 +486,8 @@ def run_b200(args):
         line["library_baseline"] = library_baseline(net, lr_dev, gt_dev)
         if line["library_baseline"].get("best"):
             line["vs_library_best"] = value / line["library_baseline"]["best"]
+    if world == 1 and not args.no_widened:
+        line["widened"] = widened_components(dev)
     if world == 1 and not args.no_cpu_baseline:
         del net
         torch.cuda.empty_cache()
@@ -530,6 +616,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--no-widened", action="store_true", help="skip the short section-8(f) component timings (discriminator, GAN step)")
     ap.add_argument("--workload", default="train", choices=["train", "c4"],
                     help="train: the contract's workload (configs[1]/[2]); c4: large-frame halo-tiled inference (configs[3])")
     ap.add_argument("--frame", type=int, default=1024)

@@ -275,6 +275,31 @@ def test_gpu_frozen_discriminator_gives_input_gradient_only():
 
 
 @pytest.mark.gpu
+def test_gpu_other_channel_counts():
+    """in_channels = 1 (generic ingest path), out_channels = 2 (two logit maps)"""
+    mine = _drop_in(4, in_channels=1, out_channels=2)
+    state = {k: v.clone() for k, v in mine.state_dict().items()}
+    g = torch.Generator().manual_seed(11)
+    x, dy = torch.rand(2, 1, 48, 40, generator=g), torch.randn(2, 2, 48, 40, generator=g)
+    st = {k: v.clone().float() for k, v in state.items()}
+    leaves = {k: st[k].requires_grad_(True) for k in do.param_names()}
+    st.update(leaves)
+    xin = x.clone().requires_grad_(True)
+    weights, _ = do.effective_weights(st, True)
+    yo = do.forward_from_weights(weights, st, xin)
+    yo.backward(dy)
+    mine = mine.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    y = mine(xg)
+    y.backward(dy.cuda())
+    assert y.shape == (2, 2, 48, 40)
+    assert rel_l2(y, yo.detach()) <= 2e-2
+    assert rel_l2(xg.grad, xin.grad) <= 0.2
+    for n, p in mine.named_parameters():
+        assert rel_l2(p.grad, leaves[n].grad) <= 0.2, n
+
+
+@pytest.mark.gpu
 def test_gpu_eval_no_grad_and_determinism():
     mine = _drop_in(2).cuda().eval()
     x, _ = _inputs(2, 48, 56, seed=9)
