@@ -218,6 +218,8 @@ def widened_components(dev, steps=5):
     passes (native vs the same module through stock torch ops: fp16 autocast as the reference scripts run it, and channels_last on
     top -- the fastest library arm) and the BSRGAN GAN step (BASELINE configs[4]) with every component native."""
     import importlib.util
+
+    import torch
     out = {}
     try:
         from sr_gan_fd_b200.discriminator import discriminator_unet

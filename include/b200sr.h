@@ -179,6 +179,8 @@ typedef struct b200sr_disc_desc {
   int32_t channels;     /* 64 */
   int32_t batch, height, width; /* height and width multiples of 8 (the reference's skip additions need that, too) */
   int32_t training;     /* 1: build the backward schedule */
+  int32_t fp16;         /* 16-bit format of the activations / packed weights / gradients: 1 = fp16 (what the reference's autocast runs
+                         * this network in; needs in_channels == 3, other widths fall back to bf16), 0 = bf16 (wider range) */
 } b200sr_disc_desc;
 int b200sr_disc_plan_create(const b200sr_disc_desc* desc, b200sr_plan** out);
 /* x: [batch, in_channels, height, width], element strides x_strides[4], dtype per b200sr_dtype;

@@ -36,6 +36,7 @@ struct PackOp {
   int mode;
   int nseg;
   int k32;         // 1: a single K chunk of 32 channels, packed as 64-byte rows under the 64B swizzle (half the bytes of a padded 128-byte row)
+  int f16;         // 1: packed as fp16 (U-Net discriminator plans in the reference's autocast format) instead of bf16
   int down_c;      // > 0 (modes kPackDownFwd / kPackDownDgrad): channels of one unshuffle phase; only the FOUR non-zero tap tiles of every
                    // (chunk, column group) are packed, rows [chunk][column group][tap 0..3][n] (see ConvParams::down_mode)
   PackSeg seg[5];
@@ -85,7 +86,7 @@ __device__ __forceinline__ float pack_fetch(const PackOp& op, const float* const
       for (int dy = ylo; dy < yhi; ++dy)
         for (int dx = xlo; dx < xhi; ++dx) v += wp[dy * 3 + dx];
     }
-    if (sg.part == 1) v = v - __bfloat162float(__float2bfloat16_rn(v));
+    if (sg.part == 1) v = v - (op.f16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v)));
     return v;
   }
   return 0.f;
@@ -138,7 +139,8 @@ __global__ void pack_weights_kernel(const PackOp* __restrict__ ops, int num_ops,
   const int n = cg * op.n_cols + ng;
   float v = (c < op.num_chunks) ? pack_fetch(op, params, n, c * 64 + kk, dy, dx) : 0.f;
   const int chunk16 = (kk >> 3) ^ (ng & 7);
-  packed[row * 64 + chunk16 * 8 + (kk & 7)] = __float2bfloat16_rn(v);
+  if (op.f16) reinterpret_cast<__half*>(packed)[row * 64 + chunk16 * 8 + (kk & 7)] = __float2half_rn(v);
+  else packed[row * 64 + chunk16 * 8 + (kk & 7)] = __float2bfloat16_rn(v);
 }
 
 // biases: flat fp32 copy (bias_index < 0 -> zeros)
@@ -208,7 +210,10 @@ __global__ void ingest_grad_kernel(const float* __restrict__ dy, const unsigned 
 // Thread layout: (ncols/2) channel-pair lanes x PL pixel lanes, so a warp reads consecutive channels of one pixel row
 // (coalesced); pixel lanes are reduced through shared memory, one atomicAdd per channel and block.
 struct BiasGradSeg { int col_begin, col_end; float* out; int n_valid; };
-struct BiasGradParams { const __nv_bfloat16* g; long long P; int stride; int c0; int ncols; int nseg; BiasGradSeg seg[5]; };
+struct BiasGradParams { const __nv_bfloat16* g; long long P; int stride; int c0; int ncols; int nseg; BiasGradSeg seg[5]; int f16; };
+__device__ __forceinline__ float2 ld16x2_f32(const __nv_bfloat162* p, bool f16) {
+  return f16 ? __half22float2(*reinterpret_cast<const __half2*>(p)) : __bfloat1622float2(*p);
+}
 constexpr int kBiasGradThreads = 256;
 
 __global__ void __launch_bounds__(kBiasGradThreads) bias_grad_kernel(const BiasGradParams p) {
@@ -226,14 +231,15 @@ __global__ void __launch_bounds__(kBiasGradThreads) bias_grad_kernel(const BiasG
     // four independent loads in flight per thread (the loop is latency-bound otherwise)
     float2 a1 = make_float2(0.f, 0.f), a2 = a1, a3 = a1;
     for (; px + 3 * step < p.P; px += 4 * step) {
-      const float2 v0 = __bfloat1622float2(base[px * sp]);
-      const float2 v1 = __bfloat1622float2(base[(px + step) * sp]);
-      const float2 v2 = __bfloat1622float2(base[(px + 2 * step) * sp]);
-      const float2 v3 = __bfloat1622float2(base[(px + 3 * step) * sp]);
+      const bool hf = p.f16 != 0;
+      const float2 v0 = ld16x2_f32(base + px * sp, hf);
+      const float2 v1 = ld16x2_f32(base + (px + step) * sp, hf);
+      const float2 v2 = ld16x2_f32(base + (px + 2 * step) * sp, hf);
+      const float2 v3 = ld16x2_f32(base + (px + 3 * step) * sp, hf);
       acc.x += v0.x; acc.y += v0.y; a1.x += v1.x; a1.y += v1.y; a2.x += v2.x; a2.y += v2.y; a3.x += v3.x; a3.y += v3.y;
     }
     for (; px < p.P; px += step) {
-      const float2 v = __bfloat1622float2(base[px * sp]);
+      const float2 v = ld16x2_f32(base + px * sp, p.f16 != 0);
       acc.x += v.x; acc.y += v.y;
     }
     acc.x += a1.x + a2.x + a3.x; acc.y += a1.y + a2.y + a3.y;

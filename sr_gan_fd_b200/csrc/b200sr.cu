@@ -1263,14 +1263,14 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         __nv_bfloat16* out = (__nv_bfloat16*)((char*)b.ws + P.o_xin);
         const int blocks = (int)((npix + 127) / 128);
         if (P.is_disc && d.in_channels == 3) {  // HR-sized RGB inputs: vectorised row stores
-          if (x_dtype == B200SR_F32)
-            disc_ingest_input_kernel<float, 3><<<blocks, 128, 0, st>>>((const float*)x, xs[0], xs[1], xs[2], xs[3], d.batch, d.height, d.width, out);
-          else if (x_dtype == B200SR_F16)
-            disc_ingest_input_kernel<__half, 3><<<blocks, 128, 0, st>>>((const __half*)x, xs[0], xs[1], xs[2], xs[3], d.batch, d.height, d.width, out);
-          else if (x_dtype == B200SR_BF16)
-            disc_ingest_input_kernel<__nv_bfloat16, 3><<<blocks, 128, 0, st>>>((const __nv_bfloat16*)x, xs[0], xs[1], xs[2], xs[3], d.batch, d.height, d.width, out);
+#define B200SR_DISC_INGEST(T) (P.dd.fp16 ? disc_ingest_input_kernel<T, 3, true> : disc_ingest_input_kernel<T, 3, false>)<<<blocks, 128, 0, st>>>( \
+            (const T*)x, xs[0], xs[1], xs[2], xs[3], d.batch, d.height, d.width, out)
+          if (x_dtype == B200SR_F32) B200SR_DISC_INGEST(float);
+          else if (x_dtype == B200SR_F16) B200SR_DISC_INGEST(__half);
+          else if (x_dtype == B200SR_BF16) B200SR_DISC_INGEST(__nv_bfloat16);
           else
             return fail(B200SR_ERR_INVALID, "unknown x dtype %d", x_dtype);
+#undef B200SR_DISC_INGEST
           CUDA_TRY(cudaGetLastError());
           break;
         }
@@ -1310,35 +1310,35 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
       }
       case ST_DISC_UP: {
         const dim3 g((unsigned)((s.pw * (s.pc >> 3) + 255) / 256), (unsigned)s.ph, (unsigned)s.pn);
-        disc_bilinear_up_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
+        (P.dd.fp16 ? disc_bilinear_up_kernel<true> : disc_bilinear_up_kernel<false>)<<<g, 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
                                                                             (__nv_bfloat16*)resolve(s.c, b), s.pn, s.ph, s.pw, s.pc);
         CUDA_TRY(cudaGetLastError());
         break;
       }
       case ST_DISC_UP_BWD: {
         const dim3 g((unsigned)((s.pw * (s.pc >> 3) + 255) / 256), (unsigned)s.ph, (unsigned)s.pn);
-        disc_bilinear_bwd_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
+        (P.dd.fp16 ? disc_bilinear_bwd_kernel<true> : disc_bilinear_bwd_kernel<false>)<<<g, 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
                                                                              (__nv_bfloat16*)resolve(s.c, b), (__nv_bfloat16*)resolve(s.d2, b), s.pn, s.ph, s.pw, s.pc);
         CUDA_TRY(cudaGetLastError());
         break;
       }
       case ST_DISC_ADD: {
         const long long n = (long long)s.pn * s.ph * s.pw * (s.pc >> 3);
-        disc_add_u_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
+        (P.dd.fp16 ? disc_add_u_kernel<true> : disc_add_u_kernel<false>)<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
                                                                       (__nv_bfloat16*)resolve(s.c, b), s.pn, s.ph, s.pw, s.pc);
         CUDA_TRY(cudaGetLastError());
         break;
       }
       case ST_DISC_MASK: {
         const long long n8 = (long long)s.pn * s.ph * s.pw * (s.pc >> 3);
-        disc_lrelu_mask_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
+        (P.dd.fp16 ? disc_lrelu_mask_kernel<true> : disc_lrelu_mask_kernel<false>)<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)resolve(s.a, b), (const __nv_bfloat16*)resolve(s.b, b),
                                                                            (__nv_bfloat16*)resolve(s.c, b), n8);
         CUDA_TRY(cudaGetLastError());
         break;
       }
       case ST_DISC_INGEST_DY: {
         const long long npix = (long long)s.pn * s.ph * s.pw;
-        disc_ingest_grad_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>((const float*)b.dy, s.pn, s.pc, s.ph, s.pw, (__nv_bfloat16*)resolve(s.c, b), 64);
+        (P.dd.fp16 ? disc_ingest_grad_kernel<true> : disc_ingest_grad_kernel<false>)<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>((const float*)b.dy, s.pn, s.pc, s.ph, s.pw, (__nv_bfloat16*)resolve(s.c, b), 64);
         CUDA_TRY(cudaGetLastError());
         break;
       }
@@ -1533,6 +1533,7 @@ static int build_disc_plan(b200sr_plan& P) {
   P.is_disc = true;
   P.reassoc = false;
   P.groups = v.batch >= 2 ? 2 : 1;
+  if (v.in_channels != 3) P.dd.fp16 = 0;  // the fp16 ingest kernel is specialised for RGB inputs; other widths run in bf16
   memset(&P.d, 0, sizeof(P.d));
   P.d.in_channels = v.in_channels; P.d.out_channels = v.out_channels; P.d.channels = 64; P.d.growth = 32;
   P.d.batch = v.batch; P.d.height = v.height; P.d.width = v.width; P.d.training = v.training;
@@ -1787,10 +1788,16 @@ static int build_disc_plan(b200sr_plan& P) {
   const long long bias_base = align_up(P.total_rows * 128, 1024);
   P.packed_bytes = bias_base + P.bias_floats * 4;
   auto fix = [&](std::vector<Step>& vv) {
-    for (Step& s : vv)
+    for (Step& s : vv) {
       if (s.bias.kind == RK_PACKED) s.bias.off = bias_base + (-1 - s.bias.off) * 4;
+      // 16-bit format of every tensor of this plan: fp16 (the reference's autocast format) or bf16
+      s.cp.epi.f16 = P.dd.fp16 ? 1 : 0;
+      s.wb.f16 = P.dd.fp16 ? 1 : 0;
+      s.bp.f16 = P.dd.fp16 ? 1 : 0;
+    }
   };
   fix(P.fwd); fix(P.bwd);
+  for (PackOp& op : P.pack_ops) op.f16 = P.dd.fp16 ? 1 : 0;
   auto chainify = [&](std::vector<Step>& vv) {
     std::vector<Step> out;
     for (Step& s : vv) {

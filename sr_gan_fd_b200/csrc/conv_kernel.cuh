@@ -78,6 +78,7 @@ struct ConvEpilogue {
   const __nv_bfloat16* res_bf16;
   int res_bf16_stride;
   int shuf_c;
+  int f16;  // 1: this layer's 16-bit operands / outputs / residual are fp16 instead of bf16 (same tcgen05 kind::f16 instruction)
 };
 
 struct ConvParams {
@@ -109,7 +110,7 @@ struct ConvParams {
   // data gradient: column group / down_c64); down_c64 = channels of one phase / 64.
   int down_mode;
   int down_c64;
-  int pad_[1];
+  int pad_[3];
   ConvEpilogue epi;
 };
 
@@ -210,8 +211,9 @@ __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const 
     const float neg = (kVgg && (e.mask_relu & 1)) ? 0.f : 0.2f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      v[2 * j] *= (bf16_lo_to_f32(maskw[j]) > 0.f) ? 1.f : neg;
-      v[2 * j + 1] *= (bf16_hi_to_f32(maskw[j]) > 0.f) ? 1.f : neg;
+      // (extended build: a sign / magnitude test on the bit pattern, valid for bf16 and fp16 activations alike)
+      v[2 * j] *= (kVgg ? pos16_lo(maskw[j]) : (bf16_lo_to_f32(maskw[j]) > 0.f)) ? 1.f : neg;
+      v[2 * j + 1] *= (kVgg ? pos16_hi(maskw[j]) : (bf16_hi_to_f32(maskw[j]) > 0.f)) ? 1.f : neg;
     }
   }
   if (has_res && !res_first) {  // fp32 residuals (already combined)
@@ -286,7 +288,8 @@ __device__ __forceinline__ void conv_epilogue_write(const HW p, const ConvEpilog
     __nv_bfloat16* ob = e.out_bf16 + opix * e.ob_stride + e.ob_coff + ch;
     uint32_t hi[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1]);
+    for (int j = 0; j < 16; ++j)
+      hi[j] = kExt ? pack_16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1], e.f16 != 0) : pack_bf16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1]);
     uint32_t lo[16];
     if (e.split_off > 0) {
 #pragma unroll
@@ -327,7 +330,7 @@ struct alignas(32) EntryDesc {
 constexpr int kMaxChainLayers = 768;
 constexpr int kMaxChainEntries = 2048;
 // layer record A: x = n_cols (9 bits) | chunks<<9 (5 bits) | ksteps_last<<14 | halves<<17 | w_taps<<19 | col_groups<<23
-//                 y = acc_col0 | acc_first<<8 | acc_hold<<9 | has_epi<<10 | k32<<11 | down_mode<<12 | down_c64<<14      z = w_row0      w = a_c0
+//                 y = acc_col0 | acc_first<<8 | acc_hold<<9 | has_epi<<10 | k32<<11 | down_mode<<12 | down_c64<<14 | f16<<17      z = w_row0      w = a_c0
 // layer record B: x = tiles_x | tiles_y<<16      y = a_wrap      z = bias byte offset in the packed buffer + 1 (0: none)      w = bias floats
 // entry record  : x = layer (absolute) | slot<<20 | neighbour_sync<<21      y = tile_lo      z = tile_hi      w = rot | (dep+1)<<16
 __constant__ uint4 c_layer_rec[kMaxChainLayers * 2];
@@ -335,7 +338,8 @@ __constant__ uint4 c_entry_rec[kMaxChainEntries];
 inline void make_layer_rec(const ConvParams& p, uint4 out[2], const void* packed_base) {
   out[0].x = static_cast<uint32_t>(p.n_cols) | (p.num_chunks << 9) | (p.ksteps_last << 14) | (p.halves << 17) | (p.w_taps << 19) | (p.col_groups << 23);
   out[0].y = static_cast<uint32_t>(p.acc_col0) | ((p.acc_first ? 1u : 0u) << 8) | ((p.acc_hold ? 1u : 0u) << 9) | ((p.epi_cols > 0 ? 1u : 0u) << 10) |
-             ((p.k32 ? 1u : 0u) << 11) | (static_cast<uint32_t>(p.down_mode & 3) << 12) | (static_cast<uint32_t>(p.down_c64 & 7) << 14);
+             ((p.k32 ? 1u : 0u) << 11) | (static_cast<uint32_t>(p.down_mode & 3) << 12) | (static_cast<uint32_t>(p.down_c64 & 7) << 14) |
+             ((p.epi.f16 ? 1u : 0u) << 17);
   out[0].z = static_cast<uint32_t>(p.w_row0);
   out[0].w = static_cast<uint32_t>(p.a_c0);
   out[1].x = static_cast<uint32_t>(p.tiles_x) | (static_cast<uint32_t>(p.tiles_y) << 16);
@@ -729,7 +733,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int k32 = static_cast<int>((la.y >> 11) & 1);
       const int down_mode = kVgg ? static_cast<int>((la.y >> 12) & 3) : 0, down_c64 = kVgg ? static_cast<int>((la.y >> 14) & 7) : 1;
       const int g = (w_taps * n_cols * (k32 ? 64 : 128) + kWGranule - 1) / kWGranule;
-      const uint32_t idesc = make_idesc_bf16(128, n_cols, 0, 0);
+      const uint32_t idesc = make_idesc_16(128, n_cols, 0, 0, kVgg && ((la.y >> 17) & 1));
       const uint32_t b_dy = static_cast<uint32_t>(n_cols) * (k32 ? 4u : 8u);  // bytes of one tap tile >> 4
       const uint32_t b_hi = k32 ? smem_desc_hi_sw64(512) : smem_desc_hi(1024);
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);
@@ -933,8 +937,9 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint4 r4 = __ldcg(rp + k);
-                res[8 * k] = bf16_lo_to_f32(r4.x); res[8 * k + 1] = bf16_hi_to_f32(r4.x); res[8 * k + 2] = bf16_lo_to_f32(r4.y); res[8 * k + 3] = bf16_hi_to_f32(r4.y);
-                res[8 * k + 4] = bf16_lo_to_f32(r4.z); res[8 * k + 5] = bf16_hi_to_f32(r4.z); res[8 * k + 6] = bf16_lo_to_f32(r4.w); res[8 * k + 7] = bf16_hi_to_f32(r4.w);
+                const bool hf = ep.f16 != 0;
+                res[8 * k] = lo16_to_f32(r4.x, hf); res[8 * k + 1] = hi16_to_f32(r4.x, hf); res[8 * k + 2] = lo16_to_f32(r4.y, hf); res[8 * k + 3] = hi16_to_f32(r4.y, hf);
+                res[8 * k + 4] = lo16_to_f32(r4.z, hf); res[8 * k + 5] = hi16_to_f32(r4.z, hf); res[8 * k + 6] = lo16_to_f32(r4.w, hf); res[8 * k + 7] = hi16_to_f32(r4.w, hf);
               }
             } else {
 #pragma unroll

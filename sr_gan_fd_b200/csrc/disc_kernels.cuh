@@ -13,18 +13,21 @@ __device__ __forceinline__ long long u_layout_off(int n, int y, int x, int H, in
   return ((static_cast<long long>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * (4LL * C) + (((y & 1) << 1) | (x & 1)) * C;
 }
 
-__device__ __forceinline__ void bf16x8_to_f32(const uint4 v, float (&f)[8]) {
-  f[0] = bf16_lo_to_f32(v.x); f[1] = bf16_hi_to_f32(v.x); f[2] = bf16_lo_to_f32(v.y); f[3] = bf16_hi_to_f32(v.y);
-  f[4] = bf16_lo_to_f32(v.z); f[5] = bf16_hi_to_f32(v.z); f[6] = bf16_lo_to_f32(v.w); f[7] = bf16_hi_to_f32(v.w);
+// eight 16-bit values <-> fp32; F16 = false: bf16 (default), true: fp16 (the reference's autocast format)
+template <bool F16>
+__device__ __forceinline__ void cvt8_to_f32(const uint4 v, float (&f)[8]) {
+  f[0] = lo16_to_f32(v.x, F16); f[1] = hi16_to_f32(v.x, F16); f[2] = lo16_to_f32(v.y, F16); f[3] = hi16_to_f32(v.y, F16);
+  f[4] = lo16_to_f32(v.z, F16); f[5] = hi16_to_f32(v.z, F16); f[6] = lo16_to_f32(v.w, F16); f[7] = hi16_to_f32(v.w, F16);
 }
-__device__ __forceinline__ uint4 f32x8_to_bf16(const float (&f)[8]) {
-  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+template <bool F16>
+__device__ __forceinline__ uint4 f32x8_to_16(const float (&f)[8]) {
+  return make_uint4(pack_16x2(f[0], f[1], F16), pack_16x2(f[2], f[3], F16), pack_16x2(f[4], f[5], F16), pack_16x2(f[6], f[7], F16));
 }
 
 // x: [N, C, H, W] (any strides; fp32 / fp16 / bf16; C = 3, other widths take the generator's ingest kernel) -> [N*H*W, 64] bf16 = [hi(C) | lo(C) | hi(C) | 0...] (conv1's weights are
 // packed [w_hi | w_hi | w_lo]).  One thread per pixel: the row is assembled in registers and leaves as eight 16-byte stores (the
 // generator's ingest kernel stores element by element, fine for its 64 x 64 inputs, 0.55 ms for sixteen 256 x 256 images).
-template <typename T, int C>
+template <typename T, int C, bool F16>
 __global__ void disc_ingest_input_kernel(const T* __restrict__ x, long long sn, long long sc, long long sh, long long sw, int N, int H, int W,
                                          __nv_bfloat16* __restrict__ out) {
   const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -32,14 +35,20 @@ __global__ void disc_ingest_input_kernel(const T* __restrict__ x, long long sn, 
   const int xw = static_cast<int>(pix % W);
   const int yh = static_cast<int>((pix / W) % H);
   const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-  __nv_bfloat16 row[64];
+  unsigned short row[64];
 #pragma unroll
-  for (int c = 0; c < 64; ++c) row[c] = __float2bfloat16_rn(0.f);
+  for (int c = 0; c < 64; ++c) row[c] = 0;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     const float v = static_cast<float>(x[n * sn + c * sc + yh * sh + xw * sw]);
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    unsigned short h, l;
+    if (F16) {
+      const __half hh = __float2half_rn(v);
+      h = __half_as_ushort(hh); l = __half_as_ushort(__float2half_rn(v - __half2float(hh)));
+    } else {
+      const __nv_bfloat16 hh = __float2bfloat16_rn(v);
+      h = __bfloat16_as_ushort(hh); l = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hh)));
+    }
     row[c] = h; row[C + c] = l; row[2 * C + c] = h;
   }
   uint4* o = reinterpret_cast<uint4*>(out + pix * 64);
@@ -53,6 +62,7 @@ __global__ void disc_ingest_input_kernel(const T* __restrict__ x, long long sn, 
 // border (so the first / last output row copies the first / last input row).  in: [N, h, w, C] bf16; skip_u: nullptr or the
 // tensor added to `in` first, in U layout; out: [N, 2h, 2w, C].  One thread per INPUT pixel and 8 channels: it reads the 3 x 3
 // source neighbourhood once (18 loads with the skip) and writes the 2 x 2 output pixels that sit on top of its pixel.
+template <bool F16>
 __global__ void __launch_bounds__(256, 4)
 disc_bilinear_up_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ skip_u,
                         __nv_bfloat16* __restrict__ out, int N, int h, int w, int C) {
@@ -71,10 +81,10 @@ disc_bilinear_up_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat1
     float s[3][8];
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + sy) * w + xs[b]) * C) + cc), s[b]);
+      cvt8_to_f32<F16>(__ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + sy) * w + xs[b]) * C) + cc), s[b]);
       if (skip_u) {
         float g[8];
-        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(skip_u + u_layout_off(n, sy, xs[b], h, w, C)) + cc), g);
+        cvt8_to_f32<F16>(__ldg(reinterpret_cast<const uint4*>(skip_u + u_layout_off(n, sy, xs[b], h, w, C)) + cc), g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) s[b][k] += g[k];
       }
@@ -88,12 +98,12 @@ disc_bilinear_up_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat1
       else { bot[0][k] += 0.25f * h0; bot[1][k] += 0.25f * h1; }
     }
     if (a == 1) {
-      reinterpret_cast<uint4*>(out + orow * C)[cc] = f32x8_to_bf16(top[0]);
-      reinterpret_cast<uint4*>(out + (orow + 1) * C)[cc] = f32x8_to_bf16(top[1]);
+      reinterpret_cast<uint4*>(out + orow * C)[cc] = f32x8_to_16<F16>(top[0]);
+      reinterpret_cast<uint4*>(out + (orow + 1) * C)[cc] = f32x8_to_16<F16>(top[1]);
     }
   }
-  reinterpret_cast<uint4*>(out + (orow + 2 * w) * C)[cc] = f32x8_to_bf16(bot[0]);
-  reinterpret_cast<uint4*>(out + (orow + 2 * w + 1) * C)[cc] = f32x8_to_bf16(bot[1]);
+  reinterpret_cast<uint4*>(out + (orow + 2 * w) * C)[cc] = f32x8_to_16<F16>(bot[0]);
+  reinterpret_cast<uint4*>(out + (orow + 2 * w + 1) * C)[cc] = f32x8_to_16<F16>(bot[1]);
 }
 
 // Transpose of the above: gin[Y, X] = sum over the (up to) 4 x 4 output positions that read input (Y, X).  Per axis the output
@@ -101,6 +111,7 @@ disc_bilinear_up_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat1
 // 0.25 (Y <= h-2).  gout: [N, 2h, 2w, C] bf16.  gs_out (or nullptr): the sum itself = gradient w.r.t. the upsampled tensor
 // (in + skip), which is also the skip connection's gradient; ga_out (or nullptr): the sum times the LeakyReLU(0.2) derivative
 // taken from the saved activation `act` ([N, h, w, C], same lattice) = gradient w.r.t. the producing conv's pre-activation.
+template <bool F16>
 __global__ void __launch_bounds__(256, 4)
 disc_bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16* __restrict__ act,
                          __nv_bfloat16* __restrict__ gs_out, __nv_bfloat16* __restrict__ ga_out, int N, int h, int w, int C) {
@@ -127,23 +138,24 @@ disc_bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bflo
       const int ox = 2 * X - 1 + b;
       if (wx[b] == 0.f) continue;
       float f[8];
-      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(gout + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * C) + cc), f);
+      cvt8_to_f32<F16>(__ldg(reinterpret_cast<const uint4*>(gout + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * C) + cc), f);
       const float wgt = wy[a] * wx[b];
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] += wgt * f[k];
     }
   }
-  if (gs_out) reinterpret_cast<uint4*>(gs_out + ip * C)[cc] = f32x8_to_bf16(acc);
+  if (gs_out) reinterpret_cast<uint4*>(gs_out + ip * C)[cc] = f32x8_to_16<F16>(acc);
   if (ga_out) {
     float m[8];
-    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(act + ip * C) + cc), m);
+    cvt8_to_f32<F16>(__ldg(reinterpret_cast<const uint4*>(act + ip * C) + cc), m);
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] *= (m[k] > 0.f) ? 1.f : 0.2f;
-    reinterpret_cast<uint4*>(ga_out + ip * C)[cc] = f32x8_to_bf16(acc);
+    reinterpret_cast<uint4*>(ga_out + ip * C)[cc] = f32x8_to_16<F16>(acc);
   }
 }
 
 // out[N, H, W, C] = a (plain layout) + b_u (U layout): up3 + out1 in front of conv2 (BSRGAN/model.py:161)
+template <bool F16>
 __global__ void disc_add_u_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b_u, __nv_bfloat16* __restrict__ out,
                                   int N, int H, int W, int C) {
   const int c8 = C >> 3;
@@ -153,27 +165,29 @@ __global__ void disc_add_u_kernel(const __nv_bfloat16* __restrict__ a, const __n
   const long long p = i / c8;
   const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H), n = static_cast<int>(p / (static_cast<long long>(W) * H));
   float f[8], g[8];
-  bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(a + p * C) + cc), f);
-  bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(b_u + u_layout_off(n, y, x, H, W, C)) + cc), g);
+  cvt8_to_f32<F16>(__ldg(reinterpret_cast<const uint4*>(a + p * C) + cc), f);
+  cvt8_to_f32<F16>(__ldg(reinterpret_cast<const uint4*>(b_u + u_layout_off(n, y, x, H, W, C)) + cc), g);
 #pragma unroll
   for (int k = 0; k < 8; ++k) f[k] += g[k];
-  reinterpret_cast<uint4*>(out + p * C)[cc] = f32x8_to_bf16(f);
+  reinterpret_cast<uint4*>(out + p * C)[cc] = f32x8_to_16<F16>(f);
 }
 
 // out = g * LeakyReLU'(act): the gradient of (up3 + out1) taken through up3's activation
+template <bool F16>
 __global__ void disc_lrelu_mask_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ out,
                                        long long n8) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   float f[8], m[8];
-  bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(g) + i), f);
-  bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(act) + i), m);
+  cvt8_to_f32<F16>(__ldg(reinterpret_cast<const uint4*>(g) + i), f);
+  cvt8_to_f32<F16>(__ldg(reinterpret_cast<const uint4*>(act) + i), m);
 #pragma unroll
   for (int k = 0; k < 8; ++k) f[k] *= (m[k] > 0.f) ? 1.f : 0.2f;
-  reinterpret_cast<uint4*>(out)[i] = f32x8_to_bf16(f);
+  reinterpret_cast<uint4*>(out)[i] = f32x8_to_16<F16>(f);
 }
 
 // dy: [N, C, H, W] fp32 contiguous -> [N*H*W, out_stride] bf16, channels [C, 16) zero (upstream gradient of the logit map)
+template <bool F16>
 __global__ void disc_ingest_grad_kernel(const float* __restrict__ dy, int N, int C, int H, int W, __nv_bfloat16* __restrict__ out, int out_stride) {
   const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long plane = static_cast<long long>(H) * W;
@@ -183,8 +197,8 @@ __global__ void disc_ingest_grad_kernel(const float* __restrict__ dy, int N, int
 #pragma unroll
   for (int c = 0; c < 16; ++c) v[c] = (c < C) ? dy[(n * C + c) * plane + r] : 0.f;
   uint4* o = reinterpret_cast<uint4*>(out + pix * out_stride);
-  o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+  o[0] = make_uint4(pack_16x2(v[0], v[1], F16), pack_16x2(v[2], v[3], F16), pack_16x2(v[4], v[5], F16), pack_16x2(v[6], v[7], F16));
+  o[1] = make_uint4(pack_16x2(v[8], v[9], F16), pack_16x2(v[10], v[11], F16), pack_16x2(v[12], v[13], F16), pack_16x2(v[14], v[15], F16));
 }
 
 // Staged weight gradient of a 4x4 stride-2 conv computed as a 3x3 conv over the U-layout input -> [co][c][4][4].

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace b200sr {
 
@@ -260,5 +261,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo_to_f32(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi_to_f32(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+// fp16 operands (the U-Net discriminator path can run in the reference's autocast format): same instruction descriptor with the
+// a / b format fields left at F16 (0), and the matching 16-bit pack / unpack helpers selected by a flag
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t m, uint32_t n, uint32_t a_mn_major, uint32_t b_mn_major, bool f16) {
+  return f16 ? (make_idesc_bf16(m, n, a_mn_major, b_mn_major) & ~((1u << 7) | (1u << 10))) : make_idesc_bf16(m, n, a_mn_major, b_mn_major);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+__device__ __forceinline__ float lo16_to_f32(uint32_t v, bool f16) {
+  return f16 ? __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFFu))) : bf16_lo_to_f32(v);
+}
+__device__ __forceinline__ float hi16_to_f32(uint32_t v, bool f16) {
+  return f16 ? __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16))) : bf16_hi_to_f32(v);
+}
+// value > 0 for a bf16 OR fp16 bit pattern: sign clear and magnitude non-zero
+__device__ __forceinline__ bool pos16_lo(uint32_t v) { return (v & 0x8000u) == 0u && (v & 0x7FFFu) != 0u; }
+__device__ __forceinline__ bool pos16_hi(uint32_t v) { return (v & 0x80000000u) == 0u && (v & 0x7FFF0000u) != 0u; }
 
 }  // namespace b200sr

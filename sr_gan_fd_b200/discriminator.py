@@ -38,9 +38,10 @@ _MAX_PLANS = 6
 
 
 class _DiscPlan:
-    def __init__(self, in_channels: int, out_channels: int, channels: int, batch: int, height: int, width: int, training: bool) -> None:
+    def __init__(self, in_channels: int, out_channels: int, channels: int, batch: int, height: int, width: int, training: bool,
+                 fp16: bool = True) -> None:
         lib = _lib.load()
-        d = _lib.DiscDesc(in_channels, out_channels, channels, batch, height, width, 1 if training else 0)
+        d = _lib.DiscDesc(in_channels, out_channels, channels, batch, height, width, 1 if training else 0, 1 if fp16 else 0)
         handle = C.c_void_p()
         _lib.check(lib.b200sr_disc_plan_create(C.byref(d), C.byref(handle)))
         self.handle = handle
@@ -70,10 +71,11 @@ class _DiscRuntime:
         self.last_plan = None
 
     def plan(self, module, device, batch, height, width, training) -> _DiscPlan:
-        key = (device.index, batch, height, width, training)
+        fp16 = module.operand_dtype == "fp16"
+        key = (device.index, batch, height, width, training, fp16)
         p = self.plans.get(key)
         if p is None:
-            p = _DiscPlan(module._in_channels, module._out_channels, module._channels, batch, height, width, training)
+            p = _DiscPlan(module._in_channels, module._out_channels, module._channels, batch, height, width, training, fp16)
             self.plans[key] = p
             while len(self.plans) > _MAX_PLANS:
                 self.plans.popitem(last=False)
@@ -150,6 +152,10 @@ class DiscriminatorUNet(nn.Module):
     """``BSRGAN/model.py:91-167``.  Same constructor arguments, children and ``state_dict`` as the reference class."""
 
     use_native = True  # A/B switch (benchmarks): False sends CUDA tensors through the stock torch ops as well
+    # 16-bit format of the native path's activations, packed weights and gradients (fp32 accumulation either way): "fp16" is what the
+    # reference's scripts run this module in (torch.autocast's CUDA default, BSRGAN/train_bsrgan.py:415,425,447) and, with an 11-bit
+    # mantissa, six times closer to fp32 than "bf16", which in turn cannot overflow under an aggressive GradScaler scale
+    operand_dtype = "fp16"
 
     def __init__(
             self,

@@ -25,7 +25,7 @@ class VggDesc(C.Structure):
 
 
 class DiscDesc(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("in_channels", "out_channels", "channels", "batch", "height", "width", "training")]
+    _fields_ = [(n, C.c_int32) for n in ("in_channels", "out_channels", "channels", "batch", "height", "width", "training", "fp16")]
 
 
 _lock = threading.Lock()

@@ -4,9 +4,10 @@ CPU: the oracle restatement (oracle/disc_oracle.py) is pinned against the refere
 buffers, every parameter gradient, input gradient) and against the committed golden fixture; the drop-in's own CPU path and its
 construction (state_dict keys, shapes, seeded initial values) equal the reference class bit for bit.
 GPU: the native path (tcgen05 convs in bf16 with fp32 accumulation) against the fp32 oracle on the CPU.  BASELINE.json states no
-tolerance for the discriminator.  The bar: per tensor, not further from fp32 than 1.3 x what torch's own bf16 autocast of the same
-module loses (+ 2e-3), inside absolute caps of 2e-2 (logits) and 0.2 (gradients) relative L2; measured values are appended to
-gpurun_out/disc_parity.jsonl and the worst tensor is printed."""
+tolerance for the discriminator.  The bar: per tensor, not further from fp32 than 1.3 x what torch's own autocast of the same
+module IN THE SAME 16-BIT FORMAT loses (+ 2e-3) -- fp16, the format the reference scripts run it in and the native default, or
+bf16 -- inside absolute caps of 5e-3 / 0.1 (fp16: logits / gradients) and 2e-2 / 0.2 (bf16) relative L2; measured values are
+appended to gpurun_out/disc_parity.jsonl and the worst tensor is printed."""
 import copy
 import glob
 import io
@@ -126,7 +127,7 @@ def test_disc_plan_host_bookkeeping():
     build_native()
     L = b200lib.load()
     h = C.c_void_p()
-    d = b200lib.DiscDesc(3, 1, 64, 16, 256, 256, 1)
+    d = b200lib.DiscDesc(3, 1, 64, 16, 256, 256, 1, 1)
     assert L.b200sr_disc_plan_create(C.byref(d), C.byref(h)) == 0
     try:
         shapes = do.layer_shapes()
@@ -140,7 +141,7 @@ def test_disc_plan_host_bookkeeping():
         assert L.b200sr_workspace_bytes(h) > 0 and L.b200sr_packed_bytes(h) > 2 * numel
     finally:
         L.b200sr_plan_destroy(h)
-    for bad in (b200lib.DiscDesc(3, 1, 32, 1, 64, 64, 0), b200lib.DiscDesc(3, 1, 64, 1, 60, 64, 0), b200lib.DiscDesc(17, 1, 64, 1, 64, 64, 0)):
+    for bad in (b200lib.DiscDesc(3, 1, 32, 1, 64, 64, 0, 0), b200lib.DiscDesc(3, 1, 64, 1, 60, 64, 0, 0), b200lib.DiscDesc(17, 1, 64, 1, 64, 64, 0, 0)):
         assert L.b200sr_disc_plan_create(C.byref(bad), C.byref(h)) < 0 and L.b200sr_last_error()
 
 
@@ -199,6 +200,17 @@ def _autocast_errors(state, x, dy, training, go, yo, dxo, dtype=torch.bfloat16):
     return errs
 
 
+def _settle_power_iteration(module, x, iters=5):
+    """eval-mode forwards use the stored weight_u / weight_v as they are: a freshly constructed module holds RANDOM vectors, whose
+    sigma = u.(W v) is far from the spectral norm (weights blow up by orders of magnitude and overflow fp16 -- in the reference's
+    autocast just the same).  A few training-mode forwards give the buffers the values a trained discriminator has."""
+    module.train()
+    with torch.no_grad():
+        for _ in range(iters):
+            module(x)
+    return module
+
+
 def _record(tag, payload):
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
@@ -207,36 +219,45 @@ def _record(tag, payload):
             fh.write(json.dumps({"case": tag, **payload}) + "\n")
 
 
+CAPS = {"fp16": (5e-3, 0.1), "bf16": (2e-2, 0.2)}  # absolute caps on the relative L2 error: (logits, gradients)
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,training", [((2, 64, 64), True), ((3, 40, 72), True), ((1, 32, 32), False), ((2, 128, 96), True)])
-def test_gpu_forward_backward_against_oracle(shape, training):
-    """Native path vs the fp32 oracle, next to what torch's own bf16 autocast of the same module loses against fp32: the native
-    path (bf16 operands, fp32 accumulation) must not be further from fp32 than 1.3 x the stock bf16 path + 2e-3, per tensor, and
-    inside the absolute caps logits <= 2e-2, gradients <= 0.2 relative L2 (a plain ten-layer feed-forward net has no fp32 residual
-    carrier to lean on, unlike the generator: bf16 rounding of every activation shows in the logits at the 1e-2 level, and
-    LeakyReLU-derivative flips near zero show in the gradients)."""
+@pytest.mark.parametrize("shape,training,fmt", [((2, 64, 64), True, "fp16"), ((3, 40, 72), True, "fp16"), ((1, 32, 32), False, "fp16"),
+                                                ((2, 128, 96), True, "fp16"), ((2, 64, 64), True, "bf16"), ((1, 32, 32), False, "bf16")])
+def test_gpu_forward_backward_against_oracle(shape, training, fmt):
+    """Native path vs the fp32 oracle, next to what torch's own autocast of the same module IN THE SAME 16-BIT FORMAT loses against
+    fp32 (fp16 = the format the reference scripts run the discriminator in, and the native default; bf16 = the optional wide-range
+    format): per tensor the native path (16-bit operands, fp32 accumulation) must not be further from fp32 than 1.3 x the stock
+    autocast path + 2e-3, and inside the absolute caps -- fp16: logits <= 5e-3, gradients <= 0.1; bf16: 2e-2 / 0.2 relative L2.
+    (A plain ten-layer feed-forward net has no fp32 residual carrier to lean on, unlike the generator: the rounding of every
+    activation shows in the logits, and LeakyReLU-derivative flips near zero show in the gradients.)"""
     n, h, w = shape
     mine = _drop_in(0)
-    state = {k: v.clone() for k, v in mine.state_dict().items()}
+    mine.operand_dtype = fmt
     x, dy = _inputs(n, h, w)
+    if not training:
+        _settle_power_iteration(mine, x)
+    state = {k: v.clone() for k, v in mine.state_dict().items()}
     yo, go, effo, dxo, buffers = do.forward_backward(state, x, dy, training, input_grad=True)
-    stock = _autocast_errors(state, x, dy, training, go, yo, dxo)
+    stock = _autocast_errors(state, x, dy, training, go, yo, dxo, torch.float16 if fmt == "fp16" else torch.bfloat16)
     mine = mine.cuda().train(training)
     y, grads, effg, dx = _gpu_step(mine, x, dy, True)
     errs = {"logits": rel_l2(y, yo), "dx": rel_l2(dx, dxo)}
     for k in do.param_names():
         errs["grad " + k] = rel_l2(grads[k], go[k])
     worst = max(errs, key=errs.get)
-    print(f"disc {shape} training={training}: logits {errs['logits']:.2e} (stock bf16 {stock['logits']:.2e}) dx {errs['dx']:.2e} ({stock['dx']:.2e}) "
-          f"worst {worst} {errs[worst]:.2e} ({stock[worst]:.2e})")
-    _record(f"{shape} training={training}", {"native_vs_fp32": errs, "torch_bf16_autocast_vs_fp32": stock})
-    assert errs["logits"] <= 2e-2, errs
+    print(f"disc {shape} training={training} {fmt}: logits {errs['logits']:.2e} (stock {fmt} autocast {stock['logits']:.2e}) dx {errs['dx']:.2e} "
+          f"({stock['dx']:.2e}) worst {worst} {errs[worst]:.2e} ({stock[worst]:.2e})")
+    _record(f"{shape} training={training} {fmt}", {"native_vs_fp32": errs, f"torch_{fmt}_autocast_vs_fp32": stock})
+    cap_logits, cap_grad = CAPS[fmt]
+    assert errs["logits"] <= cap_logits, errs
     for k, e in errs.items():
-        assert e <= 0.2, (k, e)
+        assert e <= cap_grad, (k, e)
         assert e <= 1.3 * stock[k] + 2e-3, (k, e, stock[k])
     # gradients of the EFFECTIVE weights (what the library itself returns, before torch's W / sigma graph)
     for name, g in effg.items():
-        assert g is not None and rel_l2(g, effo[name]) <= 0.15, name
+        assert g is not None and rel_l2(g, effo[name]) <= cap_grad, name
     # the power-iteration buffers moved exactly as the reference moves them (torch's own hook ran once)
     after = mine.state_dict()
     for k, v in buffers.items():
@@ -257,7 +278,7 @@ def test_gpu_frozen_discriminator_gives_input_gradient_only():
     y = mine(xg)
     y.backward(dy.cuda())
     assert all(p.grad is None for p in mine.parameters())
-    assert rel_l2(xg.grad, dxo) <= 0.15
+    assert rel_l2(xg.grad, dxo) <= 0.1
     # and the discriminator update: input without gradient, parameter gradients only; fp16 autocast + GradScaler scale as the script
     for p in mine.parameters():
         p.requires_grad = True
@@ -271,7 +292,7 @@ def test_gpu_frozen_discriminator_gives_input_gradient_only():
     assert y.dtype == torch.float32
     (y * dys.cuda()).sum().mul(65536.0).backward()
     for n, p in mine.named_parameters():
-        assert rel_l2(p.grad, go[n]) <= 0.15, n
+        assert rel_l2(p.grad, go[n]) <= 0.1, n
 
 
 @pytest.mark.gpu
@@ -301,15 +322,15 @@ def test_gpu_other_channel_counts():
 
 @pytest.mark.gpu
 def test_gpu_eval_no_grad_and_determinism():
-    mine = _drop_in(2).cuda().eval()
     x, _ = _inputs(2, 48, 56, seed=9)
+    mine = _settle_power_iteration(_drop_in(2), x).cuda().eval()
     with torch.no_grad():
         a = mine(x.cuda())
         b = mine(x.cuda())
     assert not a.requires_grad and torch.equal(a, b)
     state = {k: v.cpu() for k, v in mine.state_dict().items()}
     yo, _ = do.forward(state, x, training=False)
-    assert rel_l2(a, yo) <= 2e-2
+    assert rel_l2(a, yo) <= 5e-3
 
 
 @pytest.mark.gpu
@@ -319,9 +340,9 @@ def test_gpu_matches_golden(path):
     fix = torch.load(path)
     mine = _drop_in(fix["seed"]).cuda().train()
     y, grads, _, dx = _gpu_step(mine, fix["x"], fix["dy"], True)
-    assert rel_l2(y, fix["y"]) <= 2e-2
-    assert rel_l2(dx, fix["dx"]) <= 0.15
+    assert rel_l2(y, fix["y"]) <= 5e-3
+    assert rel_l2(dx, fix["dx"]) <= 0.1
     for k, g in fix["grads"].items():
-        assert rel_l2(grads[k], g) <= 0.15, k
+        assert rel_l2(grads[k], g) <= 0.1, k
     for k, nrm in fix["grad_norms"].items():
         assert abs(float(grads[k].double().norm()) - nrm) <= 0.05 * nrm, k
