@@ -1375,6 +1375,8 @@ static const int kVggCin[16] = {3, 64, 64, 128, 128, 256, 256, 256, 256, 512, 51
 static const int kVggCout[16] = {64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512, 512, 512, 512};
 static const bool kVggPoolAfter[16] = {false, true, false, true, false, false, false, true, false, false, false, true, false, false, false, false};
 
+// B200SR_N128=0: column groups of 64 everywhere in the discriminator / VGG plans (A/B switch)
+static const bool g_n128 = [] { const char* e = getenv("B200SR_N128"); return !(e && atoi(e) == 0); }();
 static int build_vgg_plan(b200sr_plan& P) {
   const b200sr_vgg_desc& v = P.vd;
   if (v.batch < 1 || v.height < 1 || v.width < 1) return fail(B200SR_ERR_INVALID, "bad geometry");
@@ -1429,7 +1431,7 @@ static int build_vgg_plan(b200sr_plan& P) {
   { Step s; s.type = ST_VGG_INGEST; P.fwd.push_back(s); }
   for (int l = 0; l < NL; ++l) {
     const int cin = kVggCin[l], cout = kVggCout[l], hh = P.vgg_h[l], ww = P.vgg_w[l];
-    const int n_cols = 64;  // column groups of 64 (the epilogue handles up to 64 accumulator columns per work item)
+    const int n_cols = (g_n128 && cout % 128 == 0) ? 128 : 64;  // column groups of 128 for the wide layers, else 64
     PackOp op; memset(&op, 0, sizeof(op));
     op.n_total = cout; op.n_cols = n_cols; op.n_valid = cout; op.mode = kPackFwd;
     int amap, chunks, ksl;
@@ -1466,7 +1468,7 @@ static int build_vgg_plan(b200sr_plan& P) {
     for (int l = v.grad_conv; l >= 0; --l) {
       const int cin = kVggCin[l], cout = kVggCout[l], hh = P.vgg_h[l], ww = P.vgg_w[l];
       const int nin = (l == 0) ? 16 : cin;  // dgrad output channels (conv 0: 3 padded to 16, stored NCHW fp32 to dx)
-      const int n_cols = (l == 0) ? 16 : 64;
+      const int n_cols = (l == 0) ? 16 : ((g_n128 && cin % 128 == 0) ? 128 : 64);
       PackOp op; memset(&op, 0, sizeof(op));
       op.n_total = nin; op.n_cols = n_cols; op.n_valid = (l == 0) ? 3 : cin; op.num_chunks = cout / 64; op.mode = kPackDgrad; op.nseg = 1;
       op.seg[0] = seg(0, cout, 2 * l, cout, cin, 0, 0, 0);
@@ -1599,7 +1601,9 @@ static int build_disc_plan(b200sr_plan& P) {
   // generic layer: input buffer [.., c_in] (plain or U layout: the conv does not care), K = c_in channels in chunks of 64
   auto fwd_conv = [&](int c, long long in_off, int c_in, int mode, long long out_off, int out_stride, int act) {
     const int lvl = cLvl[c], cout = cO[c];
-    const int n_total = (c == 9) ? 16 : cout, n_cols = (c == 9) ? 16 : 64;
+    // column groups of 128 for the wide stride-1 layers (an N = 128 tcgen05.mma does twice the work of an N = 64 one in 4/3 of the
+    // time, and the activation tile is re-read half as often); the 4-tap stride-2 stages stay at 64 columns (32 KB per stage)
+    const int n_total = (c == 9) ? 16 : cout, n_cols = (c == 9) ? 16 : ((g_n128 && mode == kPackFwd && cout % 128 == 0) ? 128 : 64);
     PackOp op; memset(&op, 0, sizeof(op));
     op.n_total = n_total; op.n_cols = n_cols; op.n_valid = cout; op.mode = mode; op.num_chunks = c_in / 64; op.nseg = 1;
     op.seg[0] = seg(0, c_in, 2 * c, cout, cI[c], 0, 0, 0);
@@ -1689,11 +1693,11 @@ static int build_disc_plan(b200sr_plan& P) {
     { Step s = dgrad_conv(8, G5, 64, 64, kPackDgrad, 64, 64, 64); mask_by(s, A4, 64); out_to(s, G4, 64); P.bwd.push_back(s); }
     { Step s = dgrad_conv(7, G4, 64, 64, kPackDgrad, 64, 64, 64); out_to(s, GS3, 64); P.bwd.push_back(s); }   // gradient of (up3 + out1)
     { Step s; s.type = ST_DISC_MASK; s.a = ws(GS3); s.b = ws(A3); s.c = ws(G3); s.pn = N; s.ph = H; s.pw = W; s.pc = 64; P.bwd.push_back(s); }
-    { Step s = dgrad_conv(6, G3, 64, 64, kPackDgrad, 128, 64, 128); out_to(s, GB3, 128); P.bwd.push_back(s); }
+    { Step s = dgrad_conv(6, G3, 64, 64, kPackDgrad, 128, g_n128 ? 128 : 64, 128); out_to(s, GB3, 128); P.bwd.push_back(s); }
     P.bwd.push_back(up_bwd(GB3, A2, GS2, GA2, 1, 128));
-    { Step s = dgrad_conv(5, GA2, 128, 128, kPackDgrad, 256, 64, 256); out_to(s, GB2, 256); P.bwd.push_back(s); }
+    { Step s = dgrad_conv(5, GA2, 128, 128, kPackDgrad, 256, g_n128 ? 128 : 64, 256); out_to(s, GB2, 256); P.bwd.push_back(s); }
     P.bwd.push_back(up_bwd(GB2, A1, GS1, GA1, 2, 256));
-    { Step s = dgrad_conv(4, GA1, 256, 256, kPackDgrad, 512, 64, 512); out_to(s, GB1, 512); P.bwd.push_back(s); }
+    { Step s = dgrad_conv(4, GA1, 256, 256, kPackDgrad, 512, g_n128 ? 128 : 64, 512); out_to(s, GB1, 512); P.bwd.push_back(s); }
     P.bwd.push_back(up_bwd(GB1, T3, -1, GT3, 3, 512));
     // stride-2 convs: 4C output columns on the conv's own lattice, pixel-shuffled to the plain layout of the finer lattice; the
     // skip connection's gradient (plain layout, finer lattice) joins before the LeakyReLU derivative of the U-layout activation

@@ -977,8 +977,9 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         tcgen05_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * 128u + p.acc_col0;
         bool released = false;
+        constexpr int kEpiGroups = kVgg ? 4 : 2;  // 32-column groups per work item: 64 columns, or 128 in the extended build (wide layers)
 #pragma unroll
-        for (int gq = 0; gq < 2; ++gq) {
+        for (int gq = 0; gq < kEpiGroups; ++gq) {
           const int c0 = gq * 32;
           if (c0 < p.epi_cols) {
             float vv[32];
@@ -1013,7 +1014,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
             float* feat_row = (kVgg && ep.feat_out && pre && ncol == 32) ? ep.feat_out + pix * ep.feat_stride + (colbase + c0) : nullptr;
             conv_epilogue_math<kVgg>(ep, sbias, res, has_res, maskw, has_mask, colbase + c0, ncol, vv, feat_row);
             // the residual / mask registers are free again: fetch the second 32 columns' while the first are stored
-            if (gq == 0 && 32 < p.epi_cols) prefetch_cols(32);
+            if (kVgg ? ((gq + 1) * 32 < p.epi_cols) : (gq == 0 && 32 < p.epi_cols)) prefetch_cols((gq + 1) * 32);
             conv_epilogue_write<kVgg>(hw, ep, y_dyn, cbase, n, y, x, colbase + c0, vv, pre, lane);
             if (warp == 2 && gq == 0) TL_MARK(13);
           }
