@@ -48,8 +48,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
-static int g_num_sms = 0;
-static bool g_attr_set = false;
+static int g_num_sms = 0;              // SM count of the device of the LAST runtime_init() call (every entry point calls it first)
+static int g_dev_sms[64] = {0};        // per device: SM count, and whether the >48 KB dynamic shared memory opt-in has been set
+static bool g_dev_attr_set[64] = {false};
 static int g_ctas_per_sm = 1;
 static int g_debug = 0;  // timing probes only (b200sr_debug_set)
 
@@ -61,19 +62,23 @@ static int runtime_init() {
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(B200SR_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  if (!g_num_sms) {
-    int dev = 0, major = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
+  // per DEVICE state: the compute-capability check, the SM count and the shared-memory opt-in (cudaFuncSetAttribute is per device)
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  const int di = dev & 63;
+  if (!g_dev_sms[di]) {
+    int major = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) return fail(B200SR_ERR_UNSUPPORTED, "libb200sr needs an sm_100 device (found sm_%d*)", major);
-    CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&g_dev_sms[di], cudaDevAttrMultiProcessorCount, dev));
   }
-  if (!g_attr_set) {
+  g_num_sms = g_dev_sms[di];
+  if (!g_dev_attr_set[di]) {
     CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
     CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
     CUDA_TRY(cudaFuncSetAttribute(conv3x3_chain_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(1)));
     CUDA_TRY(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
-    g_attr_set = true;
+    g_dev_attr_set[di] = true;
   }
   return 0;
 }
