@@ -346,3 +346,53 @@ def test_gpu_matches_golden(path):
         assert rel_l2(grads[k], g) <= 0.1, k
     for k, nrm in fix["grad_norms"].items():
         assert abs(float(grads[k].double().norm()) - nrm) <= 0.05 * nrm, k
+
+
+@pytest.mark.gpu
+def test_gpu_guard_bands_and_forward_determinism():
+    """compute-sanitizer is closed on the GPU pool (profiles/r2_sanitizer_unavailable.log): the discriminator runs through the C ABI
+    on workspace / packed / output / gradient / input-gradient buffers framed by guard bands that must come back untouched, and the
+    forward pass (no atomics on its path) must be bit-identical over repeated runs on fresh memory."""
+    import ctypes as C
+    from sr_gan_fd_b200 import lib as _lib
+    from sr_gan_fd_b200.discriminator import _DiscPlan
+    L = _lib.load()
+    dev = torch.device("cuda", 0)
+    mine = _drop_in(0).to(dev).train()
+    weights = [mine.conv1.weight, mine.conv1.bias] + [mine._effective_weight(c).detach() for c in mine._sn_convs()] + [mine.conv4.weight, mine.conv4.bias]
+    w1, b1, d1, d2, d3, u1, u2, u3, c2, c3, w4, b4 = [t.detach().float().contiguous() for t in weights]
+    slots = [w1, b1, d1, None, d2, None, d3, None, u1, None, u2, None, u3, None, c2, None, c3, None, w4, b4]
+    G = 1 << 16
+    for shape, fp16 in [((2, 3, 40, 24), True), ((3, 3, 16, 72), False)]:
+        n, c, h, w = shape
+        plan = _DiscPlan(3, 1, 64, n, h, w, True, fp16)
+        stream = torch.cuda.current_stream().cuda_stream
+        x = torch.rand(*shape, device=dev)
+        dy = torch.randn(n, 1, h, w, device=dev)
+        outs = []
+        for rep in range(3):
+            def framed(nbytes, fill):
+                buf = torch.full((nbytes + 2 * G,), fill, dtype=torch.uint8, device=dev)
+                return buf, buf[G:G + nbytes]
+            ws_all, ws = framed((plan.workspace_bytes + 1023) // 1024 * 1024, 0xA5)
+            pk_all, pk = framed((plan.packed_bytes + 1023) // 1024 * 1024, 0x77)
+            y_all, yb = framed(n * h * w * 4, 0x5A)
+            g_all, gb = framed(plan.param_numel * 4, 0x3C)
+            dx_all, dxb = framed(n * 3 * h * w * 4, 0x69)
+            ptrs = (C.c_void_p * 20)(*[t.data_ptr() if t is not None else None for t in slots])
+            _lib.check(L.b200sr_pack_weights(plan.handle, ptrs, C.c_void_p(pk.data_ptr()), C.c_void_p(stream)))
+            strides = (C.c_int64 * 4)(*x.stride())
+            _lib.check(L.b200sr_disc_forward(plan.handle, C.c_void_p(x.data_ptr()), _lib.F32, strides, C.c_void_p(pk.data_ptr()),
+                                             C.c_void_p(ws.data_ptr()), C.c_void_p(yb.data_ptr()), C.c_void_p(stream)))
+            _lib.check(L.b200sr_disc_backward(plan.handle, C.c_void_p(dy.data_ptr()), C.c_void_p(pk.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                              C.c_void_p(gb.data_ptr()), C.c_void_p(dxb.data_ptr()), C.c_void_p(stream)))
+            torch.cuda.synchronize()
+            for name, full, fill in (("workspace", ws_all, 0xA5), ("packed", pk_all, 0x77), ("output", y_all, 0x5A), ("gradients", g_all, 0x3C),
+                                     ("input gradient", dx_all, 0x69)):
+                assert bool((full[:G] == fill).all()) and bool((full[-G:] == fill).all()), f"{name} guard band was written ({shape})"
+            outs.append((yb.view(torch.float32).clone(), gb.view(torch.float32).clone(), dxb.view(torch.float32).clone()))
+        for yb, gb, dxb in outs[1:]:
+            assert torch.equal(yb, outs[0][0]), "forward is not bit-reproducible"
+            assert torch.isfinite(gb).all() and torch.isfinite(dxb).all()
+            assert rel_l2(gb, outs[0][1]) < 1e-5  # fp32 atomics in the weight-gradient flush: order-dependent rounding only
+            assert torch.equal(dxb, outs[0][2])   # the data-gradient path has no atomics
