@@ -173,6 +173,8 @@ struct b200sr_plan {
   cudaStream_t side_stream[3] = {nullptr, nullptr, nullptr};  // extra streams for the weight-gradient launches (tails / heads overlap)
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   std::vector<long long> o_gu;
+  bool tail_f16 = false;              // conv2 / upsampling / conv3 / conv4 as ONE fp16 product each instead of three split-bf16 products:
+                                      // default for inference plans; training plans keep the split form (B200SR_TAIL_FP16=0/1 overrides)
   bool reassoc = true;                // dense blocks re-associated by input slice ("windowed": convs 1-4 resident in TMEM, 128 columns per
                                       // 128-pixel half, conv5 spread over filler layers); B200SR_REASSOC=0 or a frame with more 8x32 items
                                       // per image than SMs: plain per-conv schedule
@@ -375,9 +377,14 @@ static int build_plan(b200sr_plan& P) {
   P.o_c2 = B.alloc(carrier_bytes);
   const int ndense = train ? R : 2;
   for (int i = 0; i < ndense; ++i) P.o_dense.push_back(B.alloc(Ppix * 192 * 2));
-  P.o_splt = B.alloc(Ppix * 128 * 2);
-  for (int l = 0; l <= L; ++l) P.o_spl.push_back(B.alloc((Ppix << (2 * l)) * 128 * 2));
-  P.o_splc = B.alloc((Ppix << (2 * L)) * 128 * 2);
+  // tail activations: fp16 [pixels][64] (one fp16 product per conv), or the [hi | lo] bf16 pairs of the split-precision form
+  // (training keeps a bf16 twin of every fp16 tail activation next to it, channels [64, 128): the weight-gradient GEMM pairs it with
+  // the bf16 output gradients -- tcgen05 kind::f16 takes ONE 16-bit format for both operands, and the gradients stay bf16 for range)
+  const bool tf16 = P.tail_f16;
+  const int ts = (tf16 && !train) ? 64 : 128;  // channels per pixel of the tail activation buffers
+  P.o_splt = B.alloc(Ppix * ts * 2);
+  for (int l = 0; l <= L; ++l) P.o_spl.push_back(B.alloc((Ppix << (2 * l)) * ts * 2));
+  P.o_splc = B.alloc((Ppix << (2 * L)) * ts * 2);
   const long long HRpix = Ppix << (2 * L);
   if (train) {
     P.o_cmask = B.alloc(HRpix * d.out_channels);
@@ -468,7 +475,8 @@ static int build_plan(b200sr_plan& P) {
       if (r < R - 1) {
         s.ob = ws(dense_off(r + 1)); s.cp.epi.ob_stride = 192; s.cp.epi.ob_coff = 0;
       } else {
-        s.ob = ws(P.o_splt); s.cp.epi.ob_stride = 128; s.cp.epi.ob_coff = 0; s.cp.epi.split_off = 64;
+        s.ob = ws(P.o_splt); s.cp.epi.ob_stride = ts; s.cp.epi.ob_coff = 0; s.cp.epi.split_off = (ts == 128) ? 64 : 0;
+        s.cp.epi.f16 = tf16;  // (only the STORE format: this layer's own operands are the trunk's bf16, mma_f16 stays 0)
       }
     };
     if (reassoc) {
@@ -538,10 +546,19 @@ static int build_plan(b200sr_plan& P) {
       P.fwd.push_back(s);
     }
   }
-  // split-precision 64->64 conv helper (conv2, conv3): input [hi|lo] 128-wide, weights [w_hi|w_hi|w_lo]
+  // tail convs (conv2, upsampling, conv3, conv4): ONE fp16 product (default), or the split-precision form -- input [hi|lo] 128-wide,
+  // weights [w_hi|w_hi|w_lo], three bf16 products.  Pure bf16 misses the 5e-3 output bar (6.6e-3); fp16 operands measure 7.8e-4.
+  const int tch = tf16 ? 1 : 3, twrap = tf16 ? (1 << 20) : 2, tsplit = (ts == 128) ? 64 : 0;
+  const int tvalid = tf16 ? 64 : 128;  // channels of the tail buffers the forward convs read
+  const int wg_c0 = tf16 ? 64 : 0;     // first channel of the bf16 operand the tail weight gradients read (twin copy / hi half)
   auto split_pack = [&](int ci, int n_total, int n_valid, int mode) {
     int O, I; conv_dims(P, ci, &O, &I);
     PackOp op; memset(&op, 0, sizeof(op));
+    if (tf16) {  // ONE fp16 product: K = 64 in a single chunk
+      op.n_total = n_total; op.n_valid = n_valid; op.num_chunks = 1; op.mode = mode; op.nseg = 1; op.f16 = 1;
+      op.seg[0] = seg(0, 64, 2 * ci, O, I, 0, 0, 0);
+      return B.add_pack(op);
+    }
     op.n_total = n_total; op.n_valid = n_valid; op.num_chunks = 3; op.mode = mode; op.nseg = 3;
     op.seg[0] = seg(0, 64, 2 * ci, O, I, 0, 0, 0);
     op.seg[1] = seg(64, 64, 2 * ci, O, I, 0, 0, 0);
@@ -551,11 +568,11 @@ static int build_plan(b200sr_plan& P) {
   // conv2 (+ long skip)
   {
     const int row0 = split_pack(ci_conv2, 64, 64, kPackFwd);
-    ConvParams cp = base_conv_params(N, H, W, 3, 4, 0, 2, row0, 64, 64);
-    Step s = conv_step(B.add_map(P.o_splt, 128, 128, N, H, W, kABoxRows), cp, 1);
+    ConvParams cp = base_conv_params(N, H, W, tch, 4, 0, twrap, row0, 64, 64);
+    Step s = conv_step(B.add_map(P.o_splt, tvalid, ts, N, H, W, kABoxRows), cp, 1);
     s.bias = packed_bias(B.add_bias(64, 2 * ci_conv2 + 1, 64, 0));
     s.r1 = ws(P.o_t0);
-    s.ob = ws(P.o_spl[0]); s.cp.epi.ob_stride = 128; s.cp.epi.split_off = 64;
+    s.ob = ws(P.o_spl[0]); s.cp.epi.ob_stride = ts; s.cp.epi.split_off = tsplit; s.cp.epi.f16 = tf16; s.cp.mma_f16 = tf16;
     P.fwd.push_back(s);
   }
   // upsample stages: nearest x2 + conv == 4 phase convs on the low-res lattice, pixel-shuffled on store
@@ -563,30 +580,31 @@ static int build_plan(b200sr_plan& P) {
     const int ci = ci_up1 + (l - 1);
     const int h = H << (l - 1), w = W << (l - 1);
     const int row0 = split_pack(ci, 256, 256, kPackUpFwd);
-    ConvParams cp = base_conv_params(N, h, w, 3, 4, 0, 2, row0, 64, 256);  // 4 column groups (phases) of 64
-    Step s = conv_step(B.add_map(P.o_spl[l - 1], 128, 128, N, h, w, kABoxRows), cp, 2);
+    ConvParams cp = base_conv_params(N, h, w, tch, 4, 0, twrap, row0, 64, 256);  // 4 column groups (phases) of 64
+    Step s = conv_step(B.add_map(P.o_spl[l - 1], tvalid, ts, N, h, w, kABoxRows), cp, 2);
     s.bias = packed_bias(B.add_bias(256, 2 * ci + 1, 64, 64));
     s.cp.epi.act = 1;
     s.cp.epi.store_mode = kStoreShuffle;
-    s.ob = ws(P.o_spl[l]); s.cp.epi.ob_stride = 128; s.cp.epi.split_off = 64;
+    s.ob = ws(P.o_spl[l]); s.cp.epi.ob_stride = ts; s.cp.epi.split_off = tsplit; s.cp.epi.f16 = tf16; s.cp.mma_f16 = tf16;
     P.fwd.push_back(s);
   }
   const int hH = H << L, hW = W << L;
   // conv3
   {
     const int row0 = split_pack(ci_conv3, 64, 64, kPackFwd);
-    ConvParams cp = base_conv_params(N, hH, hW, 3, 4, 0, 2, row0, 64, 64);
-    Step s = conv_step(B.add_map(P.o_spl[L], 128, 128, N, hH, hW, kABoxRows), cp, 1);
+    ConvParams cp = base_conv_params(N, hH, hW, tch, 4, 0, twrap, row0, 64, 64);
+    Step s = conv_step(B.add_map(P.o_spl[L], tvalid, ts, N, hH, hW, kABoxRows), cp, 1);
     s.bias = packed_bias(B.add_bias(64, 2 * ci_conv3 + 1, 64, 0));
     s.cp.epi.act = 1;
-    s.ob = ws(P.o_splc); s.cp.epi.ob_stride = 128; s.cp.epi.split_off = 64;
+    s.ob = ws(P.o_splc); s.cp.epi.ob_stride = ts; s.cp.epi.split_off = tsplit; s.cp.epi.f16 = tf16; s.cp.mma_f16 = tf16;
     P.fwd.push_back(s);
   }
   // conv4 + clamp
   {
     const int row0 = split_pack(ci_conv4, 16, d.out_channels, kPackFwd);
-    ConvParams cp = base_conv_params(N, hH, hW, 3, 4, 0, 2, row0, 16, 16);
-    Step s = conv_step(B.add_map(P.o_splc, 128, 128, N, hH, hW, kABoxRows), cp, 1);
+    ConvParams cp = base_conv_params(N, hH, hW, tch, 4, 0, twrap, row0, 16, 16);
+    Step s = conv_step(B.add_map(P.o_splc, tvalid, ts, N, hH, hW, kABoxRows), cp, 1);
+    s.cp.epi.f16 = tf16; s.cp.mma_f16 = tf16;
     s.bias = packed_bias(B.add_bias(16, 2 * ci_conv4 + 1, d.out_channels, 0));
     s.cp.epi.store_mode = kStoreFinal;
     s.cp.epi.n_valid = d.out_channels;
@@ -667,7 +685,7 @@ static int build_plan(b200sr_plan& P) {
     };
     // conv4: wgrad, bias grad, dgrad (-> G3, masked by lrelu'(conv3 out))
     {
-      Step w4 = wgrad_step(P.o_splc, 64, 128, P.o_dyp, 16, 64, N, hH, hW, 0, 0, 16);
+      Step w4 = wgrad_step(P.o_splc, wg_c0 + 64, ts, P.o_dyp, 16, 64, N, hH, hW, wg_c0, 0, 16);
       add_seg(w4, 0, 16, wref(ci_conv4), 64, 0, (int)align_up(d.out_channels, 4));
       emit(w4);
       Step b4 = biasgrad_step(P.o_dyp, HRpix, 64, 0, 16);
@@ -676,13 +694,13 @@ static int build_plan(b200sr_plan& P) {
       const int row0 = dgrad_pack1(ci_conv4, 64, d.out_channels);
       ConvParams cp = base_conv_params(N, hH, hW, 1, 1, 0, 1 << 20, row0, 64, 64);
       Step s = conv_step(B.add_map(P.o_dyp, 16, 64, N, hH, hW, kABoxRows), cp, 1);
-      s.mask = ws(P.o_splc); s.cp.epi.mask_stride = 128; s.cp.epi.mask_coff = 0;
+      s.mask = ws(P.o_splc); s.cp.epi.mask_stride = ts; s.cp.epi.mask_coff = 0;
       s.ob = ws(P.o_g3); s.cp.epi.ob_stride = 64;
       emit(s);
     }
     // conv3
     {
-      Step w3 = wgrad_step(P.o_spl[L], 64, 128, P.o_g3, 64, 64, N, hH, hW, 0, 0, 64);
+      Step w3 = wgrad_step(P.o_spl[L], wg_c0 + 64, ts, P.o_g3, 64, 64, N, hH, hW, wg_c0, 0, 64);
       add_seg(w3, 0, 64, wref(ci_conv3), 64, 0, 64);
       emit(w3);
       Step b3 = biasgrad_step(P.o_g3, HRpix, 64, 0, 64);
@@ -692,7 +710,7 @@ static int build_plan(b200sr_plan& P) {
       ConvParams cp = base_conv_params(N, hH, hW, 1, 4, 0, 1 << 20, row0, 64, 64);
       Step s = conv_step(B.add_map(P.o_g3, 64, 64, N, hH, hW, kABoxRows), cp, 1);
       if (L >= 1) {
-        s.mask = ws(P.o_spl[L]); s.cp.epi.mask_stride = 128;
+        s.mask = ws(P.o_spl[L]); s.cp.epi.mask_stride = ts;
         s.ob = ws(P.o_gu[L]); s.cp.epi.ob_stride = 256; s.cp.epi.store_mode = kStoreUnshuffle;
       } else {
         s.of = ws(P.o_gt);
@@ -706,7 +724,7 @@ static int build_plan(b200sr_plan& P) {
       const int h = H << (l - 1), w = W << (l - 1);
       const long long npix = Ppix << (2 * (l - 1));
       for (int half = 0; half < 2; ++half) {
-        Step wu = wgrad_step(P.o_spl[l - 1], 64, 128, P.o_gu[l], 256, 256, N, h, w, 0, 128 * half, 128);
+        Step wu = wgrad_step(P.o_spl[l - 1], wg_c0 + 64, ts, P.o_gu[l], 256, 256, N, h, w, wg_c0, 128 * half, 128);
         Ref out = wref(ci);
         out.off += (long long)half * 32 * 64 * 4 * 4;  // 16-byte column chunks [32*half, +32) of the [tap][64 chunks][64 ci][4] staging tensor
         add_seg(wu, 0, 128, out, 64, 0, 256);
@@ -724,7 +742,7 @@ static int build_plan(b200sr_plan& P) {
       ConvParams cp = base_conv_params(N, h, w, 4, 4, 0, 1 << 20, row0, 64, 64);
       Step s = conv_step(B.add_map(P.o_gu[l], 256, 256, N, h, w, kABoxRows), cp, 1);
       if (l >= 2) {
-        s.mask = ws(P.o_spl[l - 1]); s.cp.epi.mask_stride = 128;
+        s.mask = ws(P.o_spl[l - 1]); s.cp.epi.mask_stride = ts;
         s.ob = ws(P.o_gu[l - 1]); s.cp.epi.ob_stride = 256; s.cp.epi.store_mode = kStoreUnshuffle;
       } else {
         s.of = ws(P.o_gt);
@@ -734,7 +752,7 @@ static int build_plan(b200sr_plan& P) {
     }
     // conv2
     {
-      Step w2 = wgrad_step(P.o_splt, 64, 128, P.o_gtb, 64, 64, N, H, W, 0, 0, 64);
+      Step w2 = wgrad_step(P.o_splt, wg_c0 + 64, ts, P.o_gtb, 64, 64, N, H, W, wg_c0, 0, 64);
       add_seg(w2, 0, 64, wref(ci_conv2), 64, 0, 64);
       emit(w2);
       Step b2 = biasgrad_step(P.o_gtb, Ppix, 64, 0, 64);
@@ -1801,7 +1819,8 @@ static int build_disc_plan(b200sr_plan& P) {
       if (s.bias.kind == RK_PACKED) s.bias.off = bias_base + (-1 - s.bias.off) * 4;
       // 16-bit format of every tensor of this plan: fp16 (the reference's autocast format) or bf16
       s.cp.epi.f16 = P.dd.fp16 ? 1 : 0;
-      s.wb.f16 = P.dd.fp16 ? 1 : 0;
+      s.cp.mma_f16 = P.dd.fp16 ? 1 : 0;
+      s.wb.a_f16 = s.wb.b_f16 = P.dd.fp16 ? 1 : 0;
       s.bp.f16 = P.dd.fp16 ? 1 : 0;
     }
   };
@@ -1842,6 +1861,8 @@ int b200sr_plan_create(const b200sr_net_desc* desc, b200sr_plan** out) {
   b200sr_plan* p = new b200sr_plan();
   p->d = *desc;
   if (const char* e = getenv("B200SR_REASSOC")) p->reassoc = atoi(e) != 0;  // 0: per-conv schedule everywhere
+  p->tail_f16 = desc->training == 0;  // training: the L1 loss' sign(sr - gt) amplifies the fp16 rounding of the tail past the 1e-2 gradient bar
+  if (const char* e = getenv("B200SR_TAIL_FP16")) p->tail_f16 = atoi(e) != 0;  // 0: split-precision bf16 tail everywhere, 1: fp16 tail everywhere
   int rc = build_plan(*p);
   if (rc) { delete p; return rc; }
   *out = p;

@@ -62,7 +62,8 @@ struct ConvEpilogue {
   int ob_stride;
   int ob_coff;
   float delta;
-  int split_off;  // > 0: also store lo = bf16(delta*v - hi) at channel ob_coff + split_off + col
+  int split_off;  // > 0: also store a second 16-bit copy at channel ob_coff + split_off + col: lo = bf16(delta*v - hi) (bf16 layers) or
+                  // bf16(delta*v) (fp16 layers: the bf16 twin the weight-gradient GEMM reads)
   int store_mode;
   unsigned char* clamp_mask;  // kStoreFinal, may be nullptr
   int n_valid;                // kStoreFinal: real output channels (<= 16)
@@ -78,7 +79,8 @@ struct ConvEpilogue {
   const __nv_bfloat16* res_bf16;
   int res_bf16_stride;
   int shuf_c;
-  int f16;  // 1: this layer's 16-bit operands / outputs / residual are fp16 instead of bf16 (same tcgen05 kind::f16 instruction)
+  int f16;  // 1: this layer's 16-bit operands / outputs / residual are fp16 instead of bf16 (same tcgen05 kind::f16 instruction): the
+            // generator's head / tail convs (one fp16 product instead of three split-bf16 ones) and the discriminator plans
 };
 
 struct ConvParams {
@@ -110,7 +112,8 @@ struct ConvParams {
   // data gradient: column group / down_c64); down_c64 = channels of one phase / 64.
   int down_mode;
   int down_c64;
-  int pad_[3];
+  int mma_f16;     // 1: the layer's activation AND weight tiles are fp16 (instruction descriptor a / b format); epi.f16 is the STORE format
+  int pad_[2];
   ConvEpilogue epi;
 };
 
@@ -287,14 +290,23 @@ __device__ __forceinline__ void conv_epilogue_write(const HW p, const ConvEpilog
     conv_store_dest<kExt>(p, e, n, y, x, col0, opix, ch);
     __nv_bfloat16* ob = e.out_bf16 + opix * e.ob_stride + e.ob_coff + ch;
     uint32_t hi[16];
+    if (e.f16) {  // (uniform branch: the generator's fp16 tail layers and the discriminator plans)
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      hi[j] = kExt ? pack_16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1], e.f16 != 0) : pack_bf16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1]);
+      for (int j = 0; j < 16; ++j) hi[j] = pack_f16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1]);
+    }
     uint32_t lo[16];
     if (e.split_off > 0) {
+      if (e.f16) {  // fp16 primary copy: the second copy is the SAME value in bf16 (weight-gradient operand: its MMA partner, dY, is bf16)
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        lo[j] = pack_bf16x2(e.delta * v[2 * j] - bf16_lo_to_f32(hi[j]), e.delta * v[2 * j + 1] - bf16_hi_to_f32(hi[j]));
+        for (int j = 0; j < 16; ++j) lo[j] = pack_bf16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1]);
+      } else {      // bf16 primary copy: the second copy is the rounding residual (split-precision operand pair [hi | lo])
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          lo[j] = pack_bf16x2(e.delta * v[2 * j] - bf16_lo_to_f32(hi[j]), e.delta * v[2 * j + 1] - bf16_hi_to_f32(hi[j]));
+      }
     }
     store_rows_quad(hi, ob, ok && !p.nostore, lane);
     if (e.split_off > 0) store_rows_quad(lo, ob + e.split_off, ok && !p.nostore, lane);
@@ -330,7 +342,7 @@ struct alignas(32) EntryDesc {
 constexpr int kMaxChainLayers = 768;
 constexpr int kMaxChainEntries = 2048;
 // layer record A: x = n_cols (9 bits) | chunks<<9 (5 bits) | ksteps_last<<14 | halves<<17 | w_taps<<19 | col_groups<<23
-//                 y = acc_col0 | acc_first<<8 | acc_hold<<9 | has_epi<<10 | k32<<11 | down_mode<<12 | down_c64<<14 | f16<<17      z = w_row0      w = a_c0
+//                 y = acc_col0 | acc_first<<8 | acc_hold<<9 | has_epi<<10 | k32<<11 | down_mode<<12 | down_c64<<14 | mma_f16<<17      z = w_row0      w = a_c0
 // layer record B: x = tiles_x | tiles_y<<16      y = a_wrap      z = bias byte offset in the packed buffer + 1 (0: none)      w = bias floats
 // entry record  : x = layer (absolute) | slot<<20 | neighbour_sync<<21      y = tile_lo      z = tile_hi      w = rot | (dep+1)<<16
 __constant__ uint4 c_layer_rec[kMaxChainLayers * 2];
@@ -339,7 +351,7 @@ inline void make_layer_rec(const ConvParams& p, uint4 out[2], const void* packed
   out[0].x = static_cast<uint32_t>(p.n_cols) | (p.num_chunks << 9) | (p.ksteps_last << 14) | (p.halves << 17) | (p.w_taps << 19) | (p.col_groups << 23);
   out[0].y = static_cast<uint32_t>(p.acc_col0) | ((p.acc_first ? 1u : 0u) << 8) | ((p.acc_hold ? 1u : 0u) << 9) | ((p.epi_cols > 0 ? 1u : 0u) << 10) |
              ((p.k32 ? 1u : 0u) << 11) | (static_cast<uint32_t>(p.down_mode & 3) << 12) | (static_cast<uint32_t>(p.down_c64 & 7) << 14) |
-             ((p.epi.f16 ? 1u : 0u) << 17);
+             ((p.mma_f16 ? 1u : 0u) << 17);
   out[0].z = static_cast<uint32_t>(p.w_row0);
   out[0].w = static_cast<uint32_t>(p.a_c0);
   out[1].x = static_cast<uint32_t>(p.tiles_x) | (static_cast<uint32_t>(p.tiles_y) << 16);
@@ -733,7 +745,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       const int k32 = static_cast<int>((la.y >> 11) & 1);
       const int down_mode = kVgg ? static_cast<int>((la.y >> 12) & 3) : 0, down_c64 = kVgg ? static_cast<int>((la.y >> 14) & 7) : 1;
       const int g = (w_taps * n_cols * (k32 ? 64 : 128) + kWGranule - 1) / kWGranule;
-      const uint32_t idesc = make_idesc_16(128, n_cols, 0, 0, kVgg && ((la.y >> 17) & 1));
+      const uint32_t idesc = make_idesc_16(128, n_cols, 0, 0, ((la.y >> 17) & 1) != 0);
       const uint32_t b_dy = static_cast<uint32_t>(n_cols) * (k32 ? 4u : 8u);  // bytes of one tap tile >> 4
       const uint32_t b_hi = k32 ? smem_desc_hi_sw64(512) : smem_desc_hi(1024);
       const int v = static_cast<int>((blockIdx.x + grid - static_cast<unsigned int>(rot)) % grid);

@@ -263,8 +263,11 @@ __device__ __forceinline__ float bf16_lo_to_f32(uint32_t v) { return __uint_as_f
 __device__ __forceinline__ float bf16_hi_to_f32(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 // fp16 operands (the U-Net discriminator path can run in the reference's autocast format): same instruction descriptor with the
 // a / b format fields left at F16 (0), and the matching 16-bit pack / unpack helpers selected by a flag
+__host__ __device__ constexpr uint32_t make_idesc_ab(uint32_t m, uint32_t n, uint32_t a_mn_major, uint32_t b_mn_major, bool a_f16, bool b_f16) {
+  return make_idesc_bf16(m, n, a_mn_major, b_mn_major) & ~((a_f16 ? (1u << 7) : 0u) | (b_f16 ? (1u << 10) : 0u));
+}
 __host__ __device__ constexpr uint32_t make_idesc_16(uint32_t m, uint32_t n, uint32_t a_mn_major, uint32_t b_mn_major, bool f16) {
-  return f16 ? (make_idesc_bf16(m, n, a_mn_major, b_mn_major) & ~((1u << 7) | (1u << 10))) : make_idesc_bf16(m, n, a_mn_major, b_mn_major);
+  return make_idesc_ab(m, n, a_mn_major, b_mn_major, f16, f16);
 }
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   __half2 v = __floats2half2_rn(lo, hi);

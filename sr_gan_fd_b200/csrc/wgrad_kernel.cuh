@@ -58,7 +58,7 @@ struct WgradBatch {
   int N, H, W;
   int tiles_x, tiles_y, num_tiles;
   int num_problems;
-  int f16;  // 1: X and dY are fp16 (discriminator plans in the reference's autocast format)
+  int a_f16, b_f16;  // 1: X (a) / dY (b) tiles are fp16 instead of bf16 (discriminator plans: both; the generator's fp16 tail activations: a)
   int cta_begin[kWgMaxProblems + 1];
   WgradParams prob[kWgMaxProblems];
 };
@@ -115,7 +115,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
   if (warp == 1) tmem_alloc_imm<512>(tmem_slot);
   if (p.bias_mode) {
-    for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += kWgThreads) reinterpret_cast<uint32_t*>(ones)[i] = batch.f16 ? 0x3C003C00u : 0x3F803F80u;  // 1.0 x2
+    for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += kWgThreads) reinterpret_cast<uint32_t*>(ones)[i] = batch.a_f16 ? 0x3C003C00u : 0x3F803F80u;  // 1.0 x2
     fence_proxy_async_smem();
   }
   tcgen05_fence_before();
@@ -151,7 +151,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (++s == S) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_16(128, p.n_cols, 1, 1, batch.f16 != 0);  // both operands MN-major
+    const uint32_t idesc = make_idesc_ab(128, p.n_cols, 1, 1, batch.a_f16 != 0, batch.b_f16 != 0);  // both operands MN-major
     constexpr uint32_t kHi = smem_desc_hi(1024);
     int s = 0;
     uint32_t ph = 0;

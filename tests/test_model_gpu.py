@@ -206,9 +206,11 @@ def test_full_size_config2_properties():
     F.l1_loss(sr, gt).backward()
     g1 = torch.cat([p.grad.flatten() for p in net.parameters()]).clone()
     assert torch.isfinite(g1).all() and float(g1.norm()) > 0
-    with torch.no_grad():
-        alone = net(lr[5:6])
+    alone = net(lr[5:6]).detach()  # same (training) plan family: same arithmetic
     assert orc.rel_l2(alone, sr[5:6]) < 1e-5
+    with torch.no_grad():          # inference plans run the head / tail convs as ONE fp16 product (training: three split-bf16 products)
+        alone_inf = net(lr[5:6])
+    assert orc.rel_l2(alone_inf, sr[5:6]) < 2e-3
     net.zero_grad(set_to_none=True)
     (F.l1_loss(net(lr), gt) * 1024.0).backward()
     g2 = torch.cat([p.grad.flatten() for p in net.parameters()])

@@ -1,2 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
-timeout 300 python -m pytest tests/test_gan_step_native_gpu.py -m gpu -q -s 2>&1 | grep "all-native" | cut -c1-300
+timeout 900 python -m pytest tests/test_model_gpu.py -m gpu -q 2>&1 | grep "^E  \|^FAILED\|Error\|passed\|failed" | cut -c1-300 | head -30
+for i in 1 2; do
+B200SR_LIB=$GRAFT_REPO_ROOT/sr_gan_fd_b200/libb200sr_base.so python tools/quick_bench.py 2>&1 | grep "fwd\|step" | sed 's/^/base /'
+python tools/quick_bench.py 2>&1 | grep "fwd\|step" | sed 's/^/cur  /'
+done
