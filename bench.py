@@ -372,7 +372,22 @@ def run_b200(args):
             stage[i][1].copy_(gt_host, non_blocking=True)
             copied[i].record(copy_stream)
 
-    def step_e2e():
+    # The loss is read back to the host EVERY step, asynchronously: the scalar goes device -> pinned host right behind the
+    # backward pass and the host picks it up one step later (the last one before the closing timestamp), so the host can
+    # enqueue step i+1 while the GPU finishes step i.  (A blocking loss.item() per step -- the reference loop's
+    # `losses.update(loss.item(), ...)` -- leaves the GPU idle while Python re-enters the module: reported as e2e.sync_readback.)
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    losses_read = []
+
+    def read_pending():
+        j = state.get("pending")
+        if j is not None:
+            loss_ready[j].synchronize()
+            losses_read.append(float(loss_host[j]))
+            state["pending"] = None
+
+    def step_e2e(sync_readback=False):
         i = state["i"]
         if not state["primed"]:
             consumed[0].record(); consumed[1].record()
@@ -387,14 +402,19 @@ def run_b200(args):
         loss.backward()
         consumed[i].record(cur)
         state["i"] = 1 - i
-        return loss.item()  # device -> host read of the step's result
+        if sync_readback:
+            return loss.item()  # blocking device -> host read of the step's result
+        loss_host[i].copy_(loss.detach(), non_blocking=True)  # device -> host read of the step's result (4 bytes, pinned)
+        loss_ready[i].record(cur)
+        read_pending()          # the PREVIOUS step's loss
+        state["pending"] = i
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, flush=None):
         # Python's cyclic GC is collected up front and held off inside the timed region (as timeit does): one generation-2
         # sweep over torch's object graph costs ~30 ms of host time, which lands in whichever 20-step window it fires in
         # (measured: end-to-end 14.3 ms/step at --steps 20 against 12.7 at --steps 10 and 40 before this)
@@ -406,6 +426,8 @@ def run_b200(args):
         e0.record()
         for _ in range(steps):
             fn()
+        if flush:
+            flush()  # (end to end: the last step's loss is read on the host before the closing timestamp)
         e1.record()
         barrier()
         gc.enable()
@@ -431,7 +453,10 @@ def run_b200(args):
     # end-to-end through the public API, host buffers in / loss out every step
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    read_pending()
+    ms_e2e = timed(step_e2e, args.steps, flush=read_pending) / args.steps
+    assert len(losses_read) == args.steps + 2 and all(v == v and v > 0 for v in losses_read), losses_read
+    ms_e2e_sync = timed(lambda: step_e2e(True), args.steps) / args.steps
     e2e_value = world * BATCH_PER_GPU / (ms_e2e * 1e-3)
 
     # dominant kernel (conv3x3_chain_kernel: every forward conv and every data-gradient conv): the forward pass is ONE
@@ -476,6 +501,8 @@ def run_b200(args):
                      "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "frac_of_sustained": achieved / sustained,
                      "peak_source": how, "traffic": traffic, "ms_forward": ms_fwd},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
+                "readback": "every step's loss copied device -> pinned host behind its backward pass, read by the host one step later (last one before the closing timestamp)",
+                "sync_readback": {"value": world * BATCH_PER_GPU / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync, "readback": "blocking loss.item() every step"},
                 "h2d_bytes_per_step": int(lr_host.numel() * 4 + gt_host.numel() * 4), "d2h_bytes_per_step": 4},
         # kernels of libb200sr.so launched inside the timed region (chain / wgrad / bias-grad / ingest / unpack / add); with the
         # data-parallel bucket hook (N > 1) the gradient unpack runs once per bucket instead of once per step

@@ -1075,6 +1075,29 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
           P.h_entries.push_back(e);
         }
         s.nentries = (int)P.h_entries.size() - s.entry0;
+        // Per-image announcements: an entry whose consumers all run the SAME tiles on the SAME CTAs (one tile per CTA) is announced
+        // image by image, and each consumer CTA waits only for the tiles of its own image -- a conv reads nothing of another image,
+        // and everything older is covered transitively (release / acquire chains stay inside the image's CTAs, which have
+        // themselves seen every earlier whole-entry announcement).  Images then drift apart instead of meeting at a 128-CTA
+        // rendezvous after every layer.
+        static const bool img_deps = [] { const char* e = getenv("B200SR_IMG_DEPS"); return e ? atoi(e) != 0 : true; }();
+        if (img_deps) {
+          std::vector<int> ok((size_t)s.nentries, -1);  // -1: no consumer yet, 1: all consumers eligible so far, 0: not eligible
+          for (int i = 0; i < s.nentries; ++i) {
+            const EntryDesc& e = P.h_entries[s.entry0 + i];
+            if (e.dep < 0) continue;
+            const EntryDesc& dpe = P.h_entries[s.entry0 + e.dep];
+            const ConvParams& ce = P.layer_steps[e.layer].cp;
+            const ConvParams& cd = P.layer_steps[dpe.layer].cp;
+            const int tpi = ce.tiles_x * ce.tiles_y, ntiles = e.tile_hi - e.tile_lo;
+            const bool same = ce.col_groups == 1 && cd.col_groups == 1 && e.tile_lo == dpe.tile_lo && e.tile_hi == dpe.tile_hi && e.rot == dpe.rot &&
+                              ce.tiles_x == cd.tiles_x && ce.tiles_y == cd.tiles_y && ntiles <= grid && tpi >= 2 && ntiles / tpi <= kCtrStride - 1;
+            if (!same) ok[e.dep] = 0;
+            else if (ok[e.dep] < 0) ok[e.dep] = 1;
+          }
+          for (int i = 0; i < s.nentries; ++i)
+            if (ok[i] == 1) P.h_entries[s.entry0 + i].pad[0] = 1;
+        }
       }
     };
     build_entries(P.fwd);
@@ -1084,7 +1107,7 @@ static int ensure_maps(b200sr_plan& P, void* wsp, void* packed, cudaStream_t st)
   if (!P.tables_ready) {
     P.tables_ready = true;
     CUDA_TRY(cudaMalloc(&P.d_entries, P.h_entries.size() * sizeof(EntryDesc)));
-    P.counters_bytes = 16384;  // per-entry completion counters of the chain being launched
+    P.counters_bytes = (size_t)kMaxChainEntries * kCtrStride * sizeof(unsigned int);  // completion counters of the chain being launched
     CUDA_TRY(cudaMalloc(&P.d_counters, P.counters_bytes));
     CUDA_TRY(cudaMemcpyAsync(P.d_entries, P.h_entries.data(), P.h_entries.size() * sizeof(EntryDesc), cudaMemcpyHostToDevice, st));
     std::vector<uint4> lrec(P.h_layers.size() * 2), erec(P.h_entries.size());
@@ -1131,7 +1154,7 @@ static int launch_chain(b200sr_plan& P, const Step& s, const Bases& b, cudaStrea
   float* y = (float*)b.y;
   int dbg = g_debug;
   unsigned int* ctr = P.d_counters;
-  CUDA_TRY(cudaMemsetAsync(ctr, 0, 16384, st));
+  CUDA_TRY(cudaMemsetAsync(ctr, 0, (size_t)s.nentries * kCtrStride * sizeof(unsigned int), st));
   const uint8_t* pw = (const uint8_t*)b.packed;
   void* args[] = {(void*)&layers, (void*)&entries, (void*)&ne, (void*)&pw, (void*)&ctr, (void*)&y, (void*)&dbg, (void*)&layer0};
   // <1, 0>: probes compiled in; <0, 1>: the VGG feature build (ReLU, feature store, 512-column bias vectors)

@@ -332,7 +332,9 @@ struct alignas(32) EntryDesc {
   int dep;               // entry whose completion gates this entry's input reads (-1: inputs exist before the launch)
   int rot;               // CTA rotation: virtual CTA v = (blockIdx.x - rot) mod gridDim.x takes items v, v + gridDim.x, ...
   int slot;              // dense-block passes: which of the CTA's two resident accumulator blocks this image group uses
-  int pad[2];            // pad[0] = 1: wait on the per-item flags of the dependency's 3 x 3 tile neighbourhood instead of its counter
+  int pad[2];            // pad[0] = 1: this entry announces itself PER IMAGE (counter 1 + image of the entry's range) instead of on the entry's
+                         // one counter: every entry that depends on it maps the same tiles to the same CTAs, so a consumer only waits
+                         // for the tiles of its OWN image (a conv reads nothing of another image)
 };
 
 // Compact per-layer / per-entry records for the TMA-producer and MMA-issuer warps, kept in CONSTANT memory: loads with a
@@ -344,7 +346,7 @@ constexpr int kMaxChainEntries = 2048;
 // layer record A: x = n_cols (9 bits) | chunks<<9 (5 bits) | ksteps_last<<14 | halves<<17 | w_taps<<19 | col_groups<<23
 //                 y = acc_col0 | acc_first<<8 | acc_hold<<9 | has_epi<<10 | k32<<11 | down_mode<<12 | down_c64<<14 | mma_f16<<17      z = w_row0      w = a_c0
 // layer record B: x = tiles_x | tiles_y<<16      y = a_wrap      z = bias byte offset in the packed buffer + 1 (0: none)      w = bias floats
-// entry record  : x = layer (absolute) | slot<<20 | neighbour_sync<<21      y = tile_lo      z = tile_hi      w = rot | (dep+1)<<16
+// entry record  : x = layer (absolute) | slot<<20 | per_image_announce<<21      y = tile_lo      z = tile_hi      w = rot | (dep+1)<<16
 __constant__ uint4 c_layer_rec[kMaxChainLayers * 2];
 __constant__ uint4 c_entry_rec[kMaxChainEntries];
 inline void make_layer_rec(const ConvParams& p, uint4 out[2], const void* packed_base) {
@@ -403,9 +405,12 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 // Wait until every CTA has finished entry `dep` (one lane polls; bounded so a broken chain traps instead of hanging).
-__device__ __forceinline__ void wait_entry_done(const unsigned int* counters, int dep, unsigned int need) {
+// Completion counters: kCtrStride words per entry -- word 0 counts the CTAs that finished their share of the entry (consumers whose
+// tile -> CTA mapping differs wait for all of them), words 1 + i the finished tiles of image i of the entry's range (per-image announce).
+constexpr int kCtrStride = 16;
+__device__ __forceinline__ void wait_entry_done(const unsigned int* ctr, int dep, unsigned int need) {
   const long long t0 = clock64();
-  while (ld_acquire_gpu(counters + dep) < need) {
+  while (ld_acquire_gpu(ctr) < need) {
     if (clock64() - t0 > 4000000000LL) {
       printf("b200sr: dependency wait timeout (block %d entry %d)\n", blockIdx.x, dep);
       __trap();
@@ -614,21 +619,27 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
       // wait sits AFTER the first weight stage has been requested (weights do not depend on the previous layer), right
       // before the first activation load.
       unsigned int dep_need = 0;
+      const unsigned int* dep_ctr = counters;
       if (dep >= 0) {  // only the CTAs that had work in the dependency announce it
         const uint4 dr = c_entry_rec[dep];
         const uint32_t dcg = (c_layer_rec[(static_cast<int>(dr.x & 0xFFFFF) - layer0) * 2].x >> 23) & 0x1F;
         const unsigned int dwork = (dr.z - dr.y) * dcg;
         dep_need = dwork < grid ? dwork : grid;
+        dep_ctr = counters + dep * kCtrStride;
+        if ((dr.x >> 21) & 1) {  // per-image announce (same tiles on the same CTAs in both entries): wait for this CTA's image only
+          dep_need = static_cast<unsigned int>(tiles_per_img);
+          dep_ctr += 1 + (v < num_work ? v / tiles_per_img : 0);
+        }
       }
       // One look at the dependency's counter is issued NOW and consumed only when the first activation load is due: its L2
       // round trip overlaps the waits for a free activation slot / weight granules below.
       unsigned int early_seen = 0;
-      if (dep >= 0 && v < num_work && lane == 0 && !(debug & 16)) early_seen = ld_acquire_gpu(counters + dep);
+      if (dep >= 0 && v < num_work && lane == 0 && !(debug & 16)) early_seen = ld_acquire_gpu(dep_ctr);
       // the dependency's counter shows every CTA that worked on it
       auto dependency_wait = [&]() {
         PROF_T0(pf);
         if (lane == 0) {
-          if (!(debug & 16) && early_seen < dep_need) wait_entry_done(counters, dep, dep_need);
+          if (!(debug & 16) && early_seen < dep_need) wait_entry_done(dep_ctr, dep, dep_need);
           if (!(debug & 512)) asm volatile("fence.proxy.async.global;" ::: "memory");  // TMA (async proxy) reads after generic-proxy stores (bit 512: timing experiment)
           // tell this CTA's epilogue warps (they read residual carriers written by earlier entries): acquire.gpu above,
           // release.cta here, acquire.cta on their side -- causality order is transitive
@@ -828,8 +839,13 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           // release: the epilogue warps' stores (ordered before this thread by the mbarrier hand-over) become visible at gpu
           // scope before the counter update -- one red.release instead of __threadfence() (fence.sc) + atomicAdd
           // (same-box A/B: 12.14 -> 12.08 ms/step; bit 256 of the timing probes: plain relaxed add)
-          if (debug & 256) atomicAdd(counters + e, 1u);
-          else asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counters + e), "r"(1u) : "memory");
+          unsigned int* ctr = counters + e * kCtrStride;
+          if ((er.x >> 21) & 1) {  // per-image announce: one tile per CTA, image = tile / tiles of an image
+            const uint32_t txy = c_layer_rec[(static_cast<int>(er.x & 0xFFFFF) - layer0) * 2 + 1].x;
+            ctr += 1 + v / ((txy & 0xFFFF) * (txy >> 16));
+          }
+          if (debug & 256) atomicAdd(ctr, 1u);
+          else asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
         }
         *sig_done = e + 1;
       }
