@@ -1,5 +1,2 @@
-timeout 900 python -m pytest tests/test_model_gpu.py tests/test_kernels_gpu.py -m gpu -q -x 2>&1 | grep "^E  \|^FAILED\|Error\|passed\|failed" | cut -c1-300 | head -30
-for i in 1 2; do
-B200SR_IMG_DEPS=0 python tools/quick_bench.py 2>&1 | grep "fwd\|step" | sed 's/^/group /'
-python tools/quick_bench.py 2>&1 | grep "fwd\|step" | sed 's/^/image /'
-done
+echo "=== baseline"; NCP=1 LO=40 HI=56 BRIEF= python tools/probe_timeline.py 2>&1 | sed -n 1,20p | cut -c1-150
+echo "=== no proxy fence (timing only)"; DBG=512 NCP=1 LO=40 HI=56 python tools/probe_timeline.py 2>&1 | sed -n 1,20p | cut -c1-150
