@@ -21,7 +21,10 @@
 
 namespace b200sr {
 
-constexpr int kWgTileH = 16;                          // wgrad K-tile: 8 x 16 pixels
+#ifndef B200SR_WG_TILEH
+#define B200SR_WG_TILEH 16
+#endif
+constexpr int kWgTileH = B200SR_WG_TILEH;             // wgrad K-tile: 8 x 16 pixels
 constexpr int kWgXRows = kWgTileH + 2;
 constexpr int kWgXBytes = kWgXRows * kTileW * 128;   // 18432 B per 64-channel haloed X tile
 constexpr int kWgBBytes = kWgTileH * kTileW * 128;   // 16384 B per 64-channel dY tile
@@ -165,14 +168,14 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (p.bias_mode) {
           const uint32_t o_lo = smem_desc_lo(smem_u32(ones), 2048);  // every K step reads the same all-ones tile
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) umma_bf16_ss_lohi(tmem_base, o_lo, b_lo + ks * 128, kHi, idesc, (ks == 0) ? acc : 1u);
+          for (int ks = 0; ks < kWgTileH / 2; ++ks) umma_bf16_ss_lohi(tmem_base, o_lo, b_lo + ks * 128, kHi, idesc, (ks == 0) ? acc : 1u);
         } else {
           const uint32_t a_lo = smem_desc_lo(a0, kWgXBytes);  // LBO = stride between the two 64-ch M blocks
 #pragma unroll
           for (int dyi = 0; dyi < 3; ++dyi) {
             if (!((dym >> dyi) & 1)) continue;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)  // 16 pixels (two 8-pixel patch rows) per UMMA
+            for (int ks = 0; ks < kWgTileH / 2; ++ks)  // 16 pixels (two 8-pixel patch rows) per UMMA
               umma_bf16_ss_lohi(tmem_base + dyi * p.n_cols, a_lo + dyi * 64 + ks * 128, b_lo + ks * 128, kHi, idesc,
                                 (ks == 0) ? acc : 1u);
           }
