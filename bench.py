@@ -97,28 +97,64 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_step(batch, threads):
-    """One L1 fwd+bwd of the oracle restatement (fp32, CPU) on `batch` 64x64 LR images.  Returns seconds."""
+def _reference_generator():
+    """The UNMODIFIED reference generator, if a staged copy of the reference tree travels with the repo (`baseline/_ref/ESRGAN/model.py`,
+    git-ignored; /root/reference itself does not exist on the GPU box): `rrdbnet_x4` built with rrdbnet_config.py's values.  None if the
+    copy is absent (then the oracle restatement stands in, `kind: "port"`)."""
+    path = os.path.join(ROOT, "baseline", "_ref", "ESRGAN", "model.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
     import torch
-    from oracle import rrdbnet_oracle as orc
+    try:
+        spec = importlib.util.spec_from_file_location("_reference_esrgan_model", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        torch.manual_seed(0)
+        net = mod.rrdbnet_x4(in_channels=3, out_channels=3, channels=64, growth_channels=32, num_blocks=NUM_BLOCKS)
+        return net.train()
+    except Exception as exc:  # e.g. torchvision missing on the box: say so and fall back to the port
+        sys.stderr.write(f"bench.py: staged reference not usable ({exc!r}); using the oracle port\n")
+        return None
+
+
+def cpu_reference_step(batch, threads):
+    """One L1 fwd+bwd (fp32, CPU) on `batch` 64x64 LR images: the reference's own RRDBNet driven as ESRGAN/train_rrdbnet.py:252-261 does
+    (zero_grad, forward, L1 criterion, backward; its CUDA autocast / GradScaler are no-ops on CPU tensors) when the staged reference is
+    present, else the oracle restatement.  Returns seconds."""
+    import torch
     torch.set_num_threads(threads)
-    params = cpu_reference_step.params
     lr = torch.rand(batch, 3, LR_HW, LR_HW)
     gt = torch.rand(batch, 3, LR_HW * SCALE, LR_HW * SCALE)
+    net = cpu_reference_step.net
+    if net is not None:
+        t0 = time.perf_counter()
+        net.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.l1_loss(net(lr), gt)
+        loss.backward()
+        loss.item()
+        return time.perf_counter() - t0
+    from oracle import rrdbnet_oracle as orc
     t0 = time.perf_counter()
-    orc.rrdbnet_l1_step(params, lr, gt)
+    orc.rrdbnet_l1_step(cpu_reference_step.params, lr, gt)
     return time.perf_counter() - t0
 
 
 def cpu_full_batch(warmup, steps, budget_s=420.0):
-    """THE CPU method of both arms: the oracle restatement (fp32, torch CPU, every host thread) on the FULL workload batch
-    (16 images, 64x64 LR -> 256x256, fwd+bwd L1), `warmup` untimed + `steps` timed steps.  Only if the first step shows the
-    whole run would exceed `budget_s` is the per-step sample cut to 8 / 4 images (and said so in `sample`)."""
+    """THE CPU method of both arms: the reference generator (staged copy of ESRGAN/model.py; else the oracle restatement) in fp32 on torch
+    CPU with every host thread, on the FULL workload batch (16 images, 64x64 LR -> 256x256, fwd+bwd L1), `warmup` untimed + `steps`
+    timed steps.  Only if the first step shows the whole run would exceed `budget_s` is the per-step sample cut to 8 / 4 images (and
+    said so in `sample`)."""
     import torch
-    from oracle import rrdbnet_oracle as orc
     torch.manual_seed(0)
     threads = os.cpu_count() or 1
-    cpu_reference_step.params = orc.init_params(seed=0, num_blocks=NUM_BLOCKS, upscale_factor=SCALE)
+    cpu_reference_step.net = _reference_generator()
+    if cpu_reference_step.net is None:
+        from oracle import rrdbnet_oracle as orc
+        cpu_reference_step.params = orc.init_params(seed=0, num_blocks=NUM_BLOCKS, upscale_factor=SCALE)
+    kind = "reference" if cpu_reference_step.net is not None else "port"
+    what = ("the reference's own RRDBNet (baseline/_ref/ESRGAN/model.py, unmodified) driven as train_rrdbnet.py does" if kind == "reference"
+            else "oracle restatement of ESRGAN/model.py")
     cpu_reference_step(1, threads)  # allocator / oneDNN primitive warm-up (1 image, untimed)
     batch = BATCH_PER_GPU
     t_first = cpu_reference_step(batch, threads)  # counts as the first warm-up step
@@ -129,8 +165,8 @@ def cpu_full_batch(warmup, steps, budget_s=420.0):
     times = [cpu_reference_step(batch, threads) for _ in range(steps)]
     sec = sum(times) / len(times)
     sample = (f"{batch} of {BATCH_PER_GPU} images per step ({'the full batch' if batch == BATCH_PER_GPU else 'bounded sample'}), "
-              f"{steps} timed steps after {max(warmup, 1)} warm-up, fp32 fwd+bwd L1, oracle restatement of ESRGAN/model.py, torch CPU")
-    return {"value": batch / sec, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+              f"{steps} timed steps after {max(warmup, 1)} warm-up, fp32 fwd+bwd L1, {what}, torch CPU")
+    return {"value": batch / sec, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
             "sec_per_step": sec, "batch": batch}
 
 

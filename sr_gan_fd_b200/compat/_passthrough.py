@@ -28,8 +28,19 @@ def _stub_basicsr() -> None:
     sys.modules.update({"basicsr": basicsr, "basicsr.utils": utils, "basicsr.utils.registry": registry})
 
 
+def reference_root() -> str:
+    """Where the reference tree lives: $SRGANFD_REFERENCE, else /root/reference (the build container), else the unmodified copy staged
+    under <repo>/baseline/_ref (git-ignored; travels to the GPU box with the snapshot, see __graft_entry__.stage_reference)."""
+    env = os.environ.get("SRGANFD_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir("/root/reference"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "baseline", "_ref")
+
+
 def load_reference_model(folder: str, module: str = "model"):
-    root = os.environ.get("SRGANFD_REFERENCE", "/root/reference")
+    root = reference_root()
     path = os.path.join(root, folder, module + ".py")
     if not os.path.isfile(path):
         return None

@@ -54,7 +54,7 @@ class _Noop:
 
 def main(argv=None) -> None:
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    ap.add_argument("--reference", default=os.environ.get("SRGANFD_REFERENCE", "/root/reference"))
+    ap.add_argument("--reference", default=None)
     ap.add_argument("--set", action="append", default=[], metavar="module.attr=value")
     ap.add_argument("--stub", action="append", default=[], metavar="module")
     ap.add_argument("--stock", action="store_true", help="do NOT install the shim: run the reference's own model.py (A/B runs)")
@@ -66,6 +66,9 @@ def main(argv=None) -> None:
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     args = ap.parse_args(argv)
 
+    if args.reference is None:
+        from ._passthrough import reference_root
+        args.reference = reference_root()
     os.environ["SRGANFD_REFERENCE"] = args.reference
     folder = os.path.join(args.reference, args.folder)
     script = os.path.join(folder, args.script)

@@ -2,7 +2,7 @@
 own ``DiscriminatorUNet`` and ``ContentLoss`` (seeded random-init VGG19 patched into torchvision: no ImageNet weights offline),
 a discriminator optimizer step BETWEEN the generator's forward and backward, and the generator backward under the summed
 (20 x L1 + 1 x content + 0.5 x adversarial) x 65536 upstream gradient.  The generator's parameter gradients must match the fp32
-oracle driven by the SAME upstream gradient.  Needs the reference tree for the critics (skipped on the GPU box; evidence of a run
+oracle driven by the SAME upstream gradient.  Needs the reference tree for the critics (/root/reference, or the staged copy under baseline/_ref on the GPU box; a log of a run
 on a B200 with a staged copy is kept in profiles/r2_gan_step.log)."""
 import os
 import sys
@@ -13,7 +13,11 @@ import torch
 from oracle import rrdbnet_oracle as orc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.environ.get("SRGANFD_REFERENCE", "/root/reference")
+from sr_gan_fd_b200.compat._passthrough import reference_root
+# $SRGANFD_REFERENCE, /root/reference (build container), or -- on the GPU box -- the unmodified copy staged by
+# __graft_entry__.stage_reference() under baseline/_ref (git-ignored, travels with the snapshot)
+REF = reference_root()
+os.environ["SRGANFD_REFERENCE"] = REF
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "BSRGAN", "model.py")), reason="reference tree not present")]
 

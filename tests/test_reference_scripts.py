@@ -1,6 +1,6 @@
 """Script-level proof: the reference's own ``inference.py`` / ``train_rrdbnet.py`` run UNCHANGED through the drop-in shim
 (``python -m sr_gan_fd_b200.compat.run``).  Needs the reference tree (``/root/reference`` in the build container, or
-``$SRGANFD_REFERENCE``); skipped where it is absent (the GPU box).  Evidence of the GPU variants run by hand on a B200 is
+``$SRGANFD_REFERENCE``, or the unmodified copy staged under ``baseline/_ref`` that travels to the GPU box); skipped only where none exists.  A log of the GPU variants on a B200 is
 kept under ``profiles/r2_reference_scripts_gpu.log``."""
 import os
 import subprocess
@@ -11,7 +11,11 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.environ.get("SRGANFD_REFERENCE", "/root/reference")
+from sr_gan_fd_b200.compat._passthrough import reference_root
+# $SRGANFD_REFERENCE, /root/reference (build container), or -- on the GPU box -- the unmodified copy staged by
+# __graft_entry__.stage_reference() under baseline/_ref (git-ignored, travels with the snapshot)
+REF = reference_root()
+os.environ["SRGANFD_REFERENCE"] = REF
 needs_ref = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "ESRGAN", "inference.py")), reason="reference tree not present")
 
 

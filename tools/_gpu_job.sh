@@ -1,8 +1,4 @@
-run() { python tools/quick_bench.py 2>&1 | grep "step" | sed "s/^/$1 /"; }
-for i in 1 2; do
-B200SR_LIB=$GRAFT_REPO_ROOT/sr_gan_fd_b200/libb200sr_base.so run "base(2str)  "
-run "cur(4str,99)"
-B200SR_LIB=$GRAFT_REPO_ROOT/sr_gan_fd_b200/libb200sr_th8.so run "tileH8      "
-done
-B200SR_LIB=$GRAFT_REPO_ROOT/sr_gan_fd_b200/libb200sr_th8.so timeout 600 python -m pytest tests/test_model_gpu.py -m gpu -q -x -k "gradients or golden" 2>&1 | tail -2
-timeout 600 python -m pytest tests/test_model_gpu.py tests/test_kernels_gpu.py -m gpu -q -x 2>&1 | tail -2
+ls /root/reference 2>&1 | head -2
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | cut -c1-250
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
