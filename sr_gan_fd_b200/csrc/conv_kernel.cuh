@@ -1006,7 +1006,9 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * 128u + p.acc_col0;
         bool released = false;
         constexpr int kEpiGroups = kVgg ? 4 : 2;  // 32-column groups per work item: 64 columns, or 128 in the extended build (wide layers)
-#pragma unroll
+        // NOT unrolled: the epilogue's instruction footprint matters more than the loop overhead -- ncu's stall sampling shows ~15 % of the
+        // epilogue warps' active samples waiting for instruction fetch (eleven warps of three roles share the SM's instruction caches)
+#pragma unroll 1
         for (int gq = 0; gq < kEpiGroups; ++gq) {
           const int c0 = gq * 32;
           if (c0 < p.epi_cols) {

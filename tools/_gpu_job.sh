@@ -1,4 +1,5 @@
-ls /root/reference 2>&1 | head -2
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
-timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | cut -c1-250
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+for i in 1 2; do
+B200SR_LIB=$GRAFT_REPO_ROOT/sr_gan_fd_b200/libb200sr_base.so python tools/quick_bench.py 2>&1 | grep "fwd\|step" | sed 's/^/base   /'
+python tools/quick_bench.py 2>&1 | grep "fwd\|step" | sed 's/^/nounr  /'
+done
+timeout 900 python -m pytest tests/test_model_gpu.py tests/test_kernels_gpu.py -m gpu -q -x 2>&1 | tail -2
