@@ -248,7 +248,7 @@ __device__ __forceinline__ void conv_store_dest(const HW p, const ConvEpilogue& 
 template <int kExt>
 __device__ __forceinline__ void conv_epilogue_write(const HW p, const ConvEpilogue& e, float* y_dyn, long long cbase, int n, int y, int x,
                                                     int col0, float (&v)[32], bool ok, int lane) {
-  if (e.store_mode == kStoreNCHW) {
+  if (__builtin_expect(e.store_mode == kStoreNCHW, 0)) {
     if (!ok) return;
     const long long plane = static_cast<long long>(p.H) * p.W;
     const long long base = static_cast<long long>(n) * e.n_valid * plane + static_cast<long long>(y) * p.W + x;
@@ -257,7 +257,7 @@ __device__ __forceinline__ void conv_epilogue_write(const HW p, const ConvEpilog
       if (col0 + i < e.n_valid) st_global_f32(y_dyn + base + (col0 + i) * plane, v[i]);
     return;
   }
-  if (e.store_mode == kStoreFinal) {
+  if (__builtin_expect(e.store_mode == kStoreFinal, 0)) {
     if (!ok) return;
     const long long plane = static_cast<long long>(p.H) * p.W;
     const long long base = static_cast<long long>(n) * e.n_valid * plane + static_cast<long long>(y) * p.W + x;
@@ -290,7 +290,7 @@ __device__ __forceinline__ void conv_epilogue_write(const HW p, const ConvEpilog
     conv_store_dest<kExt>(p, e, n, y, x, col0, opix, ch);
     __nv_bfloat16* ob = e.out_bf16 + opix * e.ob_stride + e.ob_coff + ch;
     uint32_t hi[16];
-    if (e.f16) {  // (uniform branch: the generator's fp16 tail layers and the discriminator plans)
+    if (__builtin_expect(e.f16 != 0, 0)) {  // (uniform branch: the generator's fp16 tail layers and the discriminator plans)
 #pragma unroll
       for (int j = 0; j < 16; ++j) hi[j] = pack_f16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1]);
     } else {
@@ -298,7 +298,7 @@ __device__ __forceinline__ void conv_epilogue_write(const HW p, const ConvEpilog
       for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1]);
     }
     uint32_t lo[16];
-    if (e.split_off > 0) {
+    if (__builtin_expect(e.split_off > 0, 0)) {
       if (e.f16) {  // fp16 primary copy: the second copy is the SAME value in bf16 (weight-gradient operand: its MMA partner, dY, is bf16)
 #pragma unroll
         for (int j = 0; j < 16; ++j) lo[j] = pack_bf16x2(e.delta * v[2 * j], e.delta * v[2 * j + 1]);
@@ -309,7 +309,7 @@ __device__ __forceinline__ void conv_epilogue_write(const HW p, const ConvEpilog
       }
     }
     store_rows_quad(hi, ob, ok && !p.nostore, lane);
-    if (e.split_off > 0) store_rows_quad(lo, ob + e.split_off, ok && !p.nostore, lane);
+    if (__builtin_expect(e.split_off > 0, 0)) store_rows_quad(lo, ob + e.split_off, ok && !p.nostore, lane);
   }
 }
 
@@ -1014,7 +1014,7 @@ conv3x3_chain_kernel(const LayerDesc* __restrict__ layers, const EntryDesc* __re
           if (c0 < p.epi_cols) {
             float vv[32];
             const int ncol = (p.epi_cols - c0) >= 32 ? 32 : 16;
-            if (ncol == 32) {
+            if (__builtin_expect(ncol == 32, 1)) {
               uint32_t r[32];
               tmem_ld_32x32b_x32(t_addr + c0, r);
               tmem_ld_wait();

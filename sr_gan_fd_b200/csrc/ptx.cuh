@@ -56,7 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (__builtin_expect(clock64() - t0 > 4000000000LL, 0)) {  // ~2 s at 2 GHz
       printf("b200sr: mbarrier wait timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
              threadIdx.x, smem_u32(bar), parity);
       __trap();
