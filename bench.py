@@ -9,11 +9,15 @@ accumulation (weak scaling: N=8 is exactly config 3's global batch 128); for N>1
 all-reduced (NCCL, averaged; by default ONE coalesced call issued when backward has enqueued its last kernel -- see
 sr_gan_fd_b200/dist.py).  One "step" = one fwd+bwd(+all-reduce) of the
 generator.  `value` = images/s with inputs resident in HBM, `e2e` = the same step driven through the public module API
-with pinned-host inputs copied in and the loss read back every step.  Rank 0 prints ONE JSON line.
+with pinned-host inputs copied in (side stream, one step ahead, like the reference's CUDAPrefetcher) and every step's loss
+copied back to pinned host memory and read by the host one step later (`e2e.sync_readback`: the same with a blocking
+`loss.item()` per step).  Rank 0 prints ONE JSON line.
 
-`--impl reference` times the reference's own CPU implementation of the same step (the fp32 oracle restatement of
-ESRGAN/model.py, asserted bit-equal to the reference classes in tests/; /root/reference itself is absent on the GPU
-box) on all host cores, on a bounded sample of the workload.
+`--impl reference` times the reference's own CPU implementation of the same step on all host cores: the UNMODIFIED
+`ESRGAN/model.py::rrdbnet_x4` from the staged copy under baseline/_ref (git-ignored; `__graft_entry__.stage_reference()`
+makes it in the build container and it travels to the GPU box, where /root/reference is absent), driven as
+train_rrdbnet.py:252-261 does (`cpu_baseline.kind = "reference"`); without the staged copy, the fp32 oracle restatement
+(asserted bit-equal to the reference classes in tests/; `kind = "port"`).  Full 16-image batch per step.
 """
 import argparse
 import json
