@@ -1,7 +1,5 @@
-for i in 1 2; do
-B200SR_LIB=$GRAFT_REPO_ROOT/sr_gan_fd_b200/libb200sr_base.so python tools/quick_bench.py 2>&1 | grep "step" | sed 's/^/base    /'
-python tools/quick_bench.py 2>&1 | grep "step" | sed 's/^/tailall /'
-done
-python tools/bench_disc.py 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('disc default', d.get('b200') or d)" 2>&1 | cut -c1-300
-B200SR_WGRAD_STREAMS=4 B200SR_WGRAD_SMS=99 python tools/bench_disc.py 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('disc 4x99   ', d.get('b200') or d)" 2>&1 | cut -c1-300
-B200SR_WGRAD_STREAMS=4 python tools/bench_disc.py 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('disc 4xall  ', d.get('b200') or d)" 2>&1 | cut -c1-300
+timeout 600 python bench.py --workload c4 --steps 5 --warmup 3 2>/dev/null | tail -1 > gpurun_out/r2g_c4_n1.json; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2g_c4_n1.json').read())
+print({k:d.get(k) for k in ('metric','value','unit','ms_per_step','n_gpus')}); print(json.dumps(d.get('config'))[:600]); print({k:v for k,v in d.items() if k not in ('config','clocks','metric')})
+PY
