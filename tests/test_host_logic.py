@@ -192,3 +192,33 @@ def test_schedule_dependent_bookkeeping(L):
     finally:
         L.b200sr_plan_destroy(big)
         L.b200sr_plan_destroy(base)
+
+
+def test_reference_root_and_staged_reference_generator():
+    """The reference tree resolves to $SRGANFD_REFERENCE, /root/reference or the staged copy under baseline/_ref, and bench.py's
+    reference arm builds the reference's OWN rrdbnet_x4 from the staged copy (cpu_baseline.kind = "reference") when it exists."""
+    import importlib.util
+    import sys
+    from sr_gan_fd_b200.compat._passthrough import reference_root
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    old = os.environ.pop("SRGANFD_REFERENCE", None)
+    try:
+        r = reference_root()
+        assert r == "/root/reference" if os.path.isdir("/root/reference") else r == os.path.join(root, "baseline", "_ref")
+        os.environ["SRGANFD_REFERENCE"] = "/somewhere/else"
+        assert reference_root() == "/somewhere/else"
+    finally:
+        os.environ.pop("SRGANFD_REFERENCE", None)
+        if old is not None:
+            os.environ["SRGANFD_REFERENCE"] = old
+    if not os.path.isfile(os.path.join(root, "baseline", "_ref", "ESRGAN", "model.py")):
+        pytest.skip("no staged reference copy (run __graft_entry__.build() where /root/reference exists)")
+    spec = importlib.util.spec_from_file_location("_bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    sys.modules["_bench_for_test"] = bench
+    spec.loader.exec_module(bench)
+    net = bench._reference_generator()
+    assert net is not None and type(net).__module__ == "_reference_esrgan_model"   # the reference's class, not the drop-in
+    assert sum(p.numel() for p in net.parameters()) == 16_697_987
+    mine = b200.rrdbnet_x4()
+    assert list(net.state_dict().keys()) == list(mine.state_dict().keys())

@@ -1,5 +1,5 @@
-timeout 600 python bench.py --workload c4 --steps 5 --warmup 3 2>/dev/null | tail -1 > gpurun_out/r2g_c4_n1.json; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2g_c4_n1.json').read())
-print({k:d.get(k) for k in ('metric','value','unit','ms_per_step','n_gpus')}); print(json.dumps(d.get('config'))[:600]); print({k:v for k,v in d.items() if k not in ('config','clocks','metric')})
-PY
+for i in 1 2; do
+B200SR_LIB=$GRAFT_REPO_ROOT/sr_gan_fd_b200/libb200sr_base.so python tools/quick_bench.py 2>&1 | grep "fwd\|step" | sed 's/^/base   /'
+python tools/quick_bench.py 2>&1 | grep "fwd\|step" | sed 's/^/mmaloop /'
+done
+timeout 600 python -m pytest tests/test_model_gpu.py tests/test_kernels_gpu.py -m gpu -q -x 2>&1 | tail -2
