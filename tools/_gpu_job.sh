@@ -1,5 +1,5 @@
 for i in 1 2; do
 B200SR_LIB=$GRAFT_REPO_ROOT/sr_gan_fd_b200/libb200sr_base.so python tools/quick_bench.py 2>&1 | grep "fwd\|step" | sed 's/^/base   /'
-python tools/quick_bench.py 2>&1 | grep "fwd\|step" | sed 's/^/mmaloop /'
+python tools/quick_bench.py 2>&1 | grep "fwd\|step" | sed 's/^/afirst /'
 done
 timeout 600 python -m pytest tests/test_model_gpu.py tests/test_kernels_gpu.py -m gpu -q -x 2>&1 | tail -2
