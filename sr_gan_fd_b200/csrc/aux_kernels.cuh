@@ -259,6 +259,64 @@ __global__ void __launch_bounds__(kBiasGradThreads) bias_grad_kernel(const BiasG
   }
 }
 
+// Vector form (ncols, c0 and stride multiples of 8): each thread owns EIGHT consecutive channels of a pixel row (one 16-byte load, four of
+// them in flight) and the launch uses at most two blocks per SM -- the scalar form above spends its time in the final atomics (one per
+// channel and block onto the SAME few addresses: ~45 ns each once a thousand blocks queue up on one address), not in the loads.
+__global__ void __launch_bounds__(kBiasGradThreads) bias_grad_vec_kernel(const BiasGradParams p) {
+  __shared__ float red[8 * kBiasGradThreads];
+  const int L = p.ncols >> 3;                 // 8-channel lanes per pixel row
+  const int PL = kBiasGradThreads / L;        // pixel lanes per block
+  const int cl = threadIdx.x % L;
+  const int pl = threadIdx.x / L;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const bool hf = p.f16 != 0;
+  auto add8 = [&](const uint4& w) {
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (hf) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
+        acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
+      } else {
+        acc[2 * j] += __uint_as_float(ww[j] << 16); acc[2 * j + 1] += __uint_as_float(ww[j] & 0xFFFF0000u);
+      }
+    }
+  };
+  if (pl < PL) {
+    const uint4* base = reinterpret_cast<const uint4*>(p.g + p.c0) + cl;
+    const long long step = static_cast<long long>(gridDim.x) * PL;
+    const long long sp = p.stride >> 3;
+    long long px = static_cast<long long>(blockIdx.x) * PL + pl;
+    for (; px + 3 * step < p.P; px += 4 * step) {
+      const uint4 v0 = __ldg(base + px * sp);
+      const uint4 v1 = __ldg(base + (px + step) * sp);
+      const uint4 v2 = __ldg(base + (px + 2 * step) * sp);
+      const uint4 v3 = __ldg(base + (px + 3 * step) * sp);
+      add8(v0); add8(v1); add8(v2); add8(v3);
+    }
+    for (; px < p.P; px += step) add8(__ldg(base + px * sp));
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[k * kBiasGradThreads + threadIdx.x] = acc[k];
+  __syncthreads();
+  if (pl == 0) {
+    for (int i = 1; i < PL; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += red[k * kBiasGradThreads + i * L + cl];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = 8 * cl + k;
+      for (int sgi = 0; sgi < p.nseg; ++sgi) {
+        const BiasGradSeg& sg = p.seg[sgi];
+        if (c >= sg.col_begin && c < sg.col_end && (c - sg.col_begin) < sg.n_valid) atomicAdd(sg.out + (c - sg.col_begin), acc[k]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------ unpack staged weight gradients to the OIHW flat buffer
 // src: [tap][co_pad/4][ci][4] fp32 staging tensor written by wgrad3x3_kernel;  dst: [co][ci][3][3] (state_dict layout).
 // fold = 1: src holds the four low-res phase kernels of an upsample conv ([tap][ci][4*64]) and they are folded back

@@ -1281,6 +1281,16 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         BiasGradParams bp = s.bp;
         bp.g = (const __nv_bfloat16*)resolve(s.bg_g, b);
         for (int i = 0; i < bp.nseg; ++i) bp.seg[i].out = (float*)resolve(s.seg_out[i], b);
+        static const bool vec_ok = [] { const char* e = getenv("B200SR_BIASGRAD_VEC"); return e ? atoi(e) != 0 : true; }();
+        if (vec_ok && bp.ncols % 8 == 0 && bp.ncols / 8 <= kBiasGradThreads && bp.c0 % 8 == 0 && bp.stride % 8 == 0 &&
+            (reinterpret_cast<uintptr_t>(bp.g) & 15) == 0) {
+          const int plv = kBiasGradThreads / (bp.ncols / 8);
+          long long blocks = (bp.P + plv * 8 - 1) / (plv * 8);
+          if (blocks > 2 * g_num_sms) blocks = 2 * g_num_sms;
+          bias_grad_vec_kernel<<<(int)blocks, kBiasGradThreads, 0, st>>>(bp);
+          CUDA_TRY(cudaGetLastError());
+          break;
+        }
         const int pl = kBiasGradThreads / (bp.ncols / 2);
         long long blocks = (bp.P + pl * 16 - 1) / (pl * 16);
         if (blocks > 8 * g_num_sms) blocks = 8 * g_num_sms;
