@@ -173,6 +173,7 @@ struct b200sr_plan {
   cudaStream_t side_stream[3] = {nullptr, nullptr, nullptr};  // extra streams for the weight-gradient launches (tails / heads overlap)
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   std::vector<long long> o_gu;
+  int bwd_overlap_chain = -1;          // index in `bwd` of the trunk data-gradient chain the tail's weight gradients run beside (-1: none)
   bool tail_f16 = false;              // conv2 / upsampling / conv3 / conv4 as ONE fp16 product each instead of three split-bf16 products:
                                       // default for inference plans; training plans keep the split form (B200SR_TAIL_FP16=0/1 overrides)
   bool reassoc = true;                // dense blocks re-associated by input slice ("windowed": convs 1-4 resident in TMEM, 128 columns per
@@ -767,6 +768,16 @@ static int build_plan(b200sr_plan& P) {
       // tail bucket: conv2 .. conv4 are contiguous at the end of the flat buffer
       emit(unpack_step(ci_conv2, nconv));
     }
+    // The data-gradient chain is cut ONCE, behind the HR tail: the tail's weight / bias gradients (HR-sized, L2-heavy, 8 % of the
+    // weight-gradient FLOPs but 12 % of their time) then run on the side streams WHILE the trunk chain -- latency-bound, launched on one
+    // CTA per work item of an image group (128 of 148 SMs at config 2) -- walks the 69 dense blocks (run_steps defers them behind it).
+    static const bool bwd_split = [] { const char* e = getenv("B200SR_BWD_SPLIT"); return e ? atoi(e) != 0 : true; }();
+    const bool split_here = bwd_split && P.reassoc && P.groups >= 2;
+    if (split_here) {
+      for (const Step& c : seg_convs) P.bwd.push_back(c);
+      for (const Step& o : seg_others) P.bwd.push_back(o);
+      seg_convs.clear(); seg_others.clear();
+    }
     // trunk, last dense block first
     int bucket_hi = ci_conv2;  // conv index (exclusive) up to which trunk gradients have been announced
     for (int r = R - 1; r >= 0; --r) {
@@ -955,6 +966,22 @@ static int build_plan(b200sr_plan& P) {
   };
   chainify(P.fwd);
   chainify(P.bwd);
+  {  // a trunk-only data-gradient chain behind a cut (see above) runs on one CTA per work item of an image group
+    int nchains = 0, last = -1;
+    for (size_t i = 0; i < P.bwd.size(); ++i)
+      if (P.bwd[i].type == ST_CHAIN && !P.bwd[i].needs_dx) { ++nchains; last = (int)i; }
+    if (nchains >= 2 && P.groups >= 2) {
+      Step& c = P.bwd[last];
+      int per_group = 0;
+      for (int l = 0; l < c.nlayers; ++l) {
+        const ConvParams& cp = P.layer_steps[c.layer0 + l].cp;
+        const int w = ((cp.N + P.groups - 1) / P.groups) * cp.tiles_x * cp.tiles_y * cp.col_groups;
+        if (w > per_group) per_group = w;
+      }
+      if (per_group > 0 && per_group < c.chain_grid) c.chain_grid = per_group;
+      P.bwd_overlap_chain = last;
+    }
+  }
   return 0;
 }
 
@@ -1236,8 +1263,65 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
     }
     return 0;
   };
-  for (Step& s : steps) {
+  auto ensure_streams = [&]() -> int {
+    if (!P.ev_fork) {
+      for (int k = 0; k < 3; ++k) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&P.side_stream[k], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&P.ev_join[k], cudaEventDisableTiming));
+      }
+      CUDA_TRY(cudaEventCreateWithFlags(&P.ev_fork, cudaEventDisableTiming));
+    }
+    return 0;
+  };
+  auto do_biasgrad = [&](const Step& s, cudaStream_t bs) -> int {
+    BiasGradParams bp = s.bp;
+    bp.g = (const __nv_bfloat16*)resolve(s.bg_g, b);
+    for (int i = 0; i < bp.nseg; ++i) bp.seg[i].out = (float*)resolve(s.seg_out[i], b);
+    static const bool vec_ok = [] { const char* e = getenv("B200SR_BIASGRAD_VEC"); return e ? atoi(e) != 0 : true; }();
+    if (vec_ok && bp.ncols % 8 == 0 && bp.ncols / 8 <= kBiasGradThreads && bp.c0 % 8 == 0 && bp.stride % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(bp.g) & 15) == 0) {
+      const int plv = kBiasGradThreads / (bp.ncols / 8);
+      long long blocks = (bp.P + plv * 8 - 1) / (plv * 8);
+      if (blocks > 2 * g_num_sms) blocks = 2 * g_num_sms;
+      bias_grad_vec_kernel<<<(int)blocks, kBiasGradThreads, 0, bs>>>(bp);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
+    const int pl = kBiasGradThreads / (bp.ncols / 2);
+    long long blocks = (bp.P + pl * 16 - 1) / (pl * 16);
+    if (blocks > 8 * g_num_sms) blocks = 8 * g_num_sms;
+    bias_grad_kernel<<<(int)blocks, kBiasGradThreads, 0, bs>>>(bp);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  };
+  // Weight / bias gradients that sit between two data-gradient chains (the HR tail's, see build_plan) are DEFERRED behind the launch of
+  // the second chain and go to the side streams only: the trunk chain, enqueued first, takes its SMs, they fill the rest and run beside it.
+  const int overlap_chain = (alternate && !cb && nstreams > 1 && b.grads) ? P.bwd_overlap_chain : -1;
+  std::vector<int> deferred;
+  for (size_t si = 0; si < steps.size(); ++si) {
+    Step& s = steps[si];
     if (s.needs_wgrad && !b.grads) continue;  // discriminator backward for the generator update: data gradients only
+    if (overlap_chain >= 0 && (int)si < overlap_chain && (s.type == ST_WGRAD || s.type == ST_BIASGRAD)) {
+      deferred.push_back((int)si);
+      continue;
+    }
+    if (overlap_chain >= 0 && (int)si == overlap_chain) {
+      int rc = ensure_streams(); if (rc) return rc;
+      CUDA_TRY(cudaEventRecord(P.ev_fork, st));  // everything the deferred kernels read exists once the FIRST chain is done
+      rc = launch_chain(P, s, b, st);
+      if (rc) return rc;
+      for (int k = 0; k < nstreams - 1; ++k) CUDA_TRY(cudaStreamWaitEvent(P.side_stream[k], P.ev_fork, 0));
+      int lane = 0;
+      for (int di : deferred) {
+        cudaStream_t ds = P.side_stream[lane++ % (nstreams - 1)];
+        if (steps[di].type == ST_WGRAD) rc = launch_wgrad(steps[di], P.maps()[steps[di].xmap], P.maps()[steps[di].dymap], b, ds, wgrad_cap);
+        else rc = do_biasgrad(steps[di], ds);
+        if (rc) return rc;
+      }
+      side_dirty = true;
+      forked = false;  // the trunk's own weight gradients fork again, behind this chain
+      continue;
+    }
     if (s.type == ST_DISC_UNPACK) { int rc = join(); if (rc) return rc; }
     if (alternate) {
       // the gradient unpack consumes what the weight-gradient launches of BOTH streams produced: join first (without a
@@ -1258,13 +1342,7 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
       case ST_WGRAD: {
         cudaStream_t ws = st;
         if (alternate) {
-          if (!P.ev_fork) {
-            for (int k = 0; k < 3; ++k) {
-              CUDA_TRY(cudaStreamCreateWithFlags(&P.side_stream[k], cudaStreamNonBlocking));
-              CUDA_TRY(cudaEventCreateWithFlags(&P.ev_join[k], cudaEventDisableTiming));
-            }
-            CUDA_TRY(cudaEventCreateWithFlags(&P.ev_fork, cudaEventDisableTiming));
-          }
+          { int rc = ensure_streams(); if (rc) return rc; }
           if (!forked) {  // the side stream starts after everything enqueued so far (the data-gradient chain)
             CUDA_TRY(cudaEventRecord(P.ev_fork, st));
             for (int k = 0; k < nstreams - 1; ++k) CUDA_TRY(cudaStreamWaitEvent(P.side_stream[k], P.ev_fork, 0));
@@ -1278,24 +1356,8 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         break;
       }
       case ST_BIASGRAD: {
-        BiasGradParams bp = s.bp;
-        bp.g = (const __nv_bfloat16*)resolve(s.bg_g, b);
-        for (int i = 0; i < bp.nseg; ++i) bp.seg[i].out = (float*)resolve(s.seg_out[i], b);
-        static const bool vec_ok = [] { const char* e = getenv("B200SR_BIASGRAD_VEC"); return e ? atoi(e) != 0 : true; }();
-        if (vec_ok && bp.ncols % 8 == 0 && bp.ncols / 8 <= kBiasGradThreads && bp.c0 % 8 == 0 && bp.stride % 8 == 0 &&
-            (reinterpret_cast<uintptr_t>(bp.g) & 15) == 0) {
-          const int plv = kBiasGradThreads / (bp.ncols / 8);
-          long long blocks = (bp.P + plv * 8 - 1) / (plv * 8);
-          if (blocks > 2 * g_num_sms) blocks = 2 * g_num_sms;
-          bias_grad_vec_kernel<<<(int)blocks, kBiasGradThreads, 0, st>>>(bp);
-          CUDA_TRY(cudaGetLastError());
-          break;
-        }
-        const int pl = kBiasGradThreads / (bp.ncols / 2);
-        long long blocks = (bp.P + pl * 16 - 1) / (pl * 16);
-        if (blocks > 8 * g_num_sms) blocks = 8 * g_num_sms;
-        bias_grad_kernel<<<(int)blocks, kBiasGradThreads, 0, st>>>(bp);
-        CUDA_TRY(cudaGetLastError());
+        int rc = do_biasgrad(s, st);
+        if (rc) return rc;
         break;
       }
       case ST_UNPACK: {
