@@ -1,1 +1,2 @@
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3x3_chain -s 6 -c 3 -o gpurun_out/r2i_chain -f python tools/profile_step.py > gpurun_out/r2i_ncu_c.log 2>&1; tail -2 gpurun_out/r2i_ncu_c.log
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -4
+timeout 900 python bench.py --no-cpu-baseline 2>/dev/null | tail -1 | cut -c1-400
