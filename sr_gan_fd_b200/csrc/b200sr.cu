@@ -1242,14 +1242,14 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
   // Weight-gradient launches of different dense blocks are independent of one another: once the data-gradient chain is
   // done they alternate between the caller's stream and a side stream, so the flush tail of one launch overlaps the ramp-up
   // of the next (each launch fills the GPU with one CTA per SM).  Everything that consumes their results joins first.
-  // Generator plans (round 2, same-box scan over streams x CTAs per launch): FOUR streams with about two thirds of the SMs per launch
+  // Generator plans (round 2, same-box scans over streams x CTAs per launch): FOUR streams with HALF of the SMs per launch
   // -- fewer pixel splits per dense block = fewer partial sums flushed with red.global.add into the same addresses, and the launches
   // of neighbouring blocks run side by side -- 11.93 -> 11.73 ms/step (2 streams x all SMs: the round-1 setting, kept for the
   // discriminator / VGG plans).  B200SR_WGRAD_STREAMS / B200SR_WGRAD_SMS override both.
   static const int env_streams = [] { const char* e = getenv("B200SR_WGRAD_STREAMS"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 4 ? 4 : v); }();
   const bool gen_plan = !P.is_disc && !P.is_vgg;
   const int nstreams = env_streams > 0 ? env_streams : (gen_plan ? 4 : 2);
-  const int wgrad_cap = gen_plan ? (g_num_sms * 2 + 1) / 3 : 0;
+  const int wgrad_cap = gen_plan ? g_num_sms / 2 : 0;  // two launches exactly side by side (74 + 74 on 148 SMs)
   const bool alternate = nstreams > 1 && (&steps == &P.bwd);
   bool forked = false, side_dirty = false;
   int wcount = 0;
