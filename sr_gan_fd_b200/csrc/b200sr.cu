@@ -1337,6 +1337,7 @@ static int run_steps(b200sr_plan& P, std::vector<Step>& steps, const Bases& b, c
         if (s.needs_dx && !b.y) break;  // nobody asked for the input gradient
         int rc = launch_chain(P, s, b, st);
         if (rc) return rc;
+        forked = false;  // weight gradients behind this chain read what it produces: the side streams fork again after it
         break;
       }
       case ST_WGRAD: {
